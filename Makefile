@@ -1,0 +1,50 @@
+# Build recipe for libsmgpu.so (product), the smoothMesh CLI and the CPU oracle.
+# __graft_entry__.build() runs `make all`.
+NVCC      ?= nvcc
+CXX       := $(shell test -x /usr/bin/g++ && echo /usr/bin/g++ || echo g++)
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+# --fmad=false: FP64 results must match a scalar IEEE evaluation bit for bit
+NVFLAGS   := -ccbin $(CXX) $(ARCH) -O3 -lineinfo --fmad=false -std=c++17 -Xcompiler -fPIC,-fopenmp,-ffp-contract=off,-Wall
+CXXFLAGS  := -O3 -std=c++17 -fPIC -fopenmp -ffp-contract=off -Wall
+CSRC      := smoothmesh_b200/csrc
+LIBDIR    := smoothmesh_b200/lib
+BINDIR    := smoothmesh_b200/bin
+OBJDIR    := build
+
+LIB       := $(LIBDIR)/libsmgpu.so
+CLI       := $(BINDIR)/smoothMesh
+ORACLE    := oracle/_build/liboracle.so
+ORACLE_LM := oracle/_build/liboracle_libm.so
+
+all: $(LIB) $(CLI) $(ORACLE) $(ORACLE_LM)
+
+$(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
+	@mkdir -p $(OBJDIR)
+	$(CXX) $(CXXFLAGS) -c $< -o $@
+
+$(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) $(wildcard include/*.h)
+	@mkdir -p $(OBJDIR)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
+
+LIBOBJS := $(OBJDIR)/smgpu.o $(OBJDIR)/comm.o $(OBJDIR)/polymesh.o $(OBJDIR)/topology.o $(OBJDIR)/smmesh_api.o
+
+$(LIB): $(LIBOBJS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(LIBOBJS) -Xcompiler -fopenmp -lnccl
+
+$(CLI): $(CSRC)/smoothmesh_cli.cpp $(LIB)
+	@mkdir -p $(BINDIR)
+	$(CXX) $(CXXFLAGS) -o $@ $< -L$(LIBDIR) -lsmgpu -Wl,-rpath,'$$ORIGIN/../lib'
+
+$(ORACLE): oracle/oracle.cpp $(CSRC)/sm_math.h
+	@mkdir -p oracle/_build
+	$(CXX) $(CXXFLAGS) -shared -o $@ oracle/oracle.cpp
+
+$(ORACLE_LM): oracle/oracle.cpp $(CSRC)/sm_math.h
+	@mkdir -p oracle/_build
+	$(CXX) $(CXXFLAGS) -DORACLE_LIBM_ACOS -shared -o $@ oracle/oracle.cpp
+
+clean:
+	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) oracle/_build
+
+.PHONY: all clean

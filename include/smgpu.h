@@ -1,0 +1,147 @@
+/* smgpu.h -- C ABI of libsmgpu.so: the B200 (sm_100a) implementation of
+ * smoothMesh's centroidal smoothing iteration.
+ *
+ * The reference (tkeskita/smoothMesh) has no FFI: its hot path is a set of
+ * free functions called from main()'s loop, src/smoothMesh.C:2257-2437, on
+ * OpenFOAM containers.  This header is the seam a maintainer binds instead
+ * (see INTEGRATION.md for the OpenFOAM-side shim): plain pointers and sizes,
+ * int status codes, no exceptions, no C++/torch types.
+ *
+ * Conventions
+ *   - label = int32_t (OpenFOAM default), scalar = double, vector = 3 doubles
+ *     (pointField storage), boolList = one uint8_t per element.
+ *   - every function returns SMGPU_OK (0) or a negative error code;
+ *     smgpu_last_error() returns the message of the last failure on the
+ *     calling thread.  Conditions on which the reference calls
+ *     FatalError/abort (src/smoothMesh.C:61-66, 354-362, 1073, 1087) are
+ *     reported as SMGPU_ERR_MESH with the reference's message text.
+ *   - one host thread per handle; calls on one handle must be serialised.
+ *   - there is no CPU fallback: without a CUDA device smgpu_create fails.
+ */
+#ifndef SMGPU_H
+#define SMGPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define SMGPU_OK 0
+#define SMGPU_ERR_ARG -1
+#define SMGPU_ERR_MESH -2
+#define SMGPU_ERR_CUDA -3
+#define SMGPU_ERR_COMM -4
+#define SMGPU_ERR_IO -5
+
+#define SMGPU_PATCH_BOUNDARY 0  /* wall, patch, ... : points on it are not "internal" */
+#define SMGPU_PATCH_PROCESSOR 1 /* processorPolyPatch: skipped, src/smoothMesh.C:57-58 */
+#define SMGPU_PATCH_EMPTY 2     /* emptyPolyPatch: fatal, src/smoothMesh.C:61-66 */
+
+    /* What the host flattens an fvMesh into (replaces the `const fvMesh& mesh`
+     * argument of every L3 function, e.g. src/smoothMesh.C:96-101). */
+    typedef struct smgpu_mesh_desc
+    {
+        int64_t n_points, n_cells, n_faces, n_internal_faces;
+        const double *points;        /* [3*n_points]  mesh.points()            */
+        const int32_t *face_offsets; /* [n_faces+1]   mesh.faces() flattened   */
+        const int32_t *face_verts;   /* [face_offsets[n_faces]]                */
+        const int32_t *owner;        /* [n_faces]     mesh.faceOwner()         */
+        const int32_t *neighbour;    /* [n_internal_faces] mesh.faceNeighbour() */
+        int32_t n_patches;           /* mesh.boundaryMesh()                    */
+        const int32_t *patch_start;  /* [n_patches]                            */
+        const int32_t *patch_size;   /* [n_patches]                            */
+        const int32_t *patch_kind;   /* [n_patches] SMGPU_PATCH_*              */
+        /* decomposed (multi-GPU) runs only, else NULL: global label of every local
+         * point (decomposePar's pointProcAddressing); defines which points are
+         * shared between ranks for the syncTools::syncPointList replacements. */
+        const int64_t *point_global_id;
+    } smgpu_mesh_desc;
+
+    /* The options of src/smoothMesh.C:1861-1918 that reach the hot path.
+     * Negative min_edge_length / max_step_length select the reference defaults
+     * (0.5 * mesh min edge length, 0.3 * min_edge_length; :1861-1865). */
+    typedef struct smgpu_params
+    {
+        double min_edge_length;
+        double max_step_length;
+        double rel_step_frac;  /* 0.5  */
+        double min_angle_deg;  /* 35   */
+        double max_angle_deg;  /* 160  */
+        double rel_tol;        /* 0.02 */
+        int32_t total_min_freeze;      /* 0 */
+        int32_t edge_angle_constraint; /* 1 */
+        int32_t face_angle_constraint; /* 1 */
+        int32_t geometry_variant;      /* 0 = openfoam.com face-centre formula, 1 = openfoam.org */
+        int32_t device;                /* CUDA device ordinal */
+        int32_t renumber;              /* 0 = keep mesh order in HBM, 1 = space-filling-curve storage order */
+    } smgpu_params;
+
+    typedef struct smgpu_handle smgpu_handle;
+
+    void smgpu_default_params(smgpu_params *p);
+    const char *smgpu_last_error(void);
+    const char *smgpu_version(void);
+
+    /* Build derived connectivity, upload everything once, keep it resident in HBM. */
+    int smgpu_create(const smgpu_mesh_desc *mesh, const smgpu_params *params, smgpu_handle **out);
+    int smgpu_destroy(smgpu_handle *h);
+
+    /* Effective parameters after default resolution, and mesh statistics
+     * (getMeshStats, src/smoothMesh.C:1478-1541; findInternalMeshPoints :40-91). */
+    int smgpu_get_params(smgpu_handle *h, smgpu_params *out);
+    int smgpu_set_params(smgpu_handle *h, const smgpu_params *p);
+    int smgpu_mesh_stats(smgpu_handle *h, double *min_edge, double *max_edge, int64_t *n_internal_points,
+                         int64_t *n_edges);
+
+    /* Run up to max_iters smoothing iterations (the loop body of
+     * src/smoothMesh.C:2257-2437 minus file output).  Stops after the first
+     * iteration whose residual < rel_tol (:2401).  n_frozen[i] / residual[i]
+     * receive what the reference prints at :2396 for iteration i (either may be
+     * NULL).  *iters_done = iterations executed.  In a multi-rank run the values
+     * are the global sum / max on every rank. */
+    int smgpu_iterate(smgpu_handle *h, int32_t max_iters, int64_t *n_frozen, double *residual, int32_t *iters_done);
+
+    /* mesh.points() / isFrozenPoint of the last executed iteration. */
+    int smgpu_get_points(smgpu_handle *h, double *points_out /* [3*n_points] */);
+    int smgpu_set_points(smgpu_handle *h, const double *points_in /* [3*n_points] */);
+    int smgpu_get_frozen(smgpu_handle *h, uint8_t *frozen_out /* [n_points] */);
+
+    /* Device-timed duration (CUDA events) of the last smgpu_iterate call, in
+     * milliseconds, and the number of kernels it launched. */
+    int smgpu_last_timing(smgpu_handle *h, double *ms, int64_t *launches);
+
+    /* ---- operator-level entry points -------------------------------------------
+     * One call per reference L3 function, for parity tests and for hosts that
+     * keep the reference's loop structure.  They operate on the handle's device
+     * state: `points` (current mesh), `newPoints` (proposal), `isFrozenPoint`. */
+    /* OpenFOAM geometry after movePoints: mesh.cellCentres() (src/smoothMesh.C:129,1218) */
+    int smgpu_op_cell_centres(smgpu_handle *h, double *cell_centres_out /* [3*n_cells] or NULL */);
+    /* isFrozenPoint = false (:2262), centroidalSmoothing (:96-166) + aspectRatioSmoothing
+     * (:548-593) + constrainMaxStepLength (:684-754) -> newPoints */
+    int smgpu_op_predict(smgpu_handle *h, double *new_points_out /* [3*n_points] or NULL */);
+    /* restrictEdgeShortening (:602-652) then, if enabled, restrictMinEdgeAngleDecrease (:900-930) */
+    int smgpu_op_edge_constraints(smgpu_handle *h, uint8_t *frozen_out /* or NULL */);
+    /* restrictFaceAngleDeterioration (:1320-1437) */
+    int smgpu_op_face_angle_constraint(smgpu_handle *h, uint8_t *frozen_out /* or NULL */);
+    /* restore + count + calculateResidual + movePoints (:2384-2399) */
+    int smgpu_op_commit(smgpu_handle *h, int64_t *n_frozen, double *residual);
+    /* calcMinMaxFaceAngleForEdge for the current mesh (:1135-1231): per-edge min/max */
+    int smgpu_op_edge_face_angles(smgpu_handle *h, double *min_out /* [n_edges] */, double *max_out /* [n_edges] */);
+    /* edge list (lo,hi) in the library's (OpenFOAM upper-triangular) numbering */
+    int smgpu_get_edges(smgpu_handle *h, int32_t *edges_out /* [2*n_edges] */);
+    /* derived tables, flattened: name in {pointCells, pointPoints, pointEdges, edgeFaces, edgeCells};
+     * offsets may be NULL to query the number of values (returned through *n_values). */
+    int smgpu_get_csr(smgpu_handle *h, const char *name, int32_t *offsets, int32_t *values, int64_t *n_values);
+
+    /* ---- multi-GPU (one process per GPU) ------------------------------------------
+     * Replaces syncTools::syncPointList / returnReduce over MPI by
+     * NCCL.  nccl_unique_id is the 128-byte ncclUniqueId produced on rank 0
+     * (smgpu_comm_unique_id) and distributed by the host. */
+    int smgpu_comm_unique_id(uint8_t id_out[128]);
+    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t nccl_unique_id[128]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

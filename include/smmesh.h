@@ -1,0 +1,68 @@
+/* smmesh.h -- C ABI of the host-side polyMesh helpers in libsmgpu.so:
+ * reading/writing OpenFOAM polyMesh directories, synthetic mesh generators
+ * (stand-ins for blockMesh / polyDualMesh, which are not available without
+ * OpenFOAM) and cell decomposition (stand-in for decomposePar).
+ *
+ * Reference interfaces replaced: the fvMesh constructed by createMesh.H
+ * (src/smoothMesh.C:1814-1818), mesh.write() (:2430), and the mesh
+ * utilities the test scripts call (testcase/run_serial:11-16,
+ * testcase/system/decomposeParDict).  Everything here is CPU-side setup; none
+ * of it is on the per-iteration path.
+ */
+#ifndef SMMESH_H
+#define SMMESH_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+    typedef struct smmesh smmesh;
+
+    const char *smmesh_last_error(void);
+    void smmesh_free(smmesh *m);
+
+    /* constructors: return NULL on failure */
+    smmesh *smmesh_gen_hex_block(int32_t nx, int32_t ny, int32_t nz, const double lo[3], const double hi[3]);
+    smmesh *smmesh_gen_kelvin(int32_t n, double h);
+    smmesh *smmesh_from_cells(int64_t n_points, const double *points, int32_t n_cells, const int32_t *cell_face_offsets,
+                              const int32_t *cf_vert_offsets, const int32_t *cf_verts, const int32_t *cf_patch,
+                              int32_t n_patches, const char *const *patch_names, const char *const *patch_types);
+    smmesh *smmesh_from_arrays(int64_t n_points, const double *points, int64_t n_faces, const int32_t *face_offsets,
+                               const int32_t *face_verts, const int32_t *owner, int64_t n_internal_faces,
+                               const int32_t *neighbour, int64_t n_cells, int32_t n_patches, const int32_t *patch_start,
+                               const int32_t *patch_size, const int32_t *patch_kind);
+    smmesh *smmesh_read(const char *polymesh_dir);
+    /* replace the point coordinates of m by those of an OpenFOAM points file (same point count) */
+    int smmesh_read_points(smmesh *m, const char *points_file);
+    int smmesh_write(const smmesh *m, const char *polymesh_dir, int32_t binary, int32_t precision);
+    int smmesh_write_points(const double *points, int64_t n_points, const char *polymesh_dir, int32_t binary,
+                            int32_t precision, const char *location);
+
+    /* in-place: interior point jitter U(-amp, amp), counter-based RNG keyed on global point label */
+    int smmesh_jitter(smmesh *m, double amp, uint64_t seed);
+
+    /* sizes: what = 0 points, 1 cells, 2 faces, 3 internal faces, 4 face-vertex entries, 5 patches */
+    int64_t smmesh_size(const smmesh *m, int32_t what);
+    /* borrowed pointers, valid until smmesh_free */
+    const double *smmesh_points(const smmesh *m);
+    double *smmesh_points_mut(smmesh *m);
+    const int32_t *smmesh_face_offsets(const smmesh *m);
+    const int32_t *smmesh_face_verts(const smmesh *m);
+    const int32_t *smmesh_owner(const smmesh *m);
+    const int32_t *smmesh_neighbour(const smmesh *m);
+    /* patch table: kind per smgpu.h SMGPU_PATCH_* */
+    int smmesh_patches(const smmesh *m, int32_t *start, int32_t *size, int32_t *kind);
+    const char *smmesh_patch_name(const smmesh *m, int32_t i);
+    const int64_t *smmesh_point_global_id(const smmesh *m); /* NULL for undecomposed meshes */
+    const int64_t *smmesh_cell_global_id(const smmesh *m);
+
+    /* decomposition: method 0 = bricks px*py*pz, 1 = recursive coordinate bisection into px parts.
+     * parts_out receives n_parts (= px*py*pz or px) new meshes. */
+    int smmesh_decompose(const smmesh *m, int32_t method, int32_t px, int32_t py, int32_t pz, smmesh **parts_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

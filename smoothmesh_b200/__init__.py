@@ -1,0 +1,435 @@
+"""smoothmesh_b200 -- thin ctypes binding over libsmgpu.so (include/smgpu.h, include/smmesh.h).
+
+The product is the CUDA library and the C++ `smoothMesh` CLI; this module only
+exists so that tests and bench.py can drive the C ABI from Python.  Names mirror
+the reference's vocabulary (src/smoothMesh.C): `Mesh` is the polyMesh, `Smoother`
+owns the device-resident state and runs the iteration loop of :2257-2437.
+
+There is no CPU fallback: `Smoother` raises if the library or a CUDA device is
+missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsmgpu.so")
+CLI_PATH = os.path.join(_HERE, "bin", "smoothMesh")
+
+_lib = None
+
+
+class SmoothMeshError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """smgpu_params (include/smgpu.h); defaults = src/smoothMesh.C:1861-1914."""
+
+    _fields_ = [
+        ("min_edge_length", C.c_double),
+        ("max_step_length", C.c_double),
+        ("rel_step_frac", C.c_double),
+        ("min_angle_deg", C.c_double),
+        ("max_angle_deg", C.c_double),
+        ("rel_tol", C.c_double),
+        ("total_min_freeze", C.c_int32),
+        ("edge_angle_constraint", C.c_int32),
+        ("face_angle_constraint", C.c_int32),
+        ("geometry_variant", C.c_int32),
+        ("device", C.c_int32),
+        ("renumber", C.c_int32),
+    ]
+
+
+class _MeshDesc(C.Structure):
+    _fields_ = [
+        ("n_points", C.c_int64),
+        ("n_cells", C.c_int64),
+        ("n_faces", C.c_int64),
+        ("n_internal_faces", C.c_int64),
+        ("points", C.c_void_p),
+        ("face_offsets", C.c_void_p),
+        ("face_verts", C.c_void_p),
+        ("owner", C.c_void_p),
+        ("neighbour", C.c_void_p),
+        ("n_patches", C.c_int32),
+        ("patch_start", C.c_void_p),
+        ("patch_size", C.c_void_p),
+        ("patch_kind", C.c_void_p),
+        ("point_global_id", C.c_void_p),
+    ]
+
+
+def lib():
+    """Load libsmgpu.so (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SmoothMeshError(f"{LIB_PATH} not found: run `make` (or __graft_entry__.build()) first")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        L.smgpu_last_error.restype = C.c_char_p
+        L.smgpu_version.restype = C.c_char_p
+        L.smmesh_last_error.restype = C.c_char_p
+        L.smmesh_patch_name.restype = C.c_char_p
+        for f in ("smmesh_gen_hex_block", "smmesh_gen_kelvin", "smmesh_from_cells", "smmesh_from_arrays", "smmesh_read"):
+            getattr(L, f).restype = C.c_void_p
+        for f in ("smmesh_points", "smmesh_points_mut", "smmesh_face_offsets", "smmesh_face_verts", "smmesh_owner",
+                  "smmesh_neighbour", "smmesh_point_global_id", "smmesh_cell_global_id"):
+            getattr(L, f).restype = C.c_void_p
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.smmesh_size.restype = C.c_int64
+        L.smmesh_size.argtypes = [C.c_void_p, C.c_int32]
+        L.smmesh_free.argtypes = [C.c_void_p]
+        L.smmesh_jitter.argtypes = [C.c_void_p, C.c_double, C.c_uint64]
+        L.smmesh_patches.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smmesh_patch_name.argtypes = [C.c_void_p, C.c_int32]
+        L.smmesh_write.argtypes = [C.c_void_p, C.c_char_p, C.c_int32, C.c_int32]
+        L.smmesh_read.argtypes = [C.c_char_p]
+        L.smmesh_read_points.argtypes = [C.c_void_p, C.c_char_p]
+        L.smmesh_write_points.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p]
+        L.smmesh_gen_hex_block.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.smmesh_gen_kelvin.argtypes = [C.c_int32, C.c_double]
+        L.smmesh_decompose.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.smmesh_from_cells.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p]
+        L.smmesh_from_arrays.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for f in ("smgpu_destroy", "smgpu_get_params", "smgpu_set_params", "smgpu_get_points", "smgpu_set_points",
+                  "smgpu_get_frozen", "smgpu_op_cell_centres", "smgpu_op_predict", "smgpu_op_edge_constraints",
+                  "smgpu_op_face_angle_constraint", "smgpu_get_edges"):
+            getattr(L, f).argtypes = [C.c_void_p] + ([C.c_void_p] if f != "smgpu_destroy" else [])
+        L.smgpu_mesh_stats.argtypes = [C.c_void_p] + [C.c_void_p] * 4
+        L.smgpu_iterate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_last_timing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_op_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_op_edge_face_angles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_get_csr.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_comm_unique_id.argtypes = [C.c_void_p]
+        L.smgpu_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().smgpu_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _view(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n)
+
+
+PATCH_BOUNDARY, PATCH_PROCESSOR, PATCH_EMPTY = 0, 1, 2
+
+
+class Mesh:
+    """A polyMesh held by the host library (points, faces, owner, neighbour, boundary)."""
+
+    def __init__(self, handle):
+        if not handle:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+        self._h = C.c_void_p(handle)
+
+    def __del__(self):
+        try:
+            if self._h:
+                lib().smmesh_free(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ---- constructors ----
+    @staticmethod
+    def hex_block(nx, ny, nz, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0)) -> "Mesh":
+        lo = np.asarray(lo, dtype=np.float64)
+        hi = np.asarray(hi, dtype=np.float64)
+        return Mesh(lib().smmesh_gen_hex_block(nx, ny, nz, _ptr(lo), _ptr(hi)))
+
+    @staticmethod
+    def kelvin(n, h=1.0) -> "Mesh":
+        return Mesh(lib().smmesh_gen_kelvin(n, h))
+
+    @staticmethod
+    def read(polymesh_dir) -> "Mesh":
+        return Mesh(lib().smmesh_read(str(polymesh_dir).encode()))
+
+    @staticmethod
+    def from_cells(points, cells, patch_of_face=None, patch_names=("walls",), patch_types=("wall",)) -> "Mesh":
+        """cells: list of cells, each a list of outward-oriented faces (vertex-label lists)."""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        cfo = [0]
+        cvo = [0]
+        cv = []
+        cp = []
+        for ci, cell in enumerate(cells):
+            for fi, f in enumerate(cell):
+                cv.extend(int(v) for v in f)
+                cvo.append(len(cv))
+                cp.append(patch_of_face(ci, fi, f) if patch_of_face else 0)
+            cfo.append(len(cvo) - 1)
+        cfo = np.asarray(cfo, dtype=np.int32)
+        cvo = np.asarray(cvo, dtype=np.int32)
+        cv = np.asarray(cv, dtype=np.int32)
+        cp = np.asarray(cp, dtype=np.int32)
+        names = (C.c_char_p * len(patch_names))(*[s.encode() for s in patch_names])
+        types = (C.c_char_p * len(patch_types))(*[s.encode() for s in patch_types])
+        return Mesh(lib().smmesh_from_cells(len(pts), _ptr(pts), len(cells), _ptr(cfo), _ptr(cvo), _ptr(cv), _ptr(cp),
+                                            len(patch_names), names, types))
+
+    @staticmethod
+    def from_arrays(points, face_offsets, face_verts, owner, neighbour, n_cells, patch_start, patch_size,
+                    patch_kind) -> "Mesh":
+        a = [np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)]
+        a += [np.ascontiguousarray(x, dtype=np.int32) for x in
+              (face_offsets, face_verts, owner, neighbour, patch_start, patch_size, patch_kind)]
+        return Mesh(lib().smmesh_from_arrays(len(a[0]), _ptr(a[0]), len(a[3]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]),
+                                             len(a[4]), _ptr(a[4]), int(n_cells), len(a[5]), _ptr(a[5]), _ptr(a[6]),
+                                             _ptr(a[7])))
+
+    # ---- accessors (views into library memory; copy if you keep them) ----
+    def _size(self, what):
+        return int(lib().smmesh_size(self._h, what))
+
+    n_points = property(lambda s: s._size(0))
+    n_cells = property(lambda s: s._size(1))
+    n_faces = property(lambda s: s._size(2))
+    n_internal_faces = property(lambda s: s._size(3))
+    n_patches = property(lambda s: s._size(5))
+
+    @property
+    def points(self):
+        return _view(lib().smmesh_points_mut(self._h), 3 * self.n_points, np.float64).reshape(-1, 3)
+
+    @property
+    def face_offsets(self):
+        return _view(lib().smmesh_face_offsets(self._h), self.n_faces + 1, np.int32)
+
+    @property
+    def face_verts(self):
+        return _view(lib().smmesh_face_verts(self._h), self._size(4), np.int32)
+
+    @property
+    def owner(self):
+        return _view(lib().smmesh_owner(self._h), self.n_faces, np.int32)
+
+    @property
+    def neighbour(self):
+        return _view(lib().smmesh_neighbour(self._h), self.n_internal_faces, np.int32)
+
+    @property
+    def patches(self):
+        n = self.n_patches
+        s, z, k = (np.zeros(n, dtype=np.int32) for _ in range(3))
+        lib().smmesh_patches(self._h, _ptr(s), _ptr(z), _ptr(k))
+        return s, z, k
+
+    @property
+    def patch_names(self):
+        return [lib().smmesh_patch_name(self._h, i).decode() for i in range(self.n_patches)]
+
+    @property
+    def point_global_id(self):
+        p = lib().smmesh_point_global_id(self._h)
+        return _view(p, self.n_points, np.int64) if p else None
+
+    @property
+    def cell_global_id(self):
+        p = lib().smmesh_cell_global_id(self._h)
+        return _view(p, self.n_cells, np.int64) if p else None
+
+    def faces(self):
+        off, v = self.face_offsets, self.face_verts
+        return [v[off[i]:off[i + 1]].tolist() for i in range(self.n_faces)]
+
+    # ---- operations ----
+    def jitter(self, amp, seed=12345):
+        lib().smmesh_jitter(self._h, float(amp), int(seed))
+        return self
+
+    def write(self, polymesh_dir, binary=False, precision=16):
+        if lib().smmesh_write(self._h, str(polymesh_dir).encode(), int(binary), int(precision)) != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+
+    def read_points(self, points_file):
+        if lib().smmesh_read_points(self._h, str(points_file).encode()) != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+
+    def decompose(self, px, py=1, pz=1, method="bricks"):
+        n = px * py * pz if method == "bricks" else px
+        out = (C.c_void_p * n)()
+        rc = lib().smmesh_decompose(self._h, 0 if method == "bricks" else 1, px, py, pz, out)
+        if rc != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+        return [Mesh(out[i]) for i in range(n)]
+
+    def desc_arrays(self):
+        """The arrays of smgpu_mesh_desc as contiguous numpy copies (also what the oracle takes)."""
+        s, z, k = self.patches
+        gid = self.point_global_id
+        return dict(points=np.array(self.points, dtype=np.float64), face_offsets=np.array(self.face_offsets),
+                    face_verts=np.array(self.face_verts), owner=np.array(self.owner), neighbour=np.array(self.neighbour),
+                    n_cells=self.n_cells, patch_start=s, patch_size=z, patch_kind=k,
+                    point_global_id=None if gid is None else np.array(gid))
+
+
+@dataclass
+class IterationLog:
+    iterations: int
+    n_frozen: np.ndarray  # int64 per iteration (what the reference prints at src/smoothMesh.C:2396)
+    residual: np.ndarray  # float64 per iteration
+    ms: float             # device time of the loop (CUDA events)
+    launches: int
+
+
+class Smoother:
+    """Device-resident smoothing state; the C-ABI counterpart of the reference's main() loop."""
+
+    def __init__(self, mesh: Mesh, params: Params | None = None, **kw):
+        L = lib()
+        self.params_in = params if params is not None else default_params(**kw)
+        self._arrays = mesh.desc_arrays()  # keep alive during create
+        a = self._arrays
+        d = _MeshDesc()
+        d.n_points, d.n_cells = len(a["points"]), a["n_cells"]
+        d.n_faces, d.n_internal_faces = len(a["owner"]), len(a["neighbour"])
+        d.points, d.face_offsets, d.face_verts = _ptr(a["points"]), _ptr(a["face_offsets"]), _ptr(a["face_verts"])
+        d.owner, d.neighbour = _ptr(a["owner"]), _ptr(a["neighbour"])
+        d.n_patches = len(a["patch_start"])
+        d.patch_start, d.patch_size, d.patch_kind = _ptr(a["patch_start"]), _ptr(a["patch_size"]), _ptr(a["patch_kind"])
+        d.point_global_id = _ptr(a["point_global_id"])
+        h = C.c_void_p()
+        rc = L.smgpu_create(C.byref(d), C.byref(self.params_in), C.byref(h))
+        if rc != 0:
+            raise SmoothMeshError(f"smgpu_create failed ({rc}): {L.smgpu_last_error().decode()}")
+        self._h = h
+        self.n_points, self.n_cells = int(d.n_points), int(d.n_cells)
+        self._arrays = None
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SmoothMeshError(f"libsmgpu error {rc}: {lib().smgpu_last_error().decode()}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().smgpu_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    @property
+    def params(self) -> Params:
+        p = Params()
+        self._ck(lib().smgpu_get_params(self._h, C.byref(p)))
+        return p
+
+    def set_params(self, p: Params):
+        self._ck(lib().smgpu_set_params(self._h, C.byref(p)))
+
+    def mesh_stats(self):
+        mn, mx = C.c_double(), C.c_double()
+        ni, ne = C.c_int64(), C.c_int64()
+        self._ck(lib().smgpu_mesh_stats(self._h, C.byref(mn), C.byref(mx), C.byref(ni), C.byref(ne)))
+        return dict(min_edge=mn.value, max_edge=mx.value, n_internal_points=ni.value, n_edges=ne.value)
+
+    def iterate(self, max_iters) -> IterationLog:
+        nf = np.zeros(max(max_iters, 1), dtype=np.int64)
+        res = np.zeros(max(max_iters, 1), dtype=np.float64)
+        done = C.c_int32()
+        self._ck(lib().smgpu_iterate(self._h, int(max_iters), _ptr(nf), _ptr(res), C.byref(done)))
+        ms, ln = C.c_double(), C.c_int64()
+        self._ck(lib().smgpu_last_timing(self._h, C.byref(ms), C.byref(ln)))
+        n = done.value
+        return IterationLog(n, nf[:n].copy(), res[:n].copy(), ms.value, ln.value)
+
+    def points(self):
+        out = np.zeros((self.n_points, 3), dtype=np.float64)
+        self._ck(lib().smgpu_get_points(self._h, _ptr(out)))
+        return out
+
+    def set_points(self, pts):
+        pts = np.ascontiguousarray(pts, dtype=np.float64)
+        assert pts.size == 3 * self.n_points
+        self._ck(lib().smgpu_set_points(self._h, _ptr(pts)))
+
+    def frozen(self):
+        out = np.zeros(self.n_points, dtype=np.uint8)
+        self._ck(lib().smgpu_get_frozen(self._h, _ptr(out)))
+        return out
+
+    # ---- operator-level entry points (one per reference L3 function) ----
+    def op_cell_centres(self):
+        out = np.zeros((self.n_cells, 3), dtype=np.float64)
+        self._ck(lib().smgpu_op_cell_centres(self._h, _ptr(out)))
+        return out
+
+    def op_predict(self):
+        out = np.zeros((self.n_points, 3), dtype=np.float64)
+        self._ck(lib().smgpu_op_predict(self._h, _ptr(out)))
+        return out
+
+    def op_edge_constraints(self):
+        out = np.zeros(self.n_points, dtype=np.uint8)
+        self._ck(lib().smgpu_op_edge_constraints(self._h, _ptr(out)))
+        return out
+
+    def op_face_angle_constraint(self):
+        out = np.zeros(self.n_points, dtype=np.uint8)
+        self._ck(lib().smgpu_op_face_angle_constraint(self._h, _ptr(out)))
+        return out
+
+    def op_commit(self):
+        nf, r = C.c_int64(), C.c_double()
+        self._ck(lib().smgpu_op_commit(self._h, C.byref(nf), C.byref(r)))
+        return nf.value, r.value
+
+    def op_edge_face_angles(self):
+        ne = self.mesh_stats()["n_edges"]
+        mn, mx = np.zeros(ne), np.zeros(ne)
+        self._ck(lib().smgpu_op_edge_face_angles(self._h, _ptr(mn), _ptr(mx)))
+        return mn, mx
+
+    def edges(self):
+        ne = self.mesh_stats()["n_edges"]
+        out = np.zeros((ne, 2), dtype=np.int32)
+        self._ck(lib().smgpu_get_edges(self._h, _ptr(out)))
+        return out
+
+    def csr(self, name):
+        n = C.c_int64()
+        self._ck(lib().smgpu_get_csr(self._h, name.encode(), None, None, C.byref(n)))
+        rows = self.mesh_stats()["n_edges"] if name.startswith("edge") else self.n_points
+        off = np.zeros(rows + 1, dtype=np.int32)
+        val = np.zeros(n.value, dtype=np.int32)
+        self._ck(lib().smgpu_get_csr(self._h, name.encode(), _ptr(off), _ptr(val), C.byref(n)))
+        return off, val
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = lib().smgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise SmoothMeshError(lib().smgpu_last_error().decode())
+        return bytes(buf)
+
+    def comm_init(self, rank, n_ranks, unique_id: bytes):
+        buf = (C.c_uint8 * 128)(*unique_id)
+        self._ck(lib().smgpu_comm_init(self._h, rank, n_ranks, buf))

@@ -1,0 +1,632 @@
+// smgpu.cu -- C ABI (include/smgpu.h) over the kernels in kernels.cuh.
+// Host side: flatten mesh -> derived connectivity (topology.cpp) -> upload once
+// -> launch the per-iteration kernel sequence with no host round trip inside a
+// chunk of iterations.  There is no CPU fallback anywhere in this file.
+#include "../../include/smgpu.h"
+#include "comm.hpp"
+#include "kernels.cuh"
+#include "polymesh.hpp"
+#include "topology.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+using namespace smk;
+
+static thread_local std::string g_err;
+static int setErr(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                                       \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call);             \
+    } while (0)
+
+struct smgpu_handle
+{
+    sm::Topology topo;
+    smgpu_params prm;
+    Dev d;
+    std::vector<void *> allocs;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double lastMs = 0;
+    int64_t lastLaunches = 0, launches = 0;
+    int64_t nInternal = 0;
+    int statCap = 0;
+    sm::Comm *comm = nullptr;
+    std::vector<int64_t> gid;
+
+    template <class T> T *dalloc(size_t n)
+    {
+        void *p = nullptr;
+        CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T) + 16));
+        allocs.push_back(p);
+        return (T *)p;
+    }
+    template <class T> T *upload(const std::vector<T> &v)
+    {
+        T *p = dalloc<T>(v.size());
+        if (!v.empty())
+            CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    }
+    void applyParams()
+    {
+        d.minEdgeLength = prm.min_edge_length;
+        d.maxStepLength = prm.max_step_length;
+        d.relStepFrac = prm.rel_step_frac;
+        d.relTol = prm.rel_tol;
+        d.smallAngle = M_PI * prm.min_angle_deg / 180.0; // src/smoothMesh.C:921, :1364
+        d.largeAngle = M_PI * prm.max_angle_deg / 180.0; // :1365
+        d.totalMinFreeze = prm.total_min_freeze;
+        d.edgeAngleConstraint = prm.edge_angle_constraint;
+        d.faceAngleConstraint = prm.face_angle_constraint;
+        d.geometryVariant = prm.geometry_variant;
+    }
+    void ensureStats(int n)
+    {
+        if (n <= statCap)
+            return;
+        statCap = std::max(n, 1024);
+        d.statRes = dalloc<double>(statCap);
+        d.statFrozen = dalloc<long long>(statCap);
+        d.statCap = statCap;
+    }
+    void setPoints(const double *pts)
+    {
+        std::vector<P4> h(topo.P);
+        for (int64_t i = 0; i < topo.P; ++i)
+            h[i] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], topo.isInternal[i] ? 1.0 : 0.0};
+        CK(cudaMemcpy(d.pts, h.data(), h.size() * sizeof(P4), cudaMemcpyHostToDevice));
+    }
+
+    static int grid(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
+
+    // ---- kernel launches (one method per reference operator) ----
+    void launchCellCentres()
+    {
+        k_cell_centres<<<grid(d.C, 128), 128, 0, stream>>>(d);
+        ++launches;
+    }
+    void launchPredict()
+    {
+        k_predict<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        ++launches;
+    }
+    void launchEdgeConstraints()
+    {
+        k_edge_constraints<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        ++launches;
+    }
+    void launchFaceAngle(double *dbgMin = nullptr, double *dbgMax = nullptr)
+    {
+        const int nChunks = grid(d.P, SMK_CHUNK);
+        k_face_current<<<grid(d.E, 128), 128, 0, stream>>>(d, dbgMin, dbgMax);
+        k_active_count<<<nChunks, 256, 0, stream>>>(d);
+        k_active_scan<<<1, 256, 0, stream>>>(d, nChunks);
+        k_active_fill<<<nChunks, 256, 0, stream>>>(d);
+        k_face_clear<<<148, 128, 0, stream>>>(d);
+        k_face_tests<<<148 * 4, 128, 0, stream>>>(d);
+        k_face_resolve<<<1, 32, 0, stream>>>(d);
+        launches += 7;
+    }
+    void launchCommit()
+    {
+        k_commit<<<grid(d.P, 256), 256, 0, stream>>>(d);
+        ++launches;
+    }
+    void resetControl()
+    {
+        CK(cudaMemsetAsync(d.done, 0, sizeof(int), stream));
+        CK(cudaMemsetAsync(d.iter, 0, sizeof(int), stream));
+    }
+};
+
+extern "C"
+{
+
+    const char *smgpu_last_error(void) { return g_err.c_str(); }
+    const char *smgpu_version(void) { return "smoothmesh_b200 0.1 (sm_100a, fp64, fmad=off)"; }
+
+    void smgpu_default_params(smgpu_params *p)
+    {
+        // src/smoothMesh.C:1861-1914
+        p->min_edge_length = -1.0;
+        p->max_step_length = -1.0;
+        p->rel_step_frac = 0.5;
+        p->min_angle_deg = 35.0;
+        p->max_angle_deg = 160.0;
+        p->rel_tol = 0.02;
+        p->total_min_freeze = 0;
+        p->edge_angle_constraint = 1;
+        p->face_angle_constraint = 1;
+        p->geometry_variant = 0;
+        p->device = 0;
+        p->renumber = 0;
+    }
+
+    int smgpu_create(const smgpu_mesh_desc *md, const smgpu_params *params, smgpu_handle **out)
+    {
+        if (!md || !params || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        *out = nullptr;
+        int nDev = 0;
+        if (cudaGetDeviceCount(&nDev) != cudaSuccess || nDev == 0)
+            return setErr(SMGPU_ERR_CUDA, "no CUDA device available (libsmgpu has no CPU fallback)");
+        if (params->device < 0 || params->device >= nDev)
+            return setErr(SMGPU_ERR_ARG, "device ordinal out of range");
+        smgpu_handle *h = new smgpu_handle;
+        try
+        {
+            sm::PolyMesh m;
+            m.points.assign(md->points, md->points + 3 * md->n_points);
+            m.faceOffsets.assign(md->face_offsets, md->face_offsets + md->n_faces + 1);
+            m.faceVerts.assign(md->face_verts, md->face_verts + md->face_offsets[md->n_faces]);
+            m.owner.assign(md->owner, md->owner + md->n_faces);
+            m.neighbour.assign(md->neighbour, md->neighbour + md->n_internal_faces);
+            m.nCells = md->n_cells;
+            for (int i = 0; i < md->n_patches; ++i)
+            {
+                sm::Patch p;
+                p.name = "patch" + std::to_string(i);
+                p.type = md->patch_kind[i] == SMGPU_PATCH_PROCESSOR ? "processor"
+                         : md->patch_kind[i] == SMGPU_PATCH_EMPTY   ? "empty"
+                                                                    : "patch";
+                p.start = md->patch_start[i];
+                p.size = md->patch_size[i];
+                m.patches.push_back(p);
+            }
+            if (md->point_global_id)
+                h->gid.assign(md->point_global_id, md->point_global_id + md->n_points);
+            try
+            {
+                h->topo = sm::buildTopology(m);
+            }
+            catch (const std::exception &e)
+            {
+                delete h;
+                return setErr(SMGPU_ERR_MESH, e.what());
+            }
+            const sm::Topology &t = h->topo;
+            h->prm = *params;
+            if (h->prm.min_edge_length < 0)
+                h->prm.min_edge_length = 0.5 * t.minEdgeLength; // :1861-1862
+            if (h->prm.max_step_length < 0)
+                h->prm.max_step_length = 0.3 * h->prm.min_edge_length; // :1864-1865
+            for (uint8_t f : t.isInternal)
+                h->nInternal += f;
+
+            CK(cudaSetDevice(params->device));
+            CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+            CK(cudaEventCreate(&h->ev0));
+            CK(cudaEventCreate(&h->ev1));
+            Dev &d = h->d;
+            memset(&d, 0, sizeof(d));
+            d.P = (int)t.P;
+            d.C = (int)t.C;
+            d.E = (int)t.E;
+            d.pts = h->dalloc<P4>(t.P);
+            d.newPts = h->dalloc<P4>(t.P);
+            d.cellCtr = h->dalloc<P4>(t.C);
+            d.frozen = h->dalloc<uint8_t>(t.P + 8);
+            d.pcOff = h->upload(t.pcOff);
+            d.pc = h->upload(t.pc);
+            d.ppOff = h->upload(t.ppOff);
+            d.pp = h->upload(t.pp);
+            d.pe = h->upload(t.pe);
+            d.cornerOff = h->upload(t.cornerOff);
+            d.corner = h->upload(t.corner);
+            d.edge = h->upload(t.edge);
+            d.efOff = h->upload(t.efOff);
+            d.ef = h->upload(t.ef);
+            d.ecOff = h->upload(t.ecOff);
+            d.ecCell = h->upload(t.ecCell);
+            d.ecPair = h->upload(t.ecPair);
+            d.faceOff = h->upload(t.faceOff);
+            d.faceVerts = h->upload(t.faceVerts);
+            d.cellOff = h->upload(t.cellOff);
+            d.cellStream = h->upload(t.cellStream);
+            d.curMin = h->dalloc<unsigned long long>(t.P);
+            d.curMax = h->dalloc<unsigned long long>(t.P);
+            d.activeFlag = h->dalloc<uint8_t>(t.P + 8);
+            d.selfBits = h->dalloc<uint8_t>(t.P + 8);
+            d.pairBits = h->dalloc<uint8_t>(t.pp.size() + 8);
+            d.activeList = h->dalloc<int>(t.P);
+            d.stack = h->dalloc<int>(t.P);
+            d.blockCounts = h->dalloc<int>(smgpu_handle::grid(t.P, SMK_CHUNK) + 1);
+            d.nActive = h->dalloc<int>(1);
+            d.done = h->dalloc<int>(1);
+            d.iter = h->dalloc<int>(1);
+            d.accMaxBits = h->dalloc<unsigned long long>(1);
+            d.accFrozen = h->dalloc<unsigned long long>(1);
+            d.blocksDone = h->dalloc<unsigned int>(1);
+            CK(cudaMemset(d.nActive, 0, sizeof(int)));
+            CK(cudaMemset(d.done, 0, sizeof(int)));
+            CK(cudaMemset(d.iter, 0, sizeof(int)));
+            CK(cudaMemset(d.accMaxBits, 0, 8));
+            CK(cudaMemset(d.accFrozen, 0, 8));
+            CK(cudaMemset(d.blocksDone, 0, 4));
+            CK(cudaMemset(d.frozen, 0, t.P + 8));
+            CK(cudaMemset(d.activeFlag, 0, t.P + 8));
+            CK(cudaMemset(d.newPts, 0, t.P * sizeof(P4)));
+            h->ensureStats(1024);
+            h->applyParams();
+            h->setPoints(md->points);
+            CK(cudaDeviceSynchronize());
+        }
+        catch (const std::exception &e)
+        {
+            smgpu_destroy(h);
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
+        *out = h;
+        return SMGPU_OK;
+    }
+
+    int smgpu_destroy(smgpu_handle *h)
+    {
+        if (!h)
+            return SMGPU_OK;
+        if (h->comm)
+            sm::commDestroy(h->comm);
+        for (void *p : h->allocs)
+            cudaFree(p);
+        if (h->ev0)
+            cudaEventDestroy(h->ev0);
+        if (h->ev1)
+            cudaEventDestroy(h->ev1);
+        if (h->stream)
+            cudaStreamDestroy(h->stream);
+        delete h;
+        return SMGPU_OK;
+    }
+
+    int smgpu_get_params(smgpu_handle *h, smgpu_params *out)
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        *out = h->prm;
+        return SMGPU_OK;
+    }
+
+    int smgpu_set_params(smgpu_handle *h, const smgpu_params *p)
+    {
+        if (!h || !p)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        const int dev = h->prm.device;
+        h->prm = *p;
+        h->prm.device = dev;
+        if (h->prm.min_edge_length < 0)
+            h->prm.min_edge_length = 0.5 * h->topo.minEdgeLength;
+        if (h->prm.max_step_length < 0)
+            h->prm.max_step_length = 0.3 * h->prm.min_edge_length;
+        h->applyParams();
+        return SMGPU_OK;
+    }
+
+    int smgpu_mesh_stats(smgpu_handle *h, double *min_edge, double *max_edge, int64_t *n_internal_points,
+                         int64_t *n_edges)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        if (min_edge)
+            *min_edge = h->topo.minEdgeLength;
+        if (max_edge)
+            *max_edge = h->topo.maxEdgeLength;
+        if (n_internal_points)
+            *n_internal_points = h->nInternal;
+        if (n_edges)
+            *n_edges = h->topo.E;
+        return SMGPU_OK;
+    }
+
+    int smgpu_iterate(smgpu_handle *h, int32_t max_iters, int64_t *n_frozen, double *residual, int32_t *iters_done)
+    {
+        if (!h || max_iters < 0)
+            return setErr(SMGPU_ERR_ARG, "bad argument");
+        try
+        {
+            CK(cudaSetDevice(h->prm.device));
+            h->ensureStats(max_iters);
+            h->launches = 0;
+            h->resetControl();
+            CK(cudaEventRecord(h->ev0, h->stream));
+            int done = 0, launched = 0;
+            if (h->comm)
+            {
+                // multi-rank: one iteration at a time, halo exchanges between phases
+                for (; launched < max_iters && !done; ++launched)
+                    done = sm::commIterate(h->comm, h, launched);
+            }
+            else
+            {
+                const int chunk = 16; // iterations launched between polls of the stop flag
+                while (launched < max_iters && !done)
+                {
+                    const int n = std::min(chunk, max_iters - launched);
+                    for (int i = 0; i < n; ++i)
+                    {
+                        h->launchCellCentres();
+                        h->launchPredict();
+                        h->launchEdgeConstraints();
+                        if (h->prm.face_angle_constraint)
+                            h->launchFaceAngle();
+                        h->launchCommit();
+                    }
+                    launched += n;
+                    if (launched < max_iters)
+                    {
+                        CK(cudaMemcpyAsync(&done, h->d.done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                        CK(cudaStreamSynchronize(h->stream));
+                    }
+                }
+            }
+            CK(cudaEventRecord(h->ev1, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
+            CK(cudaGetLastError());
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+            h->lastMs = ms;
+            h->lastLaunches = h->launches;
+            int it = 0;
+            CK(cudaMemcpy(&it, h->d.iter, sizeof(int), cudaMemcpyDeviceToHost));
+            if (iters_done)
+                *iters_done = it;
+            if (it > 0 && residual)
+                CK(cudaMemcpy(residual, h->d.statRes, it * sizeof(double), cudaMemcpyDeviceToHost));
+            if (it > 0 && n_frozen)
+            {
+                std::vector<long long> tmp(it);
+                CK(cudaMemcpy(tmp.data(), h->d.statFrozen, it * sizeof(long long), cudaMemcpyDeviceToHost));
+                for (int i = 0; i < it; ++i)
+                    n_frozen[i] = tmp[i];
+            }
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    static int downloadP4(smgpu_handle *h, const P4 *src, int64_t n, double *out)
+    {
+        try
+        {
+            CK(cudaSetDevice(h->prm.device));
+            std::vector<P4> tmp(n);
+            CK(cudaMemcpy(tmp.data(), src, n * sizeof(P4), cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < n; ++i)
+            {
+                out[3 * i] = tmp[i].x;
+                out[3 * i + 1] = tmp[i].y;
+                out[3 * i + 2] = tmp[i].z;
+            }
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_get_points(smgpu_handle *h, double *out)
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        return downloadP4(h, h->d.pts, h->topo.P, out);
+    }
+
+    int smgpu_set_points(smgpu_handle *h, const double *in)
+    {
+        if (!h || !in)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        try
+        {
+            CK(cudaSetDevice(h->prm.device));
+            h->setPoints(in);
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_get_frozen(smgpu_handle *h, uint8_t *out)
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (cudaSetDevice(h->prm.device) != cudaSuccess ||
+            cudaMemcpy(out, h->d.frozen, h->topo.P, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, "download failed");
+        return SMGPU_OK;
+    }
+
+    int smgpu_last_timing(smgpu_handle *h, double *ms, int64_t *launches)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        if (ms)
+            *ms = h->lastMs;
+        if (launches)
+            *launches = h->lastLaunches;
+        return SMGPU_OK;
+    }
+
+    // ---- operator-level entry points ----
+    static int finishOp(smgpu_handle *h)
+    {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e == cudaSuccess)
+            e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, cudaGetErrorString(e));
+        return SMGPU_OK;
+    }
+
+    int smgpu_op_cell_centres(smgpu_handle *h, double *out)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchCellCentres();
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && out)
+            rc = downloadP4(h, h->d.cellCtr, h->topo.C, out);
+        return rc;
+    }
+
+    int smgpu_op_predict(smgpu_handle *h, double *out)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchPredict();
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && out)
+            rc = downloadP4(h, h->d.newPts, h->topo.P, out);
+        return rc;
+    }
+
+    int smgpu_op_edge_constraints(smgpu_handle *h, uint8_t *out)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchEdgeConstraints();
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && out)
+            rc = smgpu_get_frozen(h, out);
+        return rc;
+    }
+
+    int smgpu_op_face_angle_constraint(smgpu_handle *h, uint8_t *out)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchFaceAngle();
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && out)
+            rc = smgpu_get_frozen(h, out);
+        return rc;
+    }
+
+    int smgpu_op_commit(smgpu_handle *h, int64_t *n_frozen, double *residual)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchCommit();
+        int rc = finishOp(h);
+        if (rc != SMGPU_OK)
+            return rc;
+        double r;
+        long long nf;
+        if (cudaMemcpy(&r, h->d.statRes, 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(&nf, h->d.statFrozen, 8, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, "download failed");
+        if (residual)
+            *residual = r;
+        if (n_frozen)
+            *n_frozen = nf;
+        return SMGPU_OK;
+    }
+
+    int smgpu_op_edge_face_angles(smgpu_handle *h, double *min_out, double *max_out)
+    {
+        if (!h || !min_out || !max_out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        cudaSetDevice(h->prm.device);
+        double *dmin = nullptr, *dmax = nullptr;
+        const size_t E = (size_t)h->topo.E;
+        if (cudaMalloc(&dmin, E * 8 + 8) != cudaSuccess || cudaMalloc(&dmax, E * 8 + 8) != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, "cudaMalloc failed");
+        h->resetControl();
+        // run on a scratch copy of the per-point state: k_face_current only ORs/mins into
+        // curMin/curMax/activeFlag, which k_predict resets at the start of every iteration
+        k_face_current<<<smgpu_handle::grid(h->d.E, 128), 128, 0, h->stream>>>(h->d, dmin, dmax);
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && (cudaMemcpy(min_out, dmin, E * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                               cudaMemcpy(max_out, dmax, E * 8, cudaMemcpyDeviceToHost) != cudaSuccess))
+            rc = setErr(SMGPU_ERR_CUDA, "download failed");
+        cudaFree(dmin);
+        cudaFree(dmax);
+        return rc;
+    }
+
+    int smgpu_get_edges(smgpu_handle *h, int32_t *out)
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        memcpy(out, h->topo.edge.data(), h->topo.edge.size() * sizeof(int32_t));
+        return SMGPU_OK;
+    }
+
+    int smgpu_get_csr(smgpu_handle *h, const char *name, int32_t *offsets, int32_t *values, int64_t *n_values)
+    {
+        if (!h || !name)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        const sm::Topology &t = h->topo;
+        const std::string n = name;
+        const std::vector<int32_t> *off = nullptr, *val = nullptr;
+        if (n == "pointCells")
+            off = &t.pcOff, val = &t.pc;
+        else if (n == "pointPoints")
+            off = &t.ppOff, val = &t.pp;
+        else if (n == "pointEdges")
+            off = &t.ppOff, val = &t.pe;
+        else if (n == "edgeFaces")
+            off = &t.efOff, val = &t.ef;
+        else if (n == "edgeCells")
+            off = &t.ecOff, val = &t.ecCell;
+        else
+            return setErr(SMGPU_ERR_ARG, "unknown table " + n);
+        if (n_values)
+            *n_values = (int64_t)val->size();
+        if (offsets)
+            memcpy(offsets, off->data(), off->size() * sizeof(int32_t));
+        if (values)
+            memcpy(values, val->data(), val->size() * sizeof(int32_t));
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_unique_id(uint8_t id_out[128])
+    {
+        std::string err;
+        if (!sm::commUniqueId(id_out, err))
+            return setErr(SMGPU_ERR_COMM, err);
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t id[128])
+    {
+        if (!h || !id)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (h->gid.empty())
+            return setErr(SMGPU_ERR_ARG, "mesh was created without point_global_id");
+        std::string err;
+        h->comm = sm::commCreate(h, rank, n_ranks, id, err);
+        if (!h->comm)
+            return setErr(SMGPU_ERR_COMM, err);
+        return SMGPU_OK;
+    }
+
+} // extern "C"

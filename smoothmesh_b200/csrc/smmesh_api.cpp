@@ -1,0 +1,218 @@
+// smmesh_api.cpp -- C ABI (include/smmesh.h) over polymesh.cpp.
+#include "../../include/smgpu.h"
+#include "../../include/smmesh.h"
+#include "polymesh.hpp"
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+struct smmesh
+{
+    sm::PolyMesh m;
+};
+
+static thread_local std::string g_merr;
+
+template <class Fn> static smmesh *guarded(Fn fn)
+{
+    try
+    {
+        smmesh *r = new smmesh;
+        try
+        {
+            r->m = fn();
+            r->m.check();
+        }
+        catch (...)
+        {
+            delete r;
+            throw;
+        }
+        return r;
+    }
+    catch (const std::exception &e)
+    {
+        g_merr = e.what();
+        return nullptr;
+    }
+}
+
+extern "C"
+{
+    const char *smmesh_last_error(void) { return g_merr.c_str(); }
+    void smmesh_free(smmesh *m) { delete m; }
+
+    smmesh *smmesh_gen_hex_block(int32_t nx, int32_t ny, int32_t nz, const double lo[3], const double hi[3])
+    {
+        return guarded([&] { return sm::genHexBlock(nx, ny, nz, lo, hi); });
+    }
+    smmesh *smmesh_gen_kelvin(int32_t n, double h)
+    {
+        return guarded([&] { return sm::genKelvin(n, h); });
+    }
+    smmesh *smmesh_from_cells(int64_t n_points, const double *points, int32_t n_cells, const int32_t *cfo,
+                              const int32_t *cvo, const int32_t *cv, const int32_t *cp, int32_t n_patches,
+                              const char *const *names, const char *const *types)
+    {
+        return guarded([&] {
+            std::vector<double> pts(points, points + 3 * n_points);
+            std::vector<int32_t> a(cfo, cfo + n_cells + 1);
+            const int32_t nf = a[n_cells];
+            std::vector<int32_t> b(cvo, cvo + nf + 1), c(cv, cv + b[nf]);
+            std::vector<int32_t> d;
+            if (cp)
+                d.assign(cp, cp + nf);
+            std::vector<std::string> nm, ty;
+            for (int i = 0; i < n_patches; ++i)
+            {
+                nm.push_back(names[i]);
+                ty.push_back(types[i]);
+            }
+            return sm::buildFromCells(pts, a, b, c, d, nm, ty);
+        });
+    }
+    smmesh *smmesh_from_arrays(int64_t n_points, const double *points, int64_t n_faces, const int32_t *face_offsets,
+                               const int32_t *face_verts, const int32_t *owner, int64_t n_internal_faces,
+                               const int32_t *neighbour, int64_t n_cells, int32_t n_patches, const int32_t *patch_start,
+                               const int32_t *patch_size, const int32_t *patch_kind)
+    {
+        return guarded([&] {
+            sm::PolyMesh m;
+            m.points.assign(points, points + 3 * n_points);
+            m.faceOffsets.assign(face_offsets, face_offsets + n_faces + 1);
+            m.faceVerts.assign(face_verts, face_verts + face_offsets[n_faces]);
+            m.owner.assign(owner, owner + n_faces);
+            m.neighbour.assign(neighbour, neighbour + n_internal_faces);
+            m.nCells = n_cells;
+            for (int i = 0; i < n_patches; ++i)
+            {
+                sm::Patch p;
+                p.name = "patch" + std::to_string(i);
+                p.type = patch_kind[i] == SMGPU_PATCH_PROCESSOR ? "processor"
+                         : patch_kind[i] == SMGPU_PATCH_EMPTY   ? "empty"
+                                                                : "patch";
+                p.start = patch_start[i];
+                p.size = patch_size[i];
+                m.patches.push_back(p);
+            }
+            return m;
+        });
+    }
+    smmesh *smmesh_read(const char *dir)
+    {
+        return guarded([&] { return sm::readPolyMesh(dir); });
+    }
+    int smmesh_read_points(smmesh *m, const char *file)
+    {
+        try
+        {
+            std::vector<double> pts = sm::readPoints(file);
+            if (pts.size() != m->m.points.size())
+                throw std::runtime_error("point count differs from the mesh topology");
+            m->m.points.swap(pts);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_IO;
+        }
+        return SMGPU_OK;
+    }
+    int smmesh_write(const smmesh *m, const char *dir, int32_t binary, int32_t precision)
+    {
+        try
+        {
+            sm::writePolyMesh(m->m, dir, binary != 0, precision);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_IO;
+        }
+        return SMGPU_OK;
+    }
+    int smmesh_write_points(const double *points, int64_t n_points, const char *dir, int32_t binary, int32_t precision,
+                            const char *location)
+    {
+        try
+        {
+            sm::writePoints(points, n_points, dir, binary != 0, precision, location);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_IO;
+        }
+        return SMGPU_OK;
+    }
+    int smmesh_jitter(smmesh *m, double amp, uint64_t seed)
+    {
+        sm::jitterInterior(m->m, amp, seed);
+        return SMGPU_OK;
+    }
+    int64_t smmesh_size(const smmesh *m, int32_t what)
+    {
+        switch (what)
+        {
+        case 0:
+            return m->m.nPoints();
+        case 1:
+            return m->m.nCells;
+        case 2:
+            return m->m.nFaces();
+        case 3:
+            return m->m.nInternalFaces();
+        case 4:
+            return (int64_t)m->m.faceVerts.size();
+        case 5:
+            return (int64_t)m->m.patches.size();
+        }
+        return -1;
+    }
+    const double *smmesh_points(const smmesh *m) { return m->m.points.data(); }
+    double *smmesh_points_mut(smmesh *m) { return m->m.points.data(); }
+    const int32_t *smmesh_face_offsets(const smmesh *m) { return m->m.faceOffsets.data(); }
+    const int32_t *smmesh_face_verts(const smmesh *m) { return m->m.faceVerts.data(); }
+    const int32_t *smmesh_owner(const smmesh *m) { return m->m.owner.data(); }
+    const int32_t *smmesh_neighbour(const smmesh *m) { return m->m.neighbour.data(); }
+    int smmesh_patches(const smmesh *m, int32_t *start, int32_t *size, int32_t *kind)
+    {
+        for (size_t i = 0; i < m->m.patches.size(); ++i)
+        {
+            start[i] = m->m.patches[i].start;
+            size[i] = m->m.patches[i].size;
+            kind[i] = m->m.patches[i].kind();
+        }
+        return SMGPU_OK;
+    }
+    const char *smmesh_patch_name(const smmesh *m, int32_t i) { return m->m.patches[i].name.c_str(); }
+    const int64_t *smmesh_point_global_id(const smmesh *m)
+    {
+        return m->m.pointGlobalId.empty() ? nullptr : m->m.pointGlobalId.data();
+    }
+    const int64_t *smmesh_cell_global_id(const smmesh *m)
+    {
+        return m->m.cellGlobalId.empty() ? nullptr : m->m.cellGlobalId.data();
+    }
+    int smmesh_decompose(const smmesh *m, int32_t method, int32_t px, int32_t py, int32_t pz, smmesh **parts_out)
+    {
+        try
+        {
+            const int n = method == 0 ? px * py * pz : px;
+            std::vector<int32_t> part = method == 0 ? sm::partitionBricks(m->m, px, py, pz) : sm::partitionRCB(m->m, n);
+            std::vector<sm::PolyMesh> parts = sm::decompose(m->m, part, n);
+            for (int i = 0; i < n; ++i)
+            {
+                parts[i].check();
+                parts_out[i] = new smmesh{std::move(parts[i])};
+            }
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
+}

@@ -1,0 +1,427 @@
+// smoothmesh_cli.cpp -- stand-alone `smoothMesh` executable with the reference's
+// command-line surface (src/smoothMesh.C:1642-1784), polyMesh I/O and log
+// lines, driving the GPU library through its C ABI only.
+//
+// Differences from the OpenFOAM build, all by necessity:
+//  * options are parsed here instead of by argList; -case/-time/-parallel are
+//    accepted like OpenFOAM's standard options;
+//  * system/controlDict is read for deltaT, writeFormat, writePrecision and
+//    startFrom/startTime only;
+//  * features outside the hot path (boundary-layer treatment, boundary point
+//    smoothing) are refused loudly when the options/files would enable them --
+//    there is no CPU fallback.
+#include "../../include/smgpu.h"
+#include "../../include/smmesh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dirent.h>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <sys/stat.h>
+#include <vector>
+
+static bool fileExists(const std::string &f)
+{
+    std::ifstream s(f);
+    return s.good();
+}
+static bool dirExists(const std::string &d)
+{
+    struct stat st;
+    return stat(d.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+[[noreturn]] static void fatal(const std::string &msg)
+{
+    // FatalError << ... << abort(FatalError)
+    fprintf(stderr, "\n\n--> FOAM FATAL ERROR: \n%s\n\nFOAM aborting\n\n", msg.c_str());
+    exit(1);
+}
+
+// OpenFOAM Switch parsing for bool options
+static bool parseSwitch(const std::string &v, const std::string &opt)
+{
+    std::string s = v;
+    std::transform(s.begin(), s.end(), s.begin(), ::tolower);
+    if (s == "true" || s == "on" || s == "yes" || s == "y" || s == "t" || s == "1")
+        return true;
+    if (s == "false" || s == "off" || s == "no" || s == "n" || s == "f" || s == "none" || s == "0")
+        return false;
+    fatal("bad bool value '" + v + "' for option -" + opt);
+}
+
+// minimal controlDict reader: `key value;` pairs at top level
+static std::map<std::string, std::string> readDict(const std::string &file)
+{
+    std::map<std::string, std::string> d;
+    std::ifstream in(file);
+    if (!in)
+        return d;
+    std::stringstream ss;
+    ss << in.rdbuf();
+    std::string s = ss.str(), clean;
+    for (size_t i = 0; i < s.size(); ++i)
+    { // strip comments
+        if (s.compare(i, 2, "//") == 0)
+        {
+            while (i < s.size() && s[i] != '\n')
+                ++i;
+        }
+        else if (s.compare(i, 2, "/*") == 0)
+        {
+            i = s.find("*/", i + 2);
+            if (i == std::string::npos)
+                break;
+            ++i;
+        }
+        else
+            clean += s[i];
+    }
+    int depth = 0;
+    std::string stmt;
+    for (char c : clean)
+    {
+        if (c == '{')
+            ++depth;
+        else if (c == '}')
+        {
+            --depth;
+            stmt.clear();
+        }
+        else if (c == ';')
+        {
+            if (depth == 0)
+            {
+                std::istringstream is(stmt);
+                std::string k, v;
+                is >> k;
+                std::getline(is, v);
+                const size_t b = v.find_first_not_of(" \t\n");
+                if (!k.empty() && b != std::string::npos)
+                    d[k] = v.substr(b, v.find_last_not_of(" \t\n") - b + 1);
+            }
+            stmt.clear();
+        }
+        else
+            stmt += c;
+    }
+    return d;
+}
+
+// OpenFOAM `timeFormat general; timePrecision 6;` (testcase/system/controlDict:34-36)
+static std::string timeName(double t, int precision)
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.*g", precision, t);
+    return buf;
+}
+
+static std::vector<std::pair<double, std::string>> findTimes(const std::string &caseDir)
+{
+    std::vector<std::pair<double, std::string>> out;
+    DIR *dp = opendir(caseDir.c_str());
+    if (!dp)
+        return out;
+    while (dirent *e = readdir(dp))
+    {
+        const std::string n = e->d_name;
+        char *end;
+        const double v = strtod(n.c_str(), &end);
+        if (end != n.c_str() && *end == '\0' && dirExists(caseDir + "/" + n))
+            out.push_back({v, n});
+    }
+    closedir(dp);
+    std::sort(out.begin(), out.end());
+    return out;
+}
+
+int main(int argc, char **argv)
+{
+    // ---- option table: name -> has value (src/smoothMesh.C:1642-1784 + OpenFOAM standard options)
+    const char *valued[] = {"case",
+                            "time",
+                            "centroidalIters",
+                            "maxStepLength",
+                            "relStepFrac",
+                            "edgeAngleConstraint",
+                            "faceAngleConstraint",
+                            "minEdgeLength",
+                            "totalMinFreeze",
+                            "minAngle",
+                            "maxAngle",
+                            "layerMaxBlendingFraction",
+                            "layerEdgeLength",
+                            "layerExpansionRatio",
+                            "minLayers",
+                            "maxLayers",
+                            "layerPatches",
+                            "smoothingPatches",
+                            "internalSmoothingBlendingFraction",
+                            "relTol",
+                            "writeInterval",
+                            "device",
+                            "geometryVariant"};
+    std::map<std::string, std::string> opt;
+    bool parallel = false;
+    for (int i = 1; i < argc; ++i)
+    {
+        std::string a = argv[i];
+        if (a.size() < 2 || a[0] != '-')
+            fatal("Wrong number of arguments, expected 0 found 1\nInvalid argument: " + a);
+        a = a.substr(1);
+        if (a == "parallel")
+        {
+            parallel = true;
+            continue;
+        }
+        if (a == "help")
+        {
+            printf("Usage: smoothMesh [OPTIONS]\nMove internal mesh points to increase mesh quality\n"
+                   "options: -case <dir> -time <time> -centroidalIters <label> -relTol <double> -minEdgeLength <double>\n"
+                   "  -maxStepLength <double> -relStepFrac <double> -totalMinFreeze <bool> -edgeAngleConstraint <bool>\n"
+                   "  -faceAngleConstraint <bool> -minAngle <double> -maxAngle <double> -writeInterval <label>\n"
+                   "  -layerPatches <wordRe> -smoothingPatches <wordRe> (only values that keep those features off)\n"
+                   "  -device <int> -geometryVariant com|org\n");
+            return 0;
+        }
+        bool known = false;
+        for (const char *v : valued)
+            known = known || a == v;
+        if (!known)
+            fatal("Invalid option: -" + a);
+        if (i + 1 >= argc)
+            fatal("Option -" + a + " requires a value");
+        opt[a] = argv[++i];
+    }
+    auto has = [&](const char *k) { return opt.count(k) > 0; };
+    auto num = [&](const char *k, double dflt) { return has(k) ? atof(opt[k].c_str()) : dflt; };
+
+    printf("smoothMesh (smoothmesh_b200: %s)\n\n", smgpu_version());
+    if (parallel)
+        fatal("-parallel (one process per processorN directory under mpirun) is not available in the stand-alone "
+              "build; multi-GPU runs go through the library's NCCL layer (see INTEGRATION.md)");
+
+    const std::string caseDir = has("case") ? opt["case"] : ".";
+    std::map<std::string, std::string> control = readDict(caseDir + "/system/controlDict");
+    const double deltaT = control.count("deltaT") ? atof(control["deltaT"].c_str()) : 1.0;
+    if (deltaT < 1e-300) // src/smoothMesh.C:1806-1812
+        fatal("Time step (deltaT) value " + std::to_string(deltaT) + " specified in controlDict is too small");
+    const bool binary = control.count("writeFormat") && control["writeFormat"] == "binary";
+    const int writePrecision = control.count("writePrecision") ? atoi(control["writePrecision"].c_str()) : 6;
+    const int timePrecision = control.count("timePrecision") ? atoi(control["timePrecision"].c_str()) : 6;
+
+    // ---- start time (createTime.H + :1792-1803) and mesh instance lookup (createMesh.H)
+    std::vector<std::pair<double, std::string>> times = findTimes(caseDir);
+    double startTime = 0;
+    std::string startName = "0";
+    if (has("time"))
+    {
+        if (opt["time"] == "constant")
+        {
+            startTime = 0;
+            startName = "constant";
+        }
+        else
+        {
+            startTime = atof(opt["time"].c_str());
+            startName = timeName(startTime, timePrecision);
+        }
+    }
+    else
+    {
+        const std::string startFrom = control.count("startFrom") ? control["startFrom"] : "latestTime";
+        if (startFrom == "latestTime" && !times.empty())
+        {
+            startTime = times.back().first;
+            startName = times.back().second;
+        }
+        else if (startFrom == "firstTime" && !times.empty())
+        {
+            startTime = times.front().first;
+            startName = times.front().second;
+        }
+        else
+        {
+            startTime = control.count("startTime") ? atof(control["startTime"].c_str()) : 0.0;
+            startName = timeName(startTime, timePrecision);
+        }
+    }
+    // newest time <= start time that has polyMesh/points; topology from the newest with polyMesh/faces; else constant
+    std::string pointsDir = caseDir + "/constant/polyMesh", topoDir = caseDir + "/constant/polyMesh";
+    if (startName != "constant")
+        for (auto &t : times)
+            if (t.first <= startTime * (1 + 1e-12) + 1e-300)
+            {
+                if (fileExists(caseDir + "/" + t.second + "/polyMesh/points"))
+                    pointsDir = caseDir + "/" + t.second + "/polyMesh";
+                if (fileExists(caseDir + "/" + t.second + "/polyMesh/faces"))
+                    topoDir = caseDir + "/" + t.second + "/polyMesh";
+            }
+    printf("Create time\n\nCreate mesh for time = %s\n\n", startName.c_str());
+    smmesh *mesh = smmesh_read(topoDir.c_str());
+    if (!mesh)
+        fatal(std::string("cannot read polyMesh from ") + topoDir + ": " + smmesh_last_error());
+    if (pointsDir != topoDir)
+    {
+        // points from a later time directory (mesh.write() only writes points)
+        if (smmesh_read_points(mesh, (pointsDir + "/points").c_str()) != SMGPU_OK)
+            fatal(std::string("cannot read ") + pointsDir + "/points: " + smmesh_last_error());
+    }
+    const int64_t nPoints = smmesh_size(mesh, 0);
+    const int nPatches = (int)smmesh_size(mesh, 5);
+    std::vector<int32_t> pStart(nPatches), pSize(nPatches), pKind(nPatches);
+    smmesh_patches(mesh, pStart.data(), pSize.data(), pKind.data());
+
+    // ---- features outside the hot path (:1823-1852, :2024-2098)
+    auto patchSetEmpty = [&](const std::string &expr) {
+        std::string s = expr;
+        s.erase(std::remove_if(s.begin(), s.end(), [](char c) { return isspace((unsigned char)c) || c == '"'; }), s.end());
+        return s == "()" || s == "none" || s == "(none)" || s.empty();
+    };
+    const double layerMaxBlendingFraction = num("layerMaxBlendingFraction", 0.3);
+    if (has("layerPatches") && !patchSetEmpty(opt["layerPatches"]) && layerMaxBlendingFraction > 1e-15)
+        fatal("boundary layer treatment (-layerPatches) is outside the GPU hot path and there is no CPU fallback; "
+              "rerun without -layerPatches");
+    printf("Patches for boundary layer treatment: none\n");
+    const bool smoothingPatchesEmpty = has("smoothingPatches") && patchSetEmpty(opt["smoothingPatches"]);
+    const bool surfaces = fileExists(caseDir + "/constant/geometry/targetSurfaces.obj");
+    const bool initEdges = fileExists(caseDir + "/constant/geometry/initEdges.obj");
+    if (surfaces && initEdges && !smoothingPatchesEmpty)
+        fatal("boundary point smoothing would be enabled (constant/geometry/*.obj present and smoothingPatches not "
+              "empty); it is outside the GPU hot path and there is no CPU fallback; pass -smoothingPatches '()'");
+    printf("Patches for boundary point smoothing: %s\n",
+           smoothingPatchesEmpty ? "none" : (has("smoothingPatches") ? opt["smoothingPatches"].c_str() : "(\".*\")"));
+
+    // ---- GPU handle
+    smgpu_mesh_desc md;
+    memset(&md, 0, sizeof md);
+    md.n_points = nPoints;
+    md.n_cells = smmesh_size(mesh, 1);
+    md.n_faces = smmesh_size(mesh, 2);
+    md.n_internal_faces = smmesh_size(mesh, 3);
+    md.points = smmesh_points(mesh);
+    md.face_offsets = smmesh_face_offsets(mesh);
+    md.face_verts = smmesh_face_verts(mesh);
+    md.owner = smmesh_owner(mesh);
+    md.neighbour = smmesh_neighbour(mesh);
+    md.n_patches = nPatches;
+    md.patch_start = pStart.data();
+    md.patch_size = pSize.data();
+    md.patch_kind = pKind.data();
+    smgpu_params prm;
+    smgpu_default_params(&prm);
+    prm.min_edge_length = num("minEdgeLength", -1.0);
+    prm.max_step_length = num("maxStepLength", -1.0);
+    prm.rel_step_frac = num("relStepFrac", 0.5);
+    prm.total_min_freeze = has("totalMinFreeze") ? parseSwitch(opt["totalMinFreeze"], "totalMinFreeze") : 0;
+    prm.min_angle_deg = num("minAngle", 35.0);
+    prm.max_angle_deg = num("maxAngle", 160.0);
+    prm.edge_angle_constraint = has("edgeAngleConstraint") ? parseSwitch(opt["edgeAngleConstraint"], "edgeAngleConstraint") : 1;
+    prm.face_angle_constraint = has("faceAngleConstraint") ? parseSwitch(opt["faceAngleConstraint"], "faceAngleConstraint") : 1;
+    prm.rel_tol = num("relTol", 0.02);
+    prm.device = (int)num("device", 0);
+    prm.geometry_variant = has("geometryVariant") && opt["geometryVariant"] == "org" ? 1 : 0;
+    const int centroidalIters = (int)num("centroidalIters", 1000);
+    const int writeInterval = (int)num("writeInterval", centroidalIters);
+
+    smgpu_handle *h = nullptr;
+    if (smgpu_create(&md, &prm, &h) != SMGPU_OK)
+        fatal(smgpu_last_error());
+    smgpu_get_params(h, &prm);
+    double meshMinEdge, meshMaxEdge;
+    int64_t nInternal, nEdges;
+    smgpu_mesh_stats(h, &meshMinEdge, &meshMaxEdge, &nInternal, &nEdges);
+    if (prm.max_step_length > 0.5 * prm.min_edge_length)
+        printf("WARNING: The maximum allowed step length is more than half of the minimum edge length! This may cause "
+               "unstability in smoothing.\n\n");
+
+    // parameter echo, :1933-1975
+    printf("Applying following parameter values in smoothing:\n");
+    printf("    centroidalIters        %d\n", centroidalIters);
+    printf("    relTol                 %g\n", prm.rel_tol);
+    printf("    minEdgeLength          %g\n", prm.min_edge_length);
+    printf("    maxStepLength          %g\n", prm.max_step_length);
+    printf("    relStepFrac            %g\n", prm.rel_step_frac);
+    printf("    totalMinFreeze         %d\n", prm.total_min_freeze);
+    if (prm.edge_angle_constraint)
+        printf("    edgeAngleConstraint    true\n    minAngle               %g\n", prm.min_angle_deg);
+    else
+        printf("    edgeAngleConstraint    false (edge min angle quality constraint is NOT applied)\n");
+    if (prm.face_angle_constraint)
+        printf("    faceAngleConstraint    true\n    minAngle               %g\n    maxAngle               %g\n",
+               prm.min_angle_deg, prm.max_angle_deg);
+    else
+        printf("    faceAngleConstraint    false (face angle quality constraints are NOT applied)\n");
+    printf("    layerMaxBlendingFraction 0 (boundary layer treatment is NOT applied)\n\n");
+    printf("Boundary layer treatment is disabled. Either no layerPatches were specified or boundaryMaxBlendingFraction "
+           "is zero\n\n");
+    printf("Boundary point smoothing is disabled. Missing smoothingPatches, or one or both of files:\n"
+           "constant/geometry/targetSurfaces.obj\nconstant/geometry/initEdges.obj\n\n");
+    printf("Mesh includes a total of %lld points:\n  - %lld internal (non-boundary) points\n  - %lld boundary points\n"
+           "Mesh minimum edge length = %g\nMesh maximum edge length = %g\n\n",
+           (long long)nPoints, (long long)nInternal, (long long)(nPoints - nInternal), meshMinEdge, meshMaxEdge);
+
+    // ---- iteration loop, :2257-2437.  The library stops on relTol by itself; the loop here is
+    // cut at write intervals so intermediate meshes can be written (:2416).
+    std::vector<double> pts(3 * nPoints);
+    std::vector<int64_t> nFrozen(std::max(centroidalIters, 1));
+    std::vector<double> residual(std::max(centroidalIters, 1));
+    int i = 0, logPrecision = 6;
+    double totalMs = 0;
+    bool stop = centroidalIters <= 0;
+    while (!stop)
+    {
+        int chunk = centroidalIters - i;
+        if (writeInterval > 0)
+        {
+            int toWrite = writeInterval - (i % writeInterval); // iterations until (i+1) % writeInterval == 0
+            if (i + toWrite - 1 == 0)
+                toWrite += writeInterval; // the `i > 0` quirk at :2416
+            chunk = std::min(chunk, toWrite);
+        }
+        int done = 0;
+        if (smgpu_iterate(h, chunk, nFrozen.data(), residual.data(), &done) != SMGPU_OK)
+            fatal(smgpu_last_error());
+        double ms;
+        smgpu_last_timing(h, &ms, nullptr);
+        totalMs += ms;
+        for (int k = 0; k < done; ++k)
+            printf("Smoothing iteration=%d nFrozenPoints=%lld residual=%.*g\n", i + k + 1, (long long)nFrozen[k],
+                   logPrecision, residual[k]);
+        i += done;
+        const bool reachedTol = done > 0 && residual[done - 1] < prm.rel_tol;
+        if (reachedTol)
+        {
+            printf("Residual reached relTol, stopping.\n");
+            stop = true;
+        }
+        if (i >= centroidalIters)
+        {
+            printf("Maximum centroidalIters reached, stopping.\n");
+            stop = true;
+        }
+        const int last = i - 1; // reference loop index of the iteration just finished
+        if (stop || (writeInterval > 0 && ((last + 1) % writeInterval) == 0 && last > 0))
+        {
+            const std::string tn = timeName(startTime + i * deltaT, timePrecision);
+            logPrecision = std::max(10, logPrecision); // :2425 raises the global stream precision
+            printf("Writing new mesh to time %s\n\n", tn.c_str());
+            if (smgpu_get_points(h, pts.data()) != SMGPU_OK)
+                fatal(smgpu_last_error());
+            if (smmesh_write_points(pts.data(), nPoints, (caseDir + "/" + tn + "/polyMesh").c_str(), binary,
+                                    std::max(10, writePrecision), (tn + "/polyMesh").c_str()) != SMGPU_OK)
+                fatal(smmesh_last_error());
+        }
+    }
+    printf("GPU iteration time = %.3f ms (%d iterations, %.4g point-updates/s)\n", totalMs, i,
+           totalMs > 0 ? 1e3 * double(nPoints) * i / totalMs : 0.0);
+    printf("\nEnd\n");
+    smgpu_destroy(h);
+    smmesh_free(mesh);
+    return 0;
+}

@@ -1,0 +1,320 @@
+// topology.cpp -- see topology.hpp.
+#include "topology.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+
+namespace sm
+{
+
+static void fail(const std::string &s) { throw std::runtime_error(s); }
+
+Topology buildTopology(const PolyMesh &m)
+{
+    m.check();
+    Topology t;
+    const int64_t P = m.nPoints(), C = m.nCells, F = m.nFaces(), Fi = m.nInternalFaces();
+    t.P = P;
+    t.C = C;
+    t.F = F;
+    t.Fi = Fi;
+    t.faceOff = m.faceOffsets;
+    t.faceVerts = m.faceVerts;
+    const int64_t FV = (int64_t)m.faceVerts.size();
+    if (2 * FV >= (int64_t)INT32_MAX)
+        fail("mesh too large for 32-bit offsets");
+
+    // src/smoothMesh.C:52-80: internal = not on any non-processor patch; empty patches abort
+    t.isInternal.assign(P, 1);
+    for (const Patch &p : m.patches)
+    {
+        if (p.kind() == PATCH_PROCESSOR)
+            continue;
+        if (p.kind() == PATCH_EMPTY)
+            fail("Smoothing of non-3D meshes (meshes with type empty patches) is not supported");
+        for (int32_t f = p.start; f < p.start + p.size; ++f)
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                t.isInternal[m.faceVerts[k]] = 0;
+    }
+
+    // ---- point -> face corners (pointFaces ascending) ----
+    t.cornerOff.assign(P + 1, 0);
+    for (int64_t k = 0; k < FV; ++k)
+        ++t.cornerOff[m.faceVerts[k] + 1];
+    for (int64_t p = 0; p < P; ++p)
+        t.cornerOff[p + 1] += t.cornerOff[p];
+    t.corner.resize(2 * FV);
+    std::vector<int32_t> cornerFace(FV);
+    {
+        std::vector<int32_t> cur(t.cornerOff.begin(), t.cornerOff.end() - 1);
+        for (int64_t f = 0; f < F; ++f)
+        {
+            const int32_t b = m.faceOffsets[f], n = m.faceOffsets[f + 1] - b;
+            t.maxFaceSize = std::max(t.maxFaceSize, n);
+            for (int32_t i = 0; i < n; ++i)
+            {
+                const int32_t v = m.faceVerts[b + i];
+                const int32_t slot = cur[v]++;
+                t.corner[2 * (int64_t)slot] = m.faceVerts[b + (i == 0 ? n - 1 : i - 1)];
+                t.corner[2 * (int64_t)slot + 1] = m.faceVerts[b + (i == n - 1 ? 0 : i + 1)];
+                cornerFace[slot] = (int32_t)f;
+            }
+        }
+    }
+
+    // ---- point -> cells (ascending) and point -> points (ascending) ----
+    std::vector<int32_t> pcCount(P), ppCount(P);
+#pragma omp parallel
+    {
+        std::vector<int32_t> tmp;
+#pragma omp for schedule(static)
+        for (int64_t p = 0; p < P; ++p)
+        {
+            tmp.clear();
+            for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
+            {
+                const int32_t f = cornerFace[s];
+                tmp.push_back(m.owner[f]);
+                if (f < Fi)
+                    tmp.push_back(m.neighbour[f]);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            pcCount[p] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+            tmp.clear();
+            for (int32_t s = 2 * t.cornerOff[p]; s < 2 * t.cornerOff[p + 1]; ++s)
+                tmp.push_back(t.corner[s]);
+            std::sort(tmp.begin(), tmp.end());
+            ppCount[p] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+        }
+    }
+    t.pcOff.assign(P + 1, 0);
+    t.ppOff.assign(P + 1, 0);
+    for (int64_t p = 0; p < P; ++p)
+    {
+        t.pcOff[p + 1] = t.pcOff[p] + pcCount[p];
+        t.ppOff[p + 1] = t.ppOff[p] + ppCount[p];
+        t.maxPointDegree = std::max(t.maxPointDegree, ppCount[p]);
+    }
+    t.pc.resize(t.pcOff[P]);
+    t.pp.resize(t.ppOff[P]);
+    std::vector<int32_t> upStart(P + 1, 0); // first edge label of point p = #edges (a,b) with a<p
+#pragma omp parallel
+    {
+        std::vector<int32_t> tmp;
+#pragma omp for schedule(static)
+        for (int64_t p = 0; p < P; ++p)
+        {
+            tmp.clear();
+            for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
+            {
+                const int32_t f = cornerFace[s];
+                tmp.push_back(m.owner[f]);
+                if (f < Fi)
+                    tmp.push_back(m.neighbour[f]);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            std::copy(tmp.begin(), tmp.end(), t.pc.begin() + t.pcOff[p]);
+            tmp.clear();
+            for (int32_t s = 2 * t.cornerOff[p]; s < 2 * t.cornerOff[p + 1]; ++s)
+                tmp.push_back(t.corner[s]);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            std::copy(tmp.begin(), tmp.end(), t.pp.begin() + t.ppOff[p]);
+            int32_t up = 0;
+            for (int32_t q : tmp)
+                up += (q > (int32_t)p);
+            upStart[p + 1] = up;
+        }
+    }
+    for (int64_t p = 0; p < P; ++p)
+        upStart[p + 1] += upStart[p];
+    const int64_t E = upStart[P];
+    t.E = E;
+    if ((int64_t)t.pp.size() != 2 * E)
+        fail("inconsistent edge connectivity (pointPoints is not symmetric)");
+
+    // ---- edges, pointEdges ----
+    t.edge.resize(2 * E);
+    t.pe.resize(t.pp.size());
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; ++p)
+    {
+        int32_t e = upStart[p];
+        for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+        {
+            const int32_t q = t.pp[s];
+            if (q > p)
+            {
+                t.edge[2 * (int64_t)e] = (int32_t)p;
+                t.edge[2 * (int64_t)e + 1] = q;
+                t.pe[s] = e++;
+            }
+        }
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; ++p)
+        for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+        {
+            const int32_t q = t.pp[s];
+            if (q < p)
+            { // label lives in q's row: upStart[q] + rank of p among q's higher neighbours
+                const int32_t *b = &t.pp[t.ppOff[q]], *e = &t.pp[t.ppOff[q + 1]];
+                const int32_t *firstUp = std::upper_bound(b, e, q);
+                const int32_t *pos = std::lower_bound(firstUp, e, (int32_t)p);
+                t.pe[s] = upStart[q] + (int32_t)(pos - firstUp);
+            }
+        }
+
+    // ---- edge -> faces (ascending), edge -> cells with face pairs ----
+    std::vector<int32_t> efCount(E), ecCount(E);
+    auto edgeFacesOf = [&](int64_t e, int32_t *out) {
+        const int32_t p = t.edge[2 * e], q = t.edge[2 * e + 1];
+        int32_t n = 0;
+        for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
+            if (t.corner[2 * (int64_t)s] == q || t.corner[2 * (int64_t)s + 1] == q)
+                out[n++] = cornerFace[s];
+        return n;
+    };
+    int32_t maxRow = 0;
+    for (int64_t p = 0; p < P; ++p)
+        maxRow = std::max(maxRow, t.cornerOff[p + 1] - t.cornerOff[p]);
+#pragma omp parallel
+    {
+        std::vector<int32_t> fs(maxRow), cs;
+#pragma omp for schedule(static)
+        for (int64_t e = 0; e < E; ++e)
+        {
+            const int32_t n = edgeFacesOf(e, fs.data());
+            efCount[e] = n;
+            cs.clear();
+            for (int32_t i = 0; i < n; ++i)
+            {
+                const int32_t f = fs[i];
+                if (std::find(cs.begin(), cs.end(), m.owner[f]) == cs.end())
+                    cs.push_back(m.owner[f]);
+                if (f < Fi && std::find(cs.begin(), cs.end(), m.neighbour[f]) == cs.end())
+                    cs.push_back(m.neighbour[f]);
+            }
+            ecCount[e] = (int32_t)cs.size();
+        }
+    }
+    t.efOff.assign(E + 1, 0);
+    t.ecOff.assign(E + 1, 0);
+    for (int64_t e = 0; e < E; ++e)
+    {
+        t.efOff[e + 1] = t.efOff[e] + efCount[e];
+        t.ecOff[e + 1] = t.ecOff[e] + ecCount[e];
+        t.maxEdgeFaces = std::max(t.maxEdgeFaces, efCount[e]);
+    }
+    t.ef.resize(t.efOff[E]);
+    t.ecCell.resize(t.ecOff[E]);
+    t.ecPair.resize(t.ecOff[E]);
+    int bad = 0;
+#pragma omp parallel
+    {
+        std::vector<int32_t> fs(maxRow), cs;
+#pragma omp for schedule(static)
+        for (int64_t e = 0; e < E; ++e)
+        {
+            const int32_t n = edgeFacesOf(e, fs.data());
+            std::copy(fs.begin(), fs.begin() + n, t.ef.begin() + t.efOff[e]);
+            cs.clear();
+            for (int32_t i = 0; i < n; ++i)
+            {
+                const int32_t f = fs[i];
+                if (std::find(cs.begin(), cs.end(), m.owner[f]) == cs.end())
+                    cs.push_back(m.owner[f]);
+                if (f < Fi && std::find(cs.begin(), cs.end(), m.neighbour[f]) == cs.end())
+                    cs.push_back(m.neighbour[f]);
+            }
+            for (size_t ci = 0; ci < cs.size(); ++ci)
+            {
+                const int32_t c = cs[ci];
+                int32_t f0 = -1, f1 = -1, cnt = 0;
+                for (int32_t i = 0; i < n; ++i)
+                {
+                    const int32_t f = fs[i];
+                    if (m.owner[f] == c || (f < Fi && m.neighbour[f] == c))
+                    {
+                        if (cnt == 0)
+                            f0 = i;
+                        else if (cnt == 1)
+                            f1 = i;
+                        ++cnt;
+                    }
+                }
+                if (cnt != 2 || n >= 65536)
+                {
+#pragma omp atomic write
+                    bad = (cnt > 2) ? 1 : 2;
+                }
+                t.ecCell[t.ecOff[e] + ci] = c;
+                t.ecPair[t.ecOff[e] + ci] = (f0 & 0xffff) | (f1 << 16);
+            }
+        }
+    }
+    if (bad == 1)
+        fail("Sanity broken, more than two edge faces belong to same cell");
+    if (bad == 2)
+        fail("Sanity broken, didn't find face pairs for cell");
+
+    // ---- cell geometry stream (owner faces ascending, then neighbour faces ascending) ----
+    std::vector<int64_t> words(C + 1, 0);
+    for (int64_t f = 0; f < F; ++f)
+        words[m.owner[f] + 1] += 1 + (m.faceOffsets[f + 1] - m.faceOffsets[f]);
+    for (int64_t f = 0; f < Fi; ++f)
+        words[m.neighbour[f] + 1] += 1 + (m.faceOffsets[f + 1] - m.faceOffsets[f]);
+    for (int64_t c = 0; c < C; ++c)
+        words[c + 1] += words[c];
+    if (words[C] >= (int64_t)INT32_MAX)
+        fail("mesh too large for 32-bit cell stream offsets");
+    t.cellOff.resize(C + 1);
+    for (int64_t c = 0; c <= C; ++c)
+        t.cellOff[c] = (int32_t)words[c];
+    t.cellStream.resize(words[C]);
+    {
+        std::vector<int32_t> cur(t.cellOff.begin(), t.cellOff.end() - 1);
+        auto put = [&](int32_t c, int64_t f, int32_t nbrSide) {
+            const int32_t b = m.faceOffsets[f], n = m.faceOffsets[f + 1] - b;
+            int32_t w = cur[c];
+            t.cellStream[w++] = n | (nbrSide << 30);
+            for (int32_t i = 0; i < n; ++i)
+                t.cellStream[w++] = m.faceVerts[b + i];
+            cur[c] = w;
+        };
+        for (int64_t f = 0; f < F; ++f)
+            put(m.owner[f], f, 0);
+        for (int64_t f = 0; f < Fi; ++f)
+            put(m.neighbour[f], f, 1);
+    }
+
+    // ---- findClosestPoints prerequisite (:354-362): two eligible neighbours per point ----
+    for (int64_t p = 0; p < P; ++p)
+    {
+        int32_t eligible = 0;
+        for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+            eligible += (t.isInternal[p] || !t.isInternal[t.pp[s]]);
+        if (eligible < 2)
+            fail("Failed to find cLabel" + std::to_string(eligible + 1) + " for pointI " + std::to_string(p));
+    }
+
+    // ---- getMeshStats :1495-1510 ----
+    double mn = 1e300, mx = 0.0;
+#pragma omp parallel for reduction(min : mn) reduction(max : mx) schedule(static)
+    for (int64_t e = 0; e < E; ++e)
+    {
+        const double *a = &m.points[3 * (int64_t)t.edge[2 * e]], *b = &m.points[3 * (int64_t)t.edge[2 * e + 1]];
+        const double dx = b[0] - a[0], dy = b[1] - a[1], dz = b[2] - a[2];
+        const double len = std::sqrt(dx * dx + dy * dy + dz * dz);
+        mn = std::min(mn, len);
+        mx = std::max(mx, len);
+    }
+    t.minEdgeLength = mn;
+    t.maxEdgeLength = mx;
+    return t;
+}
+
+} // namespace sm

@@ -1,0 +1,53 @@
+// topology.hpp -- derived connectivity for the smoothing kernels, built once on
+// the host and uploaded to HBM.
+//
+// Row orders follow what OpenFOAM's primitiveMesh hands the reference (SURVEY.md
+// appendix A.2): pointCells ascending cell label (sum order at
+// src/smoothMesh.C:127-130), pointPoints / pointEdges ascending neighbour label
+// (stable-sort tie-break :345-352, push order :1406-1431), pointFaces and
+// edgeFaces ascending face label.  The reference's per-call searches
+// (getNeighbourPoints :793-831, findCellFacePair :1042-1097, the share-a-cell
+// lookup :383) depend only on topology, so they are resolved here once.
+#pragma once
+#include "polymesh.hpp"
+#include <cstdint>
+#include <vector>
+
+namespace sm
+{
+
+struct Topology
+{
+    int64_t P = 0, C = 0, F = 0, Fi = 0, E = 0;
+
+    // point -> cells (ascending)
+    std::vector<int32_t> pcOff, pc;
+    // point -> edge-connected points (ascending) and the matching edge labels
+    std::vector<int32_t> ppOff, pp, pe;
+    // point -> face corners: for each face of pointFaces(p) (ascending) the previous and
+    // next vertex of p in that face: corner[2*k], corner[2*k+1]
+    std::vector<int32_t> cornerOff, corner;
+    // edges (lo,hi), numbered upper-triangular
+    std::vector<int32_t> edge;
+    // edge -> faces (ascending)
+    std::vector<int32_t> efOff, ef;
+    // edge -> cells, each with the positions (within the edge's face row) of the two
+    // faces of that cell that meet at the edge: ecPair = f0 | f1<<16
+    std::vector<int32_t> ecOff, ecCell, ecPair;
+    // faces (copied from the mesh; vertex loops)
+    std::vector<int32_t> faceOff, faceVerts;
+    // cell -> geometry stream: for each face of the cell, in OpenFOAM's accumulation
+    // order (faces it owns ascending, then faces it neighbours ascending), one header
+    // word nv | (neighbourSide << 30) followed by the nv vertex labels.
+    std::vector<int32_t> cellOff, cellStream;
+    std::vector<uint8_t> isInternal; // src/smoothMesh.C:40-91
+    double minEdgeLength = 0, maxEdgeLength = 0; // src/smoothMesh.C:1478-1541
+    int32_t maxPointDegree = 0, maxFaceSize = 0, maxEdgeFaces = 0;
+};
+
+// Throws std::runtime_error with the reference's FatalError texts where the
+// reference would abort (empty patches :61-66, <2 eligible closest points
+// :354-362, edge/cell face-pair sanity :1073,:1087).
+Topology buildTopology(const PolyMesh &m);
+
+} // namespace sm

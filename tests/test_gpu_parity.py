@@ -1,0 +1,132 @@
+"""GPU parity: libsmgpu.so (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): freeze masks, per-iteration nFrozen and iteration count bit-exact;
+positions within 1e-9 x bounding-box diagonal.  The library is built --fmad=false with the oracle's
+acos, so positions and residuals are in fact required to be bitwise equal here.
+"""
+import numpy as np
+import pytest
+
+import smoothmesh_b200 as sm
+from oracle import Oracle
+
+from meshes import CASES
+
+pytestmark = pytest.mark.gpu
+
+OPTION_SETS = {
+    "default": dict(),
+    # testcase/run_serial:18 minus -layerPatches
+    "testcase_opts": dict(min_angle_deg=15.0, max_angle_deg=160.0),
+    # BASELINE config 2: -totalMinFreeze true, tighter angle window so the freeze paths are busy
+    "total_min_freeze": dict(total_min_freeze=1, min_angle_deg=60.0, max_angle_deg=120.0),
+    "no_constraints": dict(edge_angle_constraint=0, face_angle_constraint=0),
+    "org_geometry": dict(geometry_variant=1),
+    # narrow angle window: many active points, self/neighbour freezes and stack re-visits
+    "tight_angles": dict(min_angle_deg=80.0, max_angle_deg=100.0),
+}
+
+
+def _pair(mesh, **kw):
+    g = sm.Smoother(mesh, **kw)
+    o = Oracle(mesh.desc_arrays(), **kw)
+    p = g.params
+    assert p.min_edge_length == o.prm.minEdgeLength and p.max_step_length == o.prm.maxStepLength
+    return g, o
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("opts", list(OPTION_SETS))
+def test_stage_parity_first_iteration(case, opts):
+    mesh = CASES[case]()
+    kw = dict(OPTION_SETS[opts], rel_tol=0.0)
+    g, o = _pair(mesh, **kw)
+    n, nf, res = o.iterate(1)
+    assert n == 1
+    cc = g.op_cell_centres()
+    assert np.array_equal(cc, o.get("snapCellCtr")), "cell centres differ"
+    npred = g.op_predict()
+    assert np.array_equal(npred, o.get("snapClamped")), "predictor output differs"
+    fz = g.op_edge_constraints()
+    ref = o.get("snapFrozenEdgeAngle") if kw.get("edge_angle_constraint", 1) else o.get("snapFrozenEdgeLen")
+    assert np.array_equal(fz, ref), "freeze mask after edge constraints differs"
+    if kw.get("face_angle_constraint", 1):
+        fz = g.op_face_angle_constraint()
+        assert np.array_equal(fz, o.get("snapFrozenFaceAngle")), "freeze mask after face-angle constraint differs"
+    gnf, gres = g.op_commit()
+    assert gnf == nf[0]
+    assert gres == res[0]
+    assert np.array_equal(g.points(), o.get("points"))
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("opts", ["default", "total_min_freeze", "tight_angles"])
+def test_loop_parity(case, opts):
+    mesh = CASES[case]()
+    kw = dict(OPTION_SETS[opts], rel_tol=1e-3)
+    g, o = _pair(mesh, **kw)
+    iters = 40
+    n, nf, res = o.iterate(iters)
+    log = g.iterate(iters)
+    assert log.iterations == n, "iteration count at convergence differs"
+    assert np.array_equal(log.n_frozen, nf)
+    assert np.array_equal(log.residual, res)
+    assert np.array_equal(g.frozen(), o.get("frozen"))
+    pts, ref = g.points(), o.get("points")
+    diag = np.linalg.norm(ref.max(0) - ref.min(0))
+    assert np.abs(pts - ref).max() <= 1e-9 * diag  # the stated tolerance
+    assert np.array_equal(pts, ref)  # and in fact bitwise
+
+
+def test_edge_face_angles_match_oracle():
+    mesh = CASES["hex_8x6x5_j45"]()
+    g, o = _pair(mesh)
+    mn, mx = g.op_edge_face_angles()
+    assert np.array_equal(g.edges(), o.get("edges"))
+    for e in range(0, len(mn), 7):
+        omn, omx = o.edge_face_angles(e)
+        assert mn[e] == omn and mx[e] == omx
+
+
+def test_connectivity_matches_oracle():
+    mesh = CASES["kelvin3_j20"]()
+    g, o = _pair(mesh)
+    for name in ("pointCells", "pointPoints", "pointEdges", "edgeFaces"):
+        goff, gval = g.csr(name)
+        ooff, oval = o.csr(name)
+        assert np.array_equal(goff, ooff) and np.array_equal(gval, oval), name
+    # edgeCells: same sets (row order is not observable)
+    goff, gval = g.csr("edgeCells")
+    ooff, oval = o.csr("edgeCells")
+    assert np.array_equal(goff, ooff)
+    for e in range(len(goff) - 1):
+        assert sorted(gval[goff[e]:goff[e + 1]]) == sorted(oval[ooff[e]:ooff[e + 1]])
+
+
+def test_uniform_block_known_answer():
+    # K1: uniform hex block -> nothing moves, stop at iteration 1, nFrozen = boundary points
+    n = 7
+    g = sm.Smoother(sm.Mesh.hex_block(n, n, n))
+    log = g.iterate(10)
+    assert log.iterations == 1
+    assert log.n_frozen[0] == (n + 1) ** 3 - (n - 1) ** 3
+    assert log.residual[0] < 1e-9
+
+
+def test_determinism_and_boundary_fixed():
+    mesh = CASES["hex6_j25"]()
+    runs = []
+    for _ in range(2):
+        g = sm.Smoother(mesh, rel_tol=0.0)
+        g.iterate(15)
+        runs.append((g.points(), g.frozen()))
+    assert np.array_equal(runs[0][0], runs[1][0]) and np.array_equal(runs[0][1], runs[1][1])
+    o = Oracle(mesh.desc_arrays())
+    bnd = o.get("isInternal") == 0
+    assert np.array_equal(runs[0][0][bnd], np.asarray(mesh.points)[bnd])  # K5
+
+
+def test_no_gpu_fallback_message():
+    # a bad device ordinal must fail loudly, never fall back
+    with pytest.raises(sm.SmoothMeshError):
+        sm.Smoother(CASES["hex6_j25"](), device=99)
