@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the smoothMesh hot path on B200.
+
+Metric (BASELINE.json): mesh point-updates/s per smoothing iteration.
+  step      = one smoothing iteration (the loop body of src/smoothMesh.C:2257-2437) over the mesh
+  workload  = BASELINE config 3: blockMesh-numbered 200^3 hex block on the unit cube, interior
+              points jittered U(-0.25h, 0.25h) (seed 12345), all constraints on, default options,
+              -relTol 0 so that every one of the K iterations runs
+  value     = nPoints(all ranks) * K / device time of the K iterations, inputs resident in HBM
+  e2e       = the same job through the host-buffer C ABI: upload points, K iterations, download
+              points + per-iteration log, host<->device copies inside the timed region
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n CELLS_PER_SIDE]
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 12345
+JITTER = 0.25
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(P, C, F, Fi, E, FV, PC, EC):
+    """Per-iteration algorithmic HBM bytes, SURVEY.md 8(d) (every resident array touched once per
+    phase that needs it; int32 labels, FP64 coordinates), split per kernel in DESIGN.md."""
+    state = 24 * (2 * P + 2 * P + 2 * C) + 2 * P
+    conn = 4 * ((FV + F + 1) + (F + Fi) + (PC + P + 1) + (2 * E + P + 1) + (FV + P + 1) + 2 * E
+                + (FV + E + 1) + (EC + E + 1) + (F + Fi + C + 1) + (2 * E + P + 1))
+    return state + conn
+
+
+def kernel_bytes(P, C, F, Fi, E, FV, PC, EC):
+    """Algorithmic bytes per launch of each kernel."""
+    return {
+        # points gathered once (24P) + cell stream (FV' + nFaces' words, both sides) + cellCtr written
+        "k_cell_centres": 24 * P + 4 * (2 * FV + 2 * F + C + 1) + 24 * C,
+        # cellCtr + points read, pointCells + pointPoints CSR, newPoints written, per-point state reset
+        "k_predict": 24 * C + 24 * P + 4 * (PC + P + 1) + 4 * (2 * E + P + 1) + 24 * P + 18 * P,
+        # points + newPoints read, pointPoints CSR + corner table (2 words per point-face), mask written
+        "k_edge_constraints": 48 * P + 4 * (2 * E + P + 1) + 4 * (2 * FV + P + 1) + P,
+        # points + cellCtr read, edges, edgeFaces, edgeCells(+pairs), faces CSR
+        "k_face_current": 24 * P + 24 * C + 4 * (2 * E) + 4 * (FV + E + 1) + 4 * (2 * EC + E + 1) + 4 * (FV + F + 1),
+        "k_active_compact": 2 * P,
+        "k_face_tests": 0,
+        "k_face_resolve": 0,
+        # points + newPoints + mask read, points written
+        "k_commit": 24 * P + 24 * P + P + 24 * P,
+    }
+
+
+def mesh_counts(mesh, n_edges):
+    P, C, F, Fi = mesh.n_points, mesh.n_cells, mesh.n_faces, mesh.n_internal_faces
+    FV = int(mesh.face_offsets[-1])
+    # PC = sum |pointCells|, EC = sum |edgeCells|; for a hex block: 8C and ~12C (exact values from the library)
+    return P, C, F, Fi, n_edges, FV
+
+
+def cpu_baseline(n_side, iters, threads):
+    """Times the CPU oracle (a port of the reference; the reference itself needs OpenFOAM) on a bounded
+    sample of the same workload: a jittered n_side^3 block with the same jitter rule and options."""
+    import smoothmesh_b200 as sm
+    from oracle import Oracle
+    mesh = sm.Mesh.hex_block(n_side, n_side, n_side).jitter(JITTER / n_side, SEED)
+    if threads > 1:
+        # rank emulation: decomposePar-style bricks, one thread per part (the reference's mpirun mode)
+        px = py = pz = 1
+        t = threads
+        while t % 2 == 0 and t > 1:
+            if px <= py and px <= pz:
+                px *= 2
+            elif py <= pz:
+                py *= 2
+            else:
+                pz *= 2
+            t //= 2
+        parts = mesh.decompose(px, py, pz)
+        o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, threads=px * py * pz)
+        used = px * py * pz
+    else:
+        o = Oracle(mesh.desc_arrays(), rel_tol=0.0)
+        used = 1
+    t0 = time.perf_counter()
+    n, _, _ = o.iterate(iters)
+    dt = time.perf_counter() - t0
+    return mesh.n_points * n / dt, used, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be
+    built here (OpenFOAM + wmake absent), so this times the oracle port with all host threads in
+    rank-emulation mode (the reference's `mpirun` strategy) on bounded samples of the workload."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_side = args.ref_n
+    import smoothmesh_b200 as sm
+    from oracle import Oracle
+    mesh = sm.Mesh.hex_block(n_side, n_side, n_side).jitter(JITTER / n_side, SEED)
+    p2 = 1
+    while p2 * 2 <= threads:
+        p2 *= 2
+    dims = [1, 1, 1]
+    t = p2
+    i = 0
+    while t > 1:
+        dims[i % 3] *= 2
+        t //= 2
+        i += 1
+    parts = mesh.decompose(*dims) if p2 > 1 else [mesh]
+    o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, threads=p2)
+    o.iterate(args.warmup)
+    t0 = time.perf_counter()
+    n, _, _ = o.iterate(args.steps)
+    dt = time.perf_counter() - t0
+    value = mesh.n_points * n / dt
+    line = {
+        "impl": "reference", "metric": "mesh point-updates/s per smoothing iteration", "value": value,
+        "unit": "point-updates/s", "n_gpus": args.gpus, "steps": n, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(n, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"hex {n_side}^3 jittered block (bounded sample of the 200^3 config), all constraints on",
+                   "decomposition": "x".join(map(str, dims)), "note": "CPU oracle port in rank-emulation mode; the "
+                   "OpenFOAM-linked reference cannot be built in this image"},
+        "cpu_baseline": {"value": value, "unit": "point-updates/s", "cores": p2, "kind": "port",
+                         "sample": f"{n} iterations of a jittered {n_side}^3 hex block, {p2} threads"},
+        "e2e": {"value": value, "unit": "point-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=200, help="cells per side of the (per-GPU) hex block")
+    ap.add_argument("--ref-n", type=int, default=96, help="cells per side of the CPU sample mesh")
+    ap.add_argument("--cpu-iters", type=int, default=4)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import smoothmesh_b200 as sm
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n
+    t0 = time.perf_counter()
+    if world == 1:
+        mesh = sm.Mesh.hex_block(n, n, n).jitter(JITTER / n, SEED)
+    else:
+        from smoothmesh_b200 import multi
+        mesh = multi.weak_scaling_part(n, world, rank, JITTER, SEED)
+    t_gen = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    g = sm.Smoother(mesh, rel_tol=0.0, device=local_rank)
+    if world > 1:
+        from smoothmesh_b200 import multi
+        multi.init_comm(g, rank, world, dist)
+    t_setup = time.perf_counter() - t0
+    stats = g.mesh_stats()
+    P, C, F, Fi = mesh.n_points, mesh.n_cells, mesh.n_faces, mesh.n_internal_faces
+    E, FV = stats["n_edges"], int(mesh.face_offsets[-1])
+    PC = int(g.csr("pointCells")[0][-1])
+    EC = int(g.csr("edgeCells")[0][-1])
+    init_pts = np.array(mesh.points, dtype=np.float64)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # warm-up, then restart from the initial jittered mesh so the timed region is iterations 1..K
+    g.iterate(args.warmup)
+    g.set_points(init_pts)
+    g.profile(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    log = g.iterate(args.steps)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    prof = g.profile_get()
+    g.profile(False)
+    ms = log.ms
+    total_points = P
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        tp = torch.tensor([P], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tp, op=dist.ReduceOp.SUM)
+        total_points = int(tp.item())
+    K = log.iterations
+    value = total_points * K / (ms * 1e-3)
+
+    # end-to-end through the host-buffer C ABI: H2D points, K iterations, D2H points + log
+    barrier()
+    t0 = time.perf_counter()
+    g.set_points(init_pts)
+    log2 = g.iterate(args.steps)
+    out_pts = g.points()
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    if dist is not None:
+        import torch
+        t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    e2e_value = total_points * log2.iterations / t_e2e
+    assert np.array_equal(log2.n_frozen, log.n_frozen)
+    assert np.isfinite(out_pts).all()
+
+    if rank != 0:
+        return
+
+    hbm, hbm_src = peaks()
+    kb = kernel_bytes(P, C, F, Fi, E, FV, PC, EC)
+    top = max(prof, key=lambda k: prof[k]["ms"])
+    top_ms = prof[top]["ms"] / max(prof[top]["launches"], 1)
+    if top == "k_active_compact":
+        top_ms = prof[top]["ms"] / max(prof[top]["launches"] // 4, 1)
+    achieved = kb[top] / (top_ms * 1e-3) / 1e9
+    iter_bytes = algorithmic_bytes(P, C, F, Fi, E, FV, PC, EC)
+    line = {
+        "metric": "mesh point-updates/s per smoothing iteration", "value": value, "unit": "point-updates/s",
+        "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"hex {n}^3 jittered blockMesh block per GPU (U(-0.25h,0.25h), seed {SEED}), "
+                               f"{K} iterations, edge/face angle constraints on, relTol 0",
+                   "points_per_gpu": P, "cells_per_gpu": C, "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
+                   "setup_s": {"mesh_generation": t_gen, "create_upload": t_setup}},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "point-updates/s", "h2d_bytes_per_step": 24 * P / K,
+                "d2h_bytes_per_step": (24 * P + 16 * K) / K,
+                "note": "points uploaded once, K iterations, points + log downloaded once; bytes amortised over K steps"},
+        "gpu_launches": int(log.launches),
+        "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                     "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                     "algorithmic_bytes_per_launch": kb[top], "avg_launch_ms": top_ms,
+                     "whole_iteration": {"algorithmic_bytes": iter_bytes,
+                                         "achieved": iter_bytes / (ms / K * 1e-3) / 1e9,
+                                         "frac": iter_bytes / (ms / K * 1e-3) / 1e9 / hbm}},
+        "kernel_ms_per_step": {k: v["ms"] / K for k, v in prof.items()},
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v1, c1, dt1 = cpu_baseline(args.ref_n, args.cpu_iters, 1)
+        vN, cN, dtN = cpu_baseline(args.ref_n, args.cpu_iters, threads)
+        line["cpu_baseline"] = {"value": vN, "unit": "point-updates/s", "cores": cN, "kind": "port",
+                                "sample": f"{args.cpu_iters} iterations of a jittered {args.ref_n}^3 hex block "
+                                          f"(same jitter rule/options), rank-emulation on {cN} threads ({dtN:.1f} s); "
+                                          f"serial: {v1:.4g} point-updates/s ({dt1:.1f} s)",
+                                "serial_value": v1}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -111,6 +111,14 @@ extern "C"
      * milliseconds, and the number of kernels it launched. */
     int smgpu_last_timing(smgpu_handle *h, double *ms, int64_t *launches);
 
+    /* Optional per-kernel timing: when enabled, every kernel (group) launched by
+     * smgpu_iterate is bracketed by CUDA events on the launch stream and the elapsed
+     * times are accumulated per kernel name.  smgpu_profile() also clears the counters.
+     * smgpu_profile_get: *n = number of kernel groups; arrays (any may be NULL) must hold
+     * at least 16 entries; names are static strings. */
+    int smgpu_profile(smgpu_handle *h, int32_t enable);
+    int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches);
+
     /* ---- operator-level entry points -------------------------------------------
      * One call per reference L3 function, for parity tests and for hosts that
      * keep the reference's loop structure.  They operate on the handle's device

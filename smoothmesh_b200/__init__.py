@@ -110,6 +110,8 @@ def lib():
         L.smgpu_op_commit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_op_edge_face_angles.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_get_csr.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_profile.argtypes = [C.c_void_p, C.c_int32]
+        L.smgpu_profile_get.argtypes = [C.c_void_p] * 5
         L.smgpu_comm_unique_id.argtypes = [C.c_void_p]
         L.smgpu_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         _lib = L
@@ -420,6 +422,17 @@ class Smoother:
         val = np.zeros(n.value, dtype=np.int32)
         self._ck(lib().smgpu_get_csr(self._h, name.encode(), _ptr(off), _ptr(val), C.byref(n)))
         return off, val
+
+    def profile(self, enable=True):
+        self._ck(lib().smgpu_profile(self._h, int(enable)))
+
+    def profile_get(self):
+        n = C.c_int32()
+        names = (C.c_char_p * 16)()
+        ms = (C.c_double * 16)()
+        ln = (C.c_int64 * 16)()
+        self._ck(lib().smgpu_profile_get(self._h, C.byref(n), names, ms, ln))
+        return {names[i].decode(): dict(ms=ms[i], launches=ln[i]) for i in range(n.value)}
 
     # ---- multi-GPU ----
     @staticmethod

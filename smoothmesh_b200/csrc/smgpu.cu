@@ -47,6 +47,47 @@ struct smgpu_handle
     sm::Comm *comm = nullptr;
     std::vector<int64_t> gid;
 
+    // optional per-kernel timing (CUDA events on the launch stream)
+    enum { K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_NUM };
+    bool profiling = false;
+    std::vector<cudaEvent_t> evPool;
+    std::vector<std::pair<int, size_t>> evUse; // (kernel id, index of start event)
+    size_t evNext = 0;
+    double profMs[K_NUM] = {0};
+    int64_t profLaunches[K_NUM] = {0};
+    void profBegin(int k)
+    {
+        if (!profiling)
+            return;
+        if (evNext + 2 > evPool.size())
+        {
+            evPool.resize(evPool.size() + 256);
+            for (size_t i = evPool.size() - 256; i < evPool.size(); ++i)
+                CK(cudaEventCreate(&evPool[i]));
+        }
+        evUse.push_back({k, evNext});
+        CK(cudaEventRecord(evPool[evNext], stream));
+    }
+    void profEnd(int nLaunches)
+    {
+        if (!profiling)
+            return;
+        CK(cudaEventRecord(evPool[evNext + 1], stream));
+        profLaunches[evUse.back().first] += nLaunches;
+        evNext += 2;
+    }
+    void profCollect()
+    {
+        for (auto &u : evUse)
+        {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, evPool[u.second], evPool[u.second + 1]));
+            profMs[u.first] += ms;
+        }
+        evUse.clear();
+        evNext = 0;
+    }
+
     template <class T> T *dalloc(size_t n)
     {
         void *p = nullptr;
@@ -96,34 +137,50 @@ struct smgpu_handle
     // ---- kernel launches (one method per reference operator) ----
     void launchCellCentres()
     {
+        profBegin(K_CELL);
         k_cell_centres<<<grid(d.C, 128), 128, 0, stream>>>(d);
+        profEnd(1);
         ++launches;
     }
     void launchPredict()
     {
+        profBegin(K_PREDICT);
         k_predict<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        profEnd(1);
         ++launches;
     }
     void launchEdgeConstraints()
     {
+        profBegin(K_EDGE);
         k_edge_constraints<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        profEnd(1);
         ++launches;
     }
     void launchFaceAngle(double *dbgMin = nullptr, double *dbgMax = nullptr)
     {
         const int nChunks = grid(d.P, SMK_CHUNK);
+        profBegin(K_FACE_CUR);
         k_face_current<<<grid(d.E, 128), 128, 0, stream>>>(d, dbgMin, dbgMax);
+        profEnd(1);
+        profBegin(K_COMPACT);
         k_active_count<<<nChunks, 256, 0, stream>>>(d);
         k_active_scan<<<1, 256, 0, stream>>>(d, nChunks);
         k_active_fill<<<nChunks, 256, 0, stream>>>(d);
         k_face_clear<<<148, 128, 0, stream>>>(d);
+        profEnd(4);
+        profBegin(K_FACE_TESTS);
         k_face_tests<<<148 * 4, 128, 0, stream>>>(d);
+        profEnd(1);
+        profBegin(K_FACE_RESOLVE);
         k_face_resolve<<<1, 32, 0, stream>>>(d);
+        profEnd(1);
         launches += 7;
     }
     void launchCommit()
     {
+        profBegin(K_COMMIT);
         k_commit<<<grid(d.P, 256), 256, 0, stream>>>(d);
+        profEnd(1);
         ++launches;
     }
     void resetControl()
@@ -379,6 +436,8 @@ extern "C"
             CK(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
             h->lastMs = ms;
             h->lastLaunches = h->launches;
+            if (h->profiling)
+                h->profCollect();
             int it = 0;
             CK(cudaMemcpy(&it, h->d.iter, sizeof(int), cudaMemcpyDeviceToHost));
             if (iters_done)
@@ -560,8 +619,9 @@ extern "C"
         if (cudaMalloc(&dmin, E * 8 + 8) != cudaSuccess || cudaMalloc(&dmax, E * 8 + 8) != cudaSuccess)
             return setErr(SMGPU_ERR_CUDA, "cudaMalloc failed");
         h->resetControl();
-        // run on a scratch copy of the per-point state: k_face_current only ORs/mins into
-        // curMin/curMax/activeFlag, which k_predict resets at the start of every iteration
+        h->launchCellCentres(); // mesh.C() is demand-driven in the reference (:1218)
+        // k_face_current only mins/maxes into curMin/curMax/activeFlag, which k_predict resets at
+        // the start of every iteration
         k_face_current<<<smgpu_handle::grid(h->d.E, 128), 128, 0, h->stream>>>(h->d, dmin, dmax);
         int rc = finishOp(h);
         if (rc == SMGPU_OK && (cudaMemcpy(min_out, dmin, E * 8, cudaMemcpyDeviceToHost) != cudaSuccess ||
@@ -605,6 +665,38 @@ extern "C"
             memcpy(offsets, off->data(), off->size() * sizeof(int32_t));
         if (values)
             memcpy(values, val->data(), val->size() * sizeof(int32_t));
+        return SMGPU_OK;
+    }
+
+    int smgpu_profile(smgpu_handle *h, int32_t enable)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        h->profiling = enable != 0;
+        for (int k = 0; k < smgpu_handle::K_NUM; ++k)
+        {
+            h->profMs[k] = 0;
+            h->profLaunches[k] = 0;
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches)
+    {
+        static const char *kNames[smgpu_handle::K_NUM] = {"k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
+                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit"};
+        if (!h || !n)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        *n = smgpu_handle::K_NUM;
+        for (int k = 0; k < smgpu_handle::K_NUM; ++k)
+        {
+            if (names)
+                names[k] = kNames[k];
+            if (ms_total)
+                ms_total[k] = h->profMs[k];
+            if (launches)
+                launches[k] = h->profLaunches[k];
+        }
         return SMGPU_OK;
     }
 
