@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -48,7 +49,7 @@ struct smgpu_handle
     std::vector<int64_t> gid;
 
     // optional per-kernel timing (CUDA events on the launch stream)
-    enum { K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_NUM };
+    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_NUM };
     bool profiling = false;
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<int, size_t>> evUse; // (kernel id, index of start event)
@@ -114,7 +115,21 @@ struct smgpu_handle
         d.edgeAngleConstraint = prm.edge_angle_constraint;
         d.faceAngleConstraint = prm.face_angle_constraint;
         d.geometryVariant = prm.geometry_variant;
+        // guard-banded cosine-space filters; disabled near the ends of the
+        // angle range, where the literal path is always taken
+        const double guard = 1e-9;
+        d.edgeCosT = std::cos(d.smallAngle) - guard;
+        d.edgeFilter = (d.edgeCosT > -0.9999 && d.edgeCosT < 0.9999) ? 1 : 0;
+        d.faceCosHi = std::cos(d.smallAngle) - guard;
+        d.faceCosLo = std::cos(d.largeAngle) + guard;
+        d.faceFilter = (d.smallAngle > 1e-3 && d.largeAngle < M_PI - 1e-3 && d.smallAngle < d.largeAngle &&
+                        d.faceCosLo < d.faceCosHi)
+                           ? 1
+                           : 0;
+        if (noFilters)
+            d.edgeFilter = d.faceFilter = 0;
     }
+    bool noFilters = false; // SMGPU_NO_FILTERS=1: always take the literal path (testing aid)
     void ensureStats(int n)
     {
         if (n <= statCap)
@@ -137,6 +152,10 @@ struct smgpu_handle
     // ---- kernel launches (one method per reference operator) ----
     void launchCellCentres()
     {
+        profBegin(K_FACE_GEOM);
+        k_face_geom<<<grid(d.F, 256), 256, 0, stream>>>(d);
+        profEnd(1);
+        ++launches;
         profBegin(K_CELL);
         k_cell_centres<<<grid(d.C, 128), 128, 0, stream>>>(d);
         profEnd(1);
@@ -273,6 +292,10 @@ extern "C"
             d.P = (int)t.P;
             d.C = (int)t.C;
             d.E = (int)t.E;
+            d.F = (int)t.F;
+            d.faceGeo = h->dalloc<P4>(2 * t.F);
+            d.faceMean = h->dalloc<P4>(t.F);
+            h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
             d.pts = h->dalloc<P4>(t.P);
             d.newPts = h->dalloc<P4>(t.P);
             d.cellCtr = h->dalloc<P4>(t.C);
@@ -292,8 +315,8 @@ extern "C"
             d.ecPair = h->upload(t.ecPair);
             d.faceOff = h->upload(t.faceOff);
             d.faceVerts = h->upload(t.faceVerts);
-            d.cellOff = h->upload(t.cellOff);
-            d.cellStream = h->upload(t.cellStream);
+            d.cfOff = h->upload(t.cfOff);
+            d.cf = h->upload(t.cf);
             d.curMin = h->dalloc<unsigned long long>(t.P);
             d.curMax = h->dalloc<unsigned long long>(t.P);
             d.activeFlag = h->dalloc<uint8_t>(t.P + 8);
@@ -683,7 +706,7 @@ extern "C"
 
     int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches)
     {
-        static const char *kNames[smgpu_handle::K_NUM] = {"k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
+        static const char *kNames[smgpu_handle::K_NUM] = {"k_face_geom", "k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
                                                           "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit"};
         if (!h || !n)
             return setErr(SMGPU_ERR_ARG, "null argument");

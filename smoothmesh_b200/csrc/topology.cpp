@@ -261,34 +261,22 @@ Topology buildTopology(const PolyMesh &m)
     if (bad == 2)
         fail("Sanity broken, didn't find face pairs for cell");
 
-    // ---- cell geometry stream (owner faces ascending, then neighbour faces ascending) ----
-    std::vector<int64_t> words(C + 1, 0);
+    // ---- cell -> faces in OpenFOAM's accumulation order (owned faces ascending, then
+    //      neighbour-side faces ascending; bit 31 marks the neighbour side) ----
+    t.cfOff.assign(C + 1, 0);
     for (int64_t f = 0; f < F; ++f)
-        words[m.owner[f] + 1] += 1 + (m.faceOffsets[f + 1] - m.faceOffsets[f]);
+        ++t.cfOff[m.owner[f] + 1];
     for (int64_t f = 0; f < Fi; ++f)
-        words[m.neighbour[f] + 1] += 1 + (m.faceOffsets[f + 1] - m.faceOffsets[f]);
+        ++t.cfOff[m.neighbour[f] + 1];
     for (int64_t c = 0; c < C; ++c)
-        words[c + 1] += words[c];
-    if (words[C] >= (int64_t)INT32_MAX)
-        fail("mesh too large for 32-bit cell stream offsets");
-    t.cellOff.resize(C + 1);
-    for (int64_t c = 0; c <= C; ++c)
-        t.cellOff[c] = (int32_t)words[c];
-    t.cellStream.resize(words[C]);
+        t.cfOff[c + 1] += t.cfOff[c];
+    t.cf.resize(t.cfOff[C]);
     {
-        std::vector<int32_t> cur(t.cellOff.begin(), t.cellOff.end() - 1);
-        auto put = [&](int32_t c, int64_t f, int32_t nbrSide) {
-            const int32_t b = m.faceOffsets[f], n = m.faceOffsets[f + 1] - b;
-            int32_t w = cur[c];
-            t.cellStream[w++] = n | (nbrSide << 30);
-            for (int32_t i = 0; i < n; ++i)
-                t.cellStream[w++] = m.faceVerts[b + i];
-            cur[c] = w;
-        };
+        std::vector<int32_t> cur(t.cfOff.begin(), t.cfOff.end() - 1);
         for (int64_t f = 0; f < F; ++f)
-            put(m.owner[f], f, 0);
+            t.cf[cur[m.owner[f]]++] = (int32_t)f;
         for (int64_t f = 0; f < Fi; ++f)
-            put(m.neighbour[f], f, 1);
+            t.cf[cur[m.neighbour[f]]++] = (int32_t)((uint32_t)f | 0x80000000u);
     }
 
     // ---- findClosestPoints prerequisite (:354-362): two eligible neighbours per point ----

@@ -36,10 +36,9 @@ struct Topology
     std::vector<int32_t> ecOff, ecCell, ecPair;
     // faces (copied from the mesh; vertex loops)
     std::vector<int32_t> faceOff, faceVerts;
-    // cell -> geometry stream: for each face of the cell, in OpenFOAM's accumulation
-    // order (faces it owns ascending, then faces it neighbours ascending), one header
-    // word nv | (neighbourSide << 30) followed by the nv vertex labels.
-    std::vector<int32_t> cellOff, cellStream;
+    // cell -> faces in OpenFOAM's cell-centre accumulation order: faces the cell owns
+    // (ascending), then faces it neighbours (ascending, bit 31 set)
+    std::vector<int32_t> cfOff, cf;
     std::vector<uint8_t> isInternal; // src/smoothMesh.C:40-91
     double minEdgeLength = 0, maxEdgeLength = 0; // src/smoothMesh.C:1478-1541
     int32_t maxPointDegree = 0, maxFaceSize = 0, maxEdgeFaces = 0;

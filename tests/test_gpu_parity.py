@@ -130,3 +130,17 @@ def test_no_gpu_fallback_message():
     # a bad device ordinal must fail loudly, never fall back
     with pytest.raises(sm.SmoothMeshError):
         sm.Smoother(CASES["hex6_j25"](), device=99)
+
+
+@pytest.mark.parametrize("case", ["hex_8x6x5_j45", "kelvin3_j20"])
+def test_literal_path_without_filters(case, monkeypatch):
+    # SMGPU_NO_FILTERS=1 disables the guard-banded cosine-space filters so that every point /
+    # edge takes the literal evaluation; both paths must reproduce the oracle bit for bit.
+    monkeypatch.setenv("SMGPU_NO_FILTERS", "1")
+    mesh = CASES[case]()
+    kw = dict(OPTION_SETS["tight_angles"], rel_tol=0.0)
+    g, o = _pair(mesh, **kw)
+    n, nf, res = o.iterate(10)
+    log = g.iterate(10)
+    assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
+    assert np.array_equal(g.frozen(), o.get("frozen")) and np.array_equal(g.points(), o.get("points"))
