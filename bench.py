@@ -101,14 +101,16 @@ def algorithmic_bytes(P, C, F, Fi, E, FV, PC, EC):
 def kernel_bytes(P, C, F, Fi, E, FV, PC, EC):
     """Algorithmic bytes per launch of each kernel."""
     return {
-        # points gathered once (24P) + cell stream (FV' + nFaces' words, both sides) + cellCtr written
-        "k_cell_centres": 24 * P + 4 * (2 * FV + 2 * F + C + 1) + 24 * C,
+        # points gathered once (24P), faces CSR read, face records written (centre, area, vertex mean)
+        "k_face_geom": 24 * P + 4 * (FV + F + 1) + 72 * F,
+        # face centre + area read once per side (48 B x (F + Fi)), cell->faces list, cellCtr written
+        "k_cell_centres": 48 * (F + Fi) + 4 * (F + Fi + C + 1) + 24 * C,
         # cellCtr + points read, pointCells + pointPoints CSR, newPoints written, per-point state reset
         "k_predict": 24 * C + 24 * P + 4 * (PC + P + 1) + 4 * (2 * E + P + 1) + 24 * P + 18 * P,
         # points + newPoints read, pointPoints CSR + corner table (2 words per point-face), mask written
         "k_edge_constraints": 48 * P + 4 * (2 * E + P + 1) + 4 * (2 * FV + P + 1) + P,
-        # points + cellCtr read, edges, edgeFaces, edgeCells(+pairs), faces CSR
-        "k_face_current": 24 * P + 24 * C + 4 * (2 * E) + 4 * (FV + E + 1) + 4 * (2 * EC + E + 1) + 4 * (FV + F + 1),
+        # points + cellCtr + face means read, edges, edgeFaces, edgeCells(+pairs)
+        "k_face_current": 24 * P + 24 * C + 24 * F + 4 * (2 * E) + 4 * (FV + E + 1) + 4 * (2 * EC + E + 1),
         "k_active_compact": 2 * P,
         "k_face_tests": 0,
         "k_face_resolve": 0,

@@ -69,9 +69,10 @@ def lib():
     """Load libsmgpu.so (fails loudly if it has not been built)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise SmoothMeshError(f"{LIB_PATH} not found: run `make` (or __graft_entry__.build()) first")
-        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        path = os.environ.get("SMGPU_LIB", LIB_PATH)  # override: kernel-variant experiments only
+        if not os.path.exists(path):
+            raise SmoothMeshError(f"{path} not found: run `make` (or __graft_entry__.build()) first")
+        L = C.CDLL(path, mode=C.RTLD_GLOBAL)
         L.smgpu_last_error.restype = C.c_char_p
         L.smgpu_version.restype = C.c_char_p
         L.smmesh_last_error.restype = C.c_char_p
