@@ -143,11 +143,28 @@ extern "C"
     int smgpu_get_csr(smgpu_handle *h, const char *name, int32_t *offsets, int32_t *values, int64_t *n_values);
 
     /* ---- multi-GPU (one process per GPU) ------------------------------------------
-     * Replaces syncTools::syncPointList / returnReduce over MPI by
-     * NCCL.  nccl_unique_id is the 128-byte ncclUniqueId produced on rank 0
-     * (smgpu_comm_unique_id) and distributed by the host. */
+     * Replaces syncTools::syncPointList / returnReduce over MPI (call sites
+     * src/smoothMesh.C:134,142,402,429,455,472,2374,1567,2396) by NCCL over NVLink.
+     * Every rank creates its handle from its processor mesh (decomposePar layout, with
+     * point_global_id).  Start-up, in this order on every rank:
+     *   1. smgpu_comm_local_shared: global labels of this rank's processor-patch points;
+     *   2. the host all-gathers those lists (MPI / torch.distributed / anything) into
+     *      counts[n_ranks] + the concatenation all_gids, and distributes the 128-byte
+     *      ncclUniqueId made on rank 0 by smgpu_comm_unique_id;
+     *   3. smgpu_comm_init builds the exchange plan and the NCCL communicator.
+     * Afterwards smgpu_iterate runs the exchanges itself and returns global statistics. */
     int smgpu_comm_unique_id(uint8_t id_out[128]);
-    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t nccl_unique_id[128]);
+    int smgpu_comm_local_shared(smgpu_handle *h, int64_t *n, int64_t *gids_out /* or NULL */);
+    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t nccl_unique_id[128],
+                        const int64_t *counts, const int64_t *all_gids);
+
+    /* Host-only helper (no GPU needed): the exchange plan smgpu_comm_init would build, as
+     * flat arrays, so that host-side logic can be tested without devices.  local[i] / gids[i]
+     * are this rank's processor-patch points.  Returns the number of send slots;
+     * slot_point[slot] = local point, slot_rank[slot] = neighbour rank (both may be NULL). */
+    int64_t smgpu_exchange_plan(int32_t rank, int32_t n_ranks, int64_t n_local, const int32_t *local,
+                                const int64_t *gids, const int64_t *counts, const int64_t *all_gids,
+                                int32_t *slot_point, int32_t *slot_rank);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,9 @@ extern "C"
 
     /* constructors: return NULL on failure */
     smmesh *smmesh_gen_hex_block(int32_t nx, int32_t ny, int32_t nz, const double lo[3], const double hi[3]);
+    /* brick `rank` = ix + px*(iy + py*iz) of a (nx*px) x (ny*py) x (nz*pz) block on [lo,hi], as a processor mesh */
+    smmesh *smmesh_gen_hex_block_part(int32_t nx, int32_t ny, int32_t nz, int32_t px, int32_t py, int32_t pz,
+                                      int32_t rank, const double lo[3], const double hi[3]);
     smmesh *smmesh_gen_kelvin(int32_t n, double h);
     smmesh *smmesh_from_cells(int64_t n_points, const double *points, int32_t n_cells, const int32_t *cell_face_offsets,
                               const int32_t *cf_vert_offsets, const int32_t *cf_verts, const int32_t *cf_patch,

@@ -114,7 +114,12 @@ def lib():
         L.smgpu_profile.argtypes = [C.c_void_p, C.c_int32]
         L.smgpu_profile_get.argtypes = [C.c_void_p] * 5
         L.smgpu_comm_unique_id.argtypes = [C.c_void_p]
-        L.smgpu_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.smgpu_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_comm_local_shared.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_exchange_plan.restype = C.c_int64
+        L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
+        L.smmesh_gen_hex_block_part.restype = C.c_void_p
+        L.smmesh_gen_hex_block_part.argtypes = [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -165,6 +170,13 @@ class Mesh:
         lo = np.asarray(lo, dtype=np.float64)
         hi = np.asarray(hi, dtype=np.float64)
         return Mesh(lib().smmesh_gen_hex_block(nx, ny, nz, _ptr(lo), _ptr(hi)))
+
+    @staticmethod
+    def hex_block_part(nx, ny, nz, px, py, pz, rank, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0)) -> "Mesh":
+        """Brick `rank` of a (nx*px, ny*py, nz*pz) block as a processor mesh (weak-scaling runs)."""
+        lo = np.asarray(lo, dtype=np.float64)
+        hi = np.asarray(hi, dtype=np.float64)
+        return Mesh(lib().smmesh_gen_hex_block_part(nx, ny, nz, px, py, pz, rank, _ptr(lo), _ptr(hi)))
 
     @staticmethod
     def kelvin(n, h=1.0) -> "Mesh":
@@ -444,6 +456,32 @@ class Smoother:
             raise SmoothMeshError(lib().smgpu_last_error().decode())
         return bytes(buf)
 
-    def comm_init(self, rank, n_ranks, unique_id: bytes):
+    def comm_local_shared(self) -> np.ndarray:
+        """Global labels of this rank's processor-patch points (step 1 of the multi-GPU start-up)."""
+        n = C.c_int64()
+        self._ck(lib().smgpu_comm_local_shared(self._h, C.byref(n), None))
+        g = np.zeros(max(n.value, 1), dtype=np.int64)
+        self._ck(lib().smgpu_comm_local_shared(self._h, C.byref(n), _ptr(g)))
+        return g[:n.value]
+
+    def comm_init(self, rank, n_ranks, unique_id: bytes, counts, all_gids):
         buf = (C.c_uint8 * 128)(*unique_id)
-        self._ck(lib().smgpu_comm_init(self._h, rank, n_ranks, buf))
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        all_gids = np.ascontiguousarray(all_gids, dtype=np.int64)
+        if all_gids.size == 0:
+            all_gids = np.zeros(1, dtype=np.int64)
+        self._ck(lib().smgpu_comm_init(self._h, rank, n_ranks, buf, _ptr(counts), _ptr(all_gids)))
+
+
+def exchange_plan(rank, n_ranks, local, gids, counts, all_gids):
+    """Host-only: (slot_point, slot_rank) of the exchange plan smgpu_comm_init builds."""
+    local = np.ascontiguousarray(local, dtype=np.int32)
+    gids = np.ascontiguousarray(gids, dtype=np.int64)
+    counts = np.ascontiguousarray(counts, dtype=np.int64)
+    all_gids = np.ascontiguousarray(all_gids, dtype=np.int64)
+    n = lib().smgpu_exchange_plan(rank, n_ranks, len(local), _ptr(local), _ptr(gids), _ptr(counts), _ptr(all_gids), None, None)
+    if n < 0:
+        raise SmoothMeshError(lib().smmesh_last_error().decode())
+    sp, sr = np.zeros(max(n, 1), dtype=np.int32), np.zeros(max(n, 1), dtype=np.int32)
+    lib().smgpu_exchange_plan(rank, n_ranks, len(local), _ptr(local), _ptr(gids), _ptr(counts), _ptr(all_gids), _ptr(sp), _ptr(sr))
+    return sp[:n], sr[:n]

@@ -1,0 +1,242 @@
+// comm_impl.cuh -- multi-GPU exchange layer, included by smgpu.cu after smgpu_handle.
+//
+// One process per GPU; the mesh is partitioned by cells (decomposePar-style
+// processor meshes), interface points are duplicated.  This file replaces the
+// reference's MPI traffic on the hot path:
+//   syncPointList(plusEqOp)        src/smoothMesh.C:134,142   centroidal sums / counts
+//   syncPointList(minMagSqrEqOp)   :402,429,455               closest-point merge
+//   syncPointList(orEqOp)          :472, :2374                hasCommonCell, isFrozenPoint
+//   returnReduce(max / sum)        :1567, :2396               residual, nFrozenPoints
+// by two grouped ncclSend/ncclRecv halo exchanges and one pair of all-reduces per
+// iteration.  Every rank receives the other copies' *local* predictor tuple once
+// and replays the reference's three-stage merge for all copies itself, so the
+// four point syncs of the predictor collapse into one exchange.  Copies are
+// combined in ascending rank order (the CPU oracle's rank emulation does the same).
+#pragma once
+#include "exchange.hpp"
+#include <nccl.h>
+
+namespace smk
+{
+
+#define SMK_TUPLE 16 /* doubles per interface-point record */
+#define SMK_MAXCOPIES 16
+
+struct CommDev
+{
+    int nSlots, nShared, rank;
+    const int *sendPoint, *sharedPoint, *selfSlot, *copyOff, *copyRank, *copySlot;
+    double *sendBuf, *recvBuf;
+    uint8_t *sendFz, *recvFz;
+    double *redRes;
+    long long *redFrozen;
+};
+
+// local predictor tuple of every send slot's point
+__global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
+{
+    if (*d.done)
+        return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.nSlots)
+        return;
+    const int p = c.sendPoint[i];
+    const P4 self = ld4(d.pts + p);
+    const D3 x = {self.x, self.y, self.z};
+    const bool internal = self.w != 0.0;
+    PointLocal L;
+    pointLocal(d, p, x, internal, L);
+    const bool hc = shareCell(d, d.pp[L.k1], d.pp[L.k2]);
+    double *r = c.sendBuf + (size_t)i * SMK_TUPLE;
+    r[0] = L.sum.x, r[1] = L.sum.y, r[2] = L.sum.z;
+    r[3] = (double)L.nCells;
+    r[4] = L.r1.x, r[5] = L.r1.y, r[6] = L.r1.z;
+    r[7] = L.r2.x, r[8] = L.r2.y, r[9] = L.r2.z;
+    r[10] = L.r3.x, r[11] = L.r3.y, r[12] = L.r3.z;
+    r[13] = hc ? 1.0 : 0.0;
+    r[14] = r[15] = 0.0;
+}
+
+// isSmallerByVectorElements / isCloserPoint, src/smoothMesh.C:222-272
+__device__ __forceinline__ bool isCloserPoint(D3 a, D3 b)
+{
+    if (veq(a, b))
+        return false;
+    const double delta = mag(a) - mag(b);
+    if (delta < SM_VSMALL)
+        return true;
+    if (fabs(delta) < SM_VSMALL)
+    {
+        if (a.x < b.x)
+            return true;
+        if (a.x > b.x)
+            return false;
+        if (a.y < b.y)
+            return true;
+        if (a.y > b.y)
+            return false;
+        return a.z < b.z;
+    }
+    return false;
+}
+__device__ __forceinline__ D3 minMagSqr(D3 x, D3 y) { return (magSqr(x) <= magSqr(y)) ? x : y; }
+
+// Combine all copies of every interface point (ascending rank), replay the merge of
+// findClosestPoints (:391-478) for every copy, then finish the predictor for the local copy.
+__global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
+{
+    if (*d.done)
+        return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.nShared)
+        return;
+    const int p = c.sharedPoint[s];
+    const int cb = c.copyOff[s], nOther = c.copyOff[s + 1] - cb;
+    const int n = nOther + 1;
+    D3 cp1[SMK_MAXCOPIES], cp2[SMK_MAXCOPIES], cp3[SMK_MAXCOPIES];
+    bool hc[SMK_MAXCOPIES];
+    D3 sum = {0, 0, 0};
+    double cnt = 0.0;
+    int me = -1;
+    // copies in ascending rank order, the local one inserted at its rank
+    for (int k = 0, o = 0; k < n; ++k)
+    {
+        const double *r;
+        if (me < 0 && (o >= nOther || c.copyRank[cb + o] > c.rank))
+        {
+            r = c.sendBuf + (size_t)c.selfSlot[s] * SMK_TUPLE;
+            me = k;
+        }
+        else
+        {
+            r = c.recvBuf + (size_t)c.copySlot[cb + o] * SMK_TUPLE;
+            ++o;
+        }
+        const D3 part = {r[0], r[1], r[2]};
+        if (k == 0)
+        {
+            sum = part;
+            cnt = r[3];
+        }
+        else
+        {
+            sum = sum + part; // plusEqOp<vector>, :134
+            cnt = cnt + r[3]; // plusEqOp<label>, :142 (exact in double)
+        }
+        cp1[k] = {r[4], r[5], r[6]};
+        cp2[k] = {r[7], r[8], r[9]};
+        cp3[k] = {r[10], r[11], r[12]};
+        hc[k] = r[13] != 0.0;
+    }
+    // position 1 (:395-419)
+    D3 v = cp1[0];
+    for (int k = 1; k < n; ++k)
+        v = minMagSqr(v, cp1[k]);
+    for (int k = 0; k < n; ++k)
+        if (isCloserPoint(v, cp1[k]))
+        {
+            cp3[k] = cp2[k];
+            cp2[k] = cp1[k];
+            cp1[k] = v;
+            hc[k] = false;
+        }
+    // position 2 (:424-445)
+    v = cp2[0];
+    for (int k = 1; k < n; ++k)
+        v = minMagSqr(v, cp2[k]);
+    for (int k = 0; k < n; ++k)
+        if (isCloserPoint(v, cp2[k]))
+        {
+            cp3[k] = cp2[k];
+            cp2[k] = v;
+            hc[k] = false;
+        }
+    // position 3 (:450-469)
+    v = cp3[0];
+    for (int k = 1; k < n; ++k)
+        v = minMagSqr(v, cp3[k]);
+    for (int k = 0; k < n; ++k)
+        if (isCloserPoint(v, cp3[k]))
+            cp3[k] = v;
+    bool anyCommon = false; // orEqOp<bool>, :472
+    for (int k = 0; k < n; ++k)
+        anyCommon = anyCommon || hc[k];
+
+    const P4 self = ld4(d.pts + p);
+    const D3 x = {self.x, self.y, self.z};
+    const bool internal = self.w != 0.0;
+    const D3 cen = (cnt != 0.0) ? sum / cnt : x; // :158-162
+    double blend = 0.0;
+    if (!anyCommon)
+        blend = blendFraction(cp1[me], cp2[me], mag(cp1[me]), mag(cp2[me]), mag(cp3[me]), internal);
+    st4(d.newPts + p, blendAndClamp(d, x, cen, cp1[me], cp2[me], blend), 0.0);
+}
+
+__global__ void __launch_bounds__(128) k_frozen_pack(Dev d, CommDev c)
+{
+    if (*d.done)
+        return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.nSlots)
+        c.sendFz[i] = d.frozen[c.sendPoint[i]];
+}
+// orEqOp<bool> on isFrozenPoint, :2374
+__global__ void __launch_bounds__(128) k_frozen_or(Dev d, CommDev c)
+{
+    if (*d.done)
+        return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < c.nSlots && c.recvFz[i])
+        d.frozen[c.sendPoint[i]] = 1;
+}
+// publishes the all-reduced statistics of the iteration and the stop flag (:2396-2405)
+__global__ void k_finish_iter(Dev d, CommDev c)
+{
+    if (*d.done || threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    const double res = *c.redRes;
+    const int it = *d.iter;
+    if (it < d.statCap)
+    {
+        d.statRes[it] = res;
+        d.statFrozen[it] = *c.redFrozen;
+    }
+    *d.iter = it + 1;
+    if (res < d.relTol)
+        *d.done = 1;
+}
+
+} // namespace smk
+
+namespace sm
+{
+
+struct Comm
+{
+    ncclComm_t nccl = nullptr;
+    ExchangePlan plan;
+    smk::CommDev c;
+};
+
+#define NCK(call)                                                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        ncclResult_t r_ = (call);                                                                                      \
+        if (r_ != ncclSuccess)                                                                                         \
+            throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(r_) + " at " #call);             \
+    } while (0)
+
+static void haloExchange(Comm *cm, smgpu_handle *h, const void *send, void *recv, size_t elemBytes)
+{
+    const ExchangePlan &pl = cm->plan;
+    NCK(ncclGroupStart());
+    for (size_t j = 0; j < pl.nbrRank.size(); ++j)
+    {
+        const size_t off = (size_t)pl.nbrOff[j] * elemBytes, cnt = (size_t)(pl.nbrOff[j + 1] - pl.nbrOff[j]) * elemBytes;
+        NCK(ncclSend((const char *)send + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
+        NCK(ncclRecv((char *)recv + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
+    }
+    NCK(ncclGroupEnd());
+}
+
+} // namespace sm

@@ -1073,3 +1073,89 @@ void writePolyMesh(const PolyMesh &m, const std::string &dir, bool binary, int p
 }
 
 } // namespace sm
+
+// ---------------------------------------------------- distributed hex block ----
+namespace sm
+{
+// One brick of a (nx*px) x (ny*py) x (nz*pz) hex block, generated without ever building the
+// global mesh: local numbering as genHexBlock, coordinates and pointGlobalId from the global
+// lattice, sides that touch another brick turned into processor patches (listed after the
+// six physical patches, ascending neighbour rank).
+PolyMesh genHexBlockPart(int nx, int ny, int nz, int px, int py, int pz, int rank, const double lo[3], const double hi[3])
+{
+    const int ix = rank % px, iy = (rank / px) % py, iz = rank / (px * py);
+    if (rank < 0 || iz >= pz)
+        throw std::runtime_error("genHexBlockPart: rank out of range");
+    const int64_t NX = (int64_t)nx * px, NY = (int64_t)ny * py, NZ = (int64_t)nz * pz;
+    const double l[3] = {0, 0, 0}, h[3] = {1, 1, 1};
+    PolyMesh m = genHexBlock(nx, ny, nz, l, h, "wall");
+    const int64_t lx = nx + 1, ly = ny + 1;
+    const int64_t P = m.nPoints();
+    m.pointGlobalId.resize(P);
+    for (int64_t p = 0; p < P; ++p)
+    {
+        const int64_t i = p % lx + (int64_t)ix * nx, j = (p / lx) % ly + (int64_t)iy * ny, k = p / (lx * ly) + (int64_t)iz * nz;
+        m.points[3 * p + 0] = lo[0] + (hi[0] - lo[0]) * (double(i) / double(NX));
+        m.points[3 * p + 1] = lo[1] + (hi[1] - lo[1]) * (double(j) / double(NY));
+        m.points[3 * p + 2] = lo[2] + (hi[2] - lo[2]) * (double(k) / double(NZ));
+        m.pointGlobalId[p] = i + j * (NX + 1) + k * (NX + 1) * (NY + 1);
+    }
+    m.cellGlobalId.resize(m.nCells);
+    for (int64_t c = 0; c < m.nCells; ++c)
+    {
+        const int64_t i = c % nx + (int64_t)ix * nx, j = (c / nx) % ny + (int64_t)iy * ny, k = c / ((int64_t)nx * ny) + (int64_t)iz * nz;
+        m.cellGlobalId[c] = i + j * NX + k * NX * NY;
+    }
+    // neighbour rank behind each of the six sides (xMin,xMax,yMin,yMax,zMin,zMax), -1 = physical
+    const int nbr[6] = {ix > 0 ? rank - 1 : -1,           ix + 1 < px ? rank + 1 : -1,
+                        iy > 0 ? rank - px : -1,          iy + 1 < py ? rank + px : -1,
+                        iz > 0 ? rank - px * py : -1,     iz + 1 < pz ? rank + px * py : -1};
+    // new boundary order: six physical patches (emptied where the side is internal), then
+    // processor patches by ascending neighbour rank
+    std::vector<int> procSides;
+    for (int s = 0; s < 6; ++s)
+        if (nbr[s] >= 0)
+            procSides.push_back(s);
+    std::sort(procSides.begin(), procSides.end(), [&](int a, int b) { return nbr[a] < nbr[b]; });
+    const int64_t Fi = m.nInternalFaces();
+    std::vector<int32_t> newOff(m.faceOffsets.begin(), m.faceOffsets.begin() + Fi + 1), newVerts(m.faceVerts.begin(), m.faceVerts.begin() + m.faceOffsets[Fi]),
+        newOwner(m.owner.begin(), m.owner.begin() + Fi);
+    std::vector<Patch> newPatches;
+    auto appendSide = [&](int s) {
+        const Patch &src = m.patches[s];
+        for (int32_t f = src.start; f < src.start + src.size; ++f)
+        {
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                newVerts.push_back(m.faceVerts[k]);
+            newOff.push_back((int32_t)newVerts.size());
+            newOwner.push_back(m.owner[f]);
+        }
+    };
+    for (int s = 0; s < 6; ++s)
+    {
+        Patch p = m.patches[s];
+        p.start = (int32_t)newOwner.size();
+        if (nbr[s] < 0)
+            appendSide(s);
+        p.size = (int32_t)newOwner.size() - p.start;
+        newPatches.push_back(p);
+    }
+    for (int s : procSides)
+    {
+        Patch p;
+        p.name = "procBoundary" + std::to_string(rank) + "to" + std::to_string(nbr[s]);
+        p.type = "processor";
+        p.myProc = rank;
+        p.nbrProc = nbr[s];
+        p.start = (int32_t)newOwner.size();
+        appendSide(s);
+        p.size = (int32_t)newOwner.size() - p.start;
+        newPatches.push_back(p);
+    }
+    m.faceOffsets.swap(newOff);
+    m.faceVerts.swap(newVerts);
+    m.owner.swap(newOwner);
+    m.patches.swap(newPatches);
+    return m;
+}
+} // namespace sm

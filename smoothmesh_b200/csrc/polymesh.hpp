@@ -54,6 +54,10 @@ struct PolyMesh
 // xMin,xMax,yMin,yMax,zMin,zMax of type `patchType`.
 PolyMesh genHexBlock(int nx, int ny, int nz, const double lo[3], const double hi[3], const std::string &patchType = "wall");
 
+// One brick (rank = ix + px*(iy + py*iz)) of the (nx*px) x (ny*py) x (nz*pz) block, in processor-mesh
+// form (processor patches, pointGlobalId / cellGlobalId), generated locally for weak-scaling runs.
+PolyMesh genHexBlockPart(int nx, int ny, int nz, int px, int py, int pz, int rank, const double lo[3], const double hi[3]);
+
 // Kelvin-cell (truncated octahedron, BCC Voronoi) polyhedral mesh clipped to the
 // box [0,n]^3*h: stand-in for polyDualMesh output.
 PolyMesh genKelvin(int n, double h);

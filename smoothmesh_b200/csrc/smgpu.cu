@@ -3,7 +3,6 @@
 // -> launch the per-iteration kernel sequence with no host round trip inside a
 // chunk of iterations.  There is no CPU fallback anywhere in this file.
 #include "../../include/smgpu.h"
-#include "comm.hpp"
 #include "kernels.cuh"
 #include "polymesh.hpp"
 #include "topology.hpp"
@@ -18,6 +17,11 @@
 #include <vector>
 
 using namespace smk;
+
+namespace sm
+{
+struct Comm;
+}
 
 static thread_local std::string g_err;
 static int setErr(int code, const std::string &msg)
@@ -49,7 +53,7 @@ struct smgpu_handle
     std::vector<int64_t> gid;
 
     // optional per-kernel timing (CUDA events on the launch stream)
-    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_NUM };
+    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_NUM };
     bool profiling = false;
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<int, size_t>> evUse; // (kernel id, index of start event)
@@ -208,6 +212,117 @@ struct smgpu_handle
         CK(cudaMemsetAsync(d.iter, 0, sizeof(int), stream));
     }
 };
+
+#include "comm_impl.cuh"
+
+namespace sm
+{
+
+static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[128], const int64_t *counts,
+                        const int64_t *allGids)
+{
+    Comm *cm = new Comm;
+    try
+    {
+        std::vector<int64_t> myGids;
+        for (int32_t p : h->topo.procPoints)
+            myGids.push_back(h->gid[p]);
+        std::vector<int64_t> cnt(counts, counts + nRanks);
+        int64_t total = 0;
+        for (int64_t c : cnt)
+            total += c;
+        std::vector<int64_t> all(allGids, allGids + total);
+        cm->plan = buildExchangePlan(rank, nRanks, h->topo.procPoints, myGids, cnt, all);
+        const ExchangePlan &pl = cm->plan;
+        if (pl.maxCopies > SMK_MAXCOPIES)
+            throw std::runtime_error("an interface point is shared by more ranks than the exchange layer supports");
+        CK(cudaSetDevice(h->prm.device));
+        ncclUniqueId uid;
+        static_assert(sizeof(uid) == 128, "ncclUniqueId size");
+        memcpy(&uid, id, 128);
+        NCK(ncclCommInitRank(&cm->nccl, nRanks, uid, rank));
+        smk::CommDev &c = cm->c;
+        c.rank = rank;
+        c.nSlots = (int)pl.sendPoint.size();
+        c.nShared = (int)pl.sharedPoint.size();
+        c.sendPoint = h->upload(pl.sendPoint);
+        c.sharedPoint = h->upload(pl.sharedPoint);
+        c.selfSlot = h->upload(pl.selfSlot);
+        c.copyOff = h->upload(pl.copyOff);
+        c.copyRank = h->upload(pl.copyRank);
+        c.copySlot = h->upload(pl.copySlot);
+        c.sendBuf = h->dalloc<double>((size_t)c.nSlots * SMK_TUPLE);
+        c.recvBuf = h->dalloc<double>((size_t)c.nSlots * SMK_TUPLE);
+        c.sendFz = h->dalloc<uint8_t>(c.nSlots);
+        c.recvFz = h->dalloc<uint8_t>(c.nSlots);
+        c.redRes = h->dalloc<double>(1);
+        c.redFrozen = h->dalloc<long long>(1);
+        h->d.multiRank = 1;
+        h->d.locRes = c.redRes;
+        h->d.locFrozen = c.redFrozen;
+    }
+    catch (...)
+    {
+        if (cm->nccl)
+            ncclCommDestroy(cm->nccl);
+        delete cm;
+        throw;
+    }
+    return cm;
+}
+
+static void commDestroy(Comm *cm)
+{
+    if (!cm)
+        return;
+    if (cm->nccl)
+        ncclCommDestroy(cm->nccl);
+    delete cm;
+}
+
+// One iteration with the interface exchanges (src/smoothMesh.C:2257-2399 under -parallel).
+// Returns the stop flag.
+static int commIterate(Comm *cm, smgpu_handle *h)
+{
+    const smk::CommDev &c = cm->c;
+    const int gs = smgpu_handle::grid(c.nSlots, 128);
+    h->launchCellCentres();
+    h->launchPredict();
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    if (c.nSlots > 0)
+        k_shared_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
+    haloExchange(cm, h, c.sendBuf, c.recvBuf, SMK_TUPLE * sizeof(double));
+    if (c.nShared > 0)
+        k_shared_merge<<<smgpu_handle::grid(c.nShared, 64), 64, 0, h->stream>>>(h->d, c);
+    h->profEnd(2);
+    h->launches += 2;
+    h->launchEdgeConstraints();
+    if (h->prm.face_angle_constraint)
+        h->launchFaceAngle();
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    if (c.nSlots > 0)
+        k_frozen_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
+    haloExchange(cm, h, c.sendFz, c.recvFz, 1);
+    if (c.nSlots > 0)
+        k_frozen_or<<<gs, 128, 0, h->stream>>>(h->d, c);
+    h->profEnd(2);
+    h->launches += 2;
+    h->launchCommit();
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    NCK(ncclGroupStart());
+    NCK(ncclAllReduce(c.redRes, c.redRes, 1, ncclDouble, ncclMax, cm->nccl, h->stream));
+    NCK(ncclAllReduce(c.redFrozen, c.redFrozen, 1, ncclInt64, ncclSum, cm->nccl, h->stream));
+    NCK(ncclGroupEnd());
+    k_finish_iter<<<1, 32, 0, h->stream>>>(h->d, c);
+    h->profEnd(1);
+    h->launches += 1;
+    int done = 0;
+    CK(cudaMemcpyAsync(&done, h->d.done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return done;
+}
+
+} // namespace sm
 
 extern "C"
 {
@@ -427,7 +542,7 @@ extern "C"
             {
                 // multi-rank: one iteration at a time, halo exchanges between phases
                 for (; launched < max_iters && !done; ++launched)
-                    done = sm::commIterate(h->comm, h, launched);
+                    done = sm::commIterate(h->comm, h);
             }
             else
             {
@@ -707,7 +822,7 @@ extern "C"
     int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches)
     {
         static const char *kNames[smgpu_handle::K_NUM] = {"k_face_geom", "k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
-                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit"};
+                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange"};
         if (!h || !n)
             return setErr(SMGPU_ERR_ARG, "null argument");
         *n = smgpu_handle::K_NUM;
@@ -725,22 +840,42 @@ extern "C"
 
     int smgpu_comm_unique_id(uint8_t id_out[128])
     {
-        std::string err;
-        if (!sm::commUniqueId(id_out, err))
-            return setErr(SMGPU_ERR_COMM, err);
+        ncclUniqueId uid;
+        const ncclResult_t r = ncclGetUniqueId(&uid);
+        if (r != ncclSuccess)
+            return setErr(SMGPU_ERR_COMM, ncclGetErrorString(r));
+        memcpy(id_out, &uid, 128);
         return SMGPU_OK;
     }
 
-    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t id[128])
+    int smgpu_comm_local_shared(smgpu_handle *h, int64_t *n, int64_t *gids_out)
     {
-        if (!h || !id)
+        if (!h || !n)
             return setErr(SMGPU_ERR_ARG, "null argument");
-        if (h->gid.empty())
-            return setErr(SMGPU_ERR_ARG, "mesh was created without point_global_id");
-        std::string err;
-        h->comm = sm::commCreate(h, rank, n_ranks, id, err);
-        if (!h->comm)
-            return setErr(SMGPU_ERR_COMM, err);
+        if (h->gid.empty() && !h->topo.procPoints.empty())
+            return setErr(SMGPU_ERR_ARG, "mesh has processor patches but was created without point_global_id");
+        *n = (int64_t)h->topo.procPoints.size();
+        if (gids_out)
+            for (size_t i = 0; i < h->topo.procPoints.size(); ++i)
+                gids_out[i] = h->gid[h->topo.procPoints[i]];
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t id[128], const int64_t *counts,
+                        const int64_t *all_gids)
+    {
+        if (!h || !id || !counts || (!all_gids && n_ranks > 1))
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (h->comm)
+            return setErr(SMGPU_ERR_ARG, "communicator already initialised");
+        try
+        {
+            h->comm = sm::commCreate(h, rank, n_ranks, id, counts, all_gids);
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_COMM, e.what());
+        }
         return SMGPU_OK;
     }
 

@@ -47,6 +47,11 @@ extern "C"
     {
         return guarded([&] { return sm::genHexBlock(nx, ny, nz, lo, hi); });
     }
+    smmesh *smmesh_gen_hex_block_part(int32_t nx, int32_t ny, int32_t nz, int32_t px, int32_t py, int32_t pz, int32_t rank,
+                                      const double lo[3], const double hi[3])
+    {
+        return guarded([&] { return sm::genHexBlockPart(nx, ny, nz, px, py, pz, rank, lo, hi); });
+    }
     smmesh *smmesh_gen_kelvin(int32_t n, double h)
     {
         return guarded([&] { return sm::genKelvin(n, h); });
@@ -214,5 +219,37 @@ extern "C"
             return SMGPU_ERR_MESH;
         }
         return SMGPU_OK;
+    }
+}
+
+// ---- host-only view of the multi-GPU exchange plan (declared in smgpu.h) ----
+#include "exchange.hpp"
+extern "C" int64_t smgpu_exchange_plan(int32_t rank, int32_t n_ranks, int64_t n_local, const int32_t *local,
+                                       const int64_t *gids, const int64_t *counts, const int64_t *all_gids,
+                                       int32_t *slot_point, int32_t *slot_rank)
+{
+    try
+    {
+        std::vector<int32_t> loc(local, local + n_local);
+        std::vector<int64_t> g(gids, gids + n_local), cnt(counts, counts + n_ranks);
+        int64_t total = 0;
+        for (int64_t c : cnt)
+            total += c;
+        std::vector<int64_t> all(all_gids, all_gids + total);
+        const sm::ExchangePlan pl = sm::buildExchangePlan(rank, n_ranks, loc, g, cnt, all);
+        for (size_t j = 0; j < pl.nbrRank.size(); ++j)
+            for (int32_t s = pl.nbrOff[j]; s < pl.nbrOff[j + 1]; ++s)
+            {
+                if (slot_point)
+                    slot_point[s] = pl.sendPoint[s];
+                if (slot_rank)
+                    slot_rank[s] = pl.nbrRank[j];
+            }
+        return (int64_t)pl.sendPoint.size();
+    }
+    catch (const std::exception &e)
+    {
+        g_merr = e.what();
+        return -1;
     }
 }

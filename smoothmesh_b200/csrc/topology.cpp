@@ -39,6 +39,19 @@ Topology buildTopology(const PolyMesh &m)
                 t.isInternal[m.faceVerts[k]] = 0;
     }
 
+    // points on processor patches: the candidates for inter-rank sharing
+    {
+        std::vector<uint8_t> onProc(P, 0);
+        for (const Patch &p : m.patches)
+            if (p.kind() == PATCH_PROCESSOR)
+                for (int32_t f = p.start; f < p.start + p.size; ++f)
+                    for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                        onProc[m.faceVerts[k]] = 1;
+        for (int64_t p = 0; p < P; ++p)
+            if (onProc[p])
+                t.procPoints.push_back((int32_t)p);
+    }
+
     // ---- point -> face corners (pointFaces ascending) ----
     t.cornerOff.assign(P + 1, 0);
     for (int64_t k = 0; k < FV; ++k)

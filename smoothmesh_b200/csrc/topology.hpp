@@ -40,6 +40,7 @@ struct Topology
     // (ascending), then faces it neighbours (ascending, bit 31 set)
     std::vector<int32_t> cfOff, cf;
     std::vector<uint8_t> isInternal; // src/smoothMesh.C:40-91
+    std::vector<int32_t> procPoints; // points on processor patches (ascending)
     double minEdgeLength = 0, maxEdgeLength = 0; // src/smoothMesh.C:1478-1541
     int32_t maxPointDegree = 0, maxFaceSize = 0, maxEdgeFaces = 0;
 };

@@ -1,0 +1,65 @@
+"""Multi-GPU plumbing: one process per GPU, torch.distributed for the start-up handshake,
+NCCL inside libsmgpu.so for the per-iteration interface exchanges.
+
+The reference decomposes with decomposePar and runs `mpirun -np N smoothMesh -parallel`
+(testcase/run_parallel); here every rank creates its Smoother from its processor mesh and
+`init_comm` performs the three start-up steps documented in include/smgpu.h.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def brick_dims(world):
+    """px,py,pz with px*py*pz == world, as cubic as possible (power-of-two friendly)."""
+    dims = [1, 1, 1]
+    n, f = world, 2
+    factors = []
+    while n > 1:
+        while n % f == 0:
+            factors.append(f)
+            n //= f
+        f += 1
+    for k in sorted(factors, reverse=True):
+        dims[dims.index(min(dims))] *= k
+    return tuple(sorted(dims, reverse=True))
+
+
+def weak_scaling_part(n, world, rank, jitter_frac, seed):
+    """Rank's brick (n^3 cells) of the weak-scaling hex block; jitter keyed on global point labels."""
+    import smoothmesh_b200 as sm
+    px, py, pz = brick_dims(world)
+    mesh = sm.Mesh.hex_block_part(n, n, n, px, py, pz, rank, hi=(float(px), float(py), float(pz)))
+    return mesh.jitter(jitter_frac * (1.0 / n), seed)
+
+
+def gather_shared(my_gids: np.ndarray, dist):
+    """All-gather of the variable-length processor-point lists -> (counts, concatenation)."""
+    import torch
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    world = dist.get_world_size()
+    cnt = torch.tensor([len(my_gids)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, cnt)
+    counts = np.array([int(c.item()) for c in counts], dtype=np.int64)
+    m = int(counts.max()) if world else 0
+    buf = torch.zeros(max(m, 1), dtype=torch.int64, device=dev)
+    buf[: len(my_gids)] = torch.from_numpy(np.ascontiguousarray(my_gids)).to(dev)
+    bufs = [torch.zeros(max(m, 1), dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    allg = np.concatenate([b.cpu().numpy()[: counts[r]] for r, b in enumerate(bufs)]) if world else np.zeros(0, np.int64)
+    return counts, allg
+
+
+def init_comm(smoother, rank, world, dist):
+    import torch
+    import smoothmesh_b200 as sm
+    counts, allg = gather_shared(smoother.comm_local_shared(), dist)
+    backend = dist.get_backend()
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        uid = torch.tensor(list(sm.Smoother.comm_unique_id()), dtype=torch.uint8, device=dev)
+    dist.broadcast(uid, src=0)
+    smoother.comm_init(rank, world, bytes(uid.cpu().numpy().tolist()), counts, allg)

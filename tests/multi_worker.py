@@ -1,0 +1,107 @@
+"""Worker for the multi-rank tests; launched under torch.distributed.run (tests/ only).
+
+mode=gpu : every rank owns one GPU and one brick of a jittered mesh; results are gathered on
+           rank 0 and compared with the CPU oracle's rank emulation on the same bricks.
+mode=plan: host-only (gloo, no GPU): the exchange plans of all ranks must be mutually consistent.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def make_parts(world, kind):
+    import smoothmesh_b200 as sm
+    from smoothmesh_b200 import multi
+    px, py, pz = multi.brick_dims(world)
+    if kind == "hex":
+        mesh = sm.Mesh.hex_block(4 * px, 4 * py, 3 * pz, hi=(px, py, 0.75 * pz)).jitter(0.3 / 4, 4242)
+        return mesh.decompose(px, py, pz)
+    if kind == "kelvin":
+        mesh = sm.Mesh.kelvin(3, 1.0).jitter(0.15 * 2 ** 0.5 / 4, 77)
+        return mesh.decompose(world, method="rcb")
+    raise ValueError(kind)
+
+
+def proc_points(part):
+    s, z, k = part.patches
+    off, verts = part.face_offsets, part.face_verts
+    pts = set()
+    for a, n, kind in zip(s, z, k):
+        if kind == 1:
+            pts.update(verts[off[a]:off[a + n]].tolist())
+    return np.array(sorted(pts), dtype=np.int32)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    mode, kind = sys.argv[1], sys.argv[2]
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    import smoothmesh_b200 as sm
+    from smoothmesh_b200 import multi
+    parts = make_parts(world, kind)
+    mine = parts[rank]
+    if mode == "plan":
+        dist.init_process_group("gloo")
+        local = proc_points(mine)
+        gids = mine.point_global_id[local]
+        counts, allg = multi.gather_shared(gids, dist)
+        sp, sr = sm.exchange_plan(rank, world, local, gids, counts, allg)
+        # brute force: points whose global label also appears on another rank
+        expect = {}
+        for r, p in enumerate(parts):
+            if r != rank:
+                common = np.intersect1d(p.point_global_id[proc_points(p)], gids)
+                if len(common):
+                    expect[r] = common
+        got = {}
+        for point, r in zip(sp, sr):
+            got.setdefault(int(r), []).append(int(mine.point_global_id[point]))
+        assert sorted(got) == sorted(expect), (got.keys(), expect.keys())
+        for r in expect:
+            assert got[r] == expect[r].tolist(), f"slot order towards rank {r} is not ascending global label"
+        # both sides of every pair must hold the same sequence
+        objs = [None] * world
+        dist.all_gather_object(objs, got)
+        for r in got:
+            assert objs[r][rank] == got[r]
+        print(f"rank {rank}: plan ok, {len(sp)} slots to {sorted(got)}", flush=True)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
+
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    kw = dict(rel_tol=1e-3, min_angle_deg=70.0, max_angle_deg=110.0, total_min_freeze=0)
+    iters = 25
+    g = sm.Smoother(mine, device=local_rank, **kw)
+    multi.init_comm(g, rank, world, dist)
+    log = g.iterate(iters)
+    res = dict(n=log.iterations, nf=log.n_frozen, res=log.residual, pts=g.points(), fz=g.frozen())
+    allres = [None] * world
+    dist.all_gather_object(allres, res)
+    if rank == 0:
+        from oracle import Oracle
+        o = Oracle([p.desc_arrays() for p in parts], **kw)
+        n, nf, rs = o.iterate(iters)
+        for r in range(world):
+            a = allres[r]
+            assert a["n"] == n, (a["n"], n)
+            assert np.array_equal(a["nf"], nf), (r, a["nf"], nf)
+            assert np.array_equal(a["res"], rs), (r, a["res"], rs)
+            assert np.array_equal(a["fz"], o.get("frozen", r)), f"rank {r}: freeze mask differs"
+            assert np.array_equal(a["pts"], o.get("points", r)), f"rank {r}: points differ"
+        print(f"multi-GPU parity ok: world={world} kind={kind} iterations={n} nFrozen[-1]={nf[-1]} "
+              f"frozen internal={sum(int(o.get('frozen', r).sum()) for r in range(world))}", flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
