@@ -114,6 +114,7 @@ def kernel_bytes(P, C, F, Fi, E, FV, PC, EC):
         "k_active_compact": 2 * P,
         "k_face_tests": 0,
         "k_face_resolve": 0,
+        "halo_exchange": 0,
         # points + newPoints + mask read, points written
         "k_commit": 24 * P + 24 * P + P + 24 * P,
     }
@@ -297,6 +298,8 @@ def main():
     assert np.isfinite(out_pts).all()
 
     if rank != 0:
+        dist.barrier()
+        dist.destroy_process_group()
         return
 
     hbm, hbm_src = peaks()
@@ -338,6 +341,9 @@ def main():
                                           f"serial: {v1:.4g} point-updates/s ({dt1:.1f} s)",
                                 "serial_value": v1}
     print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

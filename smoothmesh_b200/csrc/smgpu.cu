@@ -51,6 +51,20 @@ struct smgpu_handle
     int statCap = 0;
     sm::Comm *comm = nullptr;
     std::vector<int64_t> gid;
+    smgpu_params prmRequested;              // as passed by the caller (negative = reference default)
+    double meshMinEdge = 0, meshMaxEdge = 0; // getMeshStats; global (all-reduced) in multi-rank runs
+    // option defaults of src/smoothMesh.C:1861-1865 from the (global) minimum edge length
+    void resolveParams()
+    {
+        const int dev = prm.device;
+        prm = prmRequested;
+        prm.device = dev;
+        if (prm.min_edge_length < 0)
+            prm.min_edge_length = 0.5 * meshMinEdge;
+        if (prm.max_step_length < 0)
+            prm.max_step_length = 0.3 * prm.min_edge_length;
+        applyParams();
+    }
 
     // optional per-kernel timing (CUDA events on the launch stream)
     enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_NUM };
@@ -260,6 +274,17 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         h->d.multiRank = 1;
         h->d.locRes = c.redRes;
         h->d.locFrozen = c.redFrozen;
+        // getMeshStats' returnReduce(min/max) (src/smoothMesh.C:1527-1528): the option defaults
+        // must come from the global edge-length extrema, not this rank's
+        double mm[2] = {-h->topo.minEdgeLength, h->topo.maxEdgeLength};
+        double *dmm = h->dalloc<double>(2);
+        CK(cudaMemcpy(dmm, mm, sizeof mm, cudaMemcpyHostToDevice));
+        NCK(ncclAllReduce(dmm, dmm, 2, ncclDouble, ncclMax, cm->nccl, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(mm, dmm, sizeof mm, cudaMemcpyDeviceToHost));
+        h->meshMinEdge = -mm[0];
+        h->meshMaxEdge = mm[1];
+        h->resolveParams();
     }
     catch (...)
     {
@@ -391,10 +416,9 @@ extern "C"
             }
             const sm::Topology &t = h->topo;
             h->prm = *params;
-            if (h->prm.min_edge_length < 0)
-                h->prm.min_edge_length = 0.5 * t.minEdgeLength; // :1861-1862
-            if (h->prm.max_step_length < 0)
-                h->prm.max_step_length = 0.3 * h->prm.min_edge_length; // :1864-1865
+            h->prmRequested = *params;
+            h->meshMinEdge = t.minEdgeLength;
+            h->meshMaxEdge = t.maxEdgeLength;
             for (uint8_t f : t.isInternal)
                 h->nInternal += f;
 
@@ -410,7 +434,7 @@ extern "C"
             d.F = (int)t.F;
             d.faceGeo = h->dalloc<P4>(2 * t.F);
             d.faceMean = h->dalloc<P4>(t.F);
-            h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
+
             d.pts = h->dalloc<P4>(t.P);
             d.newPts = h->dalloc<P4>(t.P);
             d.cellCtr = h->dalloc<P4>(t.C);
@@ -456,7 +480,8 @@ extern "C"
             CK(cudaMemset(d.activeFlag, 0, t.P + 8));
             CK(cudaMemset(d.newPts, 0, t.P * sizeof(P4)));
             h->ensureStats(1024);
-            h->applyParams();
+            h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
+            h->resolveParams();
             h->setPoints(md->points);
             CK(cudaDeviceSynchronize());
         }
@@ -499,14 +524,8 @@ extern "C"
     {
         if (!h || !p)
             return setErr(SMGPU_ERR_ARG, "null argument");
-        const int dev = h->prm.device;
-        h->prm = *p;
-        h->prm.device = dev;
-        if (h->prm.min_edge_length < 0)
-            h->prm.min_edge_length = 0.5 * h->topo.minEdgeLength;
-        if (h->prm.max_step_length < 0)
-            h->prm.max_step_length = 0.3 * h->prm.min_edge_length;
-        h->applyParams();
+        h->prmRequested = *p;
+        h->resolveParams();
         return SMGPU_OK;
     }
 
@@ -516,9 +535,9 @@ extern "C"
         if (!h)
             return setErr(SMGPU_ERR_ARG, "null handle");
         if (min_edge)
-            *min_edge = h->topo.minEdgeLength;
+            *min_edge = h->meshMinEdge;
         if (max_edge)
-            *max_edge = h->topo.maxEdgeLength;
+            *max_edge = h->meshMaxEdge;
         if (n_internal_points)
             *n_internal_points = h->nInternal;
         if (n_edges)

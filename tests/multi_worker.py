@@ -38,6 +38,8 @@ def proc_points(part):
 
 
 def main():
+    import faulthandler
+    faulthandler.dump_traceback_later(240, exit=True)  # a hung collective must not hang the test run
     import torch
     import torch.distributed as dist
     mode, kind = sys.argv[1], sys.argv[2]
@@ -82,6 +84,24 @@ def main():
     iters = 25
     g = sm.Smoother(mine, device=local_rank, **kw)
     multi.init_comm(g, rank, world, dist)
+    if mode == "debug":
+        # step-by-step comparison against the oracle's rank emulation (every rank runs the oracle)
+        from oracle import Oracle
+        o = Oracle([p.desc_arrays() for p in parts], **kw)
+        shared = set(proc_points(mine).tolist())
+        for it in range(8):
+            log = g.iterate(1)
+            n, nf, rs = o.iterate(1)
+            gp, op = g.points(), o.get("points", rank)
+            gf, of = g.frozen(), o.get("frozen", rank)
+            badp = np.nonzero((gp != op).any(axis=1))[0]
+            badf = np.nonzero(gf != of)[0]
+            print(f"[r{rank}] it{it + 1} nf gpu={log.n_frozen} orc={nf} res gpu={log.residual} orc={rs} "
+                  f"point diffs={[(int(i), i in shared, float(np.abs(gp[i] - op[i]).max())) for i in badp[:6]]} "
+                  f"mask diffs={[(int(i), i in shared, int(gf[i]), int(of[i]), int(o.get('isInternal', rank)[i])) for i in badf[:6]]}",
+                  flush=True)
+        dist.barrier()
+        os._exit(0)
     log = g.iterate(iters)
     res = dict(n=log.iterations, nf=log.n_frozen, res=log.residual, pts=g.points(), fz=g.frozen())
     allres = [None] * world
@@ -104,4 +124,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:
+        import traceback
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)  # never wait in collectives / communicator teardown after a failure
