@@ -30,7 +30,7 @@ LIBOBJS := $(OBJDIR)/smgpu.o $(OBJDIR)/exchange.o $(OBJDIR)/polymesh.o $(OBJDIR)
 
 $(LIB): $(LIBOBJS)
 	@mkdir -p $(LIBDIR)
-	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(LIBOBJS) -Xcompiler -fopenmp -lnccl
+	$(NVCC) -ccbin $(CXX) $(ARCH) -shared -o $@ $(LIBOBJS) -Xcompiler -fopenmp -ldl
 
 $(CLI): $(CSRC)/smoothmesh_cli.cpp $(LIB)
 	@mkdir -p $(BINDIR)

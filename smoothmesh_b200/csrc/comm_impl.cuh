@@ -14,7 +14,7 @@
 // combined in ascending rank order (the CPU oracle's rank emulation does the same).
 #pragma once
 #include "exchange.hpp"
-#include <nccl.h>
+#include "nccl_dyn.hpp"
 
 namespace smk
 {
@@ -223,20 +223,20 @@ struct Comm
     {                                                                                                                  \
         ncclResult_t r_ = (call);                                                                                      \
         if (r_ != ncclSuccess)                                                                                         \
-            throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(r_) + " at " #call);             \
+            throw std::runtime_error(std::string("NCCL error: ") + sm::nccl().GetErrorString(r_) + " at " #call);             \
     } while (0)
 
 static void haloExchange(Comm *cm, smgpu_handle *h, const void *send, void *recv, size_t elemBytes)
 {
     const ExchangePlan &pl = cm->plan;
-    NCK(ncclGroupStart());
+    NCK(nccl().GroupStart());
     for (size_t j = 0; j < pl.nbrRank.size(); ++j)
     {
         const size_t off = (size_t)pl.nbrOff[j] * elemBytes, cnt = (size_t)(pl.nbrOff[j + 1] - pl.nbrOff[j]) * elemBytes;
-        NCK(ncclSend((const char *)send + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
-        NCK(ncclRecv((char *)recv + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
+        NCK(nccl().Send((const char *)send + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
+        NCK(nccl().Recv((char *)recv + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
     }
-    NCK(ncclGroupEnd());
+    NCK(nccl().GroupEnd());
 }
 
 } // namespace sm

@@ -254,7 +254,7 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         ncclUniqueId uid;
         static_assert(sizeof(uid) == 128, "ncclUniqueId size");
         memcpy(&uid, id, 128);
-        NCK(ncclCommInitRank(&cm->nccl, nRanks, uid, rank));
+        NCK(nccl().CommInitRank(&cm->nccl, nRanks, uid, rank));
         smk::CommDev &c = cm->c;
         c.rank = rank;
         c.nSlots = (int)pl.sendPoint.size();
@@ -279,7 +279,7 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         double mm[2] = {-h->topo.minEdgeLength, h->topo.maxEdgeLength};
         double *dmm = h->dalloc<double>(2);
         CK(cudaMemcpy(dmm, mm, sizeof mm, cudaMemcpyHostToDevice));
-        NCK(ncclAllReduce(dmm, dmm, 2, ncclDouble, ncclMax, cm->nccl, h->stream));
+        NCK(nccl().AllReduce(dmm, dmm, 2, ncclDouble, ncclMax, cm->nccl, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         CK(cudaMemcpy(mm, dmm, sizeof mm, cudaMemcpyDeviceToHost));
         h->meshMinEdge = -mm[0];
@@ -289,7 +289,7 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
     catch (...)
     {
         if (cm->nccl)
-            ncclCommDestroy(cm->nccl);
+            nccl().CommDestroy(cm->nccl);
         delete cm;
         throw;
     }
@@ -301,7 +301,7 @@ static void commDestroy(Comm *cm)
     if (!cm)
         return;
     if (cm->nccl)
-        ncclCommDestroy(cm->nccl);
+        nccl().CommDestroy(cm->nccl);
     delete cm;
 }
 
@@ -334,10 +334,10 @@ static int commIterate(Comm *cm, smgpu_handle *h)
     h->launches += 2;
     h->launchCommit();
     h->profBegin(smgpu_handle::K_EXCHANGE);
-    NCK(ncclGroupStart());
-    NCK(ncclAllReduce(c.redRes, c.redRes, 1, ncclDouble, ncclMax, cm->nccl, h->stream));
-    NCK(ncclAllReduce(c.redFrozen, c.redFrozen, 1, ncclInt64, ncclSum, cm->nccl, h->stream));
-    NCK(ncclGroupEnd());
+    NCK(nccl().GroupStart());
+    NCK(nccl().AllReduce(c.redRes, c.redRes, 1, ncclDouble, ncclMax, cm->nccl, h->stream));
+    NCK(nccl().AllReduce(c.redFrozen, c.redFrozen, 1, ncclInt64, ncclSum, cm->nccl, h->stream));
+    NCK(nccl().GroupEnd());
     k_finish_iter<<<1, 32, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
     h->launches += 1;
@@ -859,11 +859,18 @@ extern "C"
 
     int smgpu_comm_unique_id(uint8_t id_out[128])
     {
-        ncclUniqueId uid;
-        const ncclResult_t r = ncclGetUniqueId(&uid);
-        if (r != ncclSuccess)
-            return setErr(SMGPU_ERR_COMM, ncclGetErrorString(r));
-        memcpy(id_out, &uid, 128);
+        try
+        {
+            ncclUniqueId uid;
+            const ncclResult_t r = sm::nccl().GetUniqueId(&uid);
+            if (r != ncclSuccess)
+                return setErr(SMGPU_ERR_COMM, sm::nccl().GetErrorString(r));
+            memcpy(id_out, &uid, 128);
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_COMM, e.what());
+        }
         return SMGPU_OK;
     }
 

@@ -1,0 +1,155 @@
+#!/usr/bin/env python
+"""Generates the committed golden fixtures under tests/golden/.
+
+Run in the build container, where /root/reference is mounted:
+
+    python tests/golden/make_golden.py
+
+The reference ships no golden outputs and cannot be executed without
+OpenFOAM, so the fixtures pin (a) restatements of two bundled meshes built from the reference's
+own case inputs and (b) the CPU oracle's output on them with the command lines of
+BASELINE.json configs 1 and 2:
+
+  testcase   : testcase/MeshedSurface.obj (660 vertices, 275 triangles + 475 quads) extruded
+               15 layers x 0.1 in +y (testcase/system/extrude2DMeshDict:9-24) -> 11 250 cells;
+               options of testcase/run_serial:18 minus -layerPatches.
+  testcase4  : the 15 straight-edged 5x5x5 blocks of testcase4/system/blockMeshDict:26-655,
+               coincident block points merged -> 1 875 hex cells; -centroidalIters 200
+               -totalMinFreeze true -smoothingPatches '()'.
+
+Point/face/cell numbering is this builder's (blockMesh's / extrude2DMesh's own numbering cannot be
+reproduced without OpenFOAM); all boundary faces go into one wall patch, which is all the hot path
+distinguishes.  The files hold the mesh arrays and the oracle's per-iteration log, final points
+and freeze mask; tests/test_golden.py checks the oracle (CPU) and the CUDA path (GPU) against them.
+"""
+import os
+import re
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = "/root/reference"
+
+import smoothmesh_b200 as sm  # noqa: E402
+from oracle import Oracle  # noqa: E402
+
+
+def orient_outward(points, cell_faces):
+    """Flip every face loop whose normal points towards the cell's vertex average."""
+    verts = sorted({v for f in cell_faces for v in f})
+    cc = points[verts].mean(axis=0)
+    out = []
+    for f in cell_faces:
+        p = points[list(f)]
+        fc = p.mean(axis=0)
+        n = np.zeros(3)
+        for i in range(len(f)):
+            n += np.cross(p[i] - fc, p[(i + 1) % len(f)] - fc)
+        out.append(list(f) if np.dot(n, fc - cc) > 0 else list(f)[::-1])
+    return out
+
+
+def testcase_mesh():
+    vs, polys = [], []
+    for line in open(os.path.join(REF, "testcase", "MeshedSurface.obj")):
+        t = line.split()
+        if not t:
+            continue
+        if t[0] == "v":
+            vs.append([float(x) for x in t[1:4]])
+        elif t[0] == "f":
+            polys.append([int(x.split("/")[0]) - 1 for x in t[1:]])
+    base = np.array(vs)
+    nl, thick = 15, 1.5
+    nv = len(base)
+    points = np.concatenate([base + np.array([0.0, thick * l / nl, 0.0]) for l in range(nl + 1)])
+    cells = []
+    for l in range(nl):
+        for poly in polys:
+            bot = [v + l * nv for v in poly]
+            top = [v + (l + 1) * nv for v in poly]
+            faces = [bot, top]
+            for i in range(len(poly)):
+                j = (i + 1) % len(poly)
+                faces.append([bot[i], bot[j], top[j], top[i]])
+            cells.append(orient_outward(points, faces))
+    return sm.Mesh.from_cells(points, cells)
+
+
+def testcase4_mesh():
+    txt = open(os.path.join(REF, "testcase4", "system", "blockMeshDict")).read()
+    vtxt = txt[txt.index("vertices"):txt.index("edges")]
+    verts = np.array([[float(x) for x in m] for m in re.findall(r"\(\s*(-?[\d.eE+-]+)\s+(-?[\d.eE+-]+)\s+(-?[\d.eE+-]+)\s*\)", vtxt)])
+    blocks = [[int(x) for x in m.split()] for m in re.findall(r"hex\s*\(([\d\s]+)\)\s*\(5 5 5\)", txt)]
+    assert len(verts) == 32 and len(blocks) == 15
+    n = 5
+    key2id, pts = {}, []
+
+    def pid(x):
+        k = tuple(np.round(x / 1e-9).astype(np.int64))
+        if k not in key2id:
+            key2id[k] = len(pts)
+            pts.append(x)
+        return key2id[k]
+
+    cells = []
+    for b in blocks:
+        c = verts[b]  # blockMesh hex ordering: 0..3 bottom loop, 4..7 top loop
+        ids = np.zeros((n + 1, n + 1, n + 1), dtype=np.int64)
+        for k in range(n + 1):
+            for j in range(n + 1):
+                for i in range(n + 1):
+                    u, v, w = i / n, j / n, k / n
+                    x = ((1 - u) * (1 - v) * (1 - w) * c[0] + u * (1 - v) * (1 - w) * c[1] + u * v * (1 - w) * c[2]
+                         + (1 - u) * v * (1 - w) * c[3] + (1 - u) * (1 - v) * w * c[4] + u * (1 - v) * w * c[5]
+                         + u * v * w * c[6] + (1 - u) * v * w * c[7])
+                    ids[i, j, k] = pid(x)
+        for k in range(n):
+            for j in range(n):
+                for i in range(n):
+                    q = lambda a, b_, c_: int(ids[i + a, j + b_, k + c_])
+                    faces = [
+                        [q(0, 0, 0), q(0, 0, 1), q(0, 1, 1), q(0, 1, 0)], [q(1, 0, 0), q(1, 1, 0), q(1, 1, 1), q(1, 0, 1)],
+                        [q(0, 0, 0), q(1, 0, 0), q(1, 0, 1), q(0, 0, 1)], [q(0, 1, 0), q(0, 1, 1), q(1, 1, 1), q(1, 1, 0)],
+                        [q(0, 0, 0), q(0, 1, 0), q(1, 1, 0), q(1, 0, 0)], [q(0, 0, 1), q(1, 0, 1), q(1, 1, 1), q(0, 1, 1)],
+                    ]
+                    cells.append(faces)
+    points = np.array(pts)
+    cells = [orient_outward(points, c) for c in cells]
+    return sm.Mesh.from_cells(points, cells)
+
+
+CASES = {
+    # testcase/run_serial:18 without -layerPatches (BASELINE config 1)
+    "testcase": (testcase_mesh, dict(min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0,
+                                      max_angle_deg=160.0), 100),
+    # BASELINE config 2
+    "testcase4": (testcase4_mesh, dict(total_min_freeze=1), 200),
+}
+
+
+def main():
+    for name, (build, kw, iters) in CASES.items():
+        mesh = build()
+        a = mesh.desc_arrays()
+        o = Oracle(a, **kw)
+        n, nf, res = o.iterate(iters)
+        out = dict(points=a["points"], face_offsets=a["face_offsets"], face_verts=a["face_verts"], owner=a["owner"],
+                   neighbour=a["neighbour"], n_cells=np.int64(a["n_cells"]), patch_start=a["patch_start"],
+                   patch_size=a["patch_size"], patch_kind=a["patch_kind"],
+                   iterations=np.int64(n), n_frozen=nf, residual=res, final_points=o.get("points"),
+                   frozen=o.get("frozen"), opt_keys=np.array(sorted(kw)), opt_vals=np.array([float(kw[k]) for k in sorted(kw)]),
+                   max_iters=np.int64(iters), min_edge_length=np.float64(o.prm.minEdgeLength),
+                   max_step_length=np.float64(o.prm.maxStepLength))
+        path = os.path.join(HERE, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"{name}: {mesh.n_points} points, {mesh.n_cells} cells, {n} iterations, nFrozen {nf[0]} -> {nf[-1]}, "
+              f"residual {res[0]:.4g} -> {res[-1]:.4g}, frozen internal "
+              f"{int((o.get('frozen') & o.get('isInternal')).sum())}; wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""The stand-alone `smoothMesh` executable (reference command-line surface + polyMesh I/O) on a GPU."""
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import smoothmesh_b200 as sm
+from oracle import Oracle
+
+from meshes import hex_jittered
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(tmp_path, mesh, write_format="binary"):
+    case = tmp_path / "case"
+    mesh.write(case / "constant" / "polyMesh")
+    (case / "system").mkdir()
+    (case / "system" / "controlDict").write_text(
+        "FoamFile { version 2.0; format ascii; class dictionary; object controlDict; }\n"
+        f"startFrom latestTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat {write_format};\nwritePrecision 12;\n"
+        "timeFormat general;\ntimePrecision 6;\n")
+    return case
+
+
+def test_cli_matches_oracle_and_writes_time_directories(tmp_path):
+    mesh = hex_jittered(7, 6, 5, 0.35, seed=21)
+    case = make_case(tmp_path, mesh)
+    opts = ["-centroidalIters", "12", "-relTol", "0", "-minAngle", "60", "-maxAngle", "120", "-totalMinFreeze", "true",
+            "-writeInterval", "5", "-smoothingPatches", "()"]
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case)] + opts, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    o = Oracle(mesh.desc_arrays(), rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0, total_min_freeze=1)
+    n, nf, res = o.iterate(12)
+    lines = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    assert [int(a) for a, _, _ in lines] == list(range(1, 13))
+    assert [int(b) for _, b, _ in lines] == nf.tolist()                       # the reference's log line, :2396
+    assert np.allclose([float(c) for _, _, c in lines], res, rtol=1e-5)
+    assert "Maximum centroidalIters reached, stopping." in r.stdout
+    # writes at (i+1) % writeInterval == 0 && i > 0, and at the end (:2416): times 5, 10, 12
+    assert sorted(p.name for p in case.iterdir() if p.name[0].isdigit()) == ["10", "12", "5"]
+    final = sm.Mesh.read(case / "constant" / "polyMesh")
+    final.read_points(case / "12" / "polyMesh" / "points")
+    assert np.array_equal(final.points, o.get("points"))                      # binary writeFormat: bit exact
+    # restart from latestTime (testcase8/run_serial:16-18 runs the tool twice)
+    r2 = subprocess.run([sm.CLI_PATH, "-case", str(case), "-centroidalIters", "3", "-relTol", "0", "-minAngle", "60",
+                         "-maxAngle", "120", "-totalMinFreeze", "true"], capture_output=True, text=True)
+    assert r2.returncode == 0 and "Create mesh for time = 12" in r2.stdout
+    assert (case / "15" / "polyMesh" / "points").exists()
+
+
+def test_cli_ascii_precision_and_reltol_stop(tmp_path):
+    mesh = hex_jittered(5, 5, 5, 0.2, seed=4)
+    case = make_case(tmp_path, mesh, write_format="ascii")
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-centroidalIters", "500"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Residual reached relTol, stopping." in r.stdout
+    o = Oracle(mesh.desc_arrays())
+    n, nf, res = o.iterate(500)
+    assert len(re.findall(r"Smoothing iteration=", r.stdout)) == n             # iteration count at convergence
+    out = sm.Mesh.read(case / "constant" / "polyMesh")
+    out.read_points(case / str(n) / "polyMesh" / "points")
+    assert np.allclose(out.points, o.get("points"), rtol=0, atol=1e-11)       # precision max(10, writePrecision)

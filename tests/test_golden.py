@@ -1,0 +1,55 @@
+"""Golden fixtures (tests/golden/*.npz, made by tests/golden/make_golden.py from the reference's
+bundled testcase / testcase4 inputs): the oracle must reproduce them on CPU, the CUDA path on GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import smoothmesh_b200 as sm
+from oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(name):
+    z = np.load(os.path.join(HERE, "golden", f"{name}.npz"))
+    arrays = dict(points=z["points"], face_offsets=z["face_offsets"], face_verts=z["face_verts"], owner=z["owner"],
+                  neighbour=z["neighbour"], n_cells=int(z["n_cells"]), patch_start=z["patch_start"],
+                  patch_size=z["patch_size"], patch_kind=z["patch_kind"], point_global_id=None)
+    kw = {str(k): float(v) for k, v in zip(z["opt_keys"], z["opt_vals"])}
+    for k in ("total_min_freeze",):
+        if k in kw:
+            kw[k] = int(kw[k])
+    return z, arrays, kw
+
+
+@pytest.mark.parametrize("name", ["testcase4", "testcase"])
+def test_oracle_reproduces_golden(name):
+    z, arrays, kw = load(name)
+    iters = int(z["max_iters"]) if name == "testcase4" else 12  # keep the CPU suite short
+    o = Oracle(arrays, **kw)
+    n, nf, res = o.iterate(iters)
+    assert np.array_equal(nf, z["n_frozen"][:n]) and np.array_equal(res, z["residual"][:n])
+    if n == int(z["iterations"]):
+        assert np.array_equal(o.get("points"), z["final_points"]) and np.array_equal(o.get("frozen"), z["frozen"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["testcase4", "testcase"])
+def test_cuda_path_reproduces_golden(name):
+    z, arrays, kw = load(name)
+    mesh = sm.Mesh.from_arrays(arrays["points"], arrays["face_offsets"], arrays["face_verts"], arrays["owner"],
+                               arrays["neighbour"], arrays["n_cells"], arrays["patch_start"], arrays["patch_size"],
+                               arrays["patch_kind"])
+    g = sm.Smoother(mesh, **kw)
+    p = g.params
+    assert p.min_edge_length == float(z["min_edge_length"]) and p.max_step_length == float(z["max_step_length"])
+    log = g.iterate(int(z["max_iters"]))
+    assert log.iterations == int(z["iterations"])          # iteration count at convergence
+    assert np.array_equal(log.n_frozen, z["n_frozen"])      # integer outputs bit-exact
+    assert np.array_equal(log.residual, z["residual"])
+    assert np.array_equal(g.frozen(), z["frozen"])
+    ref = z["final_points"]
+    diag = np.linalg.norm(ref.max(0) - ref.min(0))
+    assert np.abs(g.points() - ref).max() <= 1e-9 * diag    # stated tolerance ...
+    assert np.array_equal(g.points(), ref)                  # ... and bitwise in this build

@@ -1,0 +1,127 @@
+"""Host-side polyMesh library: generators, file I/O round trips, decomposition, CLI surface."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import smoothmesh_b200 as sm
+
+from meshes import hex_jittered
+
+
+def test_hex_block_counts_and_numbering():
+    m = sm.Mesh.hex_block(4, 3, 2)
+    assert (m.n_points, m.n_cells) == (5 * 4 * 3, 24)
+    assert m.n_internal_faces == 3 * 3 * 2 + 4 * 2 * 2 + 4 * 3 * 1
+    assert m.n_faces == m.n_internal_faces + 2 * (3 * 2 + 4 * 2 + 4 * 3)
+    # blockMesh numbering: point i + j(nx+1) + k(nx+1)(ny+1)
+    assert np.allclose(m.points[1 + 5 * 2 + 20 * 1], [1 / 4, 2 / 3, 1 / 2])
+    own, nei = m.owner, m.neighbour
+    assert (nei > own[: len(nei)]).all()
+    key = own[: len(nei)].astype(np.int64) * m.n_cells + nei
+    assert (np.diff(key) > 0).all()  # upper-triangular order
+
+
+def test_generic_builder_matches_structured_generator():
+    nx, ny, nz = 3, 2, 2
+    ref = sm.Mesh.hex_block(nx, ny, nz)
+    pid = lambda i, j, k: i + j * (nx + 1) + k * (nx + 1) * (ny + 1)
+    cells = []
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                q = lambda a, b, c: pid(i + a, j + b, k + c)
+                cells.append([[q(0, 0, 0), q(0, 0, 1), q(0, 1, 1), q(0, 1, 0)], [q(1, 0, 0), q(1, 1, 0), q(1, 1, 1), q(1, 0, 1)],
+                              [q(0, 0, 0), q(1, 0, 0), q(1, 0, 1), q(0, 0, 1)], [q(0, 1, 0), q(0, 1, 1), q(1, 1, 1), q(1, 1, 0)],
+                              [q(0, 0, 0), q(0, 1, 0), q(1, 1, 0), q(1, 0, 0)], [q(0, 0, 1), q(1, 0, 1), q(1, 1, 1), q(0, 1, 1)]])
+    m = sm.Mesh.from_cells(np.array(ref.points), cells)
+    assert m.n_faces == ref.n_faces and m.n_internal_faces == ref.n_internal_faces
+    assert np.array_equal(m.owner[: m.n_internal_faces], ref.owner[: ref.n_internal_faces])
+    assert np.array_equal(m.neighbour, ref.neighbour)
+    same = lambda a, b: sorted(a) == sorted(b)
+    assert all(same(a, b) for a, b in zip(m.faces()[: m.n_internal_faces], ref.faces()[: ref.n_internal_faces]))
+
+
+def test_kelvin_mesh_is_a_valid_polyhedral_mesh():
+    m = sm.Mesh.kelvin(3)
+    assert m.n_cells == 2 * 27
+    sizes = np.diff(m.face_offsets)
+    assert set(sizes.tolist()) == {4, 6}
+    # every cell has 14 faces
+    cnt = np.bincount(m.owner, minlength=m.n_cells) + np.bincount(m.neighbour, minlength=m.n_cells)
+    assert (cnt == 14).all()
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_polymesh_write_read_round_trip(tmp_path, binary):
+    m = hex_jittered(4, 3, 3, 0.3)
+    d = tmp_path / "constant" / "polyMesh"
+    m.write(d, binary=binary, precision=17)
+    r = sm.Mesh.read(d)
+    assert np.array_equal(r.points, m.points)
+    for a in ("face_offsets", "face_verts", "owner", "neighbour"):
+        assert np.array_equal(getattr(r, a), getattr(m, a)), a
+    assert r.patch_names == m.patch_names
+    for x, y in zip(r.patches, m.patches):
+        assert np.array_equal(x, y)
+
+
+def test_reader_accepts_openfoam_grammar_variants(tmp_path):
+    d = tmp_path / "polyMesh"
+    sm.Mesh.hex_block(1, 1, 1).write(d)
+    # comments anywhere, single-line lists, uniform list N{v} for owner (all faces owned by cell 0)
+    owner = (d / "owner").read_text()
+    head = owner[: owner.index("6\n(")]
+    (d / "owner").write_text("// leading comment\n" + head + "/* block\n comment */ 6{0}\n")
+    (d / "neighbour").write_text((d / "neighbour").read_text().replace("0\n(", "0()").replace("\n)\n", "\n"))
+    m = sm.Mesh.read(d)
+    assert m.n_cells == 1 and m.n_faces == 6 and m.n_internal_faces == 0
+
+
+def test_reader_rejects_invalid_mesh(tmp_path):
+    d = tmp_path / "polyMesh"
+    sm.Mesh.hex_block(2, 1, 1).write(d)
+    txt = (d / "neighbour").read_text()
+    (d / "neighbour").write_text(txt.replace("1\n(\n1\n)", "1\n(\n0\n)"))
+    with pytest.raises(sm.SmoothMeshError, match="neighbour"):
+        sm.Mesh.read(d)
+
+
+@pytest.mark.parametrize("dims,method", [((2, 2, 1), "bricks"), ((3, 1, 1), "bricks"), ((5,), "rcb")])
+def test_decompose_produces_consistent_processor_meshes(dims, method):
+    m = hex_jittered(6, 4, 3, 0.2)
+    parts = m.decompose(*dims, method=method) if method == "bricks" else m.decompose(dims[0], method="rcb")
+    assert sum(p.n_cells for p in parts) == m.n_cells
+    all_cells = np.sort(np.concatenate([p.cell_global_id for p in parts]))
+    assert np.array_equal(all_cells, np.arange(m.n_cells))
+    for p in parts:
+        assert np.array_equal(p.points, np.asarray(m.points)[p.point_global_id])
+        s, z, k = p.patches
+        assert (k[:6] == 0).all() and (k[6:] == 1).all()
+    # every processor face appears once on each side, reversed
+    nproc = sum(int(z[k == 1].sum()) for _, z, k in (p.patches for p in parts))
+    cut = m.n_internal_faces - sum(p.n_internal_faces for p in parts)
+    assert nproc == 2 * cut
+
+
+def test_counter_rng_jitter_is_partition_independent():
+    n = 4
+    whole = sm.Mesh.hex_block(2 * n, n, n, hi=(2.0, 1.0, 1.0)).jitter(0.1 / n, 99)
+    for r in range(2):
+        part = sm.Mesh.hex_block_part(n, n, n, 2, 1, 1, r, hi=(2.0, 1.0, 1.0)).jitter(0.1 / n, 99)
+        assert np.array_equal(part.points, np.asarray(whole.points)[part.point_global_id])
+
+
+def test_cli_rejects_out_of_scope_features_loudly(tmp_path):
+    case = tmp_path / "case"
+    sm.Mesh.hex_block(2, 2, 2).write(case / "constant" / "polyMesh")
+    (case / "system").mkdir()
+    (case / "system" / "controlDict").write_text("deltaT 1;\nwriteFormat ascii;\n")
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-layerPatches", "(walls)"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-bogusOption", "1"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Invalid option" in r.stderr
+    (case / "system" / "controlDict").write_text("deltaT 0;\n")
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case)], capture_output=True, text=True)
+    assert r.returncode != 0 and "too small" in r.stderr
