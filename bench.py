@@ -215,6 +215,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        # torchrun pins OMP_NUM_THREADS=1; the one-time host-side connectivity build is OpenMP-parallel
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world))
 
     if args.impl == "reference":
         run_reference(args, rank, world)

@@ -279,7 +279,7 @@ class Mesh:
         lib().smmesh_jitter(self._h, float(amp), int(seed))
         return self
 
-    def write(self, polymesh_dir, binary=False, precision=16):
+    def write(self, polymesh_dir, binary=False, precision=17):  # 17 significant digits round-trip a double
         if lib().smmesh_write(self._h, str(polymesh_dir).encode(), int(binary), int(precision)) != 0:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
 

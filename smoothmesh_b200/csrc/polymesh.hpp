@@ -92,7 +92,7 @@ std::vector<int32_t> partitionRCB(const PolyMesh &m, int nParts);
 // ---- file I/O -----------------------------------------------------------------
 // dir = ".../polyMesh".  Reads ascii or binary (label=32, scalar=64) files.
 PolyMesh readPolyMesh(const std::string &dir);
-void writePolyMesh(const PolyMesh &m, const std::string &dir, bool binary = false, int precision = 16);
+void writePolyMesh(const PolyMesh &m, const std::string &dir, bool binary = false, int precision = 17);
 // Writes only the points file (what mesh.write() does after movePoints).
 void writePoints(const double *pts, int64_t nPoints, const std::string &dir, bool binary, int precision,
                  const std::string &location);
