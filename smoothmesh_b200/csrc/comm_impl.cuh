@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
     const bool internal = self.w != 0.0;
     PointLocal L;
     pointLocal(d, p, x, internal, L);
-    const bool hc = shareCell(d, d.pp[L.k1], d.pp[L.k2]);
+    const bool hc = shareCell(d, L.n1, L.n2);
     double *r = c.sendBuf + (size_t)i * SMK_TUPLE;
     r[0] = L.sum.x, r[1] = L.sum.y, r[2] = L.sum.z;
     r[3] = (double)L.nCells;

@@ -160,6 +160,7 @@ struct smgpu_handle
     void setPoints(const double *pts)
     {
         std::vector<P4> h(topo.P);
+#pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < topo.P; ++i)
             h[i] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], topo.isInternal[i] ? 1.0 : 0.0};
         CK(cudaMemcpy(d.pts, h.data(), h.size() * sizeof(P4), cudaMemcpyHostToDevice));
@@ -456,6 +457,8 @@ extern "C"
             d.faceVerts = h->upload(t.faceVerts);
             d.cfOff = h->upload(t.cfOff);
             d.cf = h->upload(t.cf);
+            d.pointRec = (const int4 *)h->upload(t.pointRec);
+            d.edgeRec = (const int4 *)h->upload(t.edgeRec);
             d.curMin = h->dalloc<unsigned long long>(t.P);
             d.curMax = h->dalloc<unsigned long long>(t.P);
             d.activeFlag = h->dalloc<uint8_t>(t.P + 8);
@@ -623,6 +626,7 @@ extern "C"
             CK(cudaSetDevice(h->prm.device));
             std::vector<P4> tmp(n);
             CK(cudaMemcpy(tmp.data(), src, n * sizeof(P4), cudaMemcpyDeviceToHost));
+#pragma omp parallel for schedule(static)
             for (int64_t i = 0; i < n; ++i)
             {
                 out[3 * i] = tmp[i].x;

@@ -315,6 +315,68 @@ Topology buildTopology(const PolyMesh &m)
     }
     t.minEdgeLength = mn;
     t.maxEdgeLength = mx;
+
+    // ---- fixed-size records for the common low-valence case (see topology.hpp) ----
+    t.pointRec.assign(16 * P, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; ++p)
+    {
+        int32_t *r = &t.pointRec[16 * p];
+        const int32_t npc = t.pcOff[p + 1] - t.pcOff[p], npp = t.ppOff[p + 1] - t.ppOff[p];
+        const bool generic = npc > 8 || npp > 6;
+        if (!generic)
+        {
+            for (int32_t k = 0; k < npc; ++k)
+                r[k] = t.pc[t.pcOff[p] + k];
+            for (int32_t k = 0; k < npp; ++k)
+                r[8 + k] = t.pp[t.ppOff[p] + k];
+        }
+        r[14] = npc | (npp << 8) | (generic ? (int32_t)0x80000000u : 0);
+        // corners (prev,next) as a mask over the 15 unordered pairs of the (<= 6) row positions
+        if (!generic)
+        {
+            int32_t mask = 0;
+            const int32_t *b = &t.pp[t.ppOff[p]];
+            for (int32_t k = t.cornerOff[p]; k < t.cornerOff[p + 1]; ++k)
+            {
+                int32_t sa = (int32_t)(std::lower_bound(b, b + npp, t.corner[2 * (int64_t)k]) - b);
+                int32_t sb = (int32_t)(std::lower_bound(b, b + npp, t.corner[2 * (int64_t)k + 1]) - b);
+                if (sa == sb)
+                { // degenerate face (prev == next): not expressible as a pair -> generic (literal) path
+                    r[14] |= (int32_t)0x80000000u;
+                    continue;
+                }
+                if (sa > sb)
+                    std::swap(sa, sb);
+                // index of pair (sa,sb), sa<sb, in the order (0,1),(0,2),..,(0,5),(1,2),..,(4,5)
+                mask |= 1 << (sa * 6 - sa * (sa + 1) / 2 + (sb - sa - 1));
+            }
+            r[15] = mask;
+        }
+    }
+    t.edgeRec.assign(12 * E, 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t e = 0; e < E; ++e)
+    {
+        int32_t *r = &t.edgeRec[12 * e];
+        const int32_t nf = t.efOff[e + 1] - t.efOff[e], nc = t.ecOff[e + 1] - t.ecOff[e];
+        const bool generic = nf > 4 || nc > 4;
+        r[0] = t.edge[2 * e];
+        r[1] = t.edge[2 * e + 1];
+        int32_t meta = nf | (nc << 4) | (generic ? (int32_t)0x80000000u : 0);
+        if (!generic)
+        {
+            for (int32_t k = 0; k < nf; ++k)
+                r[2 + k] = t.ef[t.efOff[e] + k];
+            for (int32_t k = 0; k < nc; ++k)
+            {
+                r[6 + k] = t.ecCell[t.ecOff[e] + k];
+                const int32_t pr = t.ecPair[t.ecOff[e] + k];
+                meta |= ((pr & 3) | (((pr >> 16) & 3) << 2)) << (8 + 4 * k);
+            }
+        }
+        r[10] = meta;
+    }
     return t;
 }
 
