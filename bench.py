@@ -164,10 +164,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_side = args.ref_n
     import smoothmesh_b200 as sm
     from oracle import Oracle
-    mesh = sm.Mesh.hex_block(n_side, n_side, n_side).jitter(JITTER / n_side, SEED)
     p2 = 1
     while p2 * 2 <= threads:
         p2 *= 2
@@ -178,8 +176,23 @@ def run_reference(args, rank, world):
         dims[i % 3] *= 2
         t //= 2
         i += 1
-    parts = mesh.decompose(*dims) if p2 > 1 else [mesh]
-    o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, threads=p2)
+
+    def build(n_side):
+        mesh = sm.Mesh.hex_block(n_side, n_side, n_side).jitter(JITTER / n_side, SEED)
+        parts = mesh.decompose(*dims) if p2 > 1 else [mesh]
+        return mesh, Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, threads=p2)
+
+    # bounded sample: size the block so that warmup + steps iterations take about args.ref_budget
+    # seconds at the rate calibrated on a 32^3 block (per-point cost is size independent)
+    n_side = args.ref_n
+    if n_side <= 0:
+        mesh, o = build(32)
+        t0 = time.perf_counter()
+        o.iterate(2)
+        rate = mesh.n_points * 2 / (time.perf_counter() - t0)
+        pts = args.ref_budget * rate / max(args.steps + args.warmup, 1)
+        n_side = int(min(128, max(24, round(pts ** (1.0 / 3.0)) - 1)))
+    mesh, o = build(n_side)
     o.iterate(args.warmup)
     t0 = time.perf_counter()
     n, _, _ = o.iterate(args.steps)
@@ -207,7 +220,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=200, help="cells per side of the (per-GPU) hex block")
-    ap.add_argument("--ref-n", type=int, default=96, help="cells per side of the CPU sample mesh")
+    ap.add_argument("--ref-n", type=int, default=0, help="cells per side of the CPU sample mesh (0 = sized from --ref-budget)")
+    ap.add_argument("--ref-budget", type=float, default=100.0, help="seconds of CPU work for --impl reference")
+    ap.add_argument("--cpu-n", type=int, default=96, help="cells per side of the cpu_baseline sample mesh")
     ap.add_argument("--cpu-iters", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
@@ -336,10 +351,10 @@ def main():
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        v1, c1, dt1 = cpu_baseline(args.ref_n, args.cpu_iters, 1)
-        vN, cN, dtN = cpu_baseline(args.ref_n, args.cpu_iters, threads)
+        v1, c1, dt1 = cpu_baseline(args.cpu_n, args.cpu_iters, 1)
+        vN, cN, dtN = cpu_baseline(args.cpu_n, args.cpu_iters, threads)
         line["cpu_baseline"] = {"value": vN, "unit": "point-updates/s", "cores": cN, "kind": "port",
-                                "sample": f"{args.cpu_iters} iterations of a jittered {args.ref_n}^3 hex block "
+                                "sample": f"{args.cpu_iters} iterations of a jittered {args.cpu_n}^3 hex block "
                                           f"(same jitter rule/options), rank-emulation on {cN} threads ({dtN:.1f} s); "
                                           f"serial: {v1:.4g} point-updates/s ({dt1:.1f} s)",
                                 "serial_value": v1}
