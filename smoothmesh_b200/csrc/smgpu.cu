@@ -342,10 +342,9 @@ static int commIterate(Comm *cm, smgpu_handle *h)
     k_finish_iter<<<1, 32, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
     h->launches += 1;
-    int done = 0;
-    CK(cudaMemcpyAsync(&done, h->d.done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
-    return done;
+    // no host round trip: the stop flag is global (it comes from the all-reduced residual), so every
+    // rank keeps launching the same sequence and the kernels turn into no-ops once it is raised
+    return 0;
 }
 
 } // namespace sm
@@ -560,13 +559,6 @@ extern "C"
             h->resetControl();
             CK(cudaEventRecord(h->ev0, h->stream));
             int done = 0, launched = 0;
-            if (h->comm)
-            {
-                // multi-rank: one iteration at a time, halo exchanges between phases
-                for (; launched < max_iters && !done; ++launched)
-                    done = sm::commIterate(h->comm, h);
-            }
-            else
             {
                 const int chunk = 16; // iterations launched between polls of the stop flag
                 while (launched < max_iters && !done)
@@ -574,6 +566,11 @@ extern "C"
                     const int n = std::min(chunk, max_iters - launched);
                     for (int i = 0; i < n; ++i)
                     {
+                        if (h->comm)
+                        { // multi-rank: the same sequence with the interface exchanges in between
+                            sm::commIterate(h->comm, h);
+                            continue;
+                        }
                         h->launchCellCentres();
                         h->launchPredict();
                         h->launchEdgeConstraints();
