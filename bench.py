@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=96, help="cells per side of the cpu_baseline sample mesh")
     ap.add_argument("--cpu-iters", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--renumber", type=int, default=0, help="1 = Morton storage order (smgpu_params.renumber)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,7 +257,7 @@ def main():
         mesh = multi.weak_scaling_part(n, world, rank, JITTER, SEED)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    g = sm.Smoother(mesh, rel_tol=0.0, device=local_rank)
+    g = sm.Smoother(mesh, rel_tol=0.0, device=local_rank, renumber=args.renumber)
     if world > 1:
         from smoothmesh_b200 import multi
         multi.init_comm(g, rank, world, dist)
@@ -334,7 +335,7 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"hex {n}^3 jittered blockMesh block per GPU (U(-0.25h,0.25h), seed {SEED}), "
                                f"{K} iterations, edge/face angle constraints on, relTol 0",
-                   "points_per_gpu": P, "cells_per_gpu": C, "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
+                   "points_per_gpu": P, "cells_per_gpu": C, "renumber": args.renumber, "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
                    "setup_s": {"mesh_generation": t_gen, "create_upload": t_setup}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "point-updates/s", "h2d_bytes_per_step": 24 * P / K,

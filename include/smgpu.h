@@ -74,7 +74,11 @@ extern "C"
         int32_t face_angle_constraint; /* 1 */
         int32_t geometry_variant;      /* 0 = openfoam.com face-centre formula, 1 = openfoam.org */
         int32_t device;                /* CUDA device ordinal */
-        int32_t renumber;              /* 0 = keep mesh order in HBM, 1 = space-filling-curve storage order */
+        int32_t renumber;              /* 0 = keep the mesh's numbering; 1 = renumber points and cells along a Morton
+                                          curve first (what OpenFOAM's renumberMesh would do before smoothMesh):
+                                          gathers become local, results are those of the renumbered mesh
+                                          (label-order-dependent tie-breaks / summation order follow the new
+                                          labels), points and masks are returned in the caller's numbering */
     } smgpu_params;
 
     typedef struct smgpu_handle smgpu_handle;

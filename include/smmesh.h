@@ -61,6 +61,12 @@ extern "C"
     const int64_t *smmesh_point_global_id(const smmesh *m); /* NULL for undecomposed meshes */
     const int64_t *smmesh_cell_global_id(const smmesh *m);
 
+    /* Morton (space-filling-curve) renumbering of points and cells, the renumberMesh stand-in: returns a new
+     * valid polyMesh whose storage order keeps the smoothing kernels' gathers local.  The optional maps
+     * receive the old label of every new point / cell.  Labels change, so label-order-dependent results are
+     * those of the renumbered mesh (as if renumberMesh had been run before smoothMesh). */
+    smmesh *smmesh_renumber(const smmesh *m, int32_t *point_old_of_new, int32_t *cell_old_of_new);
+
     /* decomposition: method 0 = bricks px*py*pz, 1 = recursive coordinate bisection into px parts.
      * parts_out receives n_parts (= px*py*pz or px) new meshes. */
     int smmesh_decompose(const smmesh *m, int32_t method, int32_t px, int32_t py, int32_t pz, smmesh **parts_out);

@@ -118,6 +118,8 @@ def lib():
         L.smgpu_comm_local_shared.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_exchange_plan.restype = C.c_int64
         L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
+        L.smmesh_renumber.restype = C.c_void_p
+        L.smmesh_renumber.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smmesh_gen_hex_block_part.restype = C.c_void_p
         L.smmesh_gen_hex_block_part.argtypes = [C.c_int32] * 7 + [C.c_void_p, C.c_void_p]
         _lib = L
@@ -286,6 +288,12 @@ class Mesh:
     def read_points(self, points_file):
         if lib().smmesh_read_points(self._h, str(points_file).encode()) != 0:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
+
+    def renumber(self):
+        """Morton renumbering (renumberMesh stand-in) -> (new Mesh, point_old_of_new, cell_old_of_new)."""
+        pm = np.zeros(self.n_points, dtype=np.int32)
+        cm = np.zeros(self.n_cells, dtype=np.int32)
+        return Mesh(lib().smmesh_renumber(self._h, _ptr(pm), _ptr(cm))), pm, cm
 
     def decompose(self, px, py=1, pz=1, method="bricks"):
         n = px * py * pz if method == "bricks" else px

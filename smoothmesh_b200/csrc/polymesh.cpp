@@ -1159,3 +1159,149 @@ PolyMesh genHexBlockPart(int nx, int ny, int nz, int px, int py, int pz, int ran
     return m;
 }
 } // namespace sm
+
+// ------------------------------------------------------------- renumbering ----
+namespace sm
+{
+namespace
+{
+inline uint64_t spread21(uint64_t v)
+{ // interleave helper: 21 bits -> every third bit
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+inline uint64_t mortonKey(const double *x, const double *lo, const double *inv)
+{
+    uint64_t k = 0;
+    for (int d = 0; d < 3; ++d)
+    {
+        double t = (x[d] - lo[d]) * inv[d];
+        t = t < 0 ? 0 : (t > 1 ? 1 : t);
+        k |= spread21((uint64_t)(t * 2097151.0)) << d;
+    }
+    return k;
+}
+} // namespace
+
+// Space-filling-curve (Morton) renumbering of points and cells, the stand-in for OpenFOAM's
+// renumberMesh utility: produces a valid polyMesh (faces re-sorted upper-triangular, flipped
+// where owner and neighbour swap) whose storage order makes the smoothing kernels' gathers
+// local.  Labels change, so label-order-dependent results (stable-sort ties, worklist order,
+// summation order) are those of the renumbered mesh -- exactly as if renumberMesh had been run
+// before the reference.
+PolyMesh renumberMorton(const PolyMesh &m, std::vector<int32_t> &pointOldOfNew, std::vector<int32_t> &cellOldOfNew)
+{
+    const int64_t P = m.nPoints(), C = m.nCells, F = m.nFaces(), Fi = m.nInternalFaces();
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}, inv[3];
+    for (int64_t p = 0; p < P; ++p)
+        for (int d = 0; d < 3; ++d)
+        {
+            lo[d] = std::min(lo[d], m.points[3 * p + d]);
+            hi[d] = std::max(hi[d], m.points[3 * p + d]);
+        }
+    for (int d = 0; d < 3; ++d)
+        inv[d] = hi[d] > lo[d] ? 1.0 / (hi[d] - lo[d]) : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> keys(P);
+    for (int64_t p = 0; p < P; ++p)
+        keys[p] = {mortonKey(&m.points[3 * p], lo, inv), (int32_t)p};
+    std::sort(keys.begin(), keys.end());
+    pointOldOfNew.resize(P);
+    std::vector<int32_t> pointNew(P);
+    for (int64_t i = 0; i < P; ++i)
+    {
+        pointOldOfNew[i] = keys[i].second;
+        pointNew[keys[i].second] = (int32_t)i;
+    }
+    std::vector<double> cx(3 * C, 0.0);
+    std::vector<int32_t> cnt(C, 0);
+    auto acc = [&](int32_t c, int64_t f) {
+        for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+        {
+            for (int d = 0; d < 3; ++d)
+                cx[3 * (int64_t)c + d] += m.points[3 * (int64_t)m.faceVerts[k] + d];
+            ++cnt[c];
+        }
+    };
+    for (int64_t f = 0; f < F; ++f)
+        acc(m.owner[f], f);
+    for (int64_t f = 0; f < Fi; ++f)
+        acc(m.neighbour[f], f);
+    keys.resize(C);
+    for (int64_t c = 0; c < C; ++c)
+    {
+        for (int d = 0; d < 3; ++d)
+            cx[3 * c + d] /= cnt[c];
+        keys[c] = {mortonKey(&cx[3 * c], lo, inv), (int32_t)c};
+    }
+    std::sort(keys.begin(), keys.end());
+    cellOldOfNew.resize(C);
+    std::vector<int32_t> cellNew(C);
+    for (int64_t i = 0; i < C; ++i)
+    {
+        cellOldOfNew[i] = keys[i].second;
+        cellNew[keys[i].second] = (int32_t)i;
+    }
+    struct IF
+    {
+        int32_t own, nei, f;
+        bool flip;
+    };
+    std::vector<IF> ifs(Fi);
+    for (int64_t f = 0; f < Fi; ++f)
+    {
+        const int32_t a = cellNew[m.owner[f]], b = cellNew[m.neighbour[f]];
+        ifs[f] = {std::min(a, b), std::max(a, b), (int32_t)f, a > b};
+    }
+    std::sort(ifs.begin(), ifs.end(), [](const IF &x, const IF &y) { return x.own != y.own ? x.own < y.own : (x.nei != y.nei ? x.nei < y.nei : x.f < y.f); });
+    PolyMesh o;
+    o.nCells = C;
+    o.points.resize(3 * P);
+    for (int64_t i = 0; i < P; ++i)
+        for (int d = 0; d < 3; ++d)
+            o.points[3 * i + d] = m.points[3 * (int64_t)pointOldOfNew[i] + d];
+    o.faceOffsets.push_back(0);
+    auto emit = [&](int64_t f, bool flip) {
+        const int32_t b = m.faceOffsets[f], e = m.faceOffsets[f + 1];
+        if (!flip)
+            for (int32_t k = b; k < e; ++k)
+                o.faceVerts.push_back(pointNew[m.faceVerts[k]]);
+        else
+        {
+            o.faceVerts.push_back(pointNew[m.faceVerts[b]]);
+            for (int32_t k = e - 1; k > b; --k)
+                o.faceVerts.push_back(pointNew[m.faceVerts[k]]);
+        }
+        o.faceOffsets.push_back((int32_t)o.faceVerts.size());
+    };
+    for (const IF &x : ifs)
+    {
+        emit(x.f, x.flip);
+        o.owner.push_back(x.own);
+        o.neighbour.push_back(x.nei);
+    }
+    o.patches = m.patches;
+    for (int64_t f = Fi; f < F; ++f)
+    {
+        emit(f, false);
+        o.owner.push_back(cellNew[m.owner[f]]);
+    }
+    if (!m.pointGlobalId.empty())
+    {
+        o.pointGlobalId.resize(P);
+        for (int64_t i = 0; i < P; ++i)
+            o.pointGlobalId[i] = m.pointGlobalId[pointOldOfNew[i]];
+    }
+    if (!m.cellGlobalId.empty())
+    {
+        o.cellGlobalId.resize(C);
+        for (int64_t i = 0; i < C; ++i)
+            o.cellGlobalId[i] = m.cellGlobalId[cellOldOfNew[i]];
+    }
+    return o;
+}
+} // namespace sm

@@ -78,6 +78,10 @@ PolyMesh buildFromCells(const std::vector<double> &points, const std::vector<int
 void jitterInterior(PolyMesh &m, double amp, uint64_t seed);
 double counterUniform(uint64_t seed, uint64_t label, uint32_t comp); // in [0,1)
 
+// Morton (space-filling-curve) renumbering of points and cells (renumberMesh stand-in); the maps give the
+// old label of every new label.
+PolyMesh renumberMorton(const PolyMesh &m, std::vector<int32_t> &pointOldOfNew, std::vector<int32_t> &cellOldOfNew);
+
 // ---- decomposition (decomposePar stand-in) ------------------------------------
 // cellPart[c] in [0,nParts).  Produces OpenFOAM-style processor meshes: local
 // points/cells/faces in ascending global order, inter-part faces become

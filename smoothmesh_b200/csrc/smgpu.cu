@@ -51,6 +51,8 @@ struct smgpu_handle
     int statCap = 0;
     sm::Comm *comm = nullptr;
     std::vector<int64_t> gid;
+    // params.renumber: storage order = Morton order; old label of every stored point / cell
+    std::vector<int32_t> pointOldOfNew, cellOldOfNew;
     smgpu_params prmRequested;              // as passed by the caller (negative = reference default)
     double meshMinEdge = 0, meshMaxEdge = 0; // getMeshStats; global (all-reduced) in multi-rank runs
     // option defaults of src/smoothMesh.C:1861-1865 from the (global) minimum edge length
@@ -162,7 +164,10 @@ struct smgpu_handle
         std::vector<P4> h(topo.P);
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < topo.P; ++i)
-            h[i] = {pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], topo.isInternal[i] ? 1.0 : 0.0};
+        {
+            const int64_t o = pointOldOfNew.empty() ? i : pointOldOfNew[i];
+            h[i] = {pts[3 * o], pts[3 * o + 1], pts[3 * o + 2], topo.isInternal[i] ? 1.0 : 0.0};
+        }
         CK(cudaMemcpy(d.pts, h.data(), h.size() * sizeof(P4), cudaMemcpyHostToDevice));
     }
 
@@ -404,9 +409,13 @@ extern "C"
                 m.patches.push_back(p);
             }
             if (md->point_global_id)
-                h->gid.assign(md->point_global_id, md->point_global_id + md->n_points);
+                m.pointGlobalId.assign(md->point_global_id, md->point_global_id + md->n_points);
             try
             {
+                if (params->renumber)
+                    m = sm::renumberMorton(m, h->pointOldOfNew, h->cellOldOfNew);
+                if (md->point_global_id)
+                    h->gid = m.pointGlobalId;
                 h->topo = sm::buildTopology(m);
             }
             catch (const std::exception &e)
@@ -486,6 +495,7 @@ extern "C"
             h->resolveParams();
             h->setPoints(md->points);
             CK(cudaDeviceSynchronize());
+            (void)m;
         }
         catch (const std::exception &e)
         {
@@ -616,7 +626,7 @@ extern "C"
         return SMGPU_OK;
     }
 
-    static int downloadP4(smgpu_handle *h, const P4 *src, int64_t n, double *out)
+    static int downloadP4(smgpu_handle *h, const P4 *src, int64_t n, double *out, const std::vector<int32_t> &oldOfNew)
     {
         try
         {
@@ -626,9 +636,10 @@ extern "C"
 #pragma omp parallel for schedule(static)
             for (int64_t i = 0; i < n; ++i)
             {
-                out[3 * i] = tmp[i].x;
-                out[3 * i + 1] = tmp[i].y;
-                out[3 * i + 2] = tmp[i].z;
+                const int64_t o = oldOfNew.empty() ? i : oldOfNew[i];
+                out[3 * o] = tmp[i].x;
+                out[3 * o + 1] = tmp[i].y;
+                out[3 * o + 2] = tmp[i].z;
             }
         }
         catch (const std::exception &e)
@@ -642,7 +653,7 @@ extern "C"
     {
         if (!h || !out)
             return setErr(SMGPU_ERR_ARG, "null argument");
-        return downloadP4(h, h->d.pts, h->topo.P, out);
+        return downloadP4(h, h->d.pts, h->topo.P, out, h->pointOldOfNew);
     }
 
     int smgpu_set_points(smgpu_handle *h, const double *in)
@@ -668,6 +679,12 @@ extern "C"
         if (cudaSetDevice(h->prm.device) != cudaSuccess ||
             cudaMemcpy(out, h->d.frozen, h->topo.P, cudaMemcpyDeviceToHost) != cudaSuccess)
             return setErr(SMGPU_ERR_CUDA, "download failed");
+        if (!h->pointOldOfNew.empty())
+        {
+            std::vector<uint8_t> tmp(out, out + h->topo.P);
+            for (int64_t i = 0; i < h->topo.P; ++i)
+                out[h->pointOldOfNew[i]] = tmp[i];
+        }
         return SMGPU_OK;
     }
 
@@ -702,7 +719,7 @@ extern "C"
         h->launchCellCentres();
         int rc = finishOp(h);
         if (rc == SMGPU_OK && out)
-            rc = downloadP4(h, h->d.cellCtr, h->topo.C, out);
+            rc = downloadP4(h, h->d.cellCtr, h->topo.C, out, h->cellOldOfNew);
         return rc;
     }
 
@@ -715,7 +732,7 @@ extern "C"
         h->launchPredict();
         int rc = finishOp(h);
         if (rc == SMGPU_OK && out)
-            rc = downloadP4(h, h->d.newPts, h->topo.P, out);
+            rc = downloadP4(h, h->d.newPts, h->topo.P, out, h->pointOldOfNew);
         return rc;
     }
 

@@ -3,6 +3,7 @@
 #include "../../include/smmesh.h"
 #include "polymesh.hpp"
 
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -199,6 +200,18 @@ extern "C"
     const int64_t *smmesh_cell_global_id(const smmesh *m)
     {
         return m->m.cellGlobalId.empty() ? nullptr : m->m.cellGlobalId.data();
+    }
+    smmesh *smmesh_renumber(const smmesh *m, int32_t *point_old_of_new, int32_t *cell_old_of_new)
+    {
+        return guarded([&] {
+            std::vector<int32_t> pm, cm;
+            sm::PolyMesh o = sm::renumberMorton(m->m, pm, cm);
+            if (point_old_of_new)
+                std::copy(pm.begin(), pm.end(), point_old_of_new);
+            if (cell_old_of_new)
+                std::copy(cm.begin(), cm.end(), cell_old_of_new);
+            return o;
+        });
     }
     int smmesh_decompose(const smmesh *m, int32_t method, int32_t px, int32_t py, int32_t pz, smmesh **parts_out)
     {
