@@ -61,6 +61,11 @@ extern "C"
     const int64_t *smmesh_point_global_id(const smmesh *m); /* NULL for undecomposed meshes */
     const int64_t *smmesh_cell_global_id(const smmesh *m);
 
+    /* checkMesh-style quality of the mesh (what run_tests.sh:29,34 inspects after smoothing):
+     * out = {max non-orthogonality [deg], average non-orthogonality [deg], max skewness, min angle between
+     * consecutive face edges [deg], min edge length, max edge length, min cell volume}. */
+    int smmesh_quality(const smmesh *m, double out[7]);
+
     /* Morton (space-filling-curve) renumbering of points and cells, the renumberMesh stand-in: returns a new
      * valid polyMesh whose storage order keeps the smoothing kernels' gathers local.  The optional maps
      * receive the old label of every new point / cell.  Labels change, so label-order-dependent results are

@@ -118,6 +118,7 @@ def lib():
         L.smgpu_comm_local_shared.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_exchange_plan.restype = C.c_int64
         L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
+        L.smmesh_quality.argtypes = [C.c_void_p, C.c_void_p]
         L.smmesh_renumber.restype = C.c_void_p
         L.smmesh_renumber.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smmesh_gen_hex_block_part.restype = C.c_void_p
@@ -288,6 +289,15 @@ class Mesh:
     def read_points(self, points_file):
         if lib().smmesh_read_points(self._h, str(points_file).encode()) != 0:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
+
+    def quality(self):
+        """checkMesh-style figures: max/avg non-orthogonality [deg], max skewness, min edge-edge angle [deg], ..."""
+        out = np.zeros(7)
+        if lib().smmesh_quality(self._h, _ptr(out)) != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+        keys = ("max_non_ortho", "avg_non_ortho", "max_skewness", "min_edge_angle", "min_edge_length",
+                "max_edge_length", "min_volume")
+        return dict(zip(keys, out.tolist()))
 
     def renumber(self):
         """Morton renumbering (renumberMesh stand-in) -> (new Mesh, point_old_of_new, cell_old_of_new)."""

@@ -1305,3 +1305,137 @@ PolyMesh renumberMorton(const PolyMesh &m, std::vector<int32_t> &pointOldOfNew, 
     return o;
 }
 } // namespace sm
+
+// ------------------------------------------------------------ mesh quality ----
+namespace sm
+{
+namespace
+{
+struct Q3
+{
+    double x, y, z;
+};
+inline Q3 operator+(Q3 a, Q3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline Q3 operator-(Q3 a, Q3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline Q3 operator*(double s, Q3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double qdot(Q3 a, Q3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline Q3 qcross(Q3 a, Q3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double qmag(Q3 a) { return std::sqrt(qdot(a, a)); }
+} // namespace
+
+// checkMesh-style quality figures ([OF-recalled] primitiveMeshTools::
+// faceOrthogonality / faceSkewness) plus smoothMesh's own minimum edge-edge angle
+// (src/smoothMesh.C:766-786, without the 0.99999 clamp).  Host-side, not on the iteration path.
+MeshQuality computeQuality(const PolyMesh &m)
+{
+    const int64_t P = m.nPoints(), C = m.nCells, F = m.nFaces(), Fi = m.nInternalFaces();
+    auto pt = [&](int32_t i) { return Q3{m.points[3 * (int64_t)i], m.points[3 * (int64_t)i + 1], m.points[3 * (int64_t)i + 2]}; };
+    std::vector<Q3> fc(F), fa(F);
+    for (int64_t f = 0; f < F; ++f)
+    {
+        const int32_t b = m.faceOffsets[f], n = m.faceOffsets[f + 1] - b;
+        if (n == 3)
+        {
+            const Q3 p0 = pt(m.faceVerts[b]), p1 = pt(m.faceVerts[b + 1]), p2 = pt(m.faceVerts[b + 2]);
+            fc[f] = (1.0 / 3.0) * (p0 + p1 + p2);
+            fa[f] = 0.5 * qcross(p1 - p0, p2 - p0);
+            continue;
+        }
+        Q3 est = {0, 0, 0};
+        for (int32_t k = 0; k < n; ++k)
+            est = est + pt(m.faceVerts[b + k]);
+        est = (1.0 / n) * est;
+        Q3 sN = {0, 0, 0}, sAc = {0, 0, 0};
+        double sA = 0;
+        for (int32_t k = 0; k < n; ++k)
+        {
+            const Q3 a = pt(m.faceVerts[b + k]), c = pt(m.faceVerts[b + (k + 1) % n]);
+            const Q3 nn = qcross(c - a, est - a);
+            const double w = qmag(nn);
+            sN = sN + nn;
+            sA += w;
+            sAc = sAc + w * (a + c + est);
+        }
+        fc[f] = sA > 1e-150 ? (1.0 / (3.0 * sA)) * sAc : est;
+        fa[f] = 0.5 * sN;
+    }
+    std::vector<Q3> est(C, Q3{0, 0, 0}), cc(C, Q3{0, 0, 0});
+    std::vector<double> vol(C, 0.0);
+    std::vector<int32_t> nf(C, 0);
+    for (int64_t f = 0; f < F; ++f)
+    {
+        est[m.owner[f]] = est[m.owner[f]] + fc[f];
+        ++nf[m.owner[f]];
+    }
+    for (int64_t f = 0; f < Fi; ++f)
+    {
+        est[m.neighbour[f]] = est[m.neighbour[f]] + fc[f];
+        ++nf[m.neighbour[f]];
+    }
+    for (int64_t c = 0; c < C; ++c)
+        est[c] = (1.0 / nf[c]) * est[c];
+    auto pyr = [&](int32_t c, int64_t f, double sign) {
+        const double v = sign * qdot(fa[f], fc[f] - est[c]);
+        cc[c] = cc[c] + v * (0.75 * fc[f] + 0.25 * est[c]);
+        vol[c] += v;
+    };
+    for (int64_t f = 0; f < F; ++f)
+        pyr(m.owner[f], f, 1.0);
+    for (int64_t f = 0; f < Fi; ++f)
+        pyr(m.neighbour[f], f, -1.0);
+    MeshQuality q;
+    q.minVolume = 1e300;
+    for (int64_t c = 0; c < C; ++c)
+    {
+        cc[c] = std::fabs(vol[c]) > 1e-300 ? (1.0 / vol[c]) * cc[c] : est[c];
+        q.minVolume = std::min(q.minVolume, vol[c] / 3.0);
+    }
+    const double VS = 1e-150;
+    double sumNonOrtho = 0;
+    for (int64_t f = 0; f < Fi; ++f)
+    {
+        const Q3 d = cc[m.neighbour[f]] - cc[m.owner[f]];
+        const double cosT = qdot(d, fa[f]) / (qmag(d) * qmag(fa[f]) + VS);
+        const double ang = std::acos(std::max(-1.0, std::min(1.0, cosT))) * 180.0 / M_PI;
+        q.maxNonOrtho = std::max(q.maxNonOrtho, ang);
+        sumNonOrtho += ang;
+        const Q3 cpf = fc[f] - cc[m.owner[f]];
+        const Q3 sv = cpf - (qdot(fa[f], cpf) / (qdot(fa[f], d) + VS)) * d;
+        const Q3 svHat = (1.0 / (qmag(sv) + VS)) * sv;
+        double fd = 0.2 * qmag(d) + VS;
+        for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+            fd = std::max(fd, std::fabs(qdot(svHat, pt(m.faceVerts[k]) - fc[f])));
+        q.maxSkewness = std::max(q.maxSkewness, qmag(sv) / fd);
+    }
+    q.avgNonOrtho = Fi ? sumNonOrtho / Fi : 0.0;
+    for (int64_t f = Fi; f < F; ++f)
+    {
+        const Q3 cpf = fc[f] - cc[m.owner[f]];
+        const Q3 nHat = (1.0 / (qmag(fa[f]) + VS)) * fa[f];
+        const Q3 d = qdot(nHat, cpf) * nHat;
+        const Q3 sv = cpf - (qdot(fa[f], cpf) / (qdot(fa[f], d) + VS)) * d;
+        const Q3 svHat = (1.0 / (qmag(sv) + VS)) * sv;
+        double fd = 0.4 * qmag(d) + VS;
+        for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+            fd = std::max(fd, std::fabs(qdot(svHat, pt(m.faceVerts[k]) - fc[f])));
+        q.maxSkewness = std::max(q.maxSkewness, qmag(sv) / fd);
+    }
+    q.minEdgeLength = 1e300;
+    q.minEdgeAngle = 180.0;
+    for (int64_t f = 0; f < F; ++f)
+    {
+        const int32_t b = m.faceOffsets[f], n = m.faceOffsets[f + 1] - b;
+        for (int32_t k = 0; k < n; ++k)
+        {
+            const Q3 c = pt(m.faceVerts[b + k]), a = pt(m.faceVerts[b + (k + n - 1) % n]), e = pt(m.faceVerts[b + (k + 1) % n]);
+            const Q3 u = a - c, v = e - c;
+            q.minEdgeLength = std::min(q.minEdgeLength, qmag(v));
+            q.maxEdgeLength = std::max(q.maxEdgeLength, qmag(v));
+            const double cosA = qdot(u, v) / (qmag(u) * qmag(v) + VS);
+            q.minEdgeAngle = std::min(q.minEdgeAngle, std::acos(std::max(-1.0, std::min(1.0, cosA))) * 180.0 / M_PI);
+        }
+    }
+    (void)P;
+    return q;
+}
+} // namespace sm

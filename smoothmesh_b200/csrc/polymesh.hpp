@@ -82,6 +82,17 @@ double counterUniform(uint64_t seed, uint64_t label, uint32_t comp); // in [0,1)
 // old label of every new label.
 PolyMesh renumberMorton(const PolyMesh &m, std::vector<int32_t> &pointOldOfNew, std::vector<int32_t> &cellOldOfNew);
 
+// checkMesh-style quality figures (acceptance criteria of BASELINE.json: max non-orthogonality, skewness,
+// min angle); host-side, evaluated on request only.
+struct MeshQuality
+{
+    double maxNonOrtho = 0, avgNonOrtho = 0; // degrees, internal faces
+    double maxSkewness = 0;                  // internal and boundary faces
+    double minEdgeAngle = 0;                 // degrees, smallest angle between consecutive face edges
+    double minEdgeLength = 0, maxEdgeLength = 0, minVolume = 0;
+};
+MeshQuality computeQuality(const PolyMesh &m);
+
 // ---- decomposition (decomposePar stand-in) ------------------------------------
 // cellPart[c] in [0,nParts).  Produces OpenFOAM-style processor meshes: local
 // points/cells/faces in ascending global order, inter-part faces become

@@ -201,6 +201,26 @@ extern "C"
     {
         return m->m.cellGlobalId.empty() ? nullptr : m->m.cellGlobalId.data();
     }
+    int smmesh_quality(const smmesh *m, double out[7])
+    {
+        try
+        {
+            const sm::MeshQuality q = sm::computeQuality(m->m);
+            out[0] = q.maxNonOrtho;
+            out[1] = q.avgNonOrtho;
+            out[2] = q.maxSkewness;
+            out[3] = q.minEdgeAngle;
+            out[4] = q.minEdgeLength;
+            out[5] = q.maxEdgeLength;
+            out[6] = q.minVolume;
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
     smmesh *smmesh_renumber(const smmesh *m, int32_t *point_old_of_new, int32_t *cell_old_of_new)
     {
         return guarded([&] {

@@ -160,3 +160,20 @@ def test_renumbered_storage_matches_oracle_on_renumbered_mesh(case):
     assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
     assert np.array_equal(g.points()[point_old_of_new], o.get("points"))
     assert np.array_equal(g.frozen()[point_old_of_new], o.get("frozen"))
+
+
+def test_mesh_quality_acceptance_after_smoothing():
+    # BASELINE acceptance: checkMesh quality (max non-orthogonality, skewness, min angle) of the GPU
+    # result within 1e-6 relative of the reference result; and smoothing must improve the mesh
+    mesh = CASES["hex6_j25"]()
+    before = mesh.quality()
+    g, o = _pair(mesh)
+    g.iterate(60)
+    o.iterate(60)
+    a, b = CASES["hex6_j25"](), CASES["hex6_j25"]()
+    a.points[:] = g.points()
+    b.points[:] = o.get("points")
+    qa, qb = a.quality(), b.quality()
+    for k in ("max_non_ortho", "max_skewness", "min_edge_angle"):
+        assert abs(qa[k] - qb[k]) <= 1e-6 * max(abs(qb[k]), 1e-30), k
+    assert qa["max_non_ortho"] < 0.2 * before["max_non_ortho"] and qa["min_edge_angle"] > before["min_edge_angle"]

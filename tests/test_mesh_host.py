@@ -125,3 +125,17 @@ def test_cli_rejects_out_of_scope_features_loudly(tmp_path):
     (case / "system" / "controlDict").write_text("deltaT 0;\n")
     r = subprocess.run([sm.CLI_PATH, "-case", str(case)], capture_output=True, text=True)
     assert r.returncode != 0 and "too small" in r.stderr
+
+
+def test_quality_metrics_known_answers():
+    q = sm.Mesh.hex_block(4, 3, 2, hi=(4.0, 3.0, 2.0)).quality()
+    assert q["max_non_ortho"] < 1e-6 and q["max_skewness"] < 1e-12          # orthogonal uniform block
+    assert abs(q["min_edge_angle"] - 90.0) < 1e-9 and abs(q["min_edge_length"] - 1.0) < 1e-12
+    assert abs(q["min_volume"] - 1.0) < 1e-12
+    # shear the block by 45 degrees in x-y: every y-normal face becomes 45 deg non-orthogonal
+    m = sm.Mesh.hex_block(3, 3, 3)
+    m.points[:, 0] += m.points[:, 1]
+    q = m.quality()
+    assert abs(q["max_non_ortho"] - 45.0) < 1e-9 and abs(q["min_edge_angle"] - 45.0) < 1e-9
+    jq = hex_jittered(6, 6, 6, 0.3).quality()
+    assert jq["max_non_ortho"] > 5 and jq["max_skewness"] > 0.05 and jq["min_volume"] > 0
