@@ -226,6 +226,10 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--renumber", type=int, default=0, help="1 = Morton storage order (smgpu_params.renumber)")
+    ap.add_argument("--workload", default="hex", choices=["hex", "kelvin"],
+                    help="hex: n^3 jittered blockMesh block per GPU (weak scaling, BASELINE configs 3/5); kelvin: "
+                         "2 n^3 Kelvin-cell polyhedral mesh in total, RCB-decomposed over the GPUs (BASELINE config 4, "
+                         "strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -250,7 +254,12 @@ def main():
 
     n = args.n
     t0 = time.perf_counter()
-    if world == 1:
+    if args.workload == "kelvin":
+        # every rank builds the same global mesh and keeps its RCB part (decomposePar stand-in)
+        whole = sm.Mesh.kelvin(n, 1.0).jitter(0.2 * 2 ** 0.5 / 4.0, SEED)
+        mesh = whole.decompose(world, method="rcb")[rank] if world > 1 else whole
+        del whole
+    elif world == 1:
         mesh = sm.Mesh.hex_block(n, n, n).jitter(JITTER / n, SEED)
     else:
         from smoothmesh_b200 import multi
@@ -332,9 +341,11 @@ def main():
     line = {
         "metric": "mesh point-updates/s per smoothing iteration", "value": value, "unit": "point-updates/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"hex {n}^3 jittered blockMesh block per GPU (U(-0.25h,0.25h), seed {SEED}), "
-                               f"{K} iterations, edge/face angle constraints on, relTol 0",
+        "scaling": "weak" if args.workload == "hex" else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": (f"hex {n}^3 jittered blockMesh block per GPU (U(-0.25h,0.25h), seed {SEED}), "
+                                if args.workload == "hex" else
+                                f"Kelvin-cell polyhedral mesh, 2x{n}^3 cells in total, jittered 0.2 x shortest edge, RCB parts, ")
+                               + f"{K} iterations, edge/face angle constraints on, relTol 0",
                    "points_per_gpu": P, "cells_per_gpu": C, "renumber": args.renumber, "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
                    "setup_s": {"mesh_generation": t_gen, "create_upload": t_setup}},
         "clocks": clocks,

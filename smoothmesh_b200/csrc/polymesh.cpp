@@ -353,29 +353,37 @@ PolyMesh genKelvin(int n, double h)
                 while (std::next_permutation(perm, perm + 3));
                 tmpl.push_back(orient(loop));
             }
-    // vertices: integer triples -> ids in lexicographic (z,y,x) order of first use, then sorted for locality
-    std::map<std::array<int, 3>, int32_t> vid;
+    // vertices: integer triples -> ids in lexicographic (z,y,x) order, through a dense lattice index
+    const int64_t G = 4 * (int64_t)n + 6; // coordinates lie in [-2, 4n+3]
+    auto slot = [&](int x, int y, int z) { return ((int64_t)(z + 2) * G + (y + 2)) * G + (x + 2); };
+    std::vector<int32_t> vid((size_t)(G * G * G), -1);
     for (auto &c : centres)
         for (auto &f : tmpl)
             for (auto &v : f)
-                vid.insert({{c[2] + v[2], c[1] + v[1], c[0] + v[0]}, 0});
+                vid[slot(c[0] + v[0], c[1] + v[1], c[2] + v[2])] = 0;
     int32_t nv = 0;
     std::vector<double> pts;
-    pts.reserve(vid.size() * 3);
-    for (auto &kv : vid)
-    {
-        kv.second = nv++;
-        pts.push_back(kv.first[2] * h / 4.0);
-        pts.push_back(kv.first[1] * h / 4.0);
-        pts.push_back(kv.first[0] * h / 4.0);
-    }
+    for (int64_t z = 0; z < G; ++z)
+        for (int64_t y = 0; y < G; ++y)
+            for (int64_t x = 0; x < G; ++x)
+            {
+                int32_t &id = vid[(size_t)((z * G + y) * G + x)];
+                if (id == 0)
+                {
+                    id = nv++;
+                    pts.push_back((x - 2) * h / 4.0);
+                    pts.push_back((y - 2) * h / 4.0);
+                    pts.push_back((z - 2) * h / 4.0);
+                }
+            }
     std::vector<int32_t> cfo{0}, cvo{0}, cv, cp;
+    cv.reserve(centres.size() * 72);
     for (auto &c : centres)
     {
         for (auto &f : tmpl)
         {
             for (auto &v : f)
-                cv.push_back(vid[{c[2] + v[2], c[1] + v[1], c[0] + v[0]}]);
+                cv.push_back(vid[slot(c[0] + v[0], c[1] + v[1], c[2] + v[2])]);
             cvo.push_back((int32_t)cv.size());
             cp.push_back(0);
         }
