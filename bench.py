@@ -10,7 +10,7 @@ Metric (BASELINE.json): mesh point-updates/s per smoothing iteration.
   e2e       = the same job through the host-buffer C ABI: upload points, K iterations, download
               points + per-iteration log, host<->device copies inside the timed region
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--n CELLS_PER_SIDE]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size CELLS_PER_SIDE]
 
 One JSON line on stdout (rank 0).
 """
@@ -219,7 +219,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=200, help="cells per side of the (per-GPU) hex block")
+    ap.add_argument("--size", "--n", dest="n", type=int, default=200,
+                    help="cells per side of the (per-GPU) hex block / of the Kelvin lattice (use --size under torchrun)")
     ap.add_argument("--ref-n", type=int, default=0, help="cells per side of the CPU sample mesh (0 = sized from --ref-budget)")
     ap.add_argument("--ref-budget", type=float, default=100.0, help="seconds of CPU work for --impl reference")
     ap.add_argument("--cpu-n", type=int, default=96, help="cells per side of the cpu_baseline sample mesh")
