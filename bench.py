@@ -339,6 +339,10 @@ def main():
         top_ms = prof[top]["ms"] / max(prof[top]["launches"] // 4, 1)
     achieved = kb[top] / (top_ms * 1e-3) / 1e9
     iter_bytes = algorithmic_bytes(P, C, F, Fi, E, FV, PC, EC)
+    traffic = None  # measured DRAM bytes per launch of the dominant kernel (one ncu --set full capture)
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic_n200.json")
+    if args.workload == "hex" and n == 200 and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["bytes_per_launch"].get(top)
     line = {
         "metric": "mesh point-updates/s per smoothing iteration", "value": value, "unit": "point-updates/s",
         "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms / K, "higher_is_better": True,
@@ -355,7 +359,7 @@ def main():
                 "note": "points uploaded once, K iterations, points + log downloaded once; bytes amortised over K steps"},
         "gpu_launches": int(log.launches),
         "roofline": {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                     "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
                      "algorithmic_bytes_per_launch": kb[top], "avg_launch_ms": top_ms,
                      "whole_iteration": {"algorithmic_bytes": iter_bytes,
                                          "achieved": iter_bytes / (ms / K * 1e-3) / 1e9,
