@@ -363,18 +363,74 @@ Topology buildTopology(const PolyMesh &m)
         const bool generic = nf > 4 || nc > 4;
         r[0] = t.edge[2 * e];
         r[1] = t.edge[2 * e + 1];
-        int32_t meta = nf | (nc << 4) | (generic ? (int32_t)0x80000000u : 0);
-        if (!generic)
+        // Faces in fan order around the edge with cell k between face k and face k+1 (mod nf), so the
+        // kernel needs no per-cell face indices: walk face -> cell -> other face, starting from a face
+        // that has only one cell at this edge if there is one (boundary fan), else from face 0.
+        int32_t fOrd[4], cOrd[4];
+        bool fan = !generic;
+        if (fan)
         {
-            for (int32_t k = 0; k < nf; ++k)
-                r[2 + k] = t.ef[t.efOff[e] + k];
+            const int32_t fb = t.efOff[e], cb = t.ecOff[e];
+            int32_t cellsOfFace[4] = {0, 0, 0, 0};
             for (int32_t k = 0; k < nc; ++k)
             {
-                r[6 + k] = t.ecCell[t.ecOff[e] + k];
-                const int32_t pr = t.ecPair[t.ecOff[e] + k];
-                meta |= ((pr & 3) | (((pr >> 16) & 3) << 2)) << (8 + 4 * k);
+                ++cellsOfFace[t.ecPair[cb + k] & 0xffff];
+                ++cellsOfFace[(t.ecPair[cb + k] >> 16) & 0xffff];
+            }
+            int32_t start = 0;
+            for (int32_t i = 0; i < nf; ++i)
+                if (cellsOfFace[i] == 1)
+                {
+                    start = i;
+                    break;
+                }
+            bool usedCell[4] = {false, false, false, false};
+            int32_t cur = start, nfo = 0, nco = 0;
+            fOrd[nfo++] = cur;
+            for (;;)
+            {
+                int32_t found = -1, other = -1;
+                for (int32_t k = 0; k < nc; ++k)
+                {
+                    if (usedCell[k])
+                        continue;
+                    const int32_t f0 = t.ecPair[cb + k] & 0xffff, f1 = (t.ecPair[cb + k] >> 16) & 0xffff;
+                    if (f0 == cur || f1 == cur)
+                    {
+                        found = k;
+                        other = (f0 == cur) ? f1 : f0;
+                        break;
+                    }
+                }
+                if (found < 0)
+                    break;
+                usedCell[found] = true;
+                cOrd[nco++] = found;
+                if (other == start)
+                    break; // closed fan
+                if (nfo >= nf)
+                {
+                    fan = false;
+                    break;
+                }
+                fOrd[nfo++] = other;
+                cur = other;
+            }
+            // valid fans: open (nf == nc + 1) or closed (nf == nc), everything visited exactly once
+            fan = fan && nfo == nf && nco == nc && (nf == nc || nf == nc + 1);
+            for (int32_t i = 0; fan && i < nf; ++i)
+                for (int32_t j = i + 1; j < nf; ++j)
+                    if (fOrd[i] == fOrd[j])
+                        fan = false;
+            if (fan)
+            {
+                for (int32_t k = 0; k < nf; ++k)
+                    r[2 + k] = t.ef[fb + fOrd[k]];
+                for (int32_t k = 0; k < nc; ++k)
+                    r[6 + k] = t.ecCell[cb + cOrd[k]];
             }
         }
+        const int32_t meta = nf | (nc << 4) | (fan ? 0 : (int32_t)0x80000000u);
         r[10] = meta;
     }
     return t;

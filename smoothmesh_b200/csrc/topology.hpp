@@ -43,7 +43,8 @@ struct Topology
     // stay authoritative and serve the generic path (flag bit 31 of the meta word).
     //   pointRec  16 words/point: pc[0..7], pp[8..13], [14] = nCells | nNbrs<<8 | generic<<31,
     //             [15] = mask over the 15 unordered pairs of pp positions that are face corners of the point
-    //   edgeRec   12 words/edge : e0,e1, f[4], c[4], [10] = nf | nc<<4 | per-cell (f0:2,f1:2)<<(8+4k) | generic<<31
+    //   edgeRec   12 words/edge : e0,e1, f[4], c[4], [10] = nf | nc<<4 | generic<<31; faces in fan order around
+    //             the edge, cell k lies between face k and face (k+1) mod nf
     std::vector<int32_t> pointRec, edgeRec;
     std::vector<uint8_t> isInternal; // src/smoothMesh.C:40-91
     std::vector<int32_t> procPoints; // points on processor patches (ascending)
