@@ -465,6 +465,14 @@ extern "C"
             d.faceVerts = h->upload(t.faceVerts);
             d.cfOff = h->upload(t.cfOff);
             d.cf = h->upload(t.cf);
+            d.uniformFaceSize = t.maxFaceSize;
+            for (int64_t f = 0; f < t.F && d.uniformFaceSize; ++f)
+                if (t.faceOff[f + 1] - t.faceOff[f] != d.uniformFaceSize)
+                    d.uniformFaceSize = 0;
+            d.uniformCellFaces = t.C ? t.cfOff[1] - t.cfOff[0] : 0;
+            for (int64_t c = 0; c < t.C && d.uniformCellFaces; ++c)
+                if (t.cfOff[c + 1] - t.cfOff[c] != d.uniformCellFaces)
+                    d.uniformCellFaces = 0;
             d.pointRec = (const int4 *)h->upload(t.pointRec);
             d.edgeRec = (const int4 *)h->upload(t.edgeRec);
             d.curMin = h->dalloc<unsigned long long>(t.P);
