@@ -146,8 +146,14 @@ struct smgpu_handle
                         d.faceCosLo < d.faceCosHi)
                            ? 1
                            : 0;
+        d.cosSmallF = (float)std::cos(d.smallAngle);
+        d.cosLargeF = (float)std::cos(d.largeAngle);
+        // the single-precision level is used when its error budget at the mesh's shortest edge is small
+        // (64 epsAbs / (edge/4) + 5e-5 < 0.05); otherwise the FP64 filter (and its face-mean table) is
+        d.faceFilter32 = d.faceFilter && !getenv("SMGPU_NO_F32") &&
+                         (64.0 * d.epsAbs / (0.25 * meshMinEdge) + 5e-5 < 0.05);
         if (noFilters)
-            d.edgeFilter = d.faceFilter = 0;
+            d.edgeFilter = d.faceFilter = d.faceFilter32 = 0;
     }
     bool noFilters = false; // SMGPU_NO_FILTERS=1: always take the literal path (testing aid)
     void ensureStats(int n)
@@ -169,6 +175,27 @@ struct smgpu_handle
             h[i] = {pts[3 * o], pts[3 * o + 1], pts[3 * o + 2], topo.isInternal[i] ? 1.0 : 0.0};
         }
         CK(cudaMemcpy(d.pts, h.data(), h.size() * sizeof(P4), cudaMemcpyHostToDevice));
+        // single-precision mirror for the first-level face-angle filter: origin = bounding-box centre,
+        // epsAbs from the half diagonal (points stay inside the hull of the initial mesh: every
+        // predictor step is a convex combination of mesh positions)
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (int64_t i = 0; i < topo.P; ++i)
+        {
+            const double c[3] = {h[i].x, h[i].y, h[i].z};
+            for (int k = 0; k < 3; ++k)
+            {
+                lo[k] = std::min(lo[k], c[k]);
+                hi[k] = std::max(hi[k], c[k]);
+            }
+        }
+        d.ox = 0.5 * (lo[0] + hi[0]);
+        d.oy = 0.5 * (lo[1] + hi[1]);
+        d.oz = 0.5 * (lo[2] + hi[2]);
+        const double R = 0.5 * std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) +
+                                         (hi[2] - lo[2]) * (hi[2] - lo[2]));
+        d.epsAbs = (float)(8.0 * 5.9604644775390625e-08 * (1.01 * R + 4.0 * topo.maxEdgeLength)); // 8 x 2^-24 x R
+        k_mirror_points<<<grid(d.P, 256), 256, 0, stream>>>(d);
+        CK(cudaStreamSynchronize(stream));
     }
 
     static int grid(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
@@ -443,6 +470,9 @@ extern "C"
             d.F = (int)t.F;
             d.faceGeo = h->dalloc<P4>(2 * t.F);
             d.faceMean = h->dalloc<P4>(t.F);
+            d.ptsF = h->dalloc<float4>(t.P);
+            d.cellCtrF = h->dalloc<float4>(t.C);
+            d.faceMeanF = h->dalloc<float4>(t.F);
 
             d.pts = h->dalloc<P4>(t.P);
             d.newPts = h->dalloc<P4>(t.P);
@@ -500,8 +530,8 @@ extern "C"
             CK(cudaMemset(d.newPts, 0, t.P * sizeof(P4)));
             h->ensureStats(1024);
             h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
+            h->setPoints(md->points); // also fixes the single-precision mirror's origin and error bound
             h->resolveParams();
-            h->setPoints(md->points);
             CK(cudaDeviceSynchronize());
             (void)m;
         }
@@ -672,6 +702,7 @@ extern "C"
         {
             CK(cudaSetDevice(h->prm.device));
             h->setPoints(in);
+            h->applyParams();
         }
         catch (const std::exception &e)
         {
