@@ -290,6 +290,7 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.4)  # let nvidia-smi start sampling before the timed region opens
     barrier()
     log = g.iterate(args.steps)
     barrier()

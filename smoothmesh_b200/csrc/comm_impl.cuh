@@ -169,7 +169,9 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
     double blend = 0.0;
     if (!anyCommon)
         blend = blendFraction(cp1[me], cp2[me], mag(cp1[me]), mag(cp2[me]), mag(cp3[me]), internal);
-    st4(d.newPts + p, blendAndClamp(d, x, cen, cp1[me], cp2[me], blend), 0.0);
+    const D3 np = blendAndClamp(d, x, cen, cp1[me], cp2[me], blend);
+    st4(d.newPts + p, np, 0.0);
+    d.newPtsF[p] = make_float4((float)(np.x - d.ox), (float)(np.y - d.oy), (float)(np.z - d.oz), 0.f);
 }
 
 __global__ void __launch_bounds__(128) k_frozen_pack(Dev d, CommDev c)

@@ -152,8 +152,10 @@ struct smgpu_handle
         // (64 epsAbs / (edge/4) + 5e-5 < 0.05); otherwise the FP64 filter (and its face-mean table) is
         d.faceFilter32 = d.faceFilter && !getenv("SMGPU_NO_F32") &&
                          (64.0 * d.epsAbs / (0.25 * meshMinEdge) + 5e-5 < 0.05);
+        d.edgeFilter32 = d.edgeFilter && !getenv("SMGPU_NO_F32") &&
+                         (16.0 * d.epsAbs / (0.5 * meshMinEdge) + 2e-5 < 0.02);
         if (noFilters)
-            d.edgeFilter = d.faceFilter = d.faceFilter32 = 0;
+            d.edgeFilter = d.faceFilter = d.faceFilter32 = d.edgeFilter32 = 0;
     }
     bool noFilters = false; // SMGPU_NO_FILTERS=1: always take the literal path (testing aid)
     void ensureStats(int n)
@@ -471,6 +473,7 @@ extern "C"
             d.faceGeo = h->dalloc<P4>(2 * t.F);
             d.faceMean = h->dalloc<P4>(t.F);
             d.ptsF = h->dalloc<float4>(t.P);
+            d.newPtsF = h->dalloc<float4>(t.P);
             d.cellCtrF = h->dalloc<float4>(t.C);
             d.faceMeanF = h->dalloc<float4>(t.F);
 
