@@ -167,20 +167,35 @@ struct smgpu_handle
         d.statFrozen = dalloc<long long>(statCap);
         d.statCap = statCap;
     }
+    // page-locked staging buffer for point uploads / downloads (host <-> device at full PCIe rate)
+    P4 *staging = nullptr;
+    size_t stagingCap = 0;
+    P4 *stage(size_t n)
+    {
+        if (n > stagingCap)
+        {
+            if (staging)
+                cudaFreeHost(staging);
+            CK(cudaMallocHost((void **)&staging, n * sizeof(P4)));
+            stagingCap = n;
+        }
+        return staging;
+    }
     void setPoints(const double *pts)
     {
-        std::vector<P4> h(topo.P);
+        P4 *h = stage(std::max<size_t>(topo.P, topo.C));
 #pragma omp parallel for schedule(static)
         for (int64_t i = 0; i < topo.P; ++i)
         {
             const int64_t o = pointOldOfNew.empty() ? i : pointOldOfNew[i];
             h[i] = {pts[3 * o], pts[3 * o + 1], pts[3 * o + 2], topo.isInternal[i] ? 1.0 : 0.0};
         }
-        CK(cudaMemcpy(d.pts, h.data(), h.size() * sizeof(P4), cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(d.pts, h, topo.P * sizeof(P4), cudaMemcpyHostToDevice, stream));
         // single-precision mirror for the first-level face-angle filter: origin = bounding-box centre,
         // epsAbs from the half diagonal (points stay inside the hull of the initial mesh: every
         // predictor step is a convex combination of mesh positions)
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+#pragma omp parallel for reduction(min : lo[:3]) reduction(max : hi[:3]) schedule(static)
         for (int64_t i = 0; i < topo.P; ++i)
         {
             const double c[3] = {h[i].x, h[i].y, h[i].z};
@@ -672,8 +687,9 @@ extern "C"
         try
         {
             CK(cudaSetDevice(h->prm.device));
-            std::vector<P4> tmp(n);
-            CK(cudaMemcpy(tmp.data(), src, n * sizeof(P4), cudaMemcpyDeviceToHost));
+            P4 *tmp = h->stage(std::max<size_t>(h->topo.P, h->topo.C));
+            CK(cudaMemcpyAsync(tmp, src, n * sizeof(P4), cudaMemcpyDeviceToHost, h->stream));
+            CK(cudaStreamSynchronize(h->stream));
 #pragma omp parallel for schedule(static)
             for (int64_t i = 0; i < n; ++i)
             {
