@@ -56,6 +56,9 @@ extern "C"
          * point (decomposePar's pointProcAddressing); defines which points are
          * shared between ranks for the syncTools::syncPointList replacements. */
         const int64_t *point_global_id;
+        /* [n_patches] or NULL: 1 = patch selected by -layerPatches for the prismatic boundary
+         * layer treatment (getPatchIdsForOption, src/smoothMesh.C:1823) */
+        const int32_t *patch_layer;
     } smgpu_mesh_desc;
 
     /* The options of src/smoothMesh.C:1861-1918 that reach the hot path.
@@ -79,6 +82,13 @@ extern "C"
                                           gathers become local, results are those of the renumbered mesh
                                           (label-order-dependent tie-breaks / summation order follow the new
                                           labels), points and masks are returned in the caller's numbering */
+        /* Boundary layer treatment (src/orthogonalBoundaryBlending.C; options :1892-1905), active when
+         * some patch has patch_layer = 1 and layer_max_blending_fraction > 1e-15 (:2025); serial runs only. */
+        double layer_max_blending_fraction; /* 0.3 */
+        double layer_edge_length;           /* negative = min_edge_length (:1895-1896) */
+        double layer_expansion_ratio;       /* 1.3 */
+        int32_t min_layers;                 /* 1 */
+        int32_t max_layers;                 /* 4 */
     } smgpu_params;
 
     typedef struct smgpu_handle smgpu_handle;
@@ -138,6 +148,10 @@ extern "C"
     int smgpu_op_face_angle_constraint(smgpu_handle *h, uint8_t *frozen_out /* or NULL */);
     /* restore + count + calculateResidual + movePoints (:2384-2399) */
     int smgpu_op_commit(smgpu_handle *h, int64_t *n_frozen, double *residual);
+    /* calculateBoundaryPointNormals (src/orthogonalBoundaryBlending.C:141-233), the call at :2266 */
+    int smgpu_op_layer_normals(smgpu_handle *h, double *normals_out /* [3*n_points] or NULL */);
+    /* updateNeighCoords + blendWithOrthogonalPoints + constrainMaxStepLength (:2283-2305) */
+    int smgpu_op_layer_blend(smgpu_handle *h, double *new_points_out /* [3*n_points] or NULL */);
     /* calcMinMaxFaceAngleForEdge for the current mesh (:1135-1231): per-edge min/max */
     int smgpu_op_edge_face_angles(smgpu_handle *h, double *min_out /* [n_edges] */, double *max_out /* [n_edges] */);
     /* edge list (lo,hi) in the library's (OpenFOAM upper-triangular) numbering */

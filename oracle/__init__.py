@@ -31,6 +31,11 @@ class OParams(C.Structure):
         ("edgeAngleConstraint", C.c_int32),
         ("faceAngleConstraint", C.c_int32),
         ("geometryVariant", C.c_int32),
+        ("layerMaxBlendingFraction", C.c_double),
+        ("layerEdgeLength", C.c_double),
+        ("layerExpansionRatio", C.c_double),
+        ("minLayers", C.c_int32),
+        ("maxLayers", C.c_int32),
     ]
 
 
@@ -41,6 +46,7 @@ class _OMesh(C.Structure):
         ("nPatches", C.c_int32),
         ("pStart", C.c_void_p), ("pSize", C.c_void_p), ("pKind", C.c_void_p),
         ("pointGlobalId", C.c_void_p),
+        ("pLayer", C.c_void_p),
     ]
 
 
@@ -63,6 +69,7 @@ def _lib(libm=False):
         L.orc_iterate.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_mesh_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_params.restype = C.c_int
         L.orc_sizes.restype = C.c_int64
         L.orc_sizes.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int64]
@@ -97,7 +104,10 @@ class Oracle:
 
     def __init__(self, meshes, min_edge_length=-1.0, max_step_length=-1.0, rel_step_frac=0.5, min_angle_deg=35.0,
                  max_angle_deg=160.0, rel_tol=0.02, total_min_freeze=0, edge_angle_constraint=1,
-                 face_angle_constraint=1, geometry_variant=0, libm=False, threads=1):
+                 face_angle_constraint=1, geometry_variant=0, libm=False, threads=1, layer_patches=None,
+                 layer_max_blending_fraction=0.3, layer_edge_length=-1.0, layer_expansion_ratio=1.3, min_layers=1,
+                 max_layers=4):
+        """layer_patches: per-patch 0/1 flags (-layerPatches), serial runs only."""
         self.L = _lib(libm)
         if isinstance(meshes, dict):
             meshes = [meshes]
@@ -115,6 +125,7 @@ class Oracle:
                 pSize=np.ascontiguousarray(m["patch_size"], dtype=np.int32),
                 pKind=np.ascontiguousarray(m["patch_kind"], dtype=np.int32),
                 gid=None if m.get("point_global_id") is None else np.ascontiguousarray(m["point_global_id"], dtype=np.int64),
+                lay=None if layer_patches is None else np.ascontiguousarray(layer_patches, dtype=np.int32),
             )
             self._keep.append(a)
             o = arr[r]
@@ -123,9 +134,11 @@ class Oracle:
             o.nPatches = a["pStart"].size
             o.pStart, o.pSize, o.pKind = _p(a["pStart"]), _p(a["pSize"]), _p(a["pKind"])
             o.pointGlobalId = _p(a["gid"])
+            o.pLayer = _p(a["lay"])
         self.prm = OParams(min_edge_length, max_step_length, rel_step_frac, min_angle_deg, max_angle_deg, rel_tol,
                            int(total_min_freeze), int(edge_angle_constraint), int(face_angle_constraint),
-                           int(geometry_variant))
+                           int(geometry_variant), layer_max_blending_fraction, layer_edge_length,
+                           layer_expansion_ratio, int(min_layers), int(max_layers))
         self.h = self.L.orc_create(self.n_ranks, C.byref(arr), C.byref(self.prm))
         if not self.h:
             raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
@@ -137,7 +150,8 @@ class Oracle:
             self.prm.minEdgeLength = 0.5 * self.min_edge
         if self.prm.maxStepLength < 0:
             self.prm.maxStepLength = 0.3 * self.prm.minEdgeLength
-        self.L.orc_set_params(self.h, C.byref(self.prm))
+        if self.L.orc_set_params(self.h, C.byref(self.prm)) != 0:
+            raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
         self.L.orc_set_threads(self.h, int(threads))
 
     def __del__(self):
@@ -168,6 +182,8 @@ class Oracle:
         "snapFrozenEdgeLen": ("points", np.uint8, 1), "snapFrozenEdgeAngle": ("points", np.uint8, 1),
         "snapFrozenFaceAngle": ("points", np.uint8, 1), "snapCurMin": ("points", np.float64, 1),
         "snapCurMax": ("points", np.float64, 1), "edges": ("edges", np.int32, 2),
+        "snapNormals": ("points", np.float64, 3), "snapLayerBlend": ("points", np.float64, 3),
+        "hopsToLayer": ("points", np.int32, 1), "pointToOuter": ("points", np.int32, 1),
     }
 
     def get(self, name, rank=0):

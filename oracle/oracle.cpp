@@ -79,6 +79,9 @@ struct Params
 {
     double minEdgeLength, maxStepLength, relStepFrac, minAngle, maxAngle, relTol;
     int32_t totalMinFreeze, edgeAngleConstraint, faceAngleConstraint, geometryVariant;
+    // boundary layer treatment (src/smoothMesh.C:1892-1905); layerEdgeLength < 0 -> minEdgeLength
+    double layerMaxBlendingFraction, layerEdgeLength, layerExpansionRatio;
+    int32_t minLayers, maxLayers;
 };
 
 struct MeshIn
@@ -89,6 +92,7 @@ struct MeshIn
     int32_t nPatches;
     const int32_t *pStart, *pSize, *pKind; // kind: 0 boundary, 1 processor, 2 empty
     const int64_t *pointGlobalId;          // may be null (serial)
+    const int32_t *pLayer;                 // may be null: 1 = patch selected by -layerPatches
 };
 
 thread_local std::string g_err;
@@ -99,8 +103,15 @@ struct Rank
     int P = 0, C = 0, F = 0, Fi = 0;
     std::vector<V3> pts;
     std::vector<int> fOff, fV, own, nei;
-    std::vector<int> pStart, pSize, pKind;
+    std::vector<int> pStart, pSize, pKind, pLayer;
     std::vector<int64_t> gid;
+    // boundary layer treatment state (src/orthogonalBoundaryBlending.C)
+    bool doLayerTreatment = false;
+    std::vector<uint8_t> isConnectedToInternal, isLayerSurface, isOuterNeighInProc, isSharpEdge;
+    std::vector<int> hopsToLayer, pointToOuter;
+    std::vector<V3> pointNormals, outerNeighCoords;
+    std::vector<double> layerLength, layerBlend; // per hop count
+    std::vector<V3> snapNormals, snapLayerBlend;
     Params prm;
 
     // derived connectivity [OF-recalled row orders, SURVEY A.2]
@@ -146,6 +157,12 @@ struct Rank
     void restrictEdgeShortening();
     void restrictMinEdgeAngleDecrease();
     bool restrictFaceAngleDeterioration();
+    void classifyBoundaryPoints();
+    void calculatePointHopsToBoundary(int maxIter);
+    void calculateBoundaryPointNormals();
+    void propagateOuterNeighInfo(int maxIter);
+    bool setupLayers();
+    bool blendWithOrthogonalPoints();
     bool calcMinMaxFaceAngleForEdge(int edgeI, double &mn, double &mx, int pI1, V3 c1, int pI2, V3 c2);
     bool calcMinMaxFaceAngleForPoint(int pI1, V3 c1, int pI2, V3 c2, double &mn, double &mx);
     void restoreAndResidual();
@@ -170,6 +187,9 @@ bool Rank::init(const MeshIn &m, const Params &p)
     pStart.assign(m.pStart, m.pStart + m.nPatches);
     pSize.assign(m.pSize, m.pSize + m.nPatches);
     pKind.assign(m.pKind, m.pKind + m.nPatches);
+    pLayer.assign(m.nPatches, 0);
+    if (m.pLayer)
+        pLayer.assign(m.pLayer, m.pLayer + m.nPatches);
     if (m.pointGlobalId)
         gid.assign(m.pointGlobalId, m.pointGlobalId + P);
     // src/smoothMesh.C:61-66: empty patches are fatal
@@ -185,6 +205,215 @@ bool Rank::init(const MeshIn &m, const Params &p)
     findInternalMeshPoints();
     getMeshStats();
     frozen.assign(P, 0);
+    return true;
+}
+
+// ------------------------------------------------- boundary layer treatment ----
+// classifyBoundaryPoints, src/boundaryPointSmoothing.C:301-423 (the parts that do not need edge
+// meshes): every boundary point is classified once, by the first patch (in patch order) that
+// contains it.
+void Rank::classifyBoundaryPoints()
+{
+    isConnectedToInternal.assign(P, 0);
+    isLayerSurface.assign(P, 0);
+    std::vector<uint8_t> visited(P, 0);
+    for (size_t patchI = 0; patchI < pKind.size(); ++patchI)
+        for (int f = pStart[patchI]; f < pStart[patchI] + pSize[patchI]; ++f)
+            for (int k = fOff[f]; k < fOff[f + 1]; ++k)
+            {
+                const int pointI = fV[k];
+                if (visited[pointI])
+                    continue;
+                visited[pointI] = 1;
+                if (isInternal[pointI])
+                    continue;
+                for (int i : pointPoints[pointI])
+                    if (isInternal[i])
+                        isConnectedToInternal[pointI] = 1;
+                if (pLayer[patchI])
+                    isLayerSurface[pointI] = 1;
+            }
+}
+
+// calculatePointHopsToBoundary, src/orthogonalBoundaryBlending.C:52-134 (serial)
+void Rank::calculatePointHopsToBoundary(int maxIter)
+{
+    hopsToLayer.assign(P, UNDEF_LABEL);
+    for (size_t patchI = 0; patchI < pKind.size(); ++patchI)
+    {
+        if (!pLayer[patchI])
+            continue;
+        for (int f = pStart[patchI]; f < pStart[patchI] + pSize[patchI]; ++f)
+            for (int k = fOff[f]; k < fOff[f + 1]; ++k)
+                if (isConnectedToInternal[fV[k]])
+                    hopsToLayer[fV[k]] = 0;
+    }
+    std::vector<int> newHopCounts(P, -1);
+    for (int iter = 0; iter < maxIter; ++iter)
+    {
+        for (int pointI = 0; pointI < P; ++pointI)
+        {
+            if (hopsToLayer[pointI] >= 0 || !isInternal[pointI])
+                continue;
+            int maxHops = -1;
+            for (int neighI : pointPoints[pointI])
+                if (hopsToLayer[neighI] > maxHops)
+                    maxHops = hopsToLayer[neighI];
+            if (maxHops >= 0)
+                newHopCounts[pointI] = maxHops + 1;
+        }
+        for (int pointI = 0; pointI < P; ++pointI)
+            if (newHopCounts[pointI] > hopsToLayer[pointI])
+                hopsToLayer[pointI] = newHopCounts[pointI];
+    }
+}
+
+// calculateBoundaryPointNormals, src/orthogonalBoundaryBlending.C:141-233.  Note that it
+// accumulates onto the normals of the previous call (no zeroing at :178) and re-normalises
+// every non-zero normal, internal points included (:224-230).
+void Rank::calculateBoundaryPointNormals()
+{
+    calcGeometry(); // patch.Sf() / patch.magSf() of the current mesh, :171-172
+    std::vector<int> nFaces(P, 0);
+    for (size_t patchI = 0; patchI < pKind.size(); ++patchI)
+    {
+        if (pKind[patchI] != 0)
+            continue;
+        for (int f = pStart[patchI]; f < pStart[patchI] + pSize[patchI]; ++f)
+        {
+            const V3 Sf = faceArea[f] / mag(faceArea[f]);
+            for (int k = fOff[f]; k < fOff[f + 1]; ++k)
+            {
+                pointNormals[fV[k]] = pointNormals[fV[k]] - Sf;
+                ++nFaces[fV[k]];
+            }
+        }
+    }
+    for (int pointI = 0; pointI < P; ++pointI)
+    {
+        if (nFaces[pointI] < 1)
+            continue;
+        if (mag(pointNormals[pointI]) < 0.1)
+        {
+            pointNormals[pointI] = ZERO_VECTOR;
+            isSharpEdge[pointI] = 1;
+        }
+        else
+            isSharpEdge[pointI] = 0;
+    }
+    for (int pointI = 0; pointI < P; ++pointI)
+        if (!veq(pointNormals[pointI], ZERO_VECTOR))
+            pointNormals[pointI] = pointNormals[pointI] / mag(pointNormals[pointI]);
+}
+
+// propagateOuterNeighInfo, src/orthogonalBoundaryBlending.C:244-391 (serial)
+void Rank::propagateOuterNeighInfo(int maxIter)
+{
+    isOuterNeighInProc.assign(P, 0);
+    pointToOuter.assign(P, UNDEF_LABEL);
+    std::vector<int> boundaryPointLabels(P, UNDEF_LABEL);
+    for (int iter = 1; iter < maxIter + 1; ++iter)
+        for (int pointI = 0; pointI < P; ++pointI)
+        {
+            const int nHops = hopsToLayer[pointI];
+            if (nHops != iter)
+                continue;
+            int nNeighHops = 0, neighPointI = UNDEF_LABEL;
+            for (int neighI : pointPoints[pointI])
+                if (hopsToLayer[neighI] == nHops - 1)
+                {
+                    ++nNeighHops;
+                    neighPointI = neighI;
+                }
+            if (nNeighHops != 1)
+                continue;
+            if (!isInternal[neighPointI] && !isLayerSurface[neighPointI])
+                continue;
+            const auto it = std::find(boundaryPointLabels.begin(), boundaryPointLabels.end(), neighPointI);
+            if (it != boundaryPointLabels.end())
+            {
+                pointNormals[pointI] = UNDEF_VECTOR;
+                pointNormals[it - boundaryPointLabels.begin()] = UNDEF_VECTOR;
+                continue;
+            }
+            isOuterNeighInProc[pointI] = 1;
+            pointToOuter[pointI] = neighPointI;
+            pointNormals[pointI] = pointNormals[neighPointI];
+            boundaryPointLabels[pointI] = neighPointI;
+        }
+    for (int pointI = 0; pointI < P; ++pointI)
+        if (veq(pointNormals[pointI], UNDEF_VECTOR))
+        {
+            pointNormals[pointI] = ZERO_VECTOR;
+            isOuterNeighInProc[pointI] = 0;
+            pointToOuter[pointI] = UNDEF_LABEL;
+        }
+}
+
+// src/smoothMesh.C:2024-2033, 2190-2221 (layer part; boundary point smoothing is out of scope)
+bool Rank::setupLayers()
+{
+    bool anyLayerPatch = false;
+    for (int f : pLayer)
+        anyLayerPatch = anyLayerPatch || f;
+    doLayerTreatment = anyLayerPatch && prm.layerMaxBlendingFraction > SM_SMALL;
+    if (!doLayerTreatment)
+        return true;
+    if (!gid.empty())
+    {
+        err = "boundary layer treatment is only restated for serial runs";
+        return false;
+    }
+    pointNormals.assign(P, ZERO_VECTOR);
+    isSharpEdge.assign(P, 0);
+    classifyBoundaryPoints();
+    calculatePointHopsToBoundary(prm.maxLayers + 1);
+    calculateBoundaryPointNormals();
+    propagateOuterNeighInfo(prm.maxLayers + 1);
+    // per-hop constants of blendWithOrthogonalPoints (:547-555); maxLayers there is maxLayers + 1 (:2300)
+    const double maxLayers = prm.maxLayers + 1, minLayers = prm.minLayers;
+    const double layerEdgeLength = prm.layerEdgeLength < 0 ? prm.minEdgeLength : prm.layerEdgeLength;
+    int maxHopSeen = 0;
+    for (int h : hopsToLayer)
+        maxHopSeen = std::max(maxHopSeen, h);
+    layerLength.assign(maxHopSeen + 2, 0.0);
+    layerBlend.assign(maxHopSeen + 2, 0.0);
+    for (int nHops = 1; nHops <= maxHopSeen + 1; ++nHops)
+    {
+        const int maxHops = (int)fmin_(double(nHops - 1), maxLayers);
+        layerLength[nHops] = layerEdgeLength * std::pow(prm.layerExpansionRatio, (double)maxHops);
+        const double slope = -prm.layerMaxBlendingFraction / (maxLayers - minLayers);
+        const double y0 = -slope * maxLayers;
+        const double y = y0 + slope * nHops;
+        layerBlend[nHops] = fmax_(0.0, fmin_(y, prm.layerMaxBlendingFraction));
+    }
+    return true;
+}
+
+// updateNeighCoords (:464-501) + blendWithOrthogonalPoints (:507-567)
+bool Rank::blendWithOrthogonalPoints()
+{
+    outerNeighCoords.assign(P, UNDEF_VECTOR);
+    for (int pointI = 0; pointI < P; ++pointI)
+        if (isOuterNeighInProc[pointI])
+            outerNeighCoords[pointI] = pts[pointToOuter[pointI]];
+    for (int pointI = 0; pointI < P; ++pointI)
+    {
+        if (veq(pointNormals[pointI], ZERO_VECTOR) || !isInternal[pointI])
+            continue;
+        const int nHops = hopsToLayer[pointI];
+        if (nHops < 1)
+            continue;
+        if (veq(outerNeighCoords[pointI], UNDEF_VECTOR))
+        {
+            err = "Sanity broken, outerNeighCoord is zero for pointI " + std::to_string(pointI);
+            return false;
+        }
+        const double length = layerLength[nHops], blendFrac = layerBlend[nHops];
+        const V3 orthoPoint = outerNeighCoords[pointI] + length * pointNormals[pointI];
+        newPts[pointI] = blendFrac * orthoPoint + (1.0 - blendFrac) * newPts[pointI];
+    }
+    snapLayerBlend = newPts;
     return true;
 }
 
@@ -1046,6 +1275,11 @@ struct Group
     {
         forRanks([](Rank &R) {
             R.frozen.assign(R.P, 0); // :2262-2263
+            if (R.doLayerTreatment)
+            { // :2266 (the call is unconditional in the reference; its result is only used here)
+                R.calculateBoundaryPointNormals();
+                R.snapNormals = R.pointNormals;
+            }
             R.centroidalPartial();   // :2269
             R.snapCellCtr = R.cellCtr;
             return true;
@@ -1064,6 +1298,12 @@ struct Group
         if (!forRanks([](Rank &R) {
                 R.aspectRatioBlend();
                 R.constrainMaxStepLength(); // :2280
+                if (R.doLayerTreatment)
+                { // :2283-2305
+                    if (!R.blendWithOrthogonalPoints())
+                        return false;
+                    R.constrainMaxStepLength();
+                }
                 R.restrictEdgeShortening(); // :2359
                 if (R.prm.edgeAngleConstraint)
                     R.restrictMinEdgeAngleDecrease(); // :2364
@@ -1115,11 +1355,14 @@ extern "C"
         int32_t nPatches;
         const int32_t *pStart, *pSize, *pKind;
         const int64_t *pointGlobalId;
+        const int32_t *pLayer;
     };
     struct orc_params
     {
         double minEdgeLength, maxStepLength, relStepFrac, minAngle, maxAngle, relTol;
         int32_t totalMinFreeze, edgeAngleConstraint, faceAngleConstraint, geometryVariant;
+        double layerMaxBlendingFraction, layerEdgeLength, layerExpansionRatio;
+        int32_t minLayers, maxLayers;
     };
 
     const char *orc_last_error() { return g_last_error.c_str(); }
@@ -1168,11 +1411,20 @@ extern "C"
         *minEdge = mn;
         *maxEdge = mx;
     }
-    void orc_set_params(void *h, const orc_params *p)
+    // Sets the resolved options and runs the one-time layer set-up (:2215-2221); 0 on success.
+    int orc_set_params(void *h, const orc_params *p)
     {
         Group *g = (Group *)h;
         for (auto &R : g->ranks)
+        {
             memcpy(&R.prm, p, sizeof(Params));
+            if (!R.setupLayers())
+            {
+                g_last_error = R.err;
+                return -1;
+            }
+        }
+        return 0;
     }
 
     // The iteration loop with the stop rule of src/smoothMesh.C:2257, 2401-2411.
@@ -1262,6 +1514,14 @@ extern "C"
             return copyOut(R.snapCurMin, out, capBytes);
         if (n == "snapCurMax")
             return copyOut(R.snapCurMax, out, capBytes);
+        if (n == "snapNormals")
+            return copyOut(R.snapNormals, out, capBytes);
+        if (n == "snapLayerBlend")
+            return copyOut(R.snapLayerBlend, out, capBytes);
+        if (n == "hopsToLayer")
+            return copyOut(R.hopsToLayer, out, capBytes);
+        if (n == "pointToOuter")
+            return copyOut(R.pointToOuter, out, capBytes);
         if (n == "edges")
             return copyOut(R.edges, out, capBytes);
         return -1;

@@ -43,6 +43,11 @@ class Params(C.Structure):
         ("geometry_variant", C.c_int32),
         ("device", C.c_int32),
         ("renumber", C.c_int32),
+        ("layer_max_blending_fraction", C.c_double),
+        ("layer_edge_length", C.c_double),
+        ("layer_expansion_ratio", C.c_double),
+        ("min_layers", C.c_int32),
+        ("max_layers", C.c_int32),
     ]
 
 
@@ -62,6 +67,7 @@ class _MeshDesc(C.Structure):
         ("patch_size", C.c_void_p),
         ("patch_kind", C.c_void_p),
         ("point_global_id", C.c_void_p),
+        ("patch_layer", C.c_void_p),
     ]
 
 
@@ -103,7 +109,7 @@ def lib():
         L.smgpu_create.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         for f in ("smgpu_destroy", "smgpu_get_params", "smgpu_set_params", "smgpu_get_points", "smgpu_set_points",
                   "smgpu_get_frozen", "smgpu_op_cell_centres", "smgpu_op_predict", "smgpu_op_edge_constraints",
-                  "smgpu_op_face_angle_constraint", "smgpu_get_edges"):
+                  "smgpu_op_face_angle_constraint", "smgpu_get_edges", "smgpu_op_layer_normals", "smgpu_op_layer_blend"):
             getattr(L, f).argtypes = [C.c_void_p] + ([C.c_void_p] if f != "smgpu_destroy" else [])
         L.smgpu_mesh_stats.argtypes = [C.c_void_p] + [C.c_void_p] * 4
         L.smgpu_iterate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -335,7 +341,8 @@ class IterationLog:
 class Smoother:
     """Device-resident smoothing state; the C-ABI counterpart of the reference's main() loop."""
 
-    def __init__(self, mesh: Mesh, params: Params | None = None, **kw):
+    def __init__(self, mesh: Mesh, params: Params | None = None, layer_patches=None, **kw):
+        """layer_patches: per-patch 0/1 flags (the patches -layerPatches selects), serial runs only."""
         L = lib()
         self.params_in = params if params is not None else default_params(**kw)
         self._arrays = mesh.desc_arrays()  # keep alive during create
@@ -348,6 +355,8 @@ class Smoother:
         d.n_patches = len(a["patch_start"])
         d.patch_start, d.patch_size, d.patch_kind = _ptr(a["patch_start"]), _ptr(a["patch_size"]), _ptr(a["patch_kind"])
         d.point_global_id = _ptr(a["point_global_id"])
+        lay = None if layer_patches is None else np.ascontiguousarray(layer_patches, dtype=np.int32)
+        d.patch_layer = _ptr(lay)
         h = C.c_void_p()
         rc = L.smgpu_create(C.byref(d), C.byref(self.params_in), C.byref(h))
         if rc != 0:
@@ -416,6 +425,16 @@ class Smoother:
     def op_predict(self):
         out = np.zeros((self.n_points, 3), dtype=np.float64)
         self._ck(lib().smgpu_op_predict(self._h, _ptr(out)))
+        return out
+
+    def op_layer_normals(self):
+        out = np.zeros((self.n_points, 3), dtype=np.float64)
+        self._ck(lib().smgpu_op_layer_normals(self._h, _ptr(out)))
+        return out
+
+    def op_layer_blend(self):
+        out = np.zeros((self.n_points, 3), dtype=np.float64)
+        self._ck(lib().smgpu_op_layer_blend(self._h, _ptr(out)))
         return out
 
     def op_edge_constraints(self):

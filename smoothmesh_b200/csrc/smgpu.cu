@@ -51,6 +51,12 @@ struct smgpu_handle
     int statCap = 0;
     sm::Comm *comm = nullptr;
     std::vector<int64_t> gid;
+    // boundary layer treatment (serial runs): one-time set-up data and per-hop tables
+    sm::LayerSetup layer;
+    bool doLayers = false;
+    bool anyLayerPatch = false;
+    double *dLayerLength = nullptr, *dLayerBlend = nullptr;
+    P4 *normalsTmp = nullptr;
     // params.renumber: storage order = Morton order; old label of every stored point / cell
     std::vector<int32_t> pointOldOfNew, cellOldOfNew;
     smgpu_params prmRequested;              // as passed by the caller (negative = reference default)
@@ -69,7 +75,7 @@ struct smgpu_handle
     }
 
     // optional per-kernel timing (CUDA events on the launch stream)
-    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_NUM };
+    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_LAYER, K_NUM };
     bool profiling = false;
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<int, size_t>> evUse; // (kernel id, index of start event)
@@ -146,6 +152,28 @@ struct smgpu_handle
                         d.faceCosLo < d.faceCosHi)
                            ? 1
                            : 0;
+        // boundary layer treatment: per-hop target edge length and blending fraction
+        // (blendWithOrthogonalPoints, src/orthogonalBoundaryBlending.C:547-555; its maxLayers is maxLayers + 1, :2300)
+        doLayers = anyLayerPatch && prm.layer_max_blending_fraction > 1e-15; // :2025, SMALL
+        d.layers = doLayers ? 1 : 0;
+        if (doLayers && dLayerLength)
+        {
+            const double maxLayers = prm.max_layers + 1, minLayers = prm.min_layers;
+            const double edgeLen = prm.layer_edge_length < 0 ? prm.min_edge_length : prm.layer_edge_length;
+            std::vector<double> len(layer.maxHop + 2, 0.0), bl(layer.maxHop + 2, 0.0);
+            for (int nHops = 1; nHops <= layer.maxHop + 1; ++nHops)
+            {
+                const double lim = (double(nHops - 1) < maxLayers) ? double(nHops - 1) : maxLayers;
+                len[nHops] = edgeLen * std::pow(prm.layer_expansion_ratio, (double)(int)lim);
+                const double slope = -prm.layer_max_blending_fraction / (maxLayers - minLayers);
+                const double y0 = -slope * maxLayers;
+                const double y = y0 + slope * nHops;
+                const double t = (y < prm.layer_max_blending_fraction) ? y : prm.layer_max_blending_fraction;
+                bl[nHops] = (0.0 > t) ? 0.0 : t;
+            }
+            cudaMemcpy(dLayerLength, len.data(), len.size() * sizeof(double), cudaMemcpyHostToDevice);
+            cudaMemcpy(dLayerBlend, bl.data(), bl.size() * sizeof(double), cudaMemcpyHostToDevice);
+        }
         d.cosSmallF = (float)std::cos(d.smallAngle);
         d.cosLargeF = (float)std::cos(d.largeAngle);
         // the single-precision level is used when its error budget at the mesh's shortest edge is small
@@ -218,16 +246,34 @@ struct smgpu_handle
     static int grid(int64_t n, int block) { return (int)std::max<int64_t>(1, (n + block - 1) / block); }
 
     // ---- kernel launches (one method per reference operator) ----
-    void launchCellCentres()
+    void launchFaceGeom()
     {
         profBegin(K_FACE_GEOM);
         k_face_geom<<<grid(d.F, 256), 256, 0, stream>>>(d);
         profEnd(1);
         ++launches;
+    }
+    void launchCells()
+    {
         profBegin(K_CELL);
         k_cell_centres<<<grid(d.C, 128), 128, 0, stream>>>(d);
         profEnd(1);
         ++launches;
+    }
+    // OpenFOAM's demand-driven geometry after movePoints: face centres/areas, then cell centres
+    void launchCellCentres()
+    {
+        launchFaceGeom();
+        launchCells();
+    }
+    // start of an iteration (src/smoothMesh.C:2262-2269): geometry and, with layer treatment, the
+    // boundary point normals of :2266 (they need the boundary face areas of the current mesh)
+    void launchGeometry()
+    {
+        launchFaceGeom();
+        if (doLayers)
+            launchLayerNormals();
+        launchCells();
     }
     void launchPredict()
     {
@@ -235,6 +281,34 @@ struct smgpu_handle
         k_predict<<<grid(d.P, 128), 128, 0, stream>>>(d);
         profEnd(1);
         ++launches;
+    }
+    void launchLayerNormals()
+    {
+        profBegin(K_LAYER);
+        k_layer_normals<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        profEnd(1);
+        ++launches;
+    }
+    void launchLayerBlend()
+    {
+        profBegin(K_LAYER);
+        k_layer_blend<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        profEnd(1);
+        ++launches;
+    }
+    // set-up call of calculateBoundaryPointNormals + propagateOuterNeighInfo's normal copies
+    // (src/smoothMesh.C:2219-2220) for the mesh currently on the device
+    void initLayerNormals()
+    {
+        if (!doLayers)
+            return;
+        CK(cudaMemsetAsync(d.normals, 0, topo.P * sizeof(P4), stream));
+        CK(cudaMemsetAsync(d.done, 0, sizeof(int), stream));
+        k_face_geom<<<grid(d.F, 256), 256, 0, stream>>>(d);
+        k_layer_normals<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        CK(cudaMemcpyAsync(normalsTmp, d.normals, topo.P * sizeof(P4), cudaMemcpyDeviceToDevice, stream));
+        k_layer_init_normals<<<grid(d.P, 128), 128, 0, stream>>>(d, normalsTmp);
+        CK(cudaStreamSynchronize(stream));
     }
     void launchEdgeConstraints()
     {
@@ -361,7 +435,7 @@ static int commIterate(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
     const int gs = smgpu_handle::grid(c.nSlots, 128);
-    h->launchCellCentres();
+    h->launchGeometry();
     h->launchPredict();
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
@@ -419,6 +493,11 @@ extern "C"
         p->geometry_variant = 0;
         p->device = 0;
         p->renumber = 0;
+        p->layer_max_blending_fraction = 0.3; // :1892-1905
+        p->layer_edge_length = -1.0;
+        p->layer_expansion_ratio = 1.3;
+        p->min_layers = 1;
+        p->max_layers = 4;
     }
 
     int smgpu_create(const smgpu_mesh_desc *md, const smgpu_params *params, smgpu_handle **out)
@@ -454,6 +533,18 @@ extern "C"
             }
             if (md->point_global_id)
                 m.pointGlobalId.assign(md->point_global_id, md->point_global_id + md->n_points);
+            std::vector<int32_t> patchLayer(md->n_patches, 0);
+            if (md->patch_layer)
+                for (int i = 0; i < md->n_patches; ++i)
+                {
+                    patchLayer[i] = md->patch_layer[i] != 0;
+                    h->anyLayerPatch = h->anyLayerPatch || patchLayer[i];
+                }
+            if (h->anyLayerPatch && md->point_global_id)
+            {
+                delete h;
+                return setErr(SMGPU_ERR_ARG, "boundary layer treatment (patch_layer) is only available in serial runs");
+            }
             try
             {
                 if (params->renumber)
@@ -548,8 +639,25 @@ extern "C"
             CK(cudaMemset(d.newPts, 0, t.P * sizeof(P4)));
             h->ensureStats(1024);
             h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
+            if (h->anyLayerPatch)
+            {
+                h->layer = sm::buildLayerSetup(m, t, patchLayer, params->max_layers);
+                d.normals = h->dalloc<P4>(t.P);
+                h->normalsTmp = h->dalloc<P4>(t.P);
+                d.hops = h->upload(h->layer.hops);
+                d.pointToOuter = h->upload(h->layer.pointToOuter);
+                d.normalSrc = h->upload(h->layer.normalSrc);
+                d.bfOff = h->upload(h->layer.bfOff);
+                d.bf = h->upload(h->layer.bf);
+                h->dLayerLength = h->dalloc<double>(h->layer.maxHop + 2);
+                h->dLayerBlend = h->dalloc<double>(h->layer.maxHop + 2);
+                d.layerLength = h->dLayerLength;
+                d.layerBlend = h->dLayerBlend;
+            }
+            h->prm = *params;
             h->setPoints(md->points); // also fixes the single-precision mirror's origin and error bound
             h->resolveParams();
+            h->initLayerNormals();
             CK(cudaDeviceSynchronize());
             (void)m;
         }
@@ -592,6 +700,8 @@ extern "C"
     {
         if (!h || !p)
             return setErr(SMGPU_ERR_ARG, "null argument");
+        if (h->anyLayerPatch && p->max_layers != h->prmRequested.max_layers)
+            return setErr(SMGPU_ERR_ARG, "max_layers fixes the layer set-up and cannot be changed after smgpu_create");
         h->prmRequested = *p;
         h->resolveParams();
         return SMGPU_OK;
@@ -637,8 +747,10 @@ extern "C"
                             sm::commIterate(h->comm, h);
                             continue;
                         }
-                        h->launchCellCentres();
+                        h->launchGeometry();
                         h->launchPredict();
+                        if (h->doLayers)
+                            h->launchLayerBlend(); // :2283-2305
                         h->launchEdgeConstraints();
                         if (h->prm.face_angle_constraint)
                             h->launchFaceAngle();
@@ -722,6 +834,7 @@ extern "C"
             CK(cudaSetDevice(h->prm.device));
             h->setPoints(in);
             h->applyParams();
+            h->initLayerNormals(); // a fresh run starts from the set-up normals of the new mesh
         }
         catch (const std::exception &e)
         {
@@ -788,6 +901,37 @@ extern "C"
         cudaSetDevice(h->prm.device);
         h->resetControl();
         h->launchPredict();
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && out)
+            rc = downloadP4(h, h->d.newPts, h->topo.P, out, h->pointOldOfNew);
+        return rc;
+    }
+
+    int smgpu_op_layer_normals(smgpu_handle *h, double *out)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        if (!h->doLayers)
+            return setErr(SMGPU_ERR_ARG, "boundary layer treatment is not enabled for this handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchFaceGeom();
+        h->launchLayerNormals();
+        int rc = finishOp(h);
+        if (rc == SMGPU_OK && out)
+            rc = downloadP4(h, h->d.normals, h->topo.P, out, h->pointOldOfNew);
+        return rc;
+    }
+
+    int smgpu_op_layer_blend(smgpu_handle *h, double *out)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        if (!h->doLayers)
+            return setErr(SMGPU_ERR_ARG, "boundary layer treatment is not enabled for this handle");
+        cudaSetDevice(h->prm.device);
+        h->resetControl();
+        h->launchLayerBlend();
         int rc = finishOp(h);
         if (rc == SMGPU_OK && out)
             rc = downloadP4(h, h->d.newPts, h->topo.P, out, h->pointOldOfNew);
@@ -917,7 +1061,7 @@ extern "C"
     int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches)
     {
         static const char *kNames[smgpu_handle::K_NUM] = {"k_face_geom", "k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
-                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange"};
+                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange", "k_layer"};
         if (!h || !n)
             return setErr(SMGPU_ERR_ARG, "null argument");
         *n = smgpu_handle::K_NUM;

@@ -21,6 +21,7 @@
 #include <dirent.h>
 #include <fstream>
 #include <map>
+#include <regex>
 #include <sstream>
 #include <string>
 #include <sys/stat.h>
@@ -138,6 +139,61 @@ static std::vector<std::pair<double, std::string>> findTimes(const std::string &
     closedir(dp);
     std::sort(out.begin(), out.end());
     return out;
+}
+
+// OpenFOAM wordRe list, e.g.  walls   '(walls "rotor.*")'   '("def.*")' : quoted entries are regular
+// expressions (full match), unquoted ones literal names (getPatchIdsForOption, src/smoothMesh.C:1442-1471)
+static std::vector<int32_t> selectPatches(const std::string &expr, const std::vector<std::string> &names)
+{
+    std::vector<int32_t> sel(names.size(), 0);
+    std::string s = expr;
+    for (char &c : s)
+        if (c == '(' || c == ')')
+            c = ' ';
+    size_t i = 0;
+    while (i < s.size())
+    {
+        while (i < s.size() && isspace((unsigned char)s[i]))
+            ++i;
+        if (i >= s.size())
+            break;
+        bool isRe = false;
+        std::string tok;
+        if (s[i] == '"')
+        {
+            isRe = true;
+            const size_t e = s.find('"', i + 1);
+            tok = s.substr(i + 1, (e == std::string::npos ? s.size() : e) - i - 1);
+            i = (e == std::string::npos) ? s.size() : e + 1;
+        }
+        else
+        {
+            const size_t b = i;
+            while (i < s.size() && !isspace((unsigned char)s[i]))
+                ++i;
+            tok = s.substr(b, i - b);
+        }
+        for (size_t k = 0; k < names.size(); ++k)
+        {
+            bool hit = false;
+            if (isRe)
+            {
+                try
+                {
+                    hit = std::regex_match(names[k], std::regex(tok, std::regex::extended));
+                }
+                catch (const std::regex_error &)
+                {
+                    fatal("bad regular expression \"" + tok + "\" in patch list");
+                }
+            }
+            else
+                hit = names[k] == tok;
+            if (hit)
+                sel[k] = 1;
+        }
+    }
+    return sel;
 }
 
 int main(int argc, char **argv)
@@ -284,10 +340,22 @@ int main(int argc, char **argv)
         return s == "()" || s == "none" || s == "(none)" || s.empty();
     };
     const double layerMaxBlendingFraction = num("layerMaxBlendingFraction", 0.3);
-    if (has("layerPatches") && !patchSetEmpty(opt["layerPatches"]) && layerMaxBlendingFraction > 1e-15)
-        fatal("boundary layer treatment (-layerPatches) is outside the GPU hot path and there is no CPU fallback; "
-              "rerun without -layerPatches");
-    printf("Patches for boundary layer treatment: none\n");
+    std::vector<std::string> patchNames;
+    for (int i = 0; i < nPatches; ++i)
+        patchNames.push_back(smmesh_patch_name(mesh, i));
+    std::vector<int32_t> layerSel(nPatches, 0);
+    bool anyLayerPatch = false;
+    if (has("layerPatches"))
+    {
+        layerSel = selectPatches(opt["layerPatches"], patchNames);
+        for (int32_t f : layerSel)
+            anyLayerPatch = anyLayerPatch || f;
+    }
+    if (anyLayerPatch)
+        printf("Patches for boundary layer treatment: %s\n", opt["layerPatches"].c_str());
+    else
+        printf("Patches for boundary layer treatment: none\n");
+    const bool doLayerTreatment = anyLayerPatch && layerMaxBlendingFraction > 1e-15; // :2025
     const bool smoothingPatchesEmpty = has("smoothingPatches") && patchSetEmpty(opt["smoothingPatches"]);
     const bool surfaces = fileExists(caseDir + "/constant/geometry/targetSurfaces.obj");
     const bool initEdges = fileExists(caseDir + "/constant/geometry/initEdges.obj");
@@ -326,6 +394,12 @@ int main(int argc, char **argv)
     prm.rel_tol = num("relTol", 0.02);
     prm.device = (int)num("device", 0);
     prm.geometry_variant = has("geometryVariant") && opt["geometryVariant"] == "org" ? 1 : 0;
+    prm.layer_max_blending_fraction = layerMaxBlendingFraction;
+    prm.layer_edge_length = num("layerEdgeLength", -1.0);
+    prm.layer_expansion_ratio = num("layerExpansionRatio", 1.3);
+    prm.min_layers = (int)num("minLayers", 1);
+    prm.max_layers = (int)num("maxLayers", 4);
+    md.patch_layer = layerSel.data();
     const int centroidalIters = (int)num("centroidalIters", 1000);
     const int writeInterval = (int)num("writeInterval", centroidalIters);
 
@@ -357,9 +431,19 @@ int main(int argc, char **argv)
                prm.min_angle_deg, prm.max_angle_deg);
     else
         printf("    faceAngleConstraint    false (face angle quality constraints are NOT applied)\n");
-    printf("    layerMaxBlendingFraction 0 (boundary layer treatment is NOT applied)\n\n");
-    printf("Boundary layer treatment is disabled. Either no layerPatches were specified or boundaryMaxBlendingFraction "
-           "is zero\n\n");
+    if (layerMaxBlendingFraction > 1e-15)
+        printf("    layerMaxBlendingFraction %g\n    layerEdgeLength          %g\n    layerExpansionRatio      %g\n"
+               "    minLayers                %d\n    maxLayers                %d\n\n",
+               prm.layer_max_blending_fraction, prm.layer_edge_length < 0 ? prm.min_edge_length : prm.layer_edge_length,
+               prm.layer_expansion_ratio, prm.min_layers, prm.max_layers);
+    else
+        printf("    layerMaxBlendingFraction 0 (boundary layer treatment is NOT applied)\n\n");
+    if (doLayerTreatment)
+        printf("Enabled boundary layer treatment\n\nWARNING: Boundary layer treatment will be done without boundary "
+               "point smoothing. This can result in distorted boundary cells.\n\n");
+    else
+        printf("Boundary layer treatment is disabled. Either no layerPatches were specified or "
+               "boundaryMaxBlendingFraction is zero\n\n");
     printf("Boundary point smoothing is disabled. Missing smoothingPatches, or one or both of files:\n"
            "constant/geometry/targetSurfaces.obj\nconstant/geometry/initEdges.obj\n\n");
     printf("Mesh includes a total of %lld points:\n  - %lld internal (non-boundary) points\n  - %lld boundary points\n"

@@ -437,3 +437,138 @@ Topology buildTopology(const PolyMesh &m)
 }
 
 } // namespace sm
+
+// ------------------------------------------------- boundary layer treatment ----
+namespace sm
+{
+// One-time set-up of the prismatic boundary layer treatment (src/smoothMesh.C:2190-2221 with
+// src/boundaryPointSmoothing.C:301-423 and src/orthogonalBoundaryBlending.C:52-134, 244-391),
+// serial form.  Everything here depends on topology and patch selection only; the normal
+// *values* are computed on the device and copied along `normalSrc`.
+LayerSetup buildLayerSetup(const PolyMesh &m, const Topology &t, const std::vector<int32_t> &patchLayer, int maxLayers)
+{
+    LayerSetup L;
+    const int64_t P = t.P;
+    // classifyBoundaryPoints: a boundary point is classified once, by the first patch containing it
+    std::vector<uint8_t> visited(P, 0), connected(P, 0), layerSurface(P, 0);
+    for (size_t pi = 0; pi < m.patches.size(); ++pi)
+    {
+        const Patch &pt = m.patches[pi];
+        for (int32_t f = pt.start; f < pt.start + pt.size; ++f)
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+            {
+                const int32_t p = m.faceVerts[k];
+                if (visited[p])
+                    continue;
+                visited[p] = 1;
+                if (t.isInternal[p])
+                    continue;
+                for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+                    if (t.isInternal[t.pp[s]])
+                        connected[p] = 1;
+                if (patchLayer[pi])
+                    layerSurface[p] = 1;
+            }
+    }
+    // calculatePointHopsToBoundary(layerPatchIds, maxIter = maxLayers + 1)
+    L.hops.assign(P, -1);
+    for (size_t pi = 0; pi < m.patches.size(); ++pi)
+    {
+        if (!patchLayer[pi])
+            continue;
+        const Patch &pt = m.patches[pi];
+        for (int32_t f = pt.start; f < pt.start + pt.size; ++f)
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                if (connected[m.faceVerts[k]])
+                    L.hops[m.faceVerts[k]] = 0;
+    }
+    std::vector<int32_t> newHops(P, -1);
+    for (int iter = 0; iter < maxLayers + 1; ++iter)
+    {
+        for (int64_t p = 0; p < P; ++p)
+        {
+            if (L.hops[p] >= 0 || !t.isInternal[p])
+                continue;
+            int32_t mx = -1;
+            for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+                mx = std::max(mx, L.hops[t.pp[s]]);
+            if (mx >= 0)
+                newHops[p] = mx + 1;
+        }
+        for (int64_t p = 0; p < P; ++p)
+            if (newHops[p] > L.hops[p])
+                L.hops[p] = newHops[p];
+    }
+    // propagateOuterNeighInfo: maps towards the boundary and the source of the propagated normal.
+    // normalSrc: >= 0 boundary point whose normal is copied, -1 none (zero normal), -2 UNDEF_VECTOR
+    // (multiply connected, undone at :372-382)
+    L.pointToOuter.assign(P, -1);
+    L.normalSrc.assign(P, -1);
+    for (int64_t p = 0; p < P; ++p)
+        if (!t.isInternal[p])
+            L.normalSrc[p] = (int32_t)p; // boundary points carry their own (device-computed) normal
+    std::vector<int32_t> boundaryPointLabels(P, -1);
+    std::vector<int32_t> firstWithLabel(P, -1); // findIndex(boundaryPointLabels, q): lowest point mapped to q
+    for (int iter = 1; iter < maxLayers + 2; ++iter)
+        for (int64_t p = 0; p < P; ++p)
+        {
+            if (L.hops[p] != iter)
+                continue;
+            int32_t n = 0, q = -1;
+            for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+                if (L.hops[t.pp[s]] == iter - 1)
+                {
+                    ++n;
+                    q = t.pp[s];
+                }
+            if (n != 1)
+                continue;
+            if (!t.isInternal[q] && !layerSurface[q])
+                continue;
+            if (firstWithLabel[q] >= 0)
+            {
+                L.normalSrc[p] = -2;
+                L.normalSrc[firstWithLabel[q]] = -2;
+                continue;
+            }
+            L.pointToOuter[p] = q;
+            L.normalSrc[p] = L.normalSrc[q];
+            boundaryPointLabels[p] = q;
+            firstWithLabel[q] = (int32_t)p; // points are visited in ascending order: the first is the lowest
+        }
+    for (int64_t p = 0; p < P; ++p)
+        if (L.normalSrc[p] == -2)
+        {
+            L.normalSrc[p] = -1;
+            L.pointToOuter[p] = -1;
+        }
+    // point -> boundary faces on non-processor, non-empty patches (ascending face label): the
+    // accumulation order of calculateBoundaryPointNormals (:151-182)
+    L.bfOff.assign(P + 1, 0);
+    for (const Patch &pt : m.patches)
+    {
+        if (pt.kind() != PATCH_BOUNDARY)
+            continue;
+        for (int32_t f = pt.start; f < pt.start + pt.size; ++f)
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                ++L.bfOff[m.faceVerts[k] + 1];
+    }
+    for (int64_t p = 0; p < P; ++p)
+        L.bfOff[p + 1] += L.bfOff[p];
+    L.bf.resize(L.bfOff[P]);
+    {
+        std::vector<int32_t> cur(L.bfOff.begin(), L.bfOff.end() - 1);
+        for (const Patch &pt : m.patches)
+        {
+            if (pt.kind() != PATCH_BOUNDARY)
+                continue;
+            for (int32_t f = pt.start; f < pt.start + pt.size; ++f)
+                for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                    L.bf[cur[m.faceVerts[k]]++] = f;
+        }
+    }
+    for (int32_t h : L.hops)
+        L.maxHop = std::max(L.maxHop, h);
+    return L;
+}
+} // namespace sm

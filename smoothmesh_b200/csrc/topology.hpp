@@ -52,6 +52,17 @@ struct Topology
     int32_t maxPointDegree = 0, maxFaceSize = 0, maxEdgeFaces = 0;
 };
 
+// One-time data of the prismatic boundary layer treatment (src/orthogonalBoundaryBlending.C), serial runs.
+struct LayerSetup
+{
+    std::vector<int32_t> hops;         // pointHopsToLayerBoundary, -1 = undefined
+    std::vector<int32_t> pointToOuter; // pointToOuterPointMap, -1 = none
+    std::vector<int32_t> normalSrc;    // boundary point whose set-up normal an internal point carries, -1 = zero
+    std::vector<int32_t> bfOff, bf;    // point -> boundary faces (non-processor patches), ascending
+    int32_t maxHop = 0;
+};
+LayerSetup buildLayerSetup(const PolyMesh &m, const Topology &t, const std::vector<int32_t> &patchLayer, int maxLayers);
+
 // Throws std::runtime_error with the reference's FatalError texts where the
 // reference would abort (empty patches :61-66, <2 eligible closest points
 // :354-362, edge/cell face-pair sanity :1073,:1087).

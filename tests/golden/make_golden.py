@@ -12,14 +12,15 @@ BASELINE.json configs 1 and 2:
 
   testcase   : testcase/MeshedSurface.obj (660 vertices, 275 triangles + 475 quads) extruded
                15 layers x 0.1 in +y (testcase/system/extrude2DMeshDict:9-24) -> 11 250 cells;
-               options of testcase/run_serial:18 minus -layerPatches.
+               options of testcase/run_serial:18 minus -layerPatches; and `testcase_layers`: the same
+               mesh with the command line exactly as shipped (-layerPatches '("def.*")').
   testcase4  : the 15 straight-edged 5x5x5 blocks of testcase4/system/blockMeshDict:26-655,
                coincident block points merged -> 1 875 hex cells; -centroidalIters 200
                -totalMinFreeze true -smoothingPatches '()'.
 
 Point/face/cell numbering is this builder's (blockMesh's / extrude2DMesh's own numbering cannot be
-reproduced without OpenFOAM); all boundary faces go into one wall patch, which is all the hot path
-distinguishes.  The files hold the mesh arrays and the oracle's per-iteration log, final points
+reproduced without OpenFOAM); testcase carries the seven patches the case scripts create, testcase4 one
+wall patch (all the hot path distinguishes there).  The files hold the mesh arrays and the oracle's per-iteration log, final points
 and freeze mask; tests/test_golden.py checks the oracle (CPU) and the CUDA path (GPU) against them.
 """
 import os
@@ -76,7 +77,31 @@ def testcase_mesh():
                 j = (i + 1) % len(poly)
                 faces.append([bot[i], bot[j], top[j], top[i]])
             cells.append(orient_outward(points, faces))
-    return sm.Mesh.from_cells(points, cells)
+
+    # patches as testcase/run_serial:11-15 leaves them: extrude2DMesh's defaultFaces (here: the walls of the
+    # holes in the surface) first, then the six box-selected side patches of testcase/system/topoSetDict:17-80
+    # and createPatchDict:19-58.  The relative order of defaultFaces and side_* is an assumption
+    # (createPatch appends new patches); it only matters for points on the junction of two patches.
+    names = ["defaultFaces", "side_front", "side_back", "side_left", "side_right", "side_top", "side_bottom"]
+
+    def patch_of(ci, fi, f):
+        c = points[list(f)].mean(axis=0)
+        if abs(c[1] - 0.75) < 0.01:
+            return 1
+        if abs(c[1] + 0.75) < 0.01:
+            return 2
+        if abs(c[0] + 1.0) < 0.01:
+            return 3
+        if abs(c[0] - 1.0) < 0.01:
+            return 4
+        if abs(c[2] - 1.0) < 0.01:
+            return 5
+        if abs(c[2] + 1.0) < 0.01:
+            return 6
+        return 0
+
+    return sm.Mesh.from_cells(points, cells, patch_of_face=patch_of, patch_names=names,
+                              patch_types=["patch"] * len(names))
 
 
 def testcase4_mesh():
@@ -126,6 +151,9 @@ CASES = {
     # testcase/run_serial:18 without -layerPatches (BASELINE config 1)
     "testcase": (testcase_mesh, dict(min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0,
                                       max_angle_deg=160.0), 100),
+    # testcase/run_serial:18 exactly as shipped: -layerPatches '("def.*")' selects defaultFaces (patch 0)
+    "testcase_layers": (testcase_mesh, dict(min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0,
+                                             max_angle_deg=160.0, layer_patches=[1, 0, 0, 0, 0, 0, 0]), 100),
     # BASELINE config 2
     "testcase4": (testcase4_mesh, dict(total_min_freeze=1), 200),
 }
@@ -135,13 +163,16 @@ def main():
     for name, (build, kw, iters) in CASES.items():
         mesh = build()
         a = mesh.desc_arrays()
-        o = Oracle(a, **kw)
+        kw = dict(kw)
+        layer = kw.pop("layer_patches", None)
+        o = Oracle(a, layer_patches=layer, **kw)
         n, nf, res = o.iterate(iters)
         out = dict(points=a["points"], face_offsets=a["face_offsets"], face_verts=a["face_verts"], owner=a["owner"],
                    neighbour=a["neighbour"], n_cells=np.int64(a["n_cells"]), patch_start=a["patch_start"],
                    patch_size=a["patch_size"], patch_kind=a["patch_kind"],
                    iterations=np.int64(n), n_frozen=nf, residual=res, final_points=o.get("points"),
                    frozen=o.get("frozen"), opt_keys=np.array(sorted(kw)), opt_vals=np.array([float(kw[k]) for k in sorted(kw)]),
+                   layer_patches=np.array(layer if layer is not None else [], dtype=np.int32),
                    max_iters=np.int64(iters), min_edge_length=np.float64(o.prm.minEdgeLength),
                    max_step_length=np.float64(o.prm.maxStepLength))
         path = os.path.join(HERE, f"{name}.npz")

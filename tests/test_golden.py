@@ -20,10 +20,12 @@ def load(name):
     for k in ("total_min_freeze",):
         if k in kw:
             kw[k] = int(kw[k])
+    if "layer_patches" in z.files and z["layer_patches"].size:
+        kw["layer_patches"] = z["layer_patches"].tolist()
     return z, arrays, kw
 
 
-@pytest.mark.parametrize("name", ["testcase4", "testcase"])
+@pytest.mark.parametrize("name", ["testcase4", "testcase", "testcase_layers"])
 def test_oracle_reproduces_golden(name):
     z, arrays, kw = load(name)
     iters = int(z["max_iters"]) if name == "testcase4" else 12  # keep the CPU suite short
@@ -35,13 +37,15 @@ def test_oracle_reproduces_golden(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["testcase4", "testcase"])
+@pytest.mark.parametrize("name", ["testcase4", "testcase", "testcase_layers"])
 def test_cuda_path_reproduces_golden(name):
     z, arrays, kw = load(name)
     mesh = sm.Mesh.from_arrays(arrays["points"], arrays["face_offsets"], arrays["face_verts"], arrays["owner"],
                                arrays["neighbour"], arrays["n_cells"], arrays["patch_start"], arrays["patch_size"],
                                arrays["patch_kind"])
-    g = sm.Smoother(mesh, **kw)
+    kw = dict(kw)
+    layer = kw.pop("layer_patches", None)
+    g = sm.Smoother(mesh, layer_patches=layer, **kw)
     p = g.params
     assert p.min_edge_length == float(z["min_edge_length"]) and p.max_step_length == float(z["max_step_length"])
     log = g.iterate(int(z["max_iters"]))
