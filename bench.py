@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--renumber", type=int, default=0, help="1 = Morton storage order (smgpu_params.renumber)")
+    ap.add_argument("--min-angle", type=float, default=35.0, help="-minAngle (default = reference default)")
+    ap.add_argument("--max-angle", type=float, default=160.0, help="-maxAngle (default = reference default)")
     ap.add_argument("--workload", default="hex", choices=["hex", "kelvin"],
                     help="hex: n^3 jittered blockMesh block per GPU (weak scaling, BASELINE configs 3/5); kelvin: "
                          "2 n^3 Kelvin-cell polyhedral mesh in total, RCB-decomposed over the GPUs (BASELINE config 4, "
@@ -267,7 +269,8 @@ def main():
         mesh = multi.weak_scaling_part(n, world, rank, JITTER, SEED)
     t_gen = time.perf_counter() - t0
     t0 = time.perf_counter()
-    g = sm.Smoother(mesh, rel_tol=0.0, device=local_rank, renumber=args.renumber)
+    g = sm.Smoother(mesh, rel_tol=0.0, device=local_rank, renumber=args.renumber, min_angle_deg=args.min_angle,
+                    max_angle_deg=args.max_angle)
     if world > 1:
         from smoothmesh_b200 import multi
         multi.init_comm(g, rank, world, dist)
@@ -352,7 +355,7 @@ def main():
                                 if args.workload == "hex" else
                                 f"Kelvin-cell polyhedral mesh, 2x{n}^3 cells in total, jittered 0.2 x shortest edge, RCB parts, ")
                                + f"{K} iterations, edge/face angle constraints on, relTol 0",
-                   "points_per_gpu": P, "cells_per_gpu": C, "renumber": args.renumber, "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
+                   "points_per_gpu": P, "cells_per_gpu": C, "renumber": args.renumber, "min_angle": args.min_angle, "max_angle": args.max_angle, "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
                    "setup_s": {"mesh_generation": t_gen, "create_upload": t_setup}},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "point-updates/s", "h2d_bytes_per_step": 24 * P / K,

@@ -53,6 +53,7 @@ struct smgpu_handle
     std::vector<int64_t> gid;
     // boundary layer treatment (serial runs): one-time set-up data and per-hop tables
     sm::LayerSetup layer;
+    int resolveBlocks = 1;
     bool doLayers = false;
     bool anyLayerPatch = false;
     double *dLayerLength = nullptr, *dLayerBlend = nullptr;
@@ -333,7 +334,10 @@ struct smgpu_handle
         k_face_tests<<<148 * 4, 128, 0, stream>>>(d);
         profEnd(1);
         profBegin(K_FACE_RESOLVE);
-        k_face_resolve<<<1, 32, 0, stream>>>(d);
+        {
+            void *args[] = {(void *)&d};
+            CK(cudaLaunchCooperativeKernel((const void *)k_face_resolve, dim3(resolveBlocks), dim3(128), args, 0, stream));
+        }
         profEnd(1);
         launches += 7;
     }
@@ -621,6 +625,17 @@ extern "C"
             d.pairBits = h->dalloc<uint8_t>(t.pp.size() + 8);
             d.activeList = h->dalloc<int>(t.P);
             d.stack = h->dalloc<int>(t.P);
+            d.compOf = h->dalloc<int>(t.P);
+            d.reach = h->dalloc<int>(t.P);
+            d.rootHi = h->dalloc<int>(t.P);
+            d.changed = h->dalloc<int>(1);
+            {
+                // cooperative launch of k_face_resolve: as many blocks as can be co-resident
+                int perSm = 0, sms = 0;
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_face_resolve, 128, 0));
+                CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, params->device));
+                h->resolveBlocks = std::max(1, sms * std::min(perSm, 4));
+            }
             d.blockCounts = h->dalloc<int>(smgpu_handle::grid(t.P, SMK_CHUNK) + 1);
             d.nActive = h->dalloc<int>(1);
             d.done = h->dalloc<int>(1);
