@@ -120,13 +120,6 @@ def kernel_bytes(P, C, F, Fi, E, FV, PC, EC):
     }
 
 
-def mesh_counts(mesh, n_edges):
-    P, C, F, Fi = mesh.n_points, mesh.n_cells, mesh.n_faces, mesh.n_internal_faces
-    FV = int(mesh.face_offsets[-1])
-    # PC = sum |pointCells|, EC = sum |edgeCells|; for a hex block: 8C and ~12C (exact values from the library)
-    return P, C, F, Fi, n_edges, FV
-
-
 def cpu_baseline(n_side, iters, threads):
     """Times the CPU oracle (a port of the reference; the reference itself needs OpenFOAM) on a bounded
     sample of the same workload: a jittered n_side^3 block with the same jitter rule and options."""

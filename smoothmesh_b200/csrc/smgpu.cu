@@ -669,12 +669,10 @@ extern "C"
                 d.layerLength = h->dLayerLength;
                 d.layerBlend = h->dLayerBlend;
             }
-            h->prm = *params;
             h->setPoints(md->points); // also fixes the single-precision mirror's origin and error bound
             h->resolveParams();
             h->initLayerNormals();
             CK(cudaDeviceSynchronize());
-            (void)m;
         }
         catch (const std::exception &e)
         {
