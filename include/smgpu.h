@@ -96,6 +96,7 @@ extern "C"
     void smgpu_default_params(smgpu_params *p);
     const char *smgpu_last_error(void);
     const char *smgpu_version(void);
+    int smgpu_device_count(int32_t *n); /* visible CUDA devices (0 and SMGPU_ERR_CUDA if none) */
 
     /* Build derived connectivity, upload everything once, keep it resident in HBM. */
     int smgpu_create(const smgpu_mesh_desc *mesh, const smgpu_params *params, smgpu_handle **out);

@@ -61,6 +61,11 @@ extern "C"
     const int64_t *smmesh_point_global_id(const smmesh *m); /* NULL for undecomposed meshes */
     const int64_t *smmesh_cell_global_id(const smmesh *m);
 
+    /* decomposed cases (decomposePar layout): processor<k>/constant/polyMesh/{points,faces,owner,neighbour,
+     * boundary,pointProcAddressing,cellProcAddressing} */
+    int smmesh_write_decomposed(smmesh *const *parts, int32_t n_parts, const char *case_dir, int32_t binary);
+    smmesh *smmesh_read_processor(const char *case_dir, int32_t k);
+
     /* checkMesh-style quality of the mesh (what run_tests.sh:29,34 inspects after smoothing):
      * out = {max non-orthogonality [deg], average non-orthogonality [deg], max skewness, min angle between
      * consecutive face edges [deg], min edge length, max edge length, min cell volume}. */

@@ -125,6 +125,9 @@ def lib():
         L.smgpu_exchange_plan.restype = C.c_int64
         L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
         L.smmesh_quality.argtypes = [C.c_void_p, C.c_void_p]
+        L.smmesh_write_decomposed.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
+        L.smmesh_read_processor.restype = C.c_void_p
+        L.smmesh_read_processor.argtypes = [C.c_char_p, C.c_int32]
         L.smmesh_renumber.restype = C.c_void_p
         L.smmesh_renumber.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smmesh_gen_hex_block_part.restype = C.c_void_p
@@ -190,6 +193,17 @@ class Mesh:
     @staticmethod
     def kelvin(n, h=1.0) -> "Mesh":
         return Mesh(lib().smmesh_gen_kelvin(n, h))
+
+    @staticmethod
+    def read_processor(case_dir, k) -> "Mesh":
+        """processor<k> mesh of a decomposed case, with its pointProcAddressing as point_global_id."""
+        return Mesh(lib().smmesh_read_processor(str(case_dir).encode(), int(k)))
+
+    @staticmethod
+    def write_decomposed(parts, case_dir, binary=False):
+        arr = (C.c_void_p * len(parts))(*[p._h for p in parts])
+        if lib().smmesh_write_decomposed(arr, len(parts), str(case_dir).encode(), int(binary)) != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
 
     @staticmethod
     def read(polymesh_dir) -> "Mesh":

@@ -28,10 +28,9 @@ struct NcclApi
 
 inline const NcclApi &nccl()
 {
-    static NcclApi api;
-    static bool loaded = false;
-    if (!loaded)
-    {
+    // function-local static: initialised once, thread-safe (several host threads may drive one GPU each)
+    static const NcclApi loadedApi = [] {
+        NcclApi api;
         void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!h)
             h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
@@ -52,8 +51,8 @@ inline const NcclApi &nccl()
         api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
         api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
         api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-        loaded = true;
-    }
-    return api;
+        return api;
+    }();
+    return loadedApi;
 }
 } // namespace sm

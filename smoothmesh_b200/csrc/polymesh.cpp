@@ -1447,3 +1447,67 @@ MeshQuality computeQuality(const PolyMesh &m)
     return q;
 }
 } // namespace sm
+
+// ------------------------------------------------ decomposed (processorN) cases ----
+namespace sm
+{
+namespace
+{
+void writeLabelListFile(const std::string &file, const std::string &object, const std::string &location,
+                        const std::vector<int64_t> &v, bool binary)
+{
+    std::ofstream o(file, std::ios::binary);
+    if (!o)
+        fail("cannot write " + file);
+    o << foamHeader("labelIOList", location, object, binary);
+    o << v.size() << "\n(";
+    if (binary)
+    {
+        std::vector<int32_t> t(v.begin(), v.end());
+        o.write((const char *)t.data(), sizeof(int32_t) * t.size());
+    }
+    else
+    {
+        o << "\n";
+        for (int64_t x : v)
+            o << x << "\n";
+    }
+    o << ")\n";
+}
+} // namespace
+
+// processor<k>/constant/polyMesh/* plus pointProcAddressing / cellProcAddressing, the layout
+// decomposePar produces (testcase/run_parallel) and the reference reads under -parallel
+void writeDecomposedCase(const std::vector<PolyMesh> &parts, const std::string &caseDir, bool binary)
+{
+    for (size_t k = 0; k < parts.size(); ++k)
+    {
+        const std::string dir = caseDir + "/processor" + std::to_string(k) + "/constant/polyMesh";
+        writePolyMesh(parts[k], dir, binary, 17);
+        const std::string loc = "constant/polyMesh";
+        writeLabelListFile(dir + "/pointProcAddressing", "pointProcAddressing", loc, parts[k].pointGlobalId, binary);
+        writeLabelListFile(dir + "/cellProcAddressing", "cellProcAddressing", loc, parts[k].cellGlobalId, binary);
+    }
+}
+
+// one processor mesh of a decomposed case, with its addressing (topology from constant/)
+PolyMesh readProcessorMesh(const std::string &caseDir, int k)
+{
+    const std::string dir = caseDir + "/processor" + std::to_string(k) + "/constant/polyMesh";
+    PolyMesh m = readPolyMesh(dir);
+    auto readIds = [&](const std::string &file) {
+        Lexer lx;
+        lx.s = slurp(file);
+        const Header h = readHeader(lx);
+        const std::vector<int32_t> v = readLabelList(lx, h.binary);
+        return std::vector<int64_t>(v.begin(), v.end());
+    };
+    m.pointGlobalId = readIds(dir + "/pointProcAddressing");
+    if ((int64_t)m.pointGlobalId.size() != m.nPoints())
+        fail("pointProcAddressing size does not match the processor mesh");
+    std::ifstream probe(dir + "/cellProcAddressing");
+    if (probe.good())
+        m.cellGlobalId = readIds(dir + "/cellProcAddressing");
+    return m;
+}
+} // namespace sm

@@ -112,5 +112,8 @@ void writePolyMesh(const PolyMesh &m, const std::string &dir, bool binary = fals
 void writePoints(const double *pts, int64_t nPoints, const std::string &dir, bool binary, int precision,
                  const std::string &location);
 std::vector<double> readPoints(const std::string &file);
+// decomposed cases: processor<k>/constant/polyMesh with pointProcAddressing / cellProcAddressing
+void writeDecomposedCase(const std::vector<PolyMesh> &parts, const std::string &caseDir, bool binary);
+PolyMesh readProcessorMesh(const std::string &caseDir, int k);
 
 } // namespace sm

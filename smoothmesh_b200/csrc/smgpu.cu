@@ -482,6 +482,16 @@ extern "C"
     const char *smgpu_last_error(void) { return g_err.c_str(); }
     const char *smgpu_version(void) { return "smoothmesh_b200 0.1 (sm_100a, fp64, fmad=off)"; }
 
+    int smgpu_device_count(int32_t *n)
+    {
+        int c = 0;
+        if (cudaGetDeviceCount(&c) != cudaSuccess)
+            c = 0;
+        if (n)
+            *n = c;
+        return c > 0 ? SMGPU_OK : setErr(SMGPU_ERR_CUDA, "no CUDA device available");
+    }
+
     void smgpu_default_params(smgpu_params *p)
     {
         // src/smoothMesh.C:1861-1914

@@ -201,6 +201,26 @@ extern "C"
     {
         return m->m.cellGlobalId.empty() ? nullptr : m->m.cellGlobalId.data();
     }
+    int smmesh_write_decomposed(smmesh *const *parts, int32_t n_parts, const char *case_dir, int32_t binary)
+    {
+        try
+        {
+            std::vector<sm::PolyMesh> v;
+            for (int i = 0; i < n_parts; ++i)
+                v.push_back(parts[i]->m);
+            sm::writeDecomposedCase(v, case_dir, binary != 0);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_IO;
+        }
+        return SMGPU_OK;
+    }
+    smmesh *smmesh_read_processor(const char *case_dir, int32_t k)
+    {
+        return guarded([&] { return sm::readProcessorMesh(case_dir, k); });
+    }
     int smmesh_quality(const smmesh *m, double out[7])
     {
         try

@@ -20,7 +20,10 @@
 #include <cstring>
 #include <dirent.h>
 #include <fstream>
+#include <condition_variable>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <regex>
 #include <sstream>
 #include <string>
@@ -196,6 +199,229 @@ static std::vector<int32_t> selectPatches(const std::string &expr, const std::ve
     return sel;
 }
 
+struct RunOptions
+{
+    smgpu_params prm;
+    int centroidalIters, writeInterval;
+    double deltaT, startTime;
+    bool binary;
+    int writePrecision, timePrecision;
+    std::string caseDir, startName;
+};
+
+namespace
+{
+struct Barrier
+{
+    std::mutex m;
+    std::condition_variable cv;
+    int n, count = 0, gen = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == n)
+        {
+            count = 0;
+            ++gen;
+            cv.notify_all();
+        }
+        else
+            cv.wait(lk, [&] { return gen != g; });
+    }
+};
+} // namespace
+
+// -parallel: the decomposed case (processor<k>/, decomposePar layout) on one GPU per processor
+// directory.  The reference runs one MPI rank per directory (testcase/run_parallel); here one host
+// thread per directory drives its GPU and the library's NCCL layer replaces syncTools/Pstream.
+static int runParallel(const RunOptions &ro)
+{
+    int nProcs = 0;
+    while (dirExists(ro.caseDir + "/processor" + std::to_string(nProcs)))
+        ++nProcs;
+    if (nProcs < 2)
+        fatal("-parallel: no processor directories found in " + ro.caseDir + " (decompose the case first, e.g. -decompose '(2 1 1)')");
+    int32_t nDev = 0;
+    smgpu_device_count(&nDev);
+    if (nDev < nProcs)
+        fatal("-parallel: " + std::to_string(nProcs) + " processor directories but only " + std::to_string(nDev) +
+              " CUDA devices (one GPU per processor mesh is required)");
+    printf("Running on %d GPUs (one per processor directory)\n\nCreate mesh for time = %s\n\n", nProcs, ro.startName.c_str());
+
+    std::vector<std::vector<int64_t>> shared(nProcs);
+    std::vector<int64_t> counts(nProcs), allGids;
+    uint8_t uid[128];
+    Barrier bar(nProcs);
+    std::mutex failMutex;
+    std::string failure;
+    auto failAll = [&](const std::string &msg) {
+        std::lock_guard<std::mutex> lk(failMutex);
+        if (failure.empty())
+            failure = msg;
+    };
+    int64_t totalPoints = 0, totalInternal = 0;
+    std::vector<std::thread> threads;
+    for (int k = 0; k < nProcs; ++k)
+        threads.emplace_back([&, k] {
+            const std::string procDir = ro.caseDir + "/processor" + std::to_string(k);
+            smmesh *mesh = smmesh_read_processor(ro.caseDir.c_str(), k);
+            smgpu_handle *h = nullptr;
+            bool ok = mesh != nullptr;
+            if (!ok)
+                failAll(std::string("cannot read ") + procDir + ": " + smmesh_last_error());
+            if (ok && ro.startName != "constant" && fileExists(procDir + "/" + ro.startName + "/polyMesh/points"))
+                if (smmesh_read_points(mesh, (procDir + "/" + ro.startName + "/polyMesh/points").c_str()) != SMGPU_OK)
+                {
+                    ok = false;
+                    failAll(smmesh_last_error());
+                }
+            int64_t nPoints = 0;
+            std::vector<int32_t> pStart, pSize, pKind;
+            if (ok)
+            {
+                nPoints = smmesh_size(mesh, 0);
+                const int nPatches = (int)smmesh_size(mesh, 5);
+                pStart.resize(nPatches), pSize.resize(nPatches), pKind.resize(nPatches);
+                smmesh_patches(mesh, pStart.data(), pSize.data(), pKind.data());
+                smgpu_mesh_desc md;
+                memset(&md, 0, sizeof md);
+                md.n_points = nPoints;
+                md.n_cells = smmesh_size(mesh, 1);
+                md.n_faces = smmesh_size(mesh, 2);
+                md.n_internal_faces = smmesh_size(mesh, 3);
+                md.points = smmesh_points(mesh);
+                md.face_offsets = smmesh_face_offsets(mesh);
+                md.face_verts = smmesh_face_verts(mesh);
+                md.owner = smmesh_owner(mesh);
+                md.neighbour = smmesh_neighbour(mesh);
+                md.n_patches = nPatches;
+                md.patch_start = pStart.data();
+                md.patch_size = pSize.data();
+                md.patch_kind = pKind.data();
+                md.point_global_id = smmesh_point_global_id(mesh);
+                smgpu_params prm = ro.prm;
+                prm.device = k;
+                if (smgpu_create(&md, &prm, &h) != SMGPU_OK)
+                {
+                    ok = false;
+                    failAll(smgpu_last_error());
+                }
+            }
+            if (ok)
+            {
+                int64_t n = 0;
+                smgpu_comm_local_shared(h, &n, nullptr);
+                shared[k].resize(n);
+                smgpu_comm_local_shared(h, &n, shared[k].data());
+            }
+            bar.wait();
+            if (k == 0 && failure.empty())
+            {
+                for (int r = 0; r < nProcs; ++r)
+                {
+                    counts[r] = (int64_t)shared[r].size();
+                    allGids.insert(allGids.end(), shared[r].begin(), shared[r].end());
+                }
+                if (allGids.empty())
+                    allGids.push_back(0);
+                if (smgpu_comm_unique_id(uid) != SMGPU_OK)
+                    failAll(smgpu_last_error());
+            }
+            bar.wait();
+            if (!failure.empty())
+                return;
+            if (smgpu_comm_init(h, k, nProcs, uid, counts.data(), allGids.data()) != SMGPU_OK)
+                failAll(smgpu_last_error());
+            bar.wait();
+            if (!failure.empty())
+                return;
+            double mn, mx;
+            int64_t nInternal, nEdges;
+            smgpu_mesh_stats(h, &mn, &mx, &nInternal, &nEdges);
+            {
+                std::lock_guard<std::mutex> lk(failMutex);
+                totalPoints += nPoints;
+                totalInternal += nInternal;
+            }
+            bar.wait();
+            smgpu_params prm;
+            smgpu_get_params(h, &prm);
+            if (k == 0)
+            {
+                printf("Applying following parameter values in smoothing:\n    centroidalIters        %d\n    relTol"
+                       "                 %g\n    minEdgeLength          %g\n    maxStepLength          %g\n    "
+                       "relStepFrac            %g\n    totalMinFreeze         %d\n\n",
+                       ro.centroidalIters, prm.rel_tol, prm.min_edge_length, prm.max_step_length, prm.rel_step_frac,
+                       prm.total_min_freeze);
+                printf("Mesh includes a total of %lld points:\n  - %lld internal (non-boundary) points\n  - %lld boundary "
+                       "points\nMesh minimum edge length = %g\nMesh maximum edge length = %g\n\n",
+                       (long long)totalPoints, (long long)totalInternal, (long long)(totalPoints - totalInternal), mn, mx);
+            }
+            std::vector<double> pts(3 * nPoints);
+            std::vector<int64_t> nFrozen(std::max(ro.centroidalIters, 1));
+            std::vector<double> residual(std::max(ro.centroidalIters, 1));
+            int i = 0, logPrecision = 6;
+            bool stop = ro.centroidalIters <= 0;
+            while (!stop && failure.empty())
+            {
+                int chunk = ro.centroidalIters - i;
+                if (ro.writeInterval > 0)
+                {
+                    int toWrite = ro.writeInterval - (i % ro.writeInterval);
+                    if (i + toWrite - 1 == 0)
+                        toWrite += ro.writeInterval; // the `i > 0` quirk at :2416
+                    chunk = std::min(chunk, toWrite);
+                }
+                int done = 0;
+                if (smgpu_iterate(h, chunk, nFrozen.data(), residual.data(), &done) != SMGPU_OK)
+                {
+                    failAll(smgpu_last_error());
+                    break;
+                }
+                if (k == 0)
+                    for (int q = 0; q < done; ++q)
+                        printf("Smoothing iteration=%d nFrozenPoints=%lld residual=%.*g\n", i + q + 1, (long long)nFrozen[q],
+                               logPrecision, residual[q]);
+                i += done;
+                if (done > 0 && residual[done - 1] < prm.rel_tol)
+                {
+                    if (k == 0)
+                        printf("Residual reached relTol, stopping.\n");
+                    stop = true;
+                }
+                if (i >= ro.centroidalIters)
+                {
+                    if (k == 0)
+                        printf("Maximum centroidalIters reached, stopping.\n");
+                    stop = true;
+                }
+                const int last = i - 1;
+                if (stop || (ro.writeInterval > 0 && ((last + 1) % ro.writeInterval) == 0 && last > 0))
+                {
+                    const std::string tn = timeName(ro.startTime + i * ro.deltaT, ro.timePrecision);
+                    logPrecision = std::max(10, logPrecision);
+                    if (k == 0)
+                        printf("Writing new mesh to time %s\n\n", tn.c_str());
+                    if (smgpu_get_points(h, pts.data()) != SMGPU_OK ||
+                        smmesh_write_points(pts.data(), nPoints, (procDir + "/" + tn + "/polyMesh").c_str(), ro.binary,
+                                            std::max(10, ro.writePrecision), (tn + "/polyMesh").c_str()) != SMGPU_OK)
+                        failAll("cannot write points of processor " + std::to_string(k));
+                }
+            }
+            bar.wait(); // nobody tears its communicator down while others still iterate
+            smgpu_destroy(h);
+            smmesh_free(mesh);
+        });
+    for (auto &t : threads)
+        t.join();
+    if (!failure.empty())
+        fatal(failure);
+    printf("\nEnd\n");
+    return 0;
+}
+
 int main(int argc, char **argv)
 {
     // ---- option table: name -> has value (src/smoothMesh.C:1642-1784 + OpenFOAM standard options)
@@ -221,7 +447,8 @@ int main(int argc, char **argv)
                             "relTol",
                             "writeInterval",
                             "device",
-                            "geometryVariant"};
+                            "geometryVariant",
+                            "decompose"};
     std::map<std::string, std::string> opt;
     bool parallel = false;
     for (int i = 1; i < argc; ++i)
@@ -258,10 +485,6 @@ int main(int argc, char **argv)
     auto num = [&](const char *k, double dflt) { return has(k) ? atof(opt[k].c_str()) : dflt; };
 
     printf("smoothMesh (smoothmesh_b200: %s)\n\n", smgpu_version());
-    if (parallel)
-        fatal("-parallel (one process per processorN directory under mpirun) is not available in the stand-alone "
-              "build; multi-GPU runs go through the library's NCCL layer (see INTEGRATION.md)");
-
     const std::string caseDir = has("case") ? opt["case"] : ".";
     std::map<std::string, std::string> control = readDict(caseDir + "/system/controlDict");
     const double deltaT = control.count("deltaT") ? atof(control["deltaT"].c_str()) : 1.0;
@@ -272,7 +495,8 @@ int main(int argc, char **argv)
     const int timePrecision = control.count("timePrecision") ? atoi(control["timePrecision"].c_str()) : 6;
 
     // ---- start time (createTime.H + :1792-1803) and mesh instance lookup (createMesh.H)
-    std::vector<std::pair<double, std::string>> times = findTimes(caseDir);
+    // -parallel looks the time directories up under processor0/ (the case root holds none after decomposePar)
+    std::vector<std::pair<double, std::string>> times = findTimes(parallel ? caseDir + "/processor0" : caseDir);
     double startTime = 0;
     std::string startName = "0";
     if (has("time"))
@@ -307,6 +531,61 @@ int main(int argc, char **argv)
             startName = timeName(startTime, timePrecision);
         }
     }
+    // ---- options -> library parameters (:1863-1931)
+    const double layerMaxBlendingFraction = num("layerMaxBlendingFraction", 0.3);
+    smgpu_params prm;
+    smgpu_default_params(&prm);
+    prm.min_edge_length = num("minEdgeLength", -1.0);
+    prm.max_step_length = num("maxStepLength", -1.0);
+    prm.rel_step_frac = num("relStepFrac", 0.5);
+    prm.total_min_freeze = has("totalMinFreeze") ? parseSwitch(opt["totalMinFreeze"], "totalMinFreeze") : 0;
+    prm.min_angle_deg = num("minAngle", 35.0);
+    prm.max_angle_deg = num("maxAngle", 160.0);
+    prm.edge_angle_constraint = has("edgeAngleConstraint") ? parseSwitch(opt["edgeAngleConstraint"], "edgeAngleConstraint") : 1;
+    prm.face_angle_constraint = has("faceAngleConstraint") ? parseSwitch(opt["faceAngleConstraint"], "faceAngleConstraint") : 1;
+    prm.rel_tol = num("relTol", 0.02);
+    prm.device = (int)num("device", 0);
+    prm.geometry_variant = has("geometryVariant") && opt["geometryVariant"] == "org" ? 1 : 0;
+    prm.layer_max_blending_fraction = layerMaxBlendingFraction;
+    prm.layer_edge_length = num("layerEdgeLength", -1.0);
+    prm.layer_expansion_ratio = num("layerExpansionRatio", 1.3);
+    prm.min_layers = (int)num("minLayers", 1);
+    prm.max_layers = (int)num("maxLayers", 4);
+    const int centroidalIters = (int)num("centroidalIters", 1000);
+    const int writeInterval = (int)num("writeInterval", centroidalIters);
+    auto patchSetEmpty = [&](const std::string &expr) {
+        std::string s = expr;
+        s.erase(std::remove_if(s.begin(), s.end(), [](char c) { return isspace((unsigned char)c) || c == '"'; }), s.end());
+        return s == "()" || s == "none" || s == "(none)" || s.empty();
+    };
+    const bool smoothingPatchesEmpty = has("smoothingPatches") && patchSetEmpty(opt["smoothingPatches"]);
+    const bool surfaces = fileExists(caseDir + "/constant/geometry/targetSurfaces.obj");
+    const bool initEdges = fileExists(caseDir + "/constant/geometry/initEdges.obj");
+    if (!has("decompose") && surfaces && initEdges && !smoothingPatchesEmpty)
+        fatal("boundary point smoothing would be enabled (constant/geometry/*.obj present and smoothingPatches not "
+              "empty); it is outside the GPU hot path and there is no CPU fallback; pass -smoothingPatches '()'");
+
+    if (parallel)
+    {
+        if (has("decompose"))
+            fatal("-decompose and -parallel are separate steps");
+        if (has("layerPatches") && !patchSetEmpty(opt["layerPatches"]) && layerMaxBlendingFraction > 1e-15)
+            fatal("-layerPatches with -parallel: the boundary layer treatment is single-GPU in this build");
+        RunOptions ro;
+        ro.prm = prm;
+        ro.centroidalIters = centroidalIters;
+        ro.writeInterval = writeInterval;
+        ro.deltaT = deltaT;
+        ro.startTime = startTime;
+        ro.binary = binary;
+        ro.writePrecision = writePrecision;
+        ro.timePrecision = timePrecision;
+        ro.caseDir = caseDir;
+        ro.startName = startName;
+        printf("Create time\n\n");
+        return runParallel(ro);
+    }
+
     // newest time <= start time that has polyMesh/points; topology from the newest with polyMesh/faces; else constant
     std::string pointsDir = caseDir + "/constant/polyMesh", topoDir = caseDir + "/constant/polyMesh";
     if (startName != "constant")
@@ -328,18 +607,34 @@ int main(int argc, char **argv)
         if (smmesh_read_points(mesh, (pointsDir + "/points").c_str()) != SMGPU_OK)
             fatal(std::string("cannot read ") + pointsDir + "/points: " + smmesh_last_error());
     }
+    if (has("decompose"))
+    {
+        // utility mode standing in for decomposePar (testcase/run_parallel:19): simple (nx ny nz) bricks
+        int d[3] = {0, 0, 0};
+        std::string v = opt["decompose"];
+        for (char &c : v)
+            if (c == '(' || c == ')' || c == ',')
+                c = ' ';
+        if (sscanf(v.c_str(), "%d %d %d", &d[0], &d[1], &d[2]) != 3 || d[0] < 1 || d[1] < 1 || d[2] < 1)
+            fatal("-decompose expects '(nx ny nz)'");
+        const int nParts = d[0] * d[1] * d[2];
+        std::vector<smmesh *> parts(nParts, nullptr);
+        if (smmesh_decompose(mesh, 0, d[0], d[1], d[2], parts.data()) != SMGPU_OK ||
+            smmesh_write_decomposed(parts.data(), nParts, caseDir.c_str(), binary) != SMGPU_OK)
+            fatal(smmesh_last_error());
+        for (smmesh *q : parts)
+            smmesh_free(q);
+        printf("Decomposed mesh of time %s into %d processor directories under %s\n\nEnd\n", startName.c_str(),
+               d[0] * d[1] * d[2], caseDir.c_str());
+        smmesh_free(mesh);
+        return 0;
+    }
     const int64_t nPoints = smmesh_size(mesh, 0);
     const int nPatches = (int)smmesh_size(mesh, 5);
     std::vector<int32_t> pStart(nPatches), pSize(nPatches), pKind(nPatches);
     smmesh_patches(mesh, pStart.data(), pSize.data(), pKind.data());
 
     // ---- features outside the hot path (:1823-1852, :2024-2098)
-    auto patchSetEmpty = [&](const std::string &expr) {
-        std::string s = expr;
-        s.erase(std::remove_if(s.begin(), s.end(), [](char c) { return isspace((unsigned char)c) || c == '"'; }), s.end());
-        return s == "()" || s == "none" || s == "(none)" || s.empty();
-    };
-    const double layerMaxBlendingFraction = num("layerMaxBlendingFraction", 0.3);
     std::vector<std::string> patchNames;
     for (int i = 0; i < nPatches; ++i)
         patchNames.push_back(smmesh_patch_name(mesh, i));
@@ -356,12 +651,6 @@ int main(int argc, char **argv)
     else
         printf("Patches for boundary layer treatment: none\n");
     const bool doLayerTreatment = anyLayerPatch && layerMaxBlendingFraction > 1e-15; // :2025
-    const bool smoothingPatchesEmpty = has("smoothingPatches") && patchSetEmpty(opt["smoothingPatches"]);
-    const bool surfaces = fileExists(caseDir + "/constant/geometry/targetSurfaces.obj");
-    const bool initEdges = fileExists(caseDir + "/constant/geometry/initEdges.obj");
-    if (surfaces && initEdges && !smoothingPatchesEmpty)
-        fatal("boundary point smoothing would be enabled (constant/geometry/*.obj present and smoothingPatches not "
-              "empty); it is outside the GPU hot path and there is no CPU fallback; pass -smoothingPatches '()'");
     printf("Patches for boundary point smoothing: %s\n",
            smoothingPatchesEmpty ? "none" : (has("smoothingPatches") ? opt["smoothingPatches"].c_str() : "(\".*\")"));
 
@@ -381,27 +670,7 @@ int main(int argc, char **argv)
     md.patch_start = pStart.data();
     md.patch_size = pSize.data();
     md.patch_kind = pKind.data();
-    smgpu_params prm;
-    smgpu_default_params(&prm);
-    prm.min_edge_length = num("minEdgeLength", -1.0);
-    prm.max_step_length = num("maxStepLength", -1.0);
-    prm.rel_step_frac = num("relStepFrac", 0.5);
-    prm.total_min_freeze = has("totalMinFreeze") ? parseSwitch(opt["totalMinFreeze"], "totalMinFreeze") : 0;
-    prm.min_angle_deg = num("minAngle", 35.0);
-    prm.max_angle_deg = num("maxAngle", 160.0);
-    prm.edge_angle_constraint = has("edgeAngleConstraint") ? parseSwitch(opt["edgeAngleConstraint"], "edgeAngleConstraint") : 1;
-    prm.face_angle_constraint = has("faceAngleConstraint") ? parseSwitch(opt["faceAngleConstraint"], "faceAngleConstraint") : 1;
-    prm.rel_tol = num("relTol", 0.02);
-    prm.device = (int)num("device", 0);
-    prm.geometry_variant = has("geometryVariant") && opt["geometryVariant"] == "org" ? 1 : 0;
-    prm.layer_max_blending_fraction = layerMaxBlendingFraction;
-    prm.layer_edge_length = num("layerEdgeLength", -1.0);
-    prm.layer_expansion_ratio = num("layerExpansionRatio", 1.3);
-    prm.min_layers = (int)num("minLayers", 1);
-    prm.max_layers = (int)num("maxLayers", 4);
     md.patch_layer = layerSel.data();
-    const int centroidalIters = (int)num("centroidalIters", 1000);
-    const int writeInterval = (int)num("writeInterval", centroidalIters);
 
     smgpu_handle *h = nullptr;
     if (smgpu_create(&md, &prm, &h) != SMGPU_OK)

@@ -62,3 +62,30 @@ def test_cli_ascii_precision_and_reltol_stop(tmp_path):
     out = sm.Mesh.read(case / "constant" / "polyMesh")
     out.read_points(case / str(n) / "polyMesh" / "points")
     assert np.allclose(out.points, o.get("points"), rtol=0, atol=1e-11)       # precision max(10, writePrecision)
+
+
+def test_cli_parallel_on_processor_directories(tmp_path):
+    """`smoothMesh -parallel` on a decomposed case (testcase/run_parallel:19-22: decomposePar, then
+    mpirun -np N smoothMesh -parallel): one GPU per processor directory, points written per processor."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    mesh = hex_jittered(8, 6, 5, 0.35, seed=33)
+    case = make_case(tmp_path, mesh)
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-decompose", "(2 1 1)"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    opts = ["-centroidalIters", "10", "-relTol", "0", "-minAngle", "60", "-maxAngle", "120", "-totalMinFreeze", "true",
+            "-writeInterval", "4", "-smoothingPatches", "()"]
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel"] + opts, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    parts = [sm.Mesh.read_processor(case, k) for k in range(2)]
+    o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0, total_min_freeze=1)
+    n, nf, res = o.iterate(10)
+    lines = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    assert [int(b) for _, b, _ in lines] == nf.tolist()
+    assert np.allclose([float(c) for _, _, c in lines], res, rtol=1e-5)
+    for k in range(2):
+        d = case / f"processor{k}"
+        assert sorted(p.name for p in d.iterdir() if p.name[0].isdigit()) == ["10", "4", "8"]
+        parts[k].read_points(d / "10" / "polyMesh" / "points")
+        assert np.array_equal(parts[k].points, o.get("points", rank=k))

@@ -145,3 +145,53 @@ def test_quality_metrics_known_answers():
     assert abs(q["max_non_ortho"] - 45.0) < 1e-9 and abs(q["min_edge_angle"] - 45.0) < 1e-9
     jq = hex_jittered(6, 6, 6, 0.3).quality()
     assert jq["max_non_ortho"] > 5 and jq["max_skewness"] > 0.05 and jq["min_volume"] > 0
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_decomposed_case_round_trip(tmp_path, binary):
+    """processor<k>/constant/polyMesh with pointProcAddressing / cellProcAddressing (decomposePar layout,
+    what testcase/run_parallel:19-22 leaves on disk)."""
+    m = hex_jittered(5, 4, 3, 0.2, seed=3)
+    parts = m.decompose(2, 2, 1)
+    sm.Mesh.write_decomposed(parts, tmp_path, binary=binary)
+    for k, p in enumerate(parts):
+        d = tmp_path / f"processor{k}" / "constant" / "polyMesh"
+        for f in ("points", "faces", "owner", "neighbour", "boundary", "pointProcAddressing", "cellProcAddressing"):
+            assert (d / f).exists(), f
+        q = sm.Mesh.read_processor(tmp_path, k)
+        assert np.array_equal(q.point_global_id, p.point_global_id)
+        assert np.array_equal(q.cell_global_id, p.cell_global_id)
+        assert np.array_equal(q.face_verts, p.face_verts) and np.array_equal(q.owner, p.owner)
+        assert np.array_equal(q.neighbour, p.neighbour)
+        for a, b in zip(q.patches, p.patches):
+            assert np.array_equal(a, b)                          # processor patches keep their kind
+        if binary:
+            assert np.array_equal(q.points, p.points)
+        else:
+            assert np.allclose(q.points, p.points, rtol=0, atol=1e-15)
+    # the boundary file names the neighbour rank of every processor patch
+    txt = (tmp_path / "processor0" / "constant" / "polyMesh" / "boundary").read_text()
+    assert "procBoundary0to1" in txt and "neighbProcNo" in txt and "myProcNo" in txt
+
+
+def test_cli_decompose_utility_and_parallel_refusals(tmp_path):
+    case = tmp_path / "case"
+    m = hex_jittered(4, 4, 2, 0.2, seed=5)
+    m.write(case / "constant" / "polyMesh")
+    (case / "system").mkdir()
+    (case / "system" / "controlDict").write_text("deltaT 1;\nwriteFormat binary;\n")
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-decompose", "(2 1 1)"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    expect = m.decompose(2, 1, 1)
+    for k in range(2):
+        q = sm.Mesh.read_processor(case, k)
+        assert np.array_equal(q.point_global_id, expect[k].point_global_id)
+        assert np.array_equal(q.points, expect[k].points)
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-decompose", "2"], capture_output=True, text=True)
+    assert r.returncode != 0 and "(nx ny nz)" in r.stderr
+    # -parallel without processor directories / without enough GPUs fails loudly (no serial fallback)
+    r = subprocess.run([sm.CLI_PATH, "-case", str(tmp_path / "case"), "-parallel", "-layerPatches", '("w.*")'],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "single-GPU" in r.stderr
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel"], capture_output=True, text=True)
+    assert r.returncode != 0 and "CUDA devices" in r.stderr
