@@ -107,7 +107,7 @@ class Oracle:
                  face_angle_constraint=1, geometry_variant=0, libm=False, threads=1, layer_patches=None,
                  layer_max_blending_fraction=0.3, layer_edge_length=-1.0, layer_expansion_ratio=1.3, min_layers=1,
                  max_layers=4):
-        """layer_patches: per-patch 0/1 flags (-layerPatches), serial runs only."""
+        """layer_patches: 0/1 flag per physical patch (-layerPatches)."""
         self.L = _lib(libm)
         if isinstance(meshes, dict):
             meshes = [meshes]
@@ -125,8 +125,14 @@ class Oracle:
                 pSize=np.ascontiguousarray(m["patch_size"], dtype=np.int32),
                 pKind=np.ascontiguousarray(m["patch_kind"], dtype=np.int32),
                 gid=None if m.get("point_global_id") is None else np.ascontiguousarray(m["point_global_id"], dtype=np.int64),
-                lay=None if layer_patches is None else np.ascontiguousarray(layer_patches, dtype=np.int32),
+                lay=None,
             )
+            if layer_patches is not None:
+                # flags of the physical patches; a processor mesh appends its processor patches (never selected)
+                lay = np.zeros(a["pStart"].size, dtype=np.int32)
+                k = min(lay.size, len(layer_patches))
+                lay[:k] = np.asarray(layer_patches, dtype=np.int32)[:k]
+                a["lay"] = lay
             self._keep.append(a)
             o = arr[r]
             o.P, o.C, o.F, o.Fi = a["pts"].size // 3, int(m["n_cells"]), a["own"].size, a["nei"].size

@@ -108,7 +108,7 @@ struct Rank
     // boundary layer treatment state (src/orthogonalBoundaryBlending.C)
     bool doLayerTreatment = false;
     std::vector<uint8_t> isConnectedToInternal, isLayerSurface, isOuterNeighInProc, isSharpEdge;
-    std::vector<int> hopsToLayer, pointToOuter;
+    std::vector<int> hopsToLayer, pointToOuter, newHopCounts, nBoundaryFaces, boundaryPointLabels;
     std::vector<V3> pointNormals, outerNeighCoords;
     std::vector<double> layerLength, layerBlend; // per hop count
     std::vector<V3> snapNormals, snapLayerBlend;
@@ -158,10 +158,16 @@ struct Rank
     void restrictMinEdgeAngleDecrease();
     bool restrictFaceAngleDeterioration();
     void classifyBoundaryPoints();
-    void calculatePointHopsToBoundary(int maxIter);
-    void calculateBoundaryPointNormals();
-    void propagateOuterNeighInfo(int maxIter);
-    bool setupLayers();
+    void layersBegin();
+    void hopsInit();
+    void hopsSweep();
+    void boundaryNormalsLocal();
+    void boundaryNormalsFinish();
+    void outerInit();
+    void outerSweep(int iter);
+    void outerUndo();
+    void layerTables();
+    void updateNeighCoordsLocal();
     bool blendWithOrthogonalPoints();
     bool calcMinMaxFaceAngleForEdge(int edgeI, double &mn, double &mx, int pI1, V3 c1, int pI2, V3 c2);
     bool calcMinMaxFaceAngleForPoint(int pI1, V3 c1, int pI2, V3 c2, double &mn, double &mx);
@@ -235,8 +241,9 @@ void Rank::classifyBoundaryPoints()
             }
 }
 
-// calculatePointHopsToBoundary, src/orthogonalBoundaryBlending.C:52-134 (serial)
-void Rank::calculatePointHopsToBoundary(int maxIter)
+// calculatePointHopsToBoundary, src/orthogonalBoundaryBlending.C:52-134, in two parts: the seeding
+// (:64-77) and one propagation sweep (:86-120); the caller synchronises after every sweep (:124-130).
+void Rank::hopsInit()
 {
     hopsToLayer.assign(P, UNDEF_LABEL);
     for (size_t patchI = 0; patchI < pKind.size(); ++patchI)
@@ -248,33 +255,34 @@ void Rank::calculatePointHopsToBoundary(int maxIter)
                 if (isConnectedToInternal[fV[k]])
                     hopsToLayer[fV[k]] = 0;
     }
-    std::vector<int> newHopCounts(P, -1);
-    for (int iter = 0; iter < maxIter; ++iter)
+    newHopCounts.assign(P, -1);
+}
+void Rank::hopsSweep()
+{
+    for (int pointI = 0; pointI < P; ++pointI)
     {
-        for (int pointI = 0; pointI < P; ++pointI)
-        {
-            if (hopsToLayer[pointI] >= 0 || !isInternal[pointI])
-                continue;
-            int maxHops = -1;
-            for (int neighI : pointPoints[pointI])
-                if (hopsToLayer[neighI] > maxHops)
-                    maxHops = hopsToLayer[neighI];
-            if (maxHops >= 0)
-                newHopCounts[pointI] = maxHops + 1;
-        }
-        for (int pointI = 0; pointI < P; ++pointI)
-            if (newHopCounts[pointI] > hopsToLayer[pointI])
-                hopsToLayer[pointI] = newHopCounts[pointI];
+        if (hopsToLayer[pointI] >= 0 || !isInternal[pointI])
+            continue;
+        int maxHops = -1;
+        for (int neighI : pointPoints[pointI])
+            if (hopsToLayer[neighI] > maxHops)
+                maxHops = hopsToLayer[neighI];
+        if (maxHops >= 0)
+            newHopCounts[pointI] = maxHops + 1;
     }
+    for (int pointI = 0; pointI < P; ++pointI)
+        if (newHopCounts[pointI] > hopsToLayer[pointI])
+            hopsToLayer[pointI] = newHopCounts[pointI];
 }
 
-// calculateBoundaryPointNormals, src/orthogonalBoundaryBlending.C:141-233.  Note that it
-// accumulates onto the normals of the previous call (no zeroing at :178) and re-normalises
-// every non-zero normal, internal points included (:224-230).
-void Rank::calculateBoundaryPointNormals()
+// calculateBoundaryPointNormals, src/orthogonalBoundaryBlending.C:141-233, in two parts around the
+// two sum-synchronisations at :185-198.  Note that it accumulates onto the normals of the previous
+// call (no zeroing at :178; a shared point therefore also sums the previous normal of every copy)
+// and re-normalises every non-zero normal, internal points included (:224-230).
+void Rank::boundaryNormalsLocal()
 {
     calcGeometry(); // patch.Sf() / patch.magSf() of the current mesh, :171-172
-    std::vector<int> nFaces(P, 0);
+    nBoundaryFaces.assign(P, 0);
     for (size_t patchI = 0; patchI < pKind.size(); ++patchI)
     {
         if (pKind[patchI] != 0)
@@ -285,13 +293,16 @@ void Rank::calculateBoundaryPointNormals()
             for (int k = fOff[f]; k < fOff[f + 1]; ++k)
             {
                 pointNormals[fV[k]] = pointNormals[fV[k]] - Sf;
-                ++nFaces[fV[k]];
+                ++nBoundaryFaces[fV[k]];
             }
         }
     }
+}
+void Rank::boundaryNormalsFinish()
+{
     for (int pointI = 0; pointI < P; ++pointI)
     {
-        if (nFaces[pointI] < 1)
+        if (nBoundaryFaces[pointI] < 1)
             continue;
         if (mag(pointNormals[pointI]) < 0.1)
         {
@@ -306,41 +317,47 @@ void Rank::calculateBoundaryPointNormals()
             pointNormals[pointI] = pointNormals[pointI] / mag(pointNormals[pointI]);
 }
 
-// propagateOuterNeighInfo, src/orthogonalBoundaryBlending.C:244-391 (serial)
-void Rank::propagateOuterNeighInfo(int maxIter)
+// propagateOuterNeighInfo, src/orthogonalBoundaryBlending.C:244-391: initialisation, one sweep per
+// hop count (the caller synchronises the normals with maxMagSqr after every sweep, :363-369), undo.
+void Rank::outerInit()
 {
     isOuterNeighInProc.assign(P, 0);
     pointToOuter.assign(P, UNDEF_LABEL);
-    std::vector<int> boundaryPointLabels(P, UNDEF_LABEL);
-    for (int iter = 1; iter < maxIter + 1; ++iter)
-        for (int pointI = 0; pointI < P; ++pointI)
-        {
-            const int nHops = hopsToLayer[pointI];
-            if (nHops != iter)
-                continue;
-            int nNeighHops = 0, neighPointI = UNDEF_LABEL;
-            for (int neighI : pointPoints[pointI])
-                if (hopsToLayer[neighI] == nHops - 1)
-                {
-                    ++nNeighHops;
-                    neighPointI = neighI;
-                }
-            if (nNeighHops != 1)
-                continue;
-            if (!isInternal[neighPointI] && !isLayerSurface[neighPointI])
-                continue;
-            const auto it = std::find(boundaryPointLabels.begin(), boundaryPointLabels.end(), neighPointI);
-            if (it != boundaryPointLabels.end())
+    boundaryPointLabels.assign(P, UNDEF_LABEL);
+}
+void Rank::outerSweep(int iter)
+{
+    for (int pointI = 0; pointI < P; ++pointI)
+    {
+        const int nHops = hopsToLayer[pointI];
+        if (nHops != iter)
+            continue;
+        int nNeighHops = 0, neighPointI = UNDEF_LABEL;
+        for (int neighI : pointPoints[pointI])
+            if (hopsToLayer[neighI] == nHops - 1)
             {
-                pointNormals[pointI] = UNDEF_VECTOR;
-                pointNormals[it - boundaryPointLabels.begin()] = UNDEF_VECTOR;
-                continue;
+                ++nNeighHops;
+                neighPointI = neighI;
             }
-            isOuterNeighInProc[pointI] = 1;
-            pointToOuter[pointI] = neighPointI;
-            pointNormals[pointI] = pointNormals[neighPointI];
-            boundaryPointLabels[pointI] = neighPointI;
+        if (nNeighHops != 1)
+            continue;
+        if (!isInternal[neighPointI] && !isLayerSurface[neighPointI])
+            continue;
+        const auto it = std::find(boundaryPointLabels.begin(), boundaryPointLabels.end(), neighPointI);
+        if (it != boundaryPointLabels.end())
+        {
+            pointNormals[pointI] = UNDEF_VECTOR;
+            pointNormals[it - boundaryPointLabels.begin()] = UNDEF_VECTOR;
+            continue;
         }
+        isOuterNeighInProc[pointI] = 1;
+        pointToOuter[pointI] = neighPointI;
+        pointNormals[pointI] = pointNormals[neighPointI];
+        boundaryPointLabels[pointI] = neighPointI;
+    }
+}
+void Rank::outerUndo()
+{
     for (int pointI = 0; pointI < P; ++pointI)
         if (veq(pointNormals[pointI], UNDEF_VECTOR))
         {
@@ -350,27 +367,23 @@ void Rank::propagateOuterNeighInfo(int maxIter)
         }
 }
 
-// src/smoothMesh.C:2024-2033, 2190-2221 (layer part; boundary point smoothing is out of scope)
-bool Rank::setupLayers()
+// src/smoothMesh.C:2024-2033 and the local, communication-free pieces of :2190-2221; Group::setupLayers
+// drives the phases and the synchronisations between them.
+void Rank::layersBegin()
 {
     bool anyLayerPatch = false;
     for (int f : pLayer)
         anyLayerPatch = anyLayerPatch || f;
     doLayerTreatment = anyLayerPatch && prm.layerMaxBlendingFraction > SM_SMALL;
     if (!doLayerTreatment)
-        return true;
-    if (!gid.empty())
-    {
-        err = "boundary layer treatment is only restated for serial runs";
-        return false;
-    }
+        return;
     pointNormals.assign(P, ZERO_VECTOR);
     isSharpEdge.assign(P, 0);
     classifyBoundaryPoints();
-    calculatePointHopsToBoundary(prm.maxLayers + 1);
-    calculateBoundaryPointNormals();
-    propagateOuterNeighInfo(prm.maxLayers + 1);
-    // per-hop constants of blendWithOrthogonalPoints (:547-555); maxLayers there is maxLayers + 1 (:2300)
+}
+// per-hop constants of blendWithOrthogonalPoints (:547-555); maxLayers there is maxLayers + 1 (:2300)
+void Rank::layerTables()
+{
     const double maxLayers = prm.maxLayers + 1, minLayers = prm.minLayers;
     const double layerEdgeLength = prm.layerEdgeLength < 0 ? prm.minEdgeLength : prm.layerEdgeLength;
     int maxHopSeen = 0;
@@ -387,16 +400,20 @@ bool Rank::setupLayers()
         const double y = y0 + slope * nHops;
         layerBlend[nHops] = fmax_(0.0, fmin_(y, prm.layerMaxBlendingFraction));
     }
-    return true;
 }
 
-// updateNeighCoords (:464-501) + blendWithOrthogonalPoints (:507-567)
-bool Rank::blendWithOrthogonalPoints()
+// updateNeighCoords, local part (:472-487); the caller synchronises with minMagSqr (:491-497)
+void Rank::updateNeighCoordsLocal()
 {
     outerNeighCoords.assign(P, UNDEF_VECTOR);
     for (int pointI = 0; pointI < P; ++pointI)
         if (isOuterNeighInProc[pointI])
             outerNeighCoords[pointI] = pts[pointToOuter[pointI]];
+}
+
+// blendWithOrthogonalPoints (:507-567)
+bool Rank::blendWithOrthogonalPoints()
+{
     for (int pointI = 0; pointI < P; ++pointI)
     {
         if (veq(pointNormals[pointI], ZERO_VECTOR) || !isInternal[pointI])
@@ -1269,17 +1286,70 @@ struct Group
         }
     }
 
+    // calculateBoundaryPointNormals with its two synchronisations (orthogonalBoundaryBlending.C:185-198)
+    void calculateBoundaryPointNormals()
+    {
+        forRanks([](Rank &R) {
+            if (R.doLayerTreatment)
+                R.boundaryNormalsLocal();
+            return true;
+        });
+        if (ranks[0].doLayerTreatment)
+        {
+            sync(&Rank::pointNormals, [](V3 &x, const V3 &y) { x = x + y; });    // plusEqOp<vector>
+            sync(&Rank::nBoundaryFaces, [](int &x, const int &y) { x = x + y; }); // plusEqOp<label>
+        }
+        forRanks([](Rank &R) {
+            if (R.doLayerTreatment)
+                R.boundaryNormalsFinish();
+            return true;
+        });
+    }
+
+    // One-time layer set-up, src/smoothMesh.C:2215-2221 (the layer-treatment calls), with the
+    // synchronisations of orthogonalBoundaryBlending.C:124-130 (max), :185-198 (sum), :363-369 (maxMagSqr).
+    void setupLayers()
+    {
+        for (auto &R : ranks)
+            R.layersBegin();
+        if (!ranks[0].doLayerTreatment)
+            return;
+        const int maxIter = ranks[0].prm.maxLayers + 1;
+        for (auto &R : ranks)
+            R.hopsInit();
+        for (int iter = 0; iter < maxIter; ++iter)
+        {
+            for (auto &R : ranks)
+                R.hopsSweep();
+            sync(&Rank::hopsToLayer, [](int &x, const int &y) { x = (x > y) ? x : y; }); // maxEqOp<label>
+        }
+        calculateBoundaryPointNormals();
+        for (auto &R : ranks)
+            R.outerInit();
+        for (int iter = 1; iter < maxIter + 1; ++iter)
+        {
+            for (auto &R : ranks)
+                R.outerSweep(iter);
+            // maxMagSqrEqOp<vector> [OF-recalled, ops.H]: x = (magSqr(x) >= magSqr(y)) ? x : y
+            sync(&Rank::pointNormals, [](V3 &x, const V3 &y) { x = (magSqr(x) >= magSqr(y)) ? x : y; });
+        }
+        for (auto &R : ranks)
+        {
+            R.outerUndo();
+            R.layerTables();
+        }
+    }
+
     // One smoothing iteration, src/smoothMesh.C:2257-2399.  Returns false on a
     // FatalError-equivalent.
     bool iterate(int64_t &nFrozenSum, double &res)
     {
+        // :2266 (the call is unconditional in the reference; its result is only used with layer treatment)
+        calculateBoundaryPointNormals();
         forRanks([](Rank &R) {
             R.frozen.assign(R.P, 0); // :2262-2263
             if (R.doLayerTreatment)
-            { // :2266 (the call is unconditional in the reference; its result is only used here)
-                R.calculateBoundaryPointNormals();
                 R.snapNormals = R.pointNormals;
-            }
             R.centroidalPartial();   // :2269
             R.snapCellCtr = R.cellCtr;
             return true;
@@ -1295,11 +1365,18 @@ struct Group
         mergeClosest(2);
         mergeClosest(3);
         sync(&Rank::hasCommon, [](uint8_t &x, const uint8_t &y) { x = x || y; }); // :472
+        forRanks([](Rank &R) {
+            R.aspectRatioBlend();
+            R.constrainMaxStepLength(); // :2280
+            if (R.doLayerTreatment)
+                R.updateNeighCoordsLocal(); // :2286
+            return true;
+        });
+        if (ranks[0].doLayerTreatment) // minMagSqrEqOp<vector>, orthogonalBoundaryBlending.C:491-497
+            sync(&Rank::outerNeighCoords, [](V3 &x, const V3 &y) { x = (magSqr(x) <= magSqr(y)) ? x : y; });
         if (!forRanks([](Rank &R) {
-                R.aspectRatioBlend();
-                R.constrainMaxStepLength(); // :2280
                 if (R.doLayerTreatment)
-                { // :2283-2305
+                { // :2288-2304
                     if (!R.blendWithOrthogonalPoints())
                         return false;
                     R.constrainMaxStepLength();
@@ -1416,14 +1493,8 @@ extern "C"
     {
         Group *g = (Group *)h;
         for (auto &R : g->ranks)
-        {
             memcpy(&R.prm, p, sizeof(Params));
-            if (!R.setupLayers())
-            {
-                g_last_error = R.err;
-                return -1;
-            }
-        }
+        g->setupLayers();
         return 0;
     }
 

@@ -356,7 +356,9 @@ class Smoother:
     """Device-resident smoothing state; the C-ABI counterpart of the reference's main() loop."""
 
     def __init__(self, mesh: Mesh, params: Params | None = None, layer_patches=None, **kw):
-        """layer_patches: per-patch 0/1 flags (the patches -layerPatches selects), serial runs only."""
+        """layer_patches: 0/1 flag per patch (the patches -layerPatches selects); shorter lists are padded
+        with 0, so the flags of the physical patches also fit a processor mesh (its processor patches
+        come last).  On a processor mesh the layer set-up completes in comm_init (it is collective)."""
         L = lib()
         self.params_in = params if params is not None else default_params(**kw)
         self._arrays = mesh.desc_arrays()  # keep alive during create
@@ -369,7 +371,11 @@ class Smoother:
         d.n_patches = len(a["patch_start"])
         d.patch_start, d.patch_size, d.patch_kind = _ptr(a["patch_start"]), _ptr(a["patch_size"]), _ptr(a["patch_kind"])
         d.point_global_id = _ptr(a["point_global_id"])
-        lay = None if layer_patches is None else np.ascontiguousarray(layer_patches, dtype=np.int32)
+        lay = None
+        if layer_patches is not None:
+            lay = np.zeros(d.n_patches, dtype=np.int32)
+            k = min(d.n_patches, len(layer_patches))
+            lay[:k] = np.asarray(layer_patches, dtype=np.int32)[:k]
         d.patch_layer = _ptr(lay)
         h = C.c_void_p()
         rc = L.smgpu_create(C.byref(d), C.byref(self.params_in), C.byref(h))

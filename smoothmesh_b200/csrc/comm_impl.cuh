@@ -19,12 +19,14 @@
 namespace smk
 {
 
-#define SMK_TUPLE 16 /* doubles per interface-point record */
+#define SMK_TUPLE 16       /* doubles per interface-point record */
+#define SMK_TUPLE_LAYERS 24 /* with boundary layer treatment: + accumulated normal, face count, outer neighbour */
 #define SMK_MAXCOPIES 16
 
 struct CommDev
 {
     int nSlots, nShared, rank;
+    int tuple; // doubles per record: SMK_TUPLE, or SMK_TUPLE_LAYERS with boundary layer treatment
     const int *sendPoint, *sharedPoint, *selfSlot, *copyOff, *copyRank, *copySlot;
     double *sendBuf, *recvBuf;
     uint8_t *sendFz, *recvFz;
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
     PointLocal L;
     pointLocal(d, p, x, internal, L);
     const bool hc = shareCell(d, L.n1, L.n2);
-    double *r = c.sendBuf + (size_t)i * SMK_TUPLE;
+    double *r = c.sendBuf + (size_t)i * c.tuple;
     r[0] = L.sum.x, r[1] = L.sum.y, r[2] = L.sum.z;
     r[3] = (double)L.nCells;
     r[4] = L.r1.x, r[5] = L.r1.y, r[6] = L.r1.z;
@@ -55,6 +57,27 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
     r[10] = L.r3.x, r[11] = L.r3.y, r[12] = L.r3.z;
     r[13] = hc ? 1.0 : 0.0;
     r[14] = r[15] = 0.0;
+    if (d.layers)
+    {
+        // calculateBoundaryPointNormals up to its synchronisation (orthogonalBoundaryBlending.C:151-182):
+        // this copy's previous normal minus the unit normals of its boundary faces, and the face count
+        D3 n = ld3(d.normals, p);
+        const int b = d.bfOff[p], e = d.bfOff[p + 1];
+        for (int k = b; k < e; ++k)
+        {
+            const D3 Sf = ld3(d.faceGeo, 2 * d.bf[k] + 1);
+            n = n - Sf / mag(Sf);
+        }
+        r[16] = n.x, r[17] = n.y, r[18] = n.z;
+        r[19] = (double)(e - b);
+        // updateNeighCoords before its synchronisation (:472-487)
+        const int o = d.pointToOuter[p];
+        D3 oc = {SM_GREAT, SM_GREAT, SM_GREAT};
+        if (o >= 0)
+            oc = ld3(d.pts, o);
+        r[20] = oc.x, r[21] = oc.y, r[22] = oc.z;
+        r[23] = 0.0;
+    }
 }
 
 // isSmallerByVectorElements / isCloserPoint, src/smoothMesh.C:222-272
@@ -95,8 +118,8 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
     const int n = nOther + 1;
     D3 cp1[SMK_MAXCOPIES], cp2[SMK_MAXCOPIES], cp3[SMK_MAXCOPIES];
     bool hc[SMK_MAXCOPIES];
-    D3 sum = {0, 0, 0};
-    double cnt = 0.0;
+    D3 sum = {0, 0, 0}, nrm = {0, 0, 0}, outer = {0, 0, 0};
+    double cnt = 0.0, nBoundaryFaces = 0.0;
     int me = -1;
     // copies in ascending rank order, the local one inserted at its rank
     for (int k = 0, o = 0; k < n; ++k)
@@ -104,13 +127,29 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
         const double *r;
         if (me < 0 && (o >= nOther || c.copyRank[cb + o] > c.rank))
         {
-            r = c.sendBuf + (size_t)c.selfSlot[s] * SMK_TUPLE;
+            r = c.sendBuf + (size_t)c.selfSlot[s] * c.tuple;
             me = k;
         }
         else
         {
-            r = c.recvBuf + (size_t)c.copySlot[cb + o] * SMK_TUPLE;
+            r = c.recvBuf + (size_t)c.copySlot[cb + o] * c.tuple;
             ++o;
+        }
+        if (d.layers)
+        {
+            const D3 nk = {r[16], r[17], r[18]}, ok = {r[20], r[21], r[22]};
+            if (k == 0)
+            {
+                nrm = nk;
+                nBoundaryFaces = r[19];
+                outer = ok;
+            }
+            else
+            {
+                nrm = nrm + nk;                           // plusEqOp<vector>, orthogonalBoundaryBlending.C:185
+                nBoundaryFaces = nBoundaryFaces + r[19];  // plusEqOp<label>, :193
+                outer = minMagSqr(outer, ok);             // minMagSqrEqOp<vector>, :491
+            }
         }
         const D3 part = {r[0], r[1], r[2]};
         if (k == 0)
@@ -169,7 +208,34 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
     double blend = 0.0;
     if (!anyCommon)
         blend = blendFraction(cp1[me], cp2[me], mag(cp1[me]), mag(cp2[me]), mag(cp3[me]), internal);
-    const D3 np = blendAndClamp(d, x, cen, cp1[me], cp2[me], blend);
+    D3 np = blendAndClamp(d, x, cen, cp1[me], cp2[me], blend);
+    if (d.layers)
+    {
+        // rest of calculateBoundaryPointNormals for this point (:200-230), then
+        // blendWithOrthogonalPoints + the second constrainMaxStepLength (src/smoothMesh.C:2288-2304)
+        const D3 zero = {0, 0, 0};
+        if (nBoundaryFaces >= 1.0 && mag(nrm) < 0.1)
+            nrm = zero;
+        if (!veq(nrm, zero))
+            nrm = nrm / mag(nrm);
+        st4(d.normals + p, nrm, 0.0);
+        const int nHops = d.hops[p];
+        if (!veq(nrm, zero) && internal && nHops >= 1)
+        {
+            const D3 undef = {SM_GREAT, SM_GREAT, SM_GREAT};
+            if (veq(outer, undef))
+                *d.errFlag = 1; // "Sanity broken, outerNeighCoord ..." (:537-540)
+            const double length = d.layerLength[nHops], blendFrac = d.layerBlend[nHops];
+            const D3 ortho = outer + length * nrm;
+            np = blendFrac * ortho + (1.0 - blendFrac) * np;
+        }
+        const D3 stepDir = np - x;
+        const double len = mag(stepDir);
+        double scale = 1.0;
+        if (len > d.maxStepLength)
+            scale = d.maxStepLength / (len * d.relStepFrac);
+        np = x + (d.relStepFrac * scale) * stepDir;
+    }
     st4(d.newPts + p, np, 0.0);
     d.newPtsF[p] = make_float4((float)(np.x - d.ox), (float)(np.y - d.oy), (float)(np.z - d.oz), 0.f);
 }

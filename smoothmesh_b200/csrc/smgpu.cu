@@ -21,6 +21,7 @@ using namespace smk;
 namespace sm
 {
 struct Comm;
+static void commSetupLayers(Comm *cm, struct ::smgpu_handle *h);
 }
 
 static thread_local std::string g_err;
@@ -56,6 +57,10 @@ struct smgpu_handle
     int resolveBlocks = 1;
     bool doLayers = false;
     bool anyLayerPatch = false;
+    bool layersParallel = false, layersReady = false; // processor mesh: set-up runs in smgpu_comm_init
+    sm::PolyMesh layerMesh;                           // patches + faces for that set-up
+    std::vector<int32_t> patchLayerFlags;
+    int *dHops = nullptr, *dPointToOuter = nullptr;
     double *dLayerLength = nullptr, *dLayerBlend = nullptr;
     P4 *normalsTmp = nullptr;
     // params.renumber: storage order = Morton order; old label of every stored point / cell
@@ -286,7 +291,7 @@ struct smgpu_handle
     void launchLayerNormals()
     {
         profBegin(K_LAYER);
-        k_layer_normals<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        k_layer_normals<<<grid(d.P, 128), 128, 0, stream>>>(d, 1);
         profEnd(1);
         ++launches;
     }
@@ -303,10 +308,17 @@ struct smgpu_handle
     {
         if (!doLayers)
             return;
+        if (layersParallel)
+        {
+            // processor mesh: the set-up synchronises with the other ranks (sm::commSetupLayers)
+            if (comm)
+                sm::commSetupLayers(comm, this);
+            return;
+        }
         CK(cudaMemsetAsync(d.normals, 0, topo.P * sizeof(P4), stream));
         CK(cudaMemsetAsync(d.done, 0, sizeof(int), stream));
         k_face_geom<<<grid(d.F, 256), 256, 0, stream>>>(d);
-        k_layer_normals<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        k_layer_normals<<<grid(d.P, 128), 128, 0, stream>>>(d, 1);
         CK(cudaMemcpyAsync(normalsTmp, d.normals, topo.P * sizeof(P4), cudaMemcpyDeviceToDevice, stream));
         k_layer_init_normals<<<grid(d.P, 128), 128, 0, stream>>>(d, normalsTmp);
         CK(cudaStreamSynchronize(stream));
@@ -393,8 +405,9 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         c.copyOff = h->upload(pl.copyOff);
         c.copyRank = h->upload(pl.copyRank);
         c.copySlot = h->upload(pl.copySlot);
-        c.sendBuf = h->dalloc<double>((size_t)c.nSlots * SMK_TUPLE);
-        c.recvBuf = h->dalloc<double>((size_t)c.nSlots * SMK_TUPLE);
+        c.tuple = h->anyLayerPatch ? SMK_TUPLE_LAYERS : SMK_TUPLE;
+        c.sendBuf = h->dalloc<double>((size_t)c.nSlots * c.tuple);
+        c.recvBuf = h->dalloc<double>((size_t)c.nSlots * c.tuple);
         c.sendFz = h->dalloc<uint8_t>(c.nSlots);
         c.recvFz = h->dalloc<uint8_t>(c.nSlots);
         c.redRes = h->dalloc<double>(1);
@@ -413,6 +426,7 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         h->meshMinEdge = -mm[0];
         h->meshMaxEdge = mm[1];
         h->resolveParams();
+        commSetupLayers(cm, h);
     }
     catch (...)
     {
@@ -422,6 +436,102 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         throw;
     }
     return cm;
+}
+
+// syncTools::syncPointList for a host field with N values of T per point (set-up only): the copies of
+// every interface point travel through the iteration's exchange buffers and are combined in ascending
+// rank order, like the device-side merge.
+template <class T, int N, class Op> static void hostSync(Comm *cm, smgpu_handle *h, std::vector<T> &field, Op combine)
+{
+    const ExchangePlan &pl = cm->plan;
+    const smk::CommDev &c = cm->c;
+    if (c.nSlots == 0)
+        return;
+    static_assert(sizeof(T) * N <= SMK_TUPLE * sizeof(double), "record larger than the exchange buffers");
+    std::vector<T> send((size_t)c.nSlots * N), recv((size_t)c.nSlots * N);
+    for (int i = 0; i < c.nSlots; ++i)
+        for (int k = 0; k < N; ++k)
+            send[(size_t)i * N + k] = field[(size_t)pl.sendPoint[i] * N + k];
+    CK(cudaMemcpyAsync(c.sendBuf, send.data(), send.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    haloExchange(cm, h, c.sendBuf, c.recvBuf, N * sizeof(T));
+    CK(cudaMemcpyAsync(recv.data(), c.recvBuf, recv.size() * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    for (size_t s = 0; s < pl.sharedPoint.size(); ++s)
+    {
+        const int32_t p = pl.sharedPoint[s];
+        const int cb = pl.copyOff[s], nOther = pl.copyOff[s + 1] - cb;
+        T v[N];
+        bool first = true, selfDone = false;
+        for (int k = 0, o = 0; k < nOther + 1; ++k)
+        {
+            const T *src;
+            if (!selfDone && (o >= nOther || pl.copyRank[cb + o] > pl.rank))
+            {
+                src = &field[(size_t)p * N];
+                selfDone = true;
+            }
+            else
+                src = &recv[(size_t)pl.copySlot[cb + o++] * N];
+            if (first)
+            {
+                for (int q = 0; q < N; ++q)
+                    v[q] = src[q];
+                first = false;
+            }
+            else
+                combine(v, src);
+        }
+        for (int q = 0; q < N; ++q)
+            field[(size_t)p * N + q] = v[q];
+    }
+}
+
+// One-time boundary layer set-up of a processor mesh (src/smoothMesh.C:2215-2221 under -parallel).
+// Collective: every rank of the communicator calls it (smgpu_comm_init, smgpu_set_points).
+static void commSetupLayers(Comm *cm, smgpu_handle *h)
+{
+    if (!h->doLayers || !h->layersParallel)
+        return;
+    Dev &d = h->d;
+    const int64_t P = h->topo.P;
+    // this rank's share of the set-up call of calculateBoundaryPointNormals on the current mesh
+    CK(cudaMemsetAsync(d.normals, 0, P * sizeof(P4), h->stream));
+    CK(cudaMemsetAsync(d.done, 0, sizeof(int), h->stream));
+    k_face_geom<<<smgpu_handle::grid(d.F, 256), 256, 0, h->stream>>>(d);
+    k_layer_normals<<<smgpu_handle::grid(d.P, 128), 128, 0, h->stream>>>(d, 0);
+    std::vector<P4> tmp(P);
+    CK(cudaMemcpyAsync(tmp.data(), d.normals, P * sizeof(P4), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::vector<double> normals(3 * P);
+    for (int64_t p = 0; p < P; ++p)
+        normals[3 * p] = tmp[p].x, normals[3 * p + 1] = tmp[p].y, normals[3 * p + 2] = tmp[p].z;
+    LayerSync sync;
+    sync.maxInt = [&](std::vector<int32_t> &f) {
+        hostSync<int32_t, 1>(cm, h, f, [](int32_t *x, const int32_t *y) { x[0] = (x[0] > y[0]) ? x[0] : y[0]; });
+    };
+    sync.sumInt = [&](std::vector<int32_t> &f) {
+        hostSync<int32_t, 1>(cm, h, f, [](int32_t *x, const int32_t *y) { x[0] = x[0] + y[0]; });
+    };
+    sync.sumVec = [&](std::vector<double> &f) {
+        hostSync<double, 3>(cm, h, f, [](double *x, const double *y) {
+            x[0] = x[0] + y[0], x[1] = x[1] + y[1], x[2] = x[2] + y[2];
+        });
+    };
+    sync.maxMagSqrVec = [&](std::vector<double> &f) {
+        hostSync<double, 3>(cm, h, f, [](double *x, const double *y) {
+            const double mx = x[0] * x[0] + x[1] * x[1] + x[2] * x[2], my = y[0] * y[0] + y[1] * y[1] + y[2] * y[2];
+            if (!(mx >= my))
+                x[0] = y[0], x[1] = y[1], x[2] = y[2];
+        });
+    };
+    h->layer = buildLayerSetupParallel(h->layerMesh, h->topo, h->patchLayerFlags, h->prm.max_layers, normals, sync);
+    for (int64_t p = 0; p < P; ++p)
+        tmp[p] = P4{normals[3 * p], normals[3 * p + 1], normals[3 * p + 2], 0.0};
+    CK(cudaMemcpy(d.normals, tmp.data(), P * sizeof(P4), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dHops, h->layer.hops.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dPointToOuter, h->layer.pointToOuter.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice));
+    h->layersReady = true;
+    h->applyParams(); // per-hop tables for the synchronised hop counts
 }
 
 static void commDestroy(Comm *cm)
@@ -439,15 +549,25 @@ static int commIterate(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
     const int gs = smgpu_handle::grid(c.nSlots, 128);
-    h->launchGeometry();
-    h->launchPredict();
+    // with layer treatment the interface records carry the normals of the previous iteration, so they
+    // are packed before k_layer_normals replaces those; interface points get their normal, blend and
+    // second clamp in k_shared_merge, which overwrites whatever the point-wise kernels wrote for them
+    h->launchFaceGeom();
+    h->launchCells();
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
         k_shared_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
-    haloExchange(cm, h, c.sendBuf, c.recvBuf, SMK_TUPLE * sizeof(double));
+    h->profEnd(1);
+    if (h->doLayers)
+        h->launchLayerNormals();
+    h->launchPredict();
+    if (h->doLayers)
+        h->launchLayerBlend();
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    haloExchange(cm, h, c.sendBuf, c.recvBuf, c.tuple * sizeof(double));
     if (c.nShared > 0)
         k_shared_merge<<<smgpu_handle::grid(c.nShared, 64), 64, 0, h->stream>>>(h->d, c);
-    h->profEnd(2);
+    h->profEnd(1);
     h->launches += 2;
     h->launchEdgeConstraints();
     if (h->prm.face_angle_constraint)
@@ -664,18 +784,31 @@ extern "C"
             CK(cudaMemset(d.newPts, 0, t.P * sizeof(P4)));
             h->ensureStats(1024);
             h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
+            d.errFlag = h->dalloc<int>(1);
+            CK(cudaMemset(d.errFlag, 0, sizeof(int)));
             if (h->anyLayerPatch)
             {
                 h->layer = sm::buildLayerSetup(m, t, patchLayer, params->max_layers);
+                if (!t.procPoints.empty())
+                {
+                    // decomposed case: hop counts, maps and set-up normals are synchronised between the
+                    // ranks (smgpu_comm_init); what is uploaded below is overwritten there
+                    h->layersParallel = true;
+                    h->layerMesh.faceOffsets = m.faceOffsets;
+                    h->layerMesh.faceVerts = m.faceVerts;
+                    h->layerMesh.patches = m.patches;
+                    h->patchLayerFlags = patchLayer;
+                }
                 d.normals = h->dalloc<P4>(t.P);
                 h->normalsTmp = h->dalloc<P4>(t.P);
-                d.hops = h->upload(h->layer.hops);
-                d.pointToOuter = h->upload(h->layer.pointToOuter);
+                d.hops = h->dHops = h->upload(h->layer.hops);
+                d.pointToOuter = h->dPointToOuter = h->upload(h->layer.pointToOuter);
                 d.normalSrc = h->upload(h->layer.normalSrc);
                 d.bfOff = h->upload(h->layer.bfOff);
                 d.bf = h->upload(h->layer.bf);
-                h->dLayerLength = h->dalloc<double>(h->layer.maxHop + 2);
-                h->dLayerBlend = h->dalloc<double>(h->layer.maxHop + 2);
+                const int hopCap = std::max(h->layer.maxHop, params->max_layers + 1) + 2;
+                h->dLayerLength = h->dalloc<double>(hopCap);
+                h->dLayerBlend = h->dalloc<double>(hopCap);
                 d.layerLength = h->dLayerLength;
                 d.layerBlend = h->dLayerBlend;
             }
@@ -750,6 +883,9 @@ extern "C"
     {
         if (!h || max_iters < 0)
             return setErr(SMGPU_ERR_ARG, "bad argument");
+        if (h->doLayers && h->layersParallel && !h->layersReady)
+            return setErr(SMGPU_ERR_ARG, "boundary layer treatment on a processor mesh: call smgpu_comm_init first "
+                                         "(its set-up synchronises hop counts and normals between the ranks)");
         try
         {
             CK(cudaSetDevice(h->prm.device));
@@ -796,8 +932,12 @@ extern "C"
             h->lastLaunches = h->launches;
             if (h->profiling)
                 h->profCollect();
-            int it = 0;
+            int it = 0, errFlag = 0;
             CK(cudaMemcpy(&it, h->d.iter, sizeof(int), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&errFlag, h->d.errFlag, sizeof(int), cudaMemcpyDeviceToHost));
+            if (errFlag)
+                return setErr(SMGPU_ERR_MESH, "Sanity broken, outerNeighCoord is undefined for an interface point "
+                                              "(src/orthogonalBoundaryBlending.C:537)");
             if (iters_done)
                 *iters_done = it;
             if (it > 0 && residual)

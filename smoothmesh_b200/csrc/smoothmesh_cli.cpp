@@ -207,6 +207,7 @@ struct RunOptions
     bool binary;
     int writePrecision, timePrecision;
     std::string caseDir, startName;
+    std::string layerPatches; // -layerPatches expression, empty = none
 };
 
 namespace
@@ -278,12 +279,21 @@ static int runParallel(const RunOptions &ro)
                     failAll(smmesh_last_error());
                 }
             int64_t nPoints = 0;
-            std::vector<int32_t> pStart, pSize, pKind;
+            std::vector<int32_t> pStart, pSize, pKind, layerSel;
             if (ok)
             {
                 nPoints = smmesh_size(mesh, 0);
                 const int nPatches = (int)smmesh_size(mesh, 5);
                 pStart.resize(nPatches), pSize.resize(nPatches), pKind.resize(nPatches);
+                layerSel.assign(nPatches, 0);
+                if (!ro.layerPatches.empty())
+                {
+                    // patchSet on this processor's boundary file, like every MPI rank of the reference (:1826-1833)
+                    std::vector<std::string> names;
+                    for (int i = 0; i < nPatches; ++i)
+                        names.push_back(smmesh_patch_name(mesh, i));
+                    layerSel = selectPatches(ro.layerPatches, names);
+                }
                 smmesh_patches(mesh, pStart.data(), pSize.data(), pKind.data());
                 smgpu_mesh_desc md;
                 memset(&md, 0, sizeof md);
@@ -301,6 +311,7 @@ static int runParallel(const RunOptions &ro)
                 md.patch_size = pSize.data();
                 md.patch_kind = pKind.data();
                 md.point_global_id = smmesh_point_global_id(mesh);
+                md.patch_layer = layerSel.data();
                 smgpu_params prm = ro.prm;
                 prm.device = k;
                 if (smgpu_create(&md, &prm, &h) != SMGPU_OK)
@@ -569,9 +580,9 @@ int main(int argc, char **argv)
     {
         if (has("decompose"))
             fatal("-decompose and -parallel are separate steps");
-        if (has("layerPatches") && !patchSetEmpty(opt["layerPatches"]) && layerMaxBlendingFraction > 1e-15)
-            fatal("-layerPatches with -parallel: the boundary layer treatment is single-GPU in this build");
         RunOptions ro;
+        if (has("layerPatches") && !patchSetEmpty(opt["layerPatches"]))
+            ro.layerPatches = opt["layerPatches"];
         ro.prm = prm;
         ro.centroidalIters = centroidalIters;
         ro.writeInterval = writeInterval;

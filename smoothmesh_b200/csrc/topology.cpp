@@ -1,5 +1,6 @@
 // topology.cpp -- see topology.hpp.
 #include "topology.hpp"
+#include "sm_math.h"
 
 #include <algorithm>
 #include <cmath>
@@ -567,6 +568,136 @@ LayerSetup buildLayerSetup(const PolyMesh &m, const Topology &t, const std::vect
                     L.bf[cur[m.faceVerts[k]]++] = f;
         }
     }
+    for (int32_t h : L.hops)
+        L.maxHop = std::max(L.maxHop, h);
+    return L;
+}
+
+LayerSetup buildLayerSetupParallel(const PolyMesh &m, const Topology &t, const std::vector<int32_t> &patchLayer,
+                                   int maxLayers, std::vector<double> &normals, const LayerSync &sync)
+{
+    // tables that need no communication (classification flags are local in the reference too,
+    // src/boundaryPointSmoothing.C:301-423)
+    LayerSetup L = buildLayerSetup(m, t, patchLayer, maxLayers);
+    const int64_t P = t.P;
+    std::vector<uint8_t> visited(P, 0), connected(P, 0), layerSurface(P, 0);
+    for (size_t pi = 0; pi < m.patches.size(); ++pi)
+    {
+        const Patch &pt = m.patches[pi];
+        for (int32_t f = pt.start; f < pt.start + pt.size; ++f)
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+            {
+                const int32_t p = m.faceVerts[k];
+                if (visited[p])
+                    continue;
+                visited[p] = 1;
+                if (t.isInternal[p])
+                    continue;
+                for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+                    if (t.isInternal[t.pp[s]])
+                        connected[p] = 1;
+                if (patchLayer[pi])
+                    layerSurface[p] = 1;
+            }
+    }
+    // calculatePointHopsToBoundary with the max-synchronisation after every sweep (:124-130)
+    L.hops.assign(P, -1);
+    for (size_t pi = 0; pi < m.patches.size(); ++pi)
+    {
+        if (!patchLayer[pi])
+            continue;
+        const Patch &pt = m.patches[pi];
+        for (int32_t f = pt.start; f < pt.start + pt.size; ++f)
+            for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
+                if (connected[m.faceVerts[k]])
+                    L.hops[m.faceVerts[k]] = 0;
+    }
+    std::vector<int32_t> newHops(P, -1);
+    for (int iter = 0; iter < maxLayers + 1; ++iter)
+    {
+        for (int64_t p = 0; p < P; ++p)
+        {
+            if (L.hops[p] >= 0 || !t.isInternal[p])
+                continue;
+            int32_t mx = -1;
+            for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+                mx = std::max(mx, L.hops[t.pp[s]]);
+            if (mx >= 0)
+                newHops[p] = mx + 1;
+        }
+        for (int64_t p = 0; p < P; ++p)
+            if (newHops[p] > L.hops[p])
+                L.hops[p] = newHops[p];
+        sync.maxInt(L.hops);
+    }
+    // set-up call of calculateBoundaryPointNormals: the two sum-synchronisations (:185-198), the
+    // sharp-edge zeroing (:200-218) and the normalisation (:222-230)
+    auto magOf = [&](int64_t p) {
+        const double x = normals[3 * p], y = normals[3 * p + 1], z = normals[3 * p + 2];
+        return std::sqrt(x * x + y * y + z * z);
+    };
+    auto equals = [&](int64_t p, double v) {
+        return sm_equal(normals[3 * p], v) && sm_equal(normals[3 * p + 1], v) && sm_equal(normals[3 * p + 2], v);
+    };
+    auto setAll = [&](int64_t p, double v) { normals[3 * p] = normals[3 * p + 1] = normals[3 * p + 2] = v; };
+    std::vector<int32_t> nFaces(P);
+    for (int64_t p = 0; p < P; ++p)
+        nFaces[p] = L.bfOff[p + 1] - L.bfOff[p];
+    sync.sumVec(normals);
+    sync.sumInt(nFaces);
+    for (int64_t p = 0; p < P; ++p)
+        if (nFaces[p] >= 1 && magOf(p) < 0.1)
+            setAll(p, 0.0);
+    for (int64_t p = 0; p < P; ++p)
+        if (!equals(p, 0.0))
+        {
+            const double mg = magOf(p);
+            normals[3 * p] /= mg;
+            normals[3 * p + 1] /= mg;
+            normals[3 * p + 2] /= mg;
+        }
+    // propagateOuterNeighInfo on values, maxMagSqr-synchronised after every sweep (:363-369);
+    // UNDEF_VECTOR (GREAT, GREAT, GREAT) marks multiply connected points and wins every combination
+    L.pointToOuter.assign(P, -1);
+    L.normalSrc.assign(P, -1);
+    std::vector<int32_t> firstWithLabel(P, -1);
+    for (int iter = 1; iter < maxLayers + 2; ++iter)
+    {
+        for (int64_t p = 0; p < P; ++p)
+        {
+            if (L.hops[p] != iter)
+                continue;
+            int32_t n = 0, q = -1;
+            for (int32_t s = t.ppOff[p]; s < t.ppOff[p + 1]; ++s)
+                if (L.hops[t.pp[s]] == iter - 1)
+                {
+                    ++n;
+                    q = t.pp[s];
+                }
+            if (n != 1)
+                continue;
+            if (!t.isInternal[q] && !layerSurface[q])
+                continue;
+            if (firstWithLabel[q] >= 0)
+            {
+                setAll(p, SM_GREAT);
+                setAll(firstWithLabel[q], SM_GREAT);
+                continue;
+            }
+            L.pointToOuter[p] = q;
+            for (int k = 0; k < 3; ++k)
+                normals[3 * p + k] = normals[3 * q + k];
+            firstWithLabel[q] = (int32_t)p;
+        }
+        sync.maxMagSqrVec(normals);
+    }
+    for (int64_t p = 0; p < P; ++p)
+        if (equals(p, SM_GREAT))
+        {
+            setAll(p, 0.0);
+            L.pointToOuter[p] = -1;
+        }
+    L.maxHop = 0;
     for (int32_t h : L.hops)
         L.maxHop = std::max(L.maxHop, h);
     return L;

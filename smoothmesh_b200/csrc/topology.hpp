@@ -11,6 +11,7 @@
 #pragma once
 #include "polymesh.hpp"
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 namespace sm
@@ -62,6 +63,20 @@ struct LayerSetup
     int32_t maxHop = 0;
 };
 LayerSetup buildLayerSetup(const PolyMesh &m, const Topology &t, const std::vector<int32_t> &patchLayer, int maxLayers);
+
+// The same set-up for a processor mesh of a decomposed case.  The reference synchronises the hop counts
+// (max), the boundary normals and face counts (sum) and the propagated normals (maxMagSqr) over the copies
+// of every interface point between its sweeps (src/orthogonalBoundaryBlending.C:124-130, :185-198,
+// :363-369); which copy wins depends on the normals' values, so the propagation runs on values here.
+// `normals` (xyz per point) comes in as this rank's accumulated boundary normals of the set-up call
+// (zero minus the unit normals of the point's boundary faces) and leaves as the set-up normals.
+struct LayerSync
+{
+    std::function<void(std::vector<int32_t> &)> maxInt, sumInt;
+    std::function<void(std::vector<double> &)> sumVec, maxMagSqrVec;
+};
+LayerSetup buildLayerSetupParallel(const PolyMesh &m, const Topology &t, const std::vector<int32_t> &patchLayer,
+                                   int maxLayers, std::vector<double> &normals, const LayerSync &sync);
 
 // Throws std::runtime_error with the reference's FatalError texts where the
 // reference would abort (empty patches :61-66, <2 eligible closest points

@@ -21,6 +21,17 @@ def make_parts(world, kind):
     if kind == "hex":
         mesh = sm.Mesh.hex_block(4 * px, 4 * py, 3 * pz, hi=(px, py, 0.75 * pz)).jitter(0.3 / 4, 4242)
         return mesh.decompose(px, py, pz)
+    if kind == "hexlayers":
+        # layer treatment on all six walls, bricks cut through the layers (BASELINE config 3 style options)
+        mesh = sm.Mesh.hex_block(8 * px, 7 * py, 6 * pz, hi=(px, py, pz)).jitter(0.2 / 8, 99)
+        return mesh.decompose(px, py, pz)
+    if kind == "prismlayers":
+        # the reference's own test mesh (testcase/: extruded tri/quad surface, layers on the hole walls),
+        # from the committed golden fixture
+        d = np.load(os.path.join(ROOT, "tests", "golden", "testcase_layers.npz"))
+        mesh = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"],
+                                   int(d["n_cells"]), d["patch_start"], d["patch_size"], d["patch_kind"])
+        return mesh.decompose(world, method="rcb")
     if kind == "kelvin":
         mesh = sm.Mesh.kelvin(3, 1.0).jitter(0.15 * 2 ** 0.5 / 4, 77)
         return mesh.decompose(world, method="rcb")
@@ -82,6 +93,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     kw = dict(rel_tol=1e-3, min_angle_deg=70.0, max_angle_deg=110.0, total_min_freeze=0)
     iters = 25
+    if kind == "hexlayers":
+        kw = dict(rel_tol=0.0, layer_patches=[1, 1, 1, 0, 1, 1], max_layers=3, layer_expansion_ratio=1.2)
+        iters = 12
+    if kind == "prismlayers":  # testcase/run_parallel:22
+        kw = dict(rel_tol=0.0, min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0, max_angle_deg=160.0,
+                  layer_patches=[1, 0, 0, 0, 0, 0, 0])
+        iters = 12
     g = sm.Smoother(mine, device=local_rank, **kw)
     multi.init_comm(g, rank, world, dist)
     if mode == "debug":

@@ -89,3 +89,17 @@ def test_cli_parallel_on_processor_directories(tmp_path):
         assert sorted(p.name for p in d.iterdir() if p.name[0].isdigit()) == ["10", "4", "8"]
         parts[k].read_points(d / "10" / "polyMesh" / "points")
         assert np.array_equal(parts[k].points, o.get("points", rank=k))
+    # the same case with boundary layer treatment, as most of the reference's run_parallel scripts do
+    # (testcase/run_parallel:22); '(".*")' also matches the processor patches, as the reference's patchSet would
+    parts = [sm.Mesh.read_processor(case, k) for k in range(2)]
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel", "-time", "constant", "-centroidalIters", "6",
+                        "-relTol", "0", "-layerPatches", '(".*")', "-maxLayers", "2", "-smoothingPatches", "()"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, layer_patches=[1] * 16, max_layers=2)
+    n, nf, res = o.iterate(6)
+    lines = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    assert [int(b) for _, b, _ in lines] == nf.tolist()
+    for k in range(2):
+        parts[k].read_points(case / f"processor{k}" / "6" / "polyMesh" / "points")
+        assert np.array_equal(parts[k].points, o.get("points", rank=k))

@@ -25,7 +25,7 @@ def test_exchange_plan_gloo(world, kind):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind", ["hex", "kelvin"])
+@pytest.mark.parametrize("kind", ["hex", "kelvin", "hexlayers", "prismlayers"])
 def test_multi_gpu_parity(kind):
     import torch
     n = torch.cuda.device_count()
