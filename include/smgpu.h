@@ -83,7 +83,8 @@ extern "C"
                                           (label-order-dependent tie-breaks / summation order follow the new
                                           labels), points and masks are returned in the caller's numbering */
         /* Boundary layer treatment (src/orthogonalBoundaryBlending.C; options :1892-1905), active when
-         * some patch has patch_layer = 1 and layer_max_blending_fraction > 1e-15 (:2025); serial runs only. */
+         * some patch has patch_layer = 1 and layer_max_blending_fraction > 1e-15 (:2025).  On a processor mesh
+         * the one-time set-up is collective and runs inside smgpu_comm_init (and smgpu_set_points). */
         double layer_max_blending_fraction; /* 0.3 */
         double layer_edge_length;           /* negative = min_edge_length (:1895-1896) */
         double layer_expansion_ratio;       /* 1.3 */

@@ -52,7 +52,7 @@ struct smgpu_handle
     int statCap = 0;
     sm::Comm *comm = nullptr;
     std::vector<int64_t> gid;
-    // boundary layer treatment (serial runs): one-time set-up data and per-hop tables
+    // boundary layer treatment: one-time set-up data and per-hop tables
     sm::LayerSetup layer;
     int resolveBlocks = 1;
     bool doLayers = false;
@@ -674,11 +674,6 @@ extern "C"
                     patchLayer[i] = md->patch_layer[i] != 0;
                     h->anyLayerPatch = h->anyLayerPatch || patchLayer[i];
                 }
-            if (h->anyLayerPatch && md->point_global_id)
-            {
-                delete h;
-                return setErr(SMGPU_ERR_ARG, "boundary layer treatment (patch_layer) is only available in serial runs");
-            }
             try
             {
                 if (params->renumber)

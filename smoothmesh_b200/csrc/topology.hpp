@@ -53,7 +53,7 @@ struct Topology
     int32_t maxPointDegree = 0, maxFaceSize = 0, maxEdgeFaces = 0;
 };
 
-// One-time data of the prismatic boundary layer treatment (src/orthogonalBoundaryBlending.C), serial runs.
+// One-time data of the prismatic boundary layer treatment (src/orthogonalBoundaryBlending.C).
 struct LayerSetup
 {
     std::vector<int32_t> hops;         // pointHopsToLayerBoundary, -1 = undefined

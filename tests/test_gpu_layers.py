@@ -66,10 +66,13 @@ def test_layer_loop_parity(case):
     assert np.array_equal(log2.n_frozen, nf) and np.array_equal(g.points(), o.get("points"))
 
 
-def test_layers_are_refused_in_multi_rank_meshes():
+def test_layers_on_a_processor_mesh_need_the_collective_setup():
+    # hop counts and set-up normals of a decomposed case are synchronised between the ranks
+    # (src/orthogonalBoundaryBlending.C:124,185,363): iterating before smgpu_comm_init must fail, not guess
     parts = hex_jittered(6, 4, 4, 0.1).decompose(2, 1, 1)
-    with pytest.raises(sm.SmoothMeshError, match="serial"):
-        sm.Smoother(parts[0], layer_patches=[0] * (parts[0].n_patches - 1) + [1])
+    g = sm.Smoother(parts[0], layer_patches=[1, 1, 1, 1, 1, 1])
+    with pytest.raises(sm.SmoothMeshError, match="smgpu_comm_init"):
+        g.iterate(1)
 
 
 def test_cli_layer_patches_wordre(tmp_path):
