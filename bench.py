@@ -111,6 +111,10 @@ def kernel_bytes(P, C, F, Fi, E, FV, PC, EC):
         "k_edge_constraints": 48 * P + 4 * (2 * E + P + 1) + 4 * (2 * FV + P + 1) + P,
         # points + cellCtr + face means read, edges, edgeFaces, edgeCells(+pairs)
         "k_face_current": 24 * P + 24 * C + 24 * F + 4 * (2 * E) + 4 * (FV + E + 1) + 4 * (2 * EC + E + 1),
+        # fused face + cell geometry: points gathered once, faces CSR, tile lists (cells, faces, 2-byte face
+        # references), vertex means (fp32 mirror) and cell centres (fp64 + fp32 mirror) written; no face records
+        "k_geom_tiles": 24 * P + 4 * (FV + F + 1) + 4 * (C + F) + 2 * (F + Fi) + 16 * F + (24 + 16) * C,
+        "k_layer": 0,
         "k_active_compact": 2 * P,
         "k_face_tests": 0,
         "k_face_resolve": 0,

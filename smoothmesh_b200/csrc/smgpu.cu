@@ -55,6 +55,7 @@ struct smgpu_handle
     // boundary layer treatment: one-time set-up data and per-hop tables
     sm::LayerSetup layer;
     int resolveBlocks = 1;
+    bool useTiles = false; // fused geometry kernel over sm::GeomTiles
     bool doLayers = false;
     bool anyLayerPatch = false;
     bool layersParallel = false, layersReady = false; // processor mesh: set-up runs in smgpu_comm_init
@@ -81,7 +82,7 @@ struct smgpu_handle
     }
 
     // optional per-kernel timing (CUDA events on the launch stream)
-    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_LAYER, K_NUM };
+    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_LAYER, K_GEOM_TILES, K_NUM };
     bool profiling = false;
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<int, size_t>> evUse; // (kernel id, index of start event)
@@ -266,9 +267,19 @@ struct smgpu_handle
         profEnd(1);
         ++launches;
     }
-    // OpenFOAM's demand-driven geometry after movePoints: face centres/areas, then cell centres
+    // OpenFOAM's demand-driven geometry after movePoints: face centres/areas, then cell centres --
+    // one fused launch over the geometry tiles, or the two per-face / per-cell kernels
+    // (SMGPU_NO_TILES=1, or a mesh with a cell too large for a tile)
     void launchCellCentres()
     {
+        if (useTiles)
+        {
+            profBegin(K_GEOM_TILES);
+            k_geom_tiles<<<d.nTiles, SMK_TILE_CELLS, 0, stream>>>(d);
+            profEnd(1);
+            ++launches;
+            return;
+        }
         launchFaceGeom();
         launchCells();
     }
@@ -276,6 +287,13 @@ struct smgpu_handle
     // boundary point normals of :2266 (they need the boundary face areas of the current mesh)
     void launchGeometry()
     {
+        if (useTiles)
+        {
+            launchCellCentres();
+            if (doLayers)
+                launchLayerNormals();
+            return;
+        }
         launchFaceGeom();
         if (doLayers)
             launchLayerNormals();
@@ -552,8 +570,7 @@ static int commIterate(Comm *cm, smgpu_handle *h)
     // with layer treatment the interface records carry the normals of the previous iteration, so they
     // are packed before k_layer_normals replaces those; interface points get their normal, blend and
     // second clamp in k_shared_merge, which overwrites whatever the point-wise kernels wrote for them
-    h->launchFaceGeom();
-    h->launchCells();
+    h->launchCellCentres();
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
         k_shared_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
@@ -779,6 +796,23 @@ extern "C"
             CK(cudaMemset(d.newPts, 0, t.P * sizeof(P4)));
             h->ensureStats(1024);
             h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
+            d.nInternalFaces = (int)md->n_internal_faces;
+            d.nTiles = 0;
+            if (!(getenv("SMGPU_NO_TILES") && atoi(getenv("SMGPU_NO_TILES")) != 0))
+            {
+                const sm::GeomTiles G = sm::buildGeomTiles(m, t, SMK_TILE_CELLS, SMK_TILE_FACES);
+                if (G.nTiles > 0)
+                {
+                    h->useTiles = true;
+                    d.nTiles = G.nTiles;
+                    d.tileCellOff = h->upload(G.tileCellOff);
+                    d.tileCells = h->upload(G.tileCells);
+                    d.tileFaceOff = h->upload(G.tileFaceOff);
+                    d.tileFaces = h->upload(G.tileFaces);
+                    d.slotOff = h->upload(G.slotOff);
+                    d.slotRef = h->upload(G.slotRef);
+                }
+            }
             d.errFlag = h->dalloc<int>(1);
             CK(cudaMemset(d.errFlag, 0, sizeof(int)));
             if (h->anyLayerPatch)
@@ -1219,7 +1253,7 @@ extern "C"
     int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches)
     {
         static const char *kNames[smgpu_handle::K_NUM] = {"k_face_geom", "k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
-                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange", "k_layer"};
+                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange", "k_layer", "k_geom_tiles"};
         if (!h || !n)
             return setErr(SMGPU_ERR_ARG, "null argument");
         *n = smgpu_handle::K_NUM;

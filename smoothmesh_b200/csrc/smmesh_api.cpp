@@ -2,6 +2,7 @@
 #include "../../include/smgpu.h"
 #include "../../include/smmesh.h"
 #include "polymesh.hpp"
+#include "topology.hpp"
 
 #include <algorithm>
 #include <stdexcept>
@@ -233,6 +234,67 @@ extern "C"
             out[4] = q.minEdgeLength;
             out[5] = q.maxEdgeLength;
             out[6] = q.minVolume;
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int64_t out[4])
+    {
+        try
+        {
+            const sm::Topology t = sm::buildTopology(m->m);
+            const sm::GeomTiles G = sm::buildGeomTiles(m->m, t, max_cells, max_faces);
+            // invariants the fused geometry kernel relies on
+            std::vector<int32_t> cellSeen(t.C, 0), faceStored(t.F, 0);
+            int64_t maxFaces = 0;
+            for (int32_t k = 0; k < G.nTiles; ++k)
+            {
+                const int32_t fb = G.tileFaceOff[k], nf = G.tileFaceOff[k + 1] - fb;
+                const int32_t nc = G.tileCellOff[k + 1] - G.tileCellOff[k];
+                maxFaces = std::max<int64_t>(maxFaces, nf);
+                if (nf > max_faces || nc > max_cells || nc < 1)
+                    throw std::runtime_error("tile over budget");
+                for (int32_t i = 0; i < nf; ++i)
+                {
+                    const int32_t w = G.tileFaces[fb + i];
+                    if (i > 0 && (w & 0x7fffffff) <= (G.tileFaces[fb + i - 1] & 0x7fffffff))
+                        throw std::runtime_error("tile faces not ascending");
+                    if (w < 0)
+                        ++faceStored[w & 0x7fffffff];
+                }
+                for (int32_t s = G.tileCellOff[k]; s < G.tileCellOff[k + 1]; ++s)
+                {
+                    const int32_t c = G.tileCells[s];
+                    ++cellSeen[c];
+                    if (G.slotOff[s + 1] - G.slotOff[s] != t.cfOff[c + 1] - t.cfOff[c])
+                        throw std::runtime_error("slot face count differs from the cell's");
+                    for (int32_t j = 0; j < t.cfOff[c + 1] - t.cfOff[c]; ++j)
+                    {
+                        const uint16_t ref = G.slotRef[G.slotOff[s] + j];
+                        const int32_t w = t.cf[t.cfOff[c] + j];
+                        if ((ref & 0x7fff) >= nf || (G.tileFaces[fb + (ref & 0x7fff)] & 0x7fffffff) != (w & 0x7fffffff) ||
+                            ((ref & 0x8000) != 0) != (w < 0))
+                            throw std::runtime_error("slot reference does not resolve to the cell's face");
+                    }
+                }
+            }
+            if (G.nTiles > 0)
+            {
+                for (int32_t c = 0; c < t.C; ++c)
+                    if (cellSeen[c] != 1)
+                        throw std::runtime_error("cell not in exactly one tile");
+                for (int32_t f = 0; f < t.F; ++f)
+                    if (faceStored[f] != 1)
+                        throw std::runtime_error("face outputs not stored by exactly one tile");
+            }
+            out[0] = G.nTiles;
+            out[1] = (int64_t)G.tileFaces.size();
+            out[2] = maxFaces;
+            out[3] = t.F;
         }
         catch (const std::exception &e)
         {

@@ -702,4 +702,134 @@ LayerSetup buildLayerSetupParallel(const PolyMesh &m, const Topology &t, const s
         L.maxHop = std::max(L.maxHop, h);
     return L;
 }
+
+namespace
+{
+inline uint64_t spreadBits21(uint64_t v)
+{ // 21 bits -> every third bit
+    v &= 0x1fffff;
+    v = (v | v << 32) & 0x1f00000000ffffull;
+    v = (v | v << 16) & 0x1f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+} // namespace
+
+GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces)
+{
+    GeomTiles G;
+    const int64_t C = t.C, F = t.F, P = t.P;
+    if (C == 0)
+        return G;
+    // cell order: Morton curve over the cells' vertex averages, quantised by the mean cell size so that
+    // on block-structured meshes 2^k consecutive cells form a brick
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t p = 0; p < P; ++p)
+        for (int d = 0; d < 3; ++d)
+        {
+            lo[d] = std::min(lo[d], m.points[3 * p + d]);
+            hi[d] = std::max(hi[d], m.points[3 * p + d]);
+        }
+    double vol = 1.0;
+    int dims = 0;
+    for (int d = 0; d < 3; ++d)
+        if (hi[d] - lo[d] > 0)
+        {
+            vol *= hi[d] - lo[d];
+            ++dims;
+        }
+    const double h = dims ? std::pow(vol / double(C), 1.0 / dims) : 1.0;
+    const double invH = h > 0 ? 1.0 / h : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> keys(C);
+#pragma omp parallel for schedule(static)
+    for (int64_t c = 0; c < C; ++c)
+    {
+        double x[3] = {0, 0, 0};
+        int n = 0;
+        for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+        {
+            const int32_t f = t.cf[k] & 0x7fffffff;
+            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+            {
+                for (int d = 0; d < 3; ++d)
+                    x[d] += m.points[3 * (int64_t)m.faceVerts[q] + d];
+                ++n;
+            }
+        }
+        uint64_t key = 0;
+        for (int d = 0; d < 3; ++d)
+        {
+            double q = n ? (x[d] / n - lo[d]) * invH : 0.0;
+            q = q < 0 ? 0 : (q > 2097151.0 ? 2097151.0 : q);
+            key |= spreadBits21((uint64_t)q) << d;
+        }
+        keys[c] = {key, (int32_t)c};
+    }
+    std::sort(keys.begin(), keys.end());
+
+    std::vector<int32_t> stamp(F, -1), localOf(F, 0);
+    std::vector<uint8_t> stored(F, 0);
+    G.tileCellOff.push_back(0);
+    G.tileFaceOff.push_back(0);
+    G.tileCells.reserve(C);
+    G.slotOff.reserve(C + 1);
+    G.slotOff.push_back(0);
+    G.slotRef.reserve(t.cf.size());
+    std::vector<int32_t> curCells, curFaces;
+    auto closeTile = [&]() {
+        if (curCells.empty())
+            return;
+        std::sort(curCells.begin(), curCells.end());
+        std::sort(curFaces.begin(), curFaces.end());
+        for (size_t i = 0; i < curFaces.size(); ++i)
+        {
+            const int32_t f = curFaces[i];
+            localOf[f] = (int32_t)i;
+            G.tileFaces.push_back(stored[f] ? f : (int32_t)(f | 0x80000000u));
+            stored[f] = 1;
+        }
+        for (int32_t c : curCells)
+        {
+            G.tileCells.push_back(c);
+            for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+            {
+                const int32_t w = t.cf[k];
+                G.slotRef.push_back((uint16_t)(localOf[w & 0x7fffffff] | (w < 0 ? 0x8000 : 0)));
+            }
+            G.slotOff.push_back((int32_t)G.slotRef.size());
+        }
+        G.tileCellOff.push_back((int32_t)G.tileCells.size());
+        G.tileFaceOff.push_back((int32_t)G.tileFaces.size());
+        ++G.nTiles;
+        curCells.clear();
+        curFaces.clear();
+    };
+    for (int64_t i = 0; i < C; ++i)
+    {
+        const int32_t c = keys[i].second;
+        const int32_t nCellFaces = t.cfOff[c + 1] - t.cfOff[c];
+        if (nCellFaces > maxFaces || maxFaces > 0x7fff)
+            return GeomTiles(); // a cell that does not fit a tile: the caller keeps the two-kernel path
+        int32_t fresh = 0;
+        for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+            if (stamp[t.cf[k] & 0x7fffffff] != G.nTiles)
+                ++fresh;
+        if ((int)curCells.size() == maxCells || (int)curFaces.size() + fresh > maxFaces)
+            closeTile();
+        curCells.push_back(c);
+        for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+        {
+            const int32_t f = t.cf[k] & 0x7fffffff;
+            if (stamp[f] != G.nTiles)
+            {
+                stamp[f] = G.nTiles;
+                curFaces.push_back(f);
+            }
+        }
+    }
+    closeTile();
+    return G;
+}
 } // namespace sm

@@ -78,6 +78,21 @@ struct LayerSync
 LayerSetup buildLayerSetupParallel(const PolyMesh &m, const Topology &t, const std::vector<int32_t> &patchLayer,
                                    int maxLayers, std::vector<double> &normals, const LayerSync &sync);
 
+// Tiles of the fused geometry kernel (k_geom_tiles): compact groups of cells (consecutive cells of a
+// space-filling-curve order, closed when a cell or face budget is reached) with the list of the faces
+// their cells touch.  A thread block computes every listed face once into shared memory and then the
+// centres of its cells from there, so face centres/areas never travel through HBM.  Faces on a tile
+// border are listed (and computed, bit-identically) by both tiles.
+struct GeomTiles
+{
+    int32_t nTiles = 0;
+    std::vector<int32_t> tileCellOff, tileCells; // cells of tile t: tileCells[tileCellOff[t] .. tileCellOff[t+1])
+    std::vector<int32_t> tileFaceOff, tileFaces; // its faces, ascending; bit 31: this tile stores the face's global outputs
+    std::vector<int32_t> slotOff;                // per cell slot (position in tileCells): offsets into slotRef
+    std::vector<uint16_t> slotRef;               // index of the face in the tile's list, in the order of Topology::cf; bit 15 = neighbour side
+};
+GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces);
+
 // Throws std::runtime_error with the reference's FatalError texts where the
 // reference would abort (empty patches :61-66, <2 eligible closest points
 // :354-362, edge/cell face-pair sanity :1073,:1087).

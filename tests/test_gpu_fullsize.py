@@ -25,6 +25,7 @@ def test_full_size_filtered_path_equals_literal_path(mesh, monkeypatch):
     pts, fz = g.points(), g.frozen()
     g.close()
     monkeypatch.setenv("SMGPU_NO_FILTERS", "1")
+    monkeypatch.setenv("SMGPU_NO_TILES", "1")  # and the two-kernel geometry instead of the fused tile kernel
     lit = sm.Smoother(mesh, rel_tol=0.0)
     log2 = lit.iterate(iters)
     assert np.array_equal(log.n_frozen, log2.n_frozen) and np.array_equal(log.residual, log2.residual)

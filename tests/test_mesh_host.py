@@ -192,3 +192,17 @@ def test_cli_decompose_utility_and_parallel_refusals(tmp_path):
     # -parallel without processor directories / without enough GPUs fails loudly (no serial fallback)
     r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel"], capture_output=True, text=True)
     assert r.returncode != 0 and "CUDA devices" in r.stderr
+
+
+def test_geometry_tiles_cover_the_mesh():
+    """Host tiling of the fused geometry kernel: smmesh_geom_tiles checks the invariants the kernel relies on
+    (every cell in one tile, every face stored by one tile, slot references resolve to the cell's faces in
+    OpenFOAM's accumulation order) and fails otherwise."""
+    g = hex_jittered(16, 16, 16, 0.25).geom_tiles()
+    assert g["tiles"] == 16 and g["max_faces"] == 896          # 8 x 8 x 4 bricks
+    assert g["listed_faces"] < 1.2 * g["faces"]                # border faces are listed twice
+    g = hex_jittered(7, 5, 3, 0.2).geom_tiles(max_cells=4, max_faces=20)   # ragged: budgets close tiles early
+    assert g["tiles"] >= 27 and g["max_faces"] <= 20
+    k = sm.Mesh.kelvin(3, 1.0).geom_tiles()                    # 14-faced cells: fewer cells per tile
+    assert k["tiles"] >= 1 and k["max_faces"] <= 1024
+    assert sm.Mesh.kelvin(2, 1.0).geom_tiles(max_cells=8, max_faces=10)["tiles"] == 0   # a cell does not fit
