@@ -74,8 +74,8 @@ extern "C"
     /* Tiling of the fused geometry kernel (cells grouped along a space-filling curve, each tile with the list
      * of faces its cells touch; see smoothmesh_b200/csrc/topology.hpp GeomTiles), built and checked on the
      * host: out = {tiles (0 = a cell does not fit: two-kernel path), listed faces summed over tiles, largest
-     * face list, faces of the mesh}.  Fails if an invariant the kernel relies on does not hold. */
-    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int64_t out[4]);
+     * face list, faces of the mesh, largest point list}.  Fails if an invariant the kernel relies on does not hold. */
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[5]);
 
     /* Morton (space-filling-curve) renumbering of points and cells, the renumberMesh stand-in: returns a new
      * valid polyMesh whose storage order keeps the smoothing kernels' gathers local.  The optional maps

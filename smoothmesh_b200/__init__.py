@@ -125,7 +125,7 @@ def lib():
         L.smgpu_exchange_plan.restype = C.c_int64
         L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
         L.smmesh_quality.argtypes = [C.c_void_p, C.c_void_p]
-        L.smmesh_geom_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.smmesh_geom_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.smmesh_write_decomposed.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
         L.smmesh_read_processor.restype = C.c_void_p
         L.smmesh_read_processor.argtypes = [C.c_char_p, C.c_int32]
@@ -326,12 +326,13 @@ class Mesh:
         cm = np.zeros(self.n_cells, dtype=np.int32)
         return Mesh(lib().smmesh_renumber(self._h, _ptr(pm), _ptr(cm))), pm, cm
 
-    def geom_tiles(self, max_cells=256, max_faces=1024):
-        """Host-side tiling of the fused geometry kernel, checked: dict(tiles, listed_faces, max_faces, faces)."""
-        out = (C.c_int64 * 4)()
-        if lib().smmesh_geom_tiles(self._h, int(max_cells), int(max_faces), out) != 0:
+    def geom_tiles(self, max_cells=256, max_faces=1024, max_points=1024):
+        """Host-side tiling of the fused geometry kernel, checked:
+        dict(tiles, listed_faces, max_faces, faces, max_points)."""
+        out = (C.c_int64 * 5)()
+        if lib().smmesh_geom_tiles(self._h, int(max_cells), int(max_faces), int(max_points), out) != 0:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
-        return dict(tiles=out[0], listed_faces=out[1], max_faces=out[2], faces=out[3])
+        return dict(tiles=out[0], listed_faces=out[1], max_faces=out[2], faces=out[3], max_points=out[4])
 
     def decompose(self, px, py=1, pz=1, method="bricks"):
         n = px * py * pz if method == "bricks" else px

@@ -275,7 +275,7 @@ struct smgpu_handle
         if (useTiles)
         {
             profBegin(K_GEOM_TILES);
-            k_geom_tiles<<<d.nTiles, SMK_TILE_CELLS, 0, stream>>>(d);
+            k_geom_tiles<<<d.nTiles, SMK_TILE_CELLS, SMK_TILE_SMEM, stream>>>(d);
             profEnd(1);
             ++launches;
             return;
@@ -800,7 +800,7 @@ extern "C"
             d.nTiles = 0;
             if (!(getenv("SMGPU_NO_TILES") && atoi(getenv("SMGPU_NO_TILES")) != 0))
             {
-                const sm::GeomTiles G = sm::buildGeomTiles(m, t, SMK_TILE_CELLS, SMK_TILE_FACES);
+                const sm::GeomTiles G = sm::buildGeomTiles(m, t, SMK_TILE_CELLS, SMK_TILE_FACES, SMK_TILE_POINTS);
                 if (G.nTiles > 0)
                 {
                     h->useTiles = true;
@@ -811,6 +811,11 @@ extern "C"
                     d.tileFaces = h->upload(G.tileFaces);
                     d.slotOff = h->upload(G.slotOff);
                     d.slotRef = h->upload(G.slotRef);
+                    d.tilePointOff = h->upload(G.tilePointOff);
+                    d.tilePoints = h->upload(G.tilePoints);
+                    d.faceRefOff = h->upload(G.faceRefOff);
+                    d.faceRef = h->upload(G.faceRef);
+                    CK(cudaFuncSetAttribute(k_geom_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                 }
             }
             d.errFlag = h->dalloc<int>(1);

@@ -242,18 +242,32 @@ extern "C"
         }
         return SMGPU_OK;
     }
-    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int64_t out[4])
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[5])
     {
         try
         {
             const sm::Topology t = sm::buildTopology(m->m);
-            const sm::GeomTiles G = sm::buildGeomTiles(m->m, t, max_cells, max_faces);
+            const sm::GeomTiles G = sm::buildGeomTiles(m->m, t, max_cells, max_faces, max_points);
             // invariants the fused geometry kernel relies on
             std::vector<int32_t> cellSeen(t.C, 0), faceStored(t.F, 0);
-            int64_t maxFaces = 0;
+            int64_t maxFaces = 0, maxPoints = 0;
             for (int32_t k = 0; k < G.nTiles; ++k)
             {
                 const int32_t fb = G.tileFaceOff[k], nf = G.tileFaceOff[k + 1] - fb;
+                const int32_t pb = G.tilePointOff[k], np = G.tilePointOff[k + 1] - pb;
+                maxPoints = std::max<int64_t>(maxPoints, np);
+                if (np > max_points)
+                    throw std::runtime_error("tile over its point budget");
+                for (int32_t i = 0; i < nf; ++i)
+                {
+                    const int32_t f = G.tileFaces[fb + i] & 0x7fffffff;
+                    const int32_t rb = G.faceRefOff[fb + i], nv = G.faceRefOff[fb + i + 1] - rb;
+                    if (nv != m->m.faceOffsets[f + 1] - m->m.faceOffsets[f])
+                        throw std::runtime_error("face vertex count differs");
+                    for (int32_t q = 0; q < nv; ++q)
+                        if (G.faceRef[rb + q] >= np || G.tilePoints[pb + G.faceRef[rb + q]] != m->m.faceVerts[m->m.faceOffsets[f] + q])
+                            throw std::runtime_error("face vertex reference does not resolve to the face's vertex");
+                }
                 const int32_t nc = G.tileCellOff[k + 1] - G.tileCellOff[k];
                 maxFaces = std::max<int64_t>(maxFaces, nf);
                 if (nf > max_faces || nc > max_cells || nc < 1)
@@ -295,6 +309,7 @@ extern "C"
             out[1] = (int64_t)G.tileFaces.size();
             out[2] = maxFaces;
             out[3] = t.F;
+            out[4] = maxPoints;
         }
         catch (const std::exception &e)
         {

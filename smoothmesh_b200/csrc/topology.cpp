@@ -717,7 +717,7 @@ inline uint64_t spreadBits21(uint64_t v)
 }
 } // namespace
 
-GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces)
+GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints)
 {
     GeomTiles G;
     const int64_t C = t.C, F = t.F, P = t.P;
@@ -769,8 +769,11 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
     }
     std::sort(keys.begin(), keys.end());
 
-    std::vector<int32_t> stamp(F, -1), localOf(F, 0);
+    std::vector<int32_t> stamp(F, -1), localOf(F, 0), stampP(P, -1), localOfP(P, 0);
     std::vector<uint8_t> stored(F, 0);
+    G.tilePointOff.push_back(0);
+    G.faceRefOff.push_back(0);
+    std::vector<int32_t> curPoints;
     G.tileCellOff.push_back(0);
     G.tileFaceOff.push_back(0);
     G.tileCells.reserve(C);
@@ -783,12 +786,22 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
             return;
         std::sort(curCells.begin(), curCells.end());
         std::sort(curFaces.begin(), curFaces.end());
+        std::sort(curPoints.begin(), curPoints.end());
+        for (size_t i = 0; i < curPoints.size(); ++i)
+        {
+            localOfP[curPoints[i]] = (int32_t)i;
+            G.tilePoints.push_back(curPoints[i]);
+        }
+        G.tilePointOff.push_back((int32_t)G.tilePoints.size());
         for (size_t i = 0; i < curFaces.size(); ++i)
         {
             const int32_t f = curFaces[i];
             localOf[f] = (int32_t)i;
             G.tileFaces.push_back(stored[f] ? f : (int32_t)(f | 0x80000000u));
             stored[f] = 1;
+            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+                G.faceRef.push_back((uint16_t)localOfP[m.faceVerts[q]]);
+            G.faceRefOff.push_back((int32_t)G.faceRef.size());
         }
         for (int32_t c : curCells)
         {
@@ -805,18 +818,34 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         ++G.nTiles;
         curCells.clear();
         curFaces.clear();
+        curPoints.clear();
     };
     for (int64_t i = 0; i < C; ++i)
     {
         const int32_t c = keys[i].second;
         const int32_t nCellFaces = t.cfOff[c + 1] - t.cfOff[c];
-        if (nCellFaces > maxFaces || maxFaces > 0x7fff)
+        if (nCellFaces > maxFaces || maxFaces > 0x7fff || maxPoints > 0xffff)
             return GeomTiles(); // a cell that does not fit a tile: the caller keeps the two-kernel path
-        int32_t fresh = 0;
+        // faces and points this cell would add to the open tile (a point repeated within the cell's own
+        // faces is over-counted; that only closes a tile slightly early)
+        int32_t fresh = 0, freshP = 0, cellP = 0;
         for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
-            if (stamp[t.cf[k] & 0x7fffffff] != G.nTiles)
-                ++fresh;
-        if ((int)curCells.size() == maxCells || (int)curFaces.size() + fresh > maxFaces)
+        {
+            const int32_t f = t.cf[k] & 0x7fffffff;
+            if (stamp[f] == G.nTiles)
+                continue;
+            ++fresh;
+            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+            {
+                ++cellP;
+                if (stampP[m.faceVerts[q]] != G.nTiles)
+                    ++freshP;
+            }
+        }
+        if (cellP > maxPoints)
+            return GeomTiles();
+        if ((int)curCells.size() == maxCells || (int)curFaces.size() + fresh > maxFaces ||
+            (int)curPoints.size() + freshP > maxPoints)
             closeTile();
         curCells.push_back(c);
         for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
@@ -826,6 +855,12 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
             {
                 stamp[f] = G.nTiles;
                 curFaces.push_back(f);
+                for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+                    if (stampP[m.faceVerts[q]] != G.nTiles)
+                    {
+                        stampP[m.faceVerts[q]] = G.nTiles;
+                        curPoints.push_back(m.faceVerts[q]);
+                    }
             }
         }
     }

@@ -90,8 +90,13 @@ struct GeomTiles
     std::vector<int32_t> tileFaceOff, tileFaces; // its faces, ascending; bit 31: this tile stores the face's global outputs
     std::vector<int32_t> slotOff;                // per cell slot (position in tileCells): offsets into slotRef
     std::vector<uint16_t> slotRef;               // index of the face in the tile's list, in the order of Topology::cf; bit 15 = neighbour side
+    // the points the tile's faces use (staged in shared memory before the face pass) and, per listed face,
+    // its vertices as indices into that list
+    std::vector<int32_t> tilePointOff, tilePoints; // ascending point labels
+    std::vector<int32_t> faceRefOff;               // per listed face (position in tileFaces) + 1: offsets into faceRef
+    std::vector<uint16_t> faceRef;
 };
-GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces);
+GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints);
 
 // Throws std::runtime_error with the reference's FatalError texts where the
 // reference would abort (empty patches :61-66, <2 eligible closest points
