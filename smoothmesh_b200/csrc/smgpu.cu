@@ -56,6 +56,7 @@ struct smgpu_handle
     sm::LayerSetup layer;
     int resolveBlocks = 1;
     bool useTiles = false; // fused geometry kernel over sm::GeomTiles
+    int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
     bool doLayers = false;
     bool anyLayerPatch = false;
     bool layersParallel = false, layersReady = false; // processor mesh: set-up runs in smgpu_comm_init
@@ -275,7 +276,10 @@ struct smgpu_handle
         if (useTiles)
         {
             profBegin(K_GEOM_TILES);
-            k_geom_tiles<<<d.nTiles, SMK_TILE_CELLS, SMK_TILE_SMEM, stream>>>(d);
+            if (tileMinBlocks == 3)
+                k_geom_tiles<3><<<d.nTiles, SMK_TILE_CELLS, SMK_TILE_SMEM, stream>>>(d);
+            else
+                k_geom_tiles<2><<<d.nTiles, SMK_TILE_CELLS, SMK_TILE_SMEM, stream>>>(d);
             profEnd(1);
             ++launches;
             return;
@@ -815,7 +819,10 @@ extern "C"
                     d.tilePoints = h->upload(G.tilePoints);
                     d.faceRefOff = h->upload(G.faceRefOff);
                     d.faceRef = h->upload(G.faceRef);
-                    CK(cudaFuncSetAttribute(k_geom_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
+                    CK(cudaFuncSetAttribute(k_geom_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
+                    CK(cudaFuncSetAttribute(k_geom_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
+                    if (getenv("SMGPU_TILE_MINB"))
+                        h->tileMinBlocks = atoi(getenv("SMGPU_TILE_MINB")) == 3 ? 3 : 2;
                 }
             }
             d.errFlag = h->dalloc<int>(1);
