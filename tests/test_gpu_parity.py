@@ -133,11 +133,12 @@ def test_no_gpu_fallback_message():
 
 
 @pytest.mark.parametrize("case", ["hex_8x6x5_j45", "kelvin3_j20"])
-@pytest.mark.parametrize("env", ["SMGPU_NO_FILTERS", "SMGPU_NO_F32", "SMGPU_NO_TILES"])
+@pytest.mark.parametrize("env", ["SMGPU_NO_FILTERS", "SMGPU_NO_F32", "SMGPU_NO_TILES", "SMGPU_FORCE_TILES"])
 def test_literal_path_without_filters(case, env, monkeypatch):
     # SMGPU_NO_FILTERS=1 disables the guard-banded cosine-space filters so that every point /
     # edge takes the literal evaluation; SMGPU_NO_F32=1 disables only the single-precision first
-    # level; SMGPU_NO_TILES=1 replaces the fused geometry kernel by the per-face + per-cell pair.
+    # level; SMGPU_NO_TILES=1 replaces the fused geometry kernel by the per-face + per-cell pair and
+    # SMGPU_FORCE_TILES=1 uses it on polyhedral meshes too (default: all-quad / all-hex meshes only).
     # Every combination must reproduce the oracle bit for bit.
     monkeypatch.setenv(env, "1")
     mesh = CASES[case]()
