@@ -3,7 +3,10 @@
 #include "sm_math.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -14,7 +17,19 @@ static void fail(const std::string &s) { throw std::runtime_error(s); }
 
 Topology buildTopology(const PolyMesh &m)
 {
+    // SMGPU_TIMING=1: wall time of every set-up phase on stderr
+    const bool timing = getenv("SMGPU_TIMING") && atoi(getenv("SMGPU_TIMING")) != 0;
+    auto clock = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tPrev = clock();
+    auto tick = [&](const char *what) {
+        if (!timing)
+            return;
+        const double tNow = clock();
+        fprintf(stderr, "[smgpu set-up] %-28s %.3f s\n", what, tNow - tPrev);
+        tPrev = tNow;
+    };
     m.check();
+    tick("mesh check");
     Topology t;
     const int64_t P = m.nPoints(), C = m.nCells, F = m.nFaces(), Fi = m.nInternalFaces();
     t.P = P;
@@ -78,6 +93,7 @@ Topology buildTopology(const PolyMesh &m)
         }
     }
 
+    tick("point corners");
     // ---- point -> cells (ascending) and point -> points (ascending) ----
     std::vector<int32_t> pcCount(P), ppCount(P);
 #pragma omp parallel
@@ -150,6 +166,7 @@ Topology buildTopology(const PolyMesh &m)
     if ((int64_t)t.pp.size() != 2 * E)
         fail("inconsistent edge connectivity (pointPoints is not symmetric)");
 
+    tick("pointCells / pointPoints");
     // ---- edges, pointEdges ----
     t.edge.resize(2 * E);
     t.pe.resize(t.pp.size());
@@ -182,6 +199,7 @@ Topology buildTopology(const PolyMesh &m)
             }
         }
 
+    tick("edges");
     // ---- edge -> faces (ascending), edge -> cells with face pairs ----
     std::vector<int32_t> efCount(E), ecCount(E);
     auto edgeFacesOf = [&](int64_t e, int32_t *out) {
@@ -275,6 +293,7 @@ Topology buildTopology(const PolyMesh &m)
     if (bad == 2)
         fail("Sanity broken, didn't find face pairs for cell");
 
+    tick("edgeFaces / edgeCells");
     // ---- cell -> faces in OpenFOAM's accumulation order (owned faces ascending, then
     //      neighbour-side faces ascending; bit 31 marks the neighbour side) ----
     t.cfOff.assign(C + 1, 0);
@@ -293,6 +312,7 @@ Topology buildTopology(const PolyMesh &m)
             t.cf[cur[m.neighbour[f]]++] = (int32_t)((uint32_t)f | 0x80000000u);
     }
 
+    tick("cellFaces");
     // ---- findClosestPoints prerequisite (:354-362): two eligible neighbours per point ----
     for (int64_t p = 0; p < P; ++p)
     {
@@ -303,6 +323,7 @@ Topology buildTopology(const PolyMesh &m)
             fail("Failed to find cLabel" + std::to_string(eligible + 1) + " for pointI " + std::to_string(p));
     }
 
+    tick("eligibility check");
     // ---- getMeshStats :1495-1510 ----
     double mn = 1e300, mx = 0.0;
 #pragma omp parallel for reduction(min : mn) reduction(max : mx) schedule(static)
@@ -317,6 +338,7 @@ Topology buildTopology(const PolyMesh &m)
     t.minEdgeLength = mn;
     t.maxEdgeLength = mx;
 
+    tick("mesh stats");
     // ---- fixed-size records for the common low-valence case (see topology.hpp) ----
     t.pointRec.assign(16 * P, 0);
 #pragma omp parallel for schedule(static)
@@ -434,6 +456,7 @@ Topology buildTopology(const PolyMesh &m)
         const int32_t meta = nf | (nc << 4) | (fan ? 0 : (int32_t)0x80000000u);
         r[10] = meta;
     }
+    tick("point / edge records");
     return t;
 }
 
@@ -723,6 +746,16 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
     const int64_t C = t.C, F = t.F, P = t.P;
     if (C == 0)
         return G;
+    const bool timing = getenv("SMGPU_TIMING") && atoi(getenv("SMGPU_TIMING")) != 0;
+    auto clock = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tPrev = clock();
+    auto tick = [&](const char *what) {
+        if (!timing)
+            return;
+        const double tNow = clock();
+        fprintf(stderr, "[smgpu set-up] %-28s %.3f s\n", what, tNow - tPrev);
+        tPrev = tNow;
+    };
     // cell order: Morton curve over the cells' vertex averages, quantised by the mean cell size so that
     // on block-structured meshes 2^k consecutive cells form a brick
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -767,104 +800,145 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         }
         keys[c] = {key, (int32_t)c};
     }
+    tick("tiles: cell keys");
     std::sort(keys.begin(), keys.end());
+    tick("tiles: sort");
+    if (maxFaces > 0x7fff || maxPoints > 0xffff)
+        return GeomTiles();
 
-    std::vector<int32_t> stamp(F, -1), localOf(F, 0), stampP(P, -1), localOfP(P, 0);
-    std::vector<uint8_t> stored(F, 0);
-    G.tilePointOff.push_back(0);
-    G.faceRefOff.push_back(0);
-    std::vector<int32_t> curPoints;
-    G.tileCellOff.push_back(0);
-    G.tileFaceOff.push_back(0);
-    G.tileCells.reserve(C);
-    G.slotOff.reserve(C + 1);
-    G.slotOff.push_back(0);
-    G.slotRef.reserve(t.cf.size());
-    std::vector<int32_t> curCells, curFaces;
-    auto closeTile = [&]() {
-        if (curCells.empty())
-            return;
-        std::sort(curCells.begin(), curCells.end());
-        std::sort(curFaces.begin(), curFaces.end());
-        std::sort(curPoints.begin(), curPoints.end());
-        for (size_t i = 0; i < curPoints.size(); ++i)
-        {
-            localOfP[curPoints[i]] = (int32_t)i;
-            G.tilePoints.push_back(curPoints[i]);
-        }
-        G.tilePointOff.push_back((int32_t)G.tilePoints.size());
-        for (size_t i = 0; i < curFaces.size(); ++i)
-        {
-            const int32_t f = curFaces[i];
-            localOf[f] = (int32_t)i;
-            G.tileFaces.push_back(stored[f] ? f : (int32_t)(f | 0x80000000u));
-            stored[f] = 1;
-            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
-                G.faceRef.push_back((uint16_t)localOfP[m.faceVerts[q]]);
-            G.faceRefOff.push_back((int32_t)G.faceRef.size());
-        }
-        for (int32_t c : curCells)
-        {
-            G.tileCells.push_back(c);
-            for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
-            {
-                const int32_t w = t.cf[k];
-                G.slotRef.push_back((uint16_t)(localOf[w & 0x7fffffff] | (w < 0 ? 0x8000 : 0)));
-            }
-            G.slotOff.push_back((int32_t)G.slotRef.size());
-        }
-        G.tileCellOff.push_back((int32_t)G.tileCells.size());
-        G.tileFaceOff.push_back((int32_t)G.tileFaces.size());
-        ++G.nTiles;
-        curCells.clear();
-        curFaces.clear();
-        curPoints.clear();
-    };
-    for (int64_t i = 0; i < C; ++i)
+    // Tiles = runs of consecutive cells of that order.  Start from runs of maxCells cells and halve a run
+    // until its face and point lists fit the budgets (deterministic, and independent per initial run, so
+    // the construction is parallel; halving only happens on polyhedral or very irregular meshes).
+    struct Tile
     {
-        const int32_t c = keys[i].second;
-        const int32_t nCellFaces = t.cfOff[c + 1] - t.cfOff[c];
-        if (nCellFaces > maxFaces || maxFaces > 0x7fff || maxPoints > 0xffff)
-            return GeomTiles(); // a cell that does not fit a tile: the caller keeps the two-kernel path
-        // faces and points this cell would add to the open tile (a point repeated within the cell's own
-        // faces is over-counted; that only closes a tile slightly early)
-        int32_t fresh = 0, freshP = 0, cellP = 0;
-        for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+        int32_t a, b; // cells keys[a .. b)
+        std::vector<int32_t> faces, points;
+    };
+    auto collect = [&](Tile &T) {
+        T.faces.clear();
+        T.points.clear();
+        for (int32_t i = T.a; i < T.b; ++i)
         {
-            const int32_t f = t.cf[k] & 0x7fffffff;
-            if (stamp[f] == G.nTiles)
-                continue;
-            ++fresh;
+            const int32_t c = keys[i].second;
+            for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+                T.faces.push_back(t.cf[k] & 0x7fffffff);
+        }
+        std::sort(T.faces.begin(), T.faces.end());
+        T.faces.erase(std::unique(T.faces.begin(), T.faces.end()), T.faces.end());
+        for (int32_t f : T.faces)
             for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+                T.points.push_back(m.faceVerts[q]);
+        std::sort(T.points.begin(), T.points.end());
+        T.points.erase(std::unique(T.points.begin(), T.points.end()), T.points.end());
+    };
+    const int64_t nRuns = (C + maxCells - 1) / maxCells;
+    std::vector<std::vector<Tile>> perRun(nRuns);
+    bool cellTooLarge = false;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t r = 0; r < nRuns; ++r)
+    {
+        std::vector<Tile> todo, done;
+        todo.push_back({(int32_t)(r * maxCells), (int32_t)std::min<int64_t>(C, (r + 1) * maxCells), {}, {}});
+        while (!todo.empty())
+        {
+            Tile T = std::move(todo.back());
+            todo.pop_back();
+            collect(T);
+            if ((int)T.faces.size() <= maxFaces && (int)T.points.size() <= maxPoints)
+                done.push_back(std::move(T));
+            else if (T.b - T.a == 1)
             {
-                ++cellP;
-                if (stampP[m.faceVerts[q]] != G.nTiles)
-                    ++freshP;
+#pragma omp atomic write
+                cellTooLarge = true;
+            }
+            else
+            { // second half first on the stack, so the first half is finished first (keeps the order)
+                const int32_t mid = T.a + (T.b - T.a) / 2;
+                todo.push_back({mid, T.b, {}, {}});
+                todo.push_back({T.a, mid, {}, {}});
             }
         }
-        if (cellP > maxPoints)
-            return GeomTiles();
-        if ((int)curCells.size() == maxCells || (int)curFaces.size() + fresh > maxFaces ||
-            (int)curPoints.size() + freshP > maxPoints)
-            closeTile();
-        curCells.push_back(c);
-        for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+        perRun[r] = std::move(done);
+    }
+    tick("tiles: face / point lists");
+    if (cellTooLarge)
+        return GeomTiles(); // a cell that does not fit a tile: the caller keeps the two-kernel path
+    std::vector<Tile *> tiles;
+    for (auto &v : perRun)
+        for (Tile &T : v)
+            tiles.push_back(&T);
+    G.nTiles = (int32_t)tiles.size();
+    // offsets
+    G.tileCellOff.assign(G.nTiles + 1, 0);
+    G.tileFaceOff.assign(G.nTiles + 1, 0);
+    G.tilePointOff.assign(G.nTiles + 1, 0);
+    std::vector<int64_t> slotRefOff(G.nTiles + 1, 0), faceRefBase(G.nTiles + 1, 0);
+    for (int32_t k = 0; k < G.nTiles; ++k)
+    {
+        const Tile &T = *tiles[k];
+        int64_t nSlotRefs = 0, nFaceRefs = 0;
+        for (int32_t i = T.a; i < T.b; ++i)
+            nSlotRefs += t.cfOff[keys[i].second + 1] - t.cfOff[keys[i].second];
+        for (int32_t f : T.faces)
+            nFaceRefs += m.faceOffsets[f + 1] - m.faceOffsets[f];
+        G.tileCellOff[k + 1] = G.tileCellOff[k] + (T.b - T.a);
+        G.tileFaceOff[k + 1] = G.tileFaceOff[k] + (int32_t)T.faces.size();
+        G.tilePointOff[k + 1] = G.tilePointOff[k] + (int32_t)T.points.size();
+        slotRefOff[k + 1] = slotRefOff[k] + nSlotRefs;
+        faceRefBase[k + 1] = faceRefBase[k] + nFaceRefs;
+    }
+    if (faceRefBase[G.nTiles] >= (int64_t)INT32_MAX)
+        return GeomTiles();
+    // the first tile (in tile order) that lists a face stores the face's global outputs
+    std::vector<int32_t> firstTile(F, -1);
+    for (int32_t k = 0; k < G.nTiles; ++k)
+        for (int32_t f : tiles[k]->faces)
+            if (firstTile[f] < 0)
+                firstTile[f] = k;
+    tick("tiles: offsets, first tile");
+    G.tileCells.resize(C);
+    G.tileFaces.resize(G.tileFaceOff[G.nTiles]);
+    G.tilePoints.resize(G.tilePointOff[G.nTiles]);
+    G.slotOff.resize(C + 1);
+    G.slotRef.resize(slotRefOff[G.nTiles]);
+    G.faceRefOff.resize(G.tileFaceOff[G.nTiles] + 1);
+    G.faceRef.resize(faceRefBase[G.nTiles]);
+    G.slotOff[C] = (int32_t)slotRefOff[G.nTiles];
+    G.faceRefOff[G.tileFaceOff[G.nTiles]] = (int32_t)faceRefBase[G.nTiles];
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int32_t k = 0; k < G.nTiles; ++k)
+    {
+        const Tile &T = *tiles[k];
+        std::vector<int32_t> cells;
+        for (int32_t i = T.a; i < T.b; ++i)
+            cells.push_back(keys[i].second);
+        std::sort(cells.begin(), cells.end());
+        auto localPoint = [&](int32_t p) { return (int32_t)(std::lower_bound(T.points.begin(), T.points.end(), p) - T.points.begin()); };
+        auto localFace = [&](int32_t f) { return (int32_t)(std::lower_bound(T.faces.begin(), T.faces.end(), f) - T.faces.begin()); };
+        std::copy(T.points.begin(), T.points.end(), G.tilePoints.begin() + G.tilePointOff[k]);
+        int64_t fr = faceRefBase[k];
+        for (size_t i = 0; i < T.faces.size(); ++i)
         {
-            const int32_t f = t.cf[k] & 0x7fffffff;
-            if (stamp[f] != G.nTiles)
+            const int32_t f = T.faces[i];
+            G.tileFaces[G.tileFaceOff[k] + i] = (firstTile[f] == k) ? (int32_t)(f | 0x80000000u) : f;
+            G.faceRefOff[G.tileFaceOff[k] + i] = (int32_t)fr;
+            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+                G.faceRef[fr++] = (uint16_t)localPoint(m.faceVerts[q]);
+        }
+        int64_t sr = slotRefOff[k];
+        for (size_t i = 0; i < cells.size(); ++i)
+        {
+            const int32_t c = cells[i], slot = G.tileCellOff[k] + (int32_t)i;
+            G.tileCells[slot] = c;
+            G.slotOff[slot] = (int32_t)sr;
+            for (int32_t q = t.cfOff[c]; q < t.cfOff[c + 1]; ++q)
             {
-                stamp[f] = G.nTiles;
-                curFaces.push_back(f);
-                for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
-                    if (stampP[m.faceVerts[q]] != G.nTiles)
-                    {
-                        stampP[m.faceVerts[q]] = G.nTiles;
-                        curPoints.push_back(m.faceVerts[q]);
-                    }
+                const int32_t w = t.cf[q];
+                G.slotRef[sr++] = (uint16_t)(localFace(w & 0x7fffffff) | (w < 0 ? 0x8000 : 0));
             }
         }
     }
-    closeTile();
+    tick("tiles: references");
     return G;
 }
 } // namespace sm
