@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -666,6 +667,17 @@ extern "C"
         if (params->device < 0 || params->device >= nDev)
             return setErr(SMGPU_ERR_ARG, "device ordinal out of range");
         smgpu_handle *h = new smgpu_handle;
+        // SMGPU_TIMING=1: wall time of the set-up phases on stderr (topology.cpp prints its own)
+        const bool timing = getenv("SMGPU_TIMING") && atoi(getenv("SMGPU_TIMING")) != 0;
+        auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double tPrev = wall();
+        auto tick = [&](const char *what) {
+            if (!timing)
+                return;
+            const double tNow = wall();
+            fprintf(stderr, "[smgpu create] %-28s %.3f s\n", what, tNow - tPrev);
+            tPrev = tNow;
+        };
         try
         {
             sm::PolyMesh m;
@@ -695,6 +707,7 @@ extern "C"
                     patchLayer[i] = md->patch_layer[i] != 0;
                     h->anyLayerPatch = h->anyLayerPatch || patchLayer[i];
                 }
+            tick("copy of the caller's mesh");
             try
             {
                 if (params->renumber)
@@ -708,6 +721,7 @@ extern "C"
                 delete h;
                 return setErr(SMGPU_ERR_MESH, e.what());
             }
+            tick("topology (total)");
             const sm::Topology &t = h->topo;
             h->prm = *params;
             h->prmRequested = *params;
@@ -726,6 +740,7 @@ extern "C"
             d.C = (int)t.C;
             d.E = (int)t.E;
             d.F = (int)t.F;
+            tick("CUDA context, stream");
             d.faceGeo = h->dalloc<P4>(2 * t.F);
             d.faceMean = h->dalloc<P4>(t.F);
             d.ptsF = h->dalloc<float4>(t.P);
@@ -754,6 +769,7 @@ extern "C"
             d.faceVerts = h->upload(t.faceVerts);
             d.cfOff = h->upload(t.cfOff);
             d.cf = h->upload(t.cf);
+            tick("allocation + upload of tables");
             d.uniformFaceSize = t.maxFaceSize;
             for (int64_t f = 0; f < t.F && d.uniformFaceSize; ++f)
                 if (t.faceOff[f + 1] - t.faceOff[f] != d.uniformFaceSize)
@@ -830,6 +846,7 @@ extern "C"
                         h->tileMinBlocks = atoi(getenv("SMGPU_TILE_MINB")) == 3 ? 3 : 2;
                 }
             }
+            tick("records, work space, tiles");
             d.errFlag = h->dalloc<int>(1);
             CK(cudaMemset(d.errFlag, 0, sizeof(int)));
             if (h->anyLayerPatch)
@@ -862,6 +879,7 @@ extern "C"
             h->resolveParams();
             h->initLayerNormals();
             CK(cudaDeviceSynchronize());
+            tick("points, parameters");
         }
         catch (const std::exception &e)
         {
