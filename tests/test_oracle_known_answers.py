@@ -129,6 +129,42 @@ def test_rank_emulation_matches_serial_when_constraints_are_off():
         assert np.abs(g.get("points", r) - ref[p.point_global_id]).max() <= 1e-12
 
 
+def test_layer_setup_under_rank_emulation():
+    """Boundary layer treatment on a decomposed mesh (src/orthogonalBoundaryBlending.C under -parallel).
+    Derived from the cited code: the hop counts are max-synchronised after every Jacobi sweep (:124-130), so
+    they equal the serial ones; interface copies of a point end every iteration with identical normals (sum
+    :185, maxMagSqr :363) and positions; away from the interfaces the set-up normals are the serial ones."""
+    mesh = hex_jittered(12, 10, 8, 0.2, seed=3)
+    kw = dict(rel_tol=0.0, layer_patches=[1, 1, 1, 1, 1, 1], max_layers=3)
+    s = Oracle(mesh.desc_arrays(), **kw)
+    parts = mesh.decompose(2, 2, 1)
+    g = Oracle([p.desc_arrays() for p in parts], **kw)
+    hops = s.get("hopsToLayer")
+    assert hops.max() == 4 and (hops == 0).sum() > 0        # maxLayers + 1 sweeps
+    for r, p in enumerate(parts):
+        assert np.array_equal(g.get("hopsToLayer", r), hops[p.point_global_id])
+    s.iterate(3)
+    g.iterate(3)
+    owner = {}
+    for r, p in enumerate(parts):
+        nrm, pts = g.get("snapNormals", r), g.get("points", r)
+        for i, gid in enumerate(p.point_global_id):
+            if gid in owner:
+                n0, x0 = owner[gid]
+                assert np.array_equal(nrm[i], n0) and np.array_equal(pts[i], x0)
+            else:
+                owner[gid] = (nrm[i].copy(), pts[i].copy())
+    # a layer point well inside rank 0 keeps the serial set-up normal (unit, pointing into the domain)
+    serial_n = s.get("snapNormals")
+    p0 = parts[0]
+    x = np.asarray(mesh.points)[p0.point_global_id]
+    inside = (x[:, 0] < 0.3) & (x[:, 1] < 0.3) & (hops[p0.point_global_id] >= 1)
+    n0 = g.get("snapNormals", 0)
+    assert inside.sum() > 10 and np.abs(n0[inside] - serial_n[p0.point_global_id][inside]).max() <= 1e-12
+    mag = np.linalg.norm(n0[inside], axis=1)
+    assert (np.abs(mag[mag > 0] - 1.0) < 1e-12).all()
+
+
 def test_oracle_reports_reference_fatal_errors():
     arr = sm.Mesh.hex_block(2, 2, 2).desc_arrays()
     arr["patch_kind"] = arr["patch_kind"].copy()
