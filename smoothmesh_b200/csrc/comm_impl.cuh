@@ -284,6 +284,10 @@ struct Comm
     ncclComm_t nccl = nullptr;
     ExchangePlan plan;
     smk::CommDev c;
+    // the predictor exchange runs on its own stream, fenced by these events, so that kernels that do not
+    // need its result keep the GPU busy meanwhile
+    cudaStream_t xStream = nullptr;
+    cudaEvent_t evPacked = nullptr, evExchanged = nullptr;
 };
 
 #define NCK(call)                                                                                                      \
@@ -294,15 +298,15 @@ struct Comm
             throw std::runtime_error(std::string("NCCL error: ") + sm::nccl().GetErrorString(r_) + " at " #call);             \
     } while (0)
 
-static void haloExchange(Comm *cm, smgpu_handle *h, const void *send, void *recv, size_t elemBytes)
+static void haloExchange(Comm *cm, cudaStream_t stream, const void *send, void *recv, size_t elemBytes)
 {
     const ExchangePlan &pl = cm->plan;
     NCK(nccl().GroupStart());
     for (size_t j = 0; j < pl.nbrRank.size(); ++j)
     {
         const size_t off = (size_t)pl.nbrOff[j] * elemBytes, cnt = (size_t)(pl.nbrOff[j + 1] - pl.nbrOff[j]) * elemBytes;
-        NCK(nccl().Send((const char *)send + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
-        NCK(nccl().Recv((char *)recv + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, h->stream));
+        NCK(nccl().Send((const char *)send + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, stream));
+        NCK(nccl().Recv((char *)recv + off, cnt, ncclChar, pl.nbrRank[j], cm->nccl, stream));
     }
     NCK(nccl().GroupEnd());
 }

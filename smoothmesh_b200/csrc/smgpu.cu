@@ -355,6 +355,14 @@ struct smgpu_handle
     }
     void launchFaceAngle(double *dbgMin = nullptr, double *dbgMax = nullptr)
     {
+        launchFaceCurrent(dbgMin, dbgMax);
+        launchFaceResolve();
+    }
+    // first half of restrictFaceAngleDeterioration: the angles of the *current* mesh and the ordered list
+    // of active points (:1252-1270, :1367-1368) -- independent of the proposed positions, so a multi-rank
+    // iteration runs it while the interface exchange is in flight
+    void launchFaceCurrent(double *dbgMin = nullptr, double *dbgMax = nullptr)
+    {
         const int nChunks = grid(d.P, SMK_CHUNK);
         profBegin(K_FACE_CUR);
         k_face_current<<<grid(d.E, 128), 128, 0, stream>>>(d, dbgMin, dbgMax);
@@ -365,6 +373,11 @@ struct smgpu_handle
         k_active_fill<<<nChunks, 256, 0, stream>>>(d);
         k_face_clear<<<148, 128, 0, stream>>>(d);
         profEnd(4);
+        launches += 5;
+    }
+    // second half: the tests on the proposed positions and the replay of the worklist (:1347-1434)
+    void launchFaceResolve()
+    {
         profBegin(K_FACE_TESTS);
         k_face_tests<<<148 * 4, 128, 0, stream>>>(d);
         profEnd(1);
@@ -374,7 +387,7 @@ struct smgpu_handle
             CK(cudaLaunchCooperativeKernel((const void *)k_face_resolve, dim3(resolveBlocks), dim3(128), args, 0, stream));
         }
         profEnd(1);
-        launches += 7;
+        launches += 2;
     }
     void launchCommit()
     {
@@ -418,6 +431,9 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         static_assert(sizeof(uid) == 128, "ncclUniqueId size");
         memcpy(&uid, id, 128);
         NCK(nccl().CommInitRank(&cm->nccl, nRanks, uid, rank));
+        CK(cudaStreamCreateWithFlags(&cm->xStream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&cm->evPacked, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&cm->evExchanged, cudaEventDisableTiming));
         smk::CommDev &c = cm->c;
         c.rank = rank;
         c.nSlots = (int)pl.sendPoint.size();
@@ -476,7 +492,7 @@ template <class T, int N, class Op> static void hostSync(Comm *cm, smgpu_handle 
         for (int k = 0; k < N; ++k)
             send[(size_t)i * N + k] = field[(size_t)pl.sendPoint[i] * N + k];
     CK(cudaMemcpyAsync(c.sendBuf, send.data(), send.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    haloExchange(cm, h, c.sendBuf, c.recvBuf, N * sizeof(T));
+    haloExchange(cm, h->stream, c.sendBuf, c.recvBuf, N * sizeof(T));
     CK(cudaMemcpyAsync(recv.data(), c.recvBuf, recv.size() * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     for (size_t s = 0; s < pl.sharedPoint.size(); ++s)
@@ -561,6 +577,15 @@ static void commDestroy(Comm *cm)
 {
     if (!cm)
         return;
+    if (cm->xStream)
+    {
+        cudaStreamSynchronize(cm->xStream);
+        cudaStreamDestroy(cm->xStream);
+    }
+    if (cm->evPacked)
+        cudaEventDestroy(cm->evPacked);
+    if (cm->evExchanged)
+        cudaEventDestroy(cm->evExchanged);
     if (cm->nccl)
         nccl().CommDestroy(cm->nccl);
     delete cm;
@@ -579,25 +604,32 @@ static int commIterate(Comm *cm, smgpu_handle *h)
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
         k_shared_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
+    CK(cudaEventRecord(cm->evPacked, h->stream));
+    CK(cudaStreamWaitEvent(cm->xStream, cm->evPacked, 0));
+    haloExchange(cm, cm->xStream, c.sendBuf, c.recvBuf, c.tuple * sizeof(double));
+    CK(cudaEventRecord(cm->evExchanged, cm->xStream));
     h->profEnd(1);
     if (h->doLayers)
         h->launchLayerNormals();
     h->launchPredict();
     if (h->doLayers)
         h->launchLayerBlend();
+    // (the exchange was enqueued on its own stream right after the pack, see above)
+    if (h->prm.face_angle_constraint)
+        h->launchFaceCurrent(); // current-mesh half of the face-angle constraint: needs nothing from the exchange
     h->profBegin(smgpu_handle::K_EXCHANGE);
-    haloExchange(cm, h, c.sendBuf, c.recvBuf, c.tuple * sizeof(double));
+    CK(cudaStreamWaitEvent(h->stream, cm->evExchanged, 0));
     if (c.nShared > 0)
         k_shared_merge<<<smgpu_handle::grid(c.nShared, 64), 64, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
     h->launches += 2;
     h->launchEdgeConstraints();
     if (h->prm.face_angle_constraint)
-        h->launchFaceAngle();
+        h->launchFaceResolve();
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
         k_frozen_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
-    haloExchange(cm, h, c.sendFz, c.recvFz, 1);
+    haloExchange(cm, h->stream, c.sendFz, c.recvFz, 1);
     if (c.nSlots > 0)
         k_frozen_or<<<gs, 128, 0, h->stream>>>(h->d, c);
     h->profEnd(2);
