@@ -4,6 +4,11 @@ A second, independent restatement of the smoothMesh iteration in plain Python/Nu
 the prose contract in SURVEY.md section 8 (a0-a15) rather than from oracle/oracle.cpp, so that the
 two can be checked against each other (pin K8).  Serial only, small meshes only (pure
 Python loops).  It uses math.acos (libm), i.e. the reference's literal std::acos.
+
+The prismatic boundary layer treatment (src/orthogonalBoundaryBlending.C) is restated
+here as graph logic -- breadth-first hop levels, "unique parent" maps, per-iteration normals -- not as
+the reference's sweeps, so that agreement with oracle.cpp checks the reading of the algorithm and not
+just a transcription.
 """
 from __future__ import annotations
 
@@ -41,7 +46,8 @@ def _same(a, b):
 class NumpyOracle:
     def __init__(self, m, min_edge_length=-1.0, max_step_length=-1.0, rel_step_frac=0.5, min_angle_deg=35.0,
                  max_angle_deg=160.0, rel_tol=0.02, total_min_freeze=0, edge_angle_constraint=1,
-                 face_angle_constraint=1):
+                 face_angle_constraint=1, layer_patches=None, layer_max_blending_fraction=0.3, layer_edge_length=-1.0,
+                 layer_expansion_ratio=1.3, min_layers=1, max_layers=4):
         self.x = np.array(m["points"], dtype=np.float64).reshape(-1, 3).copy()
         off, fv = m["face_offsets"], m["face_verts"]
         self.faces = [list(map(int, fv[off[i]:off[i + 1]])) for i in range(len(off) - 1)]
@@ -90,6 +96,110 @@ class NumpyOracle:
         self.total_min_freeze = bool(total_min_freeze)
         self.edge_angle, self.face_angle = bool(edge_angle_constraint), bool(face_angle_constraint)
         self.frozen = np.zeros(P, dtype=bool)
+        self.patches = [(int(a), int(n), int(k)) for a, n, k in zip(m["patch_start"], m["patch_size"], m["patch_kind"])]
+        self.layers = (layer_patches is not None and any(layer_patches) and layer_max_blending_fraction > 1e-15)
+        if self.layers:
+            self.layer_flags = [bool(layer_patches[i]) if i < len(layer_patches) else False for i in range(len(self.patches))]
+            self.layer_frac, self.layer_ratio = layer_max_blending_fraction, layer_expansion_ratio
+            self.layer_len = self.min_edge_length if layer_edge_length < 0 else layer_edge_length
+            self.min_layers, self.max_layers = min_layers, max_layers
+            self.setup_layers()
+
+    # ---- prismatic boundary layer treatment ----
+    def boundary_normals(self):
+        """Per call: every boundary point adds the negated unit normals of its boundary faces (ascending face
+        label) to whatever its normal was before -- the reference never zeroes the field -- then normals shorter
+        than 0.1 at boundary points are dropped and every non-zero normal is rescaled to unit length."""
+        touched = set()
+        for a, n, k in self.patches:
+            if k != 0:
+                continue
+            for f in range(a, a + n):
+                unit = self.face_area[f] / _mag(self.face_area[f])
+                for v in self.faces[f]:
+                    self.normal[v] = self.normal[v] - unit
+                    touched.add(v)
+        for v in touched:
+            if _mag(self.normal[v]) < 0.1:
+                self.normal[v] = np.zeros(3)
+        for v in range(len(self.x)):
+            if not _same(self.normal[v], np.zeros(3)):
+                self.normal[v] = self.normal[v] / _mag(self.normal[v])
+
+    def setup_layers(self):
+        P = len(self.x)
+        # a boundary point belongs to the first patch (in patch order) that contains it
+        first_patch = {}
+        for pi, (a, n, k) in enumerate(self.patches):
+            for f in range(a, a + n):
+                for v in self.faces[f]:
+                    first_patch.setdefault(v, pi)
+        touches_internal = [any(self.internal[q] for q in self.point_points[v]) for v in range(P)]
+        layer_surface = [(not self.internal[v]) and self.layer_flags[first_patch[v]] for v in range(P)]
+        # hop levels: breadth-first from the layer-patch points that touch the interior, through internal
+        # points only, max_layers + 1 levels deep
+        hop = [-1] * P
+        level = set()
+        for pi, (a, n, k) in enumerate(self.patches):
+            if self.layer_flags[pi]:
+                for f in range(a, a + n):
+                    level.update(v for v in self.faces[f] if (not self.internal[v]) and touches_internal[v])
+        for v in level:
+            hop[v] = 0
+        for depth in range(1, self.max_layers + 2):
+            nxt = {q for v in level for q in self.point_points[v] if hop[q] < 0 and self.internal[q]}
+            for q in nxt:
+                hop[q] = depth
+            level = nxt
+        self.hop = hop
+        # set-up normals of the boundary points
+        self.normal = np.zeros((P, 3))
+        self.geometry()
+        self.boundary_normals()
+        # an internal point is tied to an outer point if exactly one neighbour lies one level closer to the
+        # wall and that neighbour is internal or on a layer patch; an outer point claimed by two points
+        # unties both, and an untied point unties everything that hangs below it
+        self.outer = [-1] * P
+        untied = set()
+        claimed = {}
+        for depth in range(1, self.max_layers + 2):
+            for v in range(P):
+                if hop[v] != depth:
+                    continue
+                parents = [q for q in self.point_points[v] if hop[q] == depth - 1]
+                if len(parents) != 1:
+                    continue
+                q = parents[0]
+                if not self.internal[q] and not layer_surface[q]:
+                    continue
+                if q in claimed:
+                    untied.update((v, claimed[q]))
+                    continue
+                claimed[q] = v
+                self.outer[v] = q
+                if q in untied:
+                    untied.add(v)
+                else:
+                    self.normal[v] = self.normal[q]
+        for v in untied:
+            self.normal[v] = np.zeros(3)
+            self.outer[v] = -1
+
+    def layer_blend(self):
+        top = self.max_layers + 1
+        for v in range(len(self.x)):
+            if _same(self.normal[v], np.zeros(3)) or not self.internal[v] or self.hop[v] < 1:
+                continue
+            h = self.hop[v]
+            length = self.layer_len * self.layer_ratio ** min(h - 1, top)
+            slope = -self.layer_frac / (top - self.min_layers)
+            frac = max(0.0, min(-slope * top + slope * h, self.layer_frac))
+            ortho = self.x[self.outer[v]] + length * self.normal[v]
+            self.new[v] = frac * ortho + (1.0 - frac) * self.new[v]
+        for v in range(len(self.x)):  # second constrainMaxStepLength, every point
+            d = self.new[v] - self.x[v]
+            scale = self.max_step_length / (_mag(d) * self.rel_step_frac) if _mag(d) > self.max_step_length else 1.0
+            self.new[v] = self.x[v] + (self.rel_step_frac * scale) * d
 
     # a0: OpenFOAM (openfoam.com) face centres / areas and cell centres
     def geometry(self):
@@ -142,6 +252,7 @@ class NumpyOracle:
             ctr[c] = ctr[c] + pv * (0.75 * fc[f] + 0.25 * est[c])
             vol[c] += pv
         self.cell_ctr = np.array([ctr[c] / vol[c] if abs(vol[c]) > VSMALL else est[c] for c in range(self.C)])
+        self.face_area = fa
 
     # a1 + a3-a6: predictor
     def predict(self):
@@ -286,7 +397,11 @@ class NumpyOracle:
         for _ in range(max_iters):
             self.frozen[:] = False
             self.geometry()
+            if self.layers:
+                self.boundary_normals()
             self.predict()
+            if self.layers:
+                self.layer_blend()
             self.edge_shortening()
             if self.edge_angle:
                 self.edge_angles()

@@ -91,7 +91,13 @@ def test_k7_scale_invariance_of_the_tiny_graded_block():
 
 @pytest.mark.parametrize("case,opts", [("hex6_j25", dict()), ("layers_ar", dict()),
                                        ("hex_8x6x5_j45", dict(min_angle_deg=75.0, max_angle_deg=105.0)),
-                                       ("kelvin3_j20", dict(min_angle_deg=60.0, max_angle_deg=120.0, total_min_freeze=1))])
+                                       ("kelvin3_j20", dict(min_angle_deg=60.0, max_angle_deg=120.0, total_min_freeze=1)),
+                                       # boundary layer treatment (8f-2): all walls, and a subset with other options
+                                       ("hex_8x6x5_j45", dict(layer_patches=[1, 1, 1, 1, 1, 1], max_layers=2)),
+                                       ("hex6_j25", dict(layer_patches=[0, 1, 0, 0, 1, 1], max_layers=3, min_layers=2,
+                                                         layer_expansion_ratio=1.2, layer_edge_length=0.05,
+                                                         layer_max_blending_fraction=0.8, min_angle_deg=20.0)),
+                                       ("layers_ar", dict(layer_patches=[1, 0, 0, 0, 0, 0], max_layers=4))])
 def test_k8_independent_numpy_restatement_agrees(case, opts):
     mesh = CASES[case]()
     iters = 4
