@@ -16,7 +16,17 @@ CLI       := $(BINDIR)/smoothMesh
 ORACLE    := oracle/_build/liboracle.so
 ORACLE_LM := oracle/_build/liboracle_libm.so
 
-all: $(LIB) $(CLI) $(ORACLE) $(ORACLE_LM)
+# oracle/_ref: the reference's own translation unit compiled against the OpenFOAM facade (oracle/Makefile.ref);
+# only where the reference sources exist (the build container), the GPU box receives the built binary
+REFSRC = /root/reference/src/smoothMesh.C
+ifneq ($(wildcard $(REFSRC)),)
+REFBIN = oracle/_ref/smoothMesh_ref
+endif
+
+all: $(LIB) $(CLI) $(ORACLE) $(ORACLE_LM) $(REFBIN)
+
+oracle/_ref/smoothMesh_ref: oracle/of_facade/ref_main.cpp $(wildcard oracle/of_facade/*.H) oracle/oracle.cpp $(OBJDIR)/polymesh.o
+	$(MAKE) -f oracle/Makefile.ref
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)
 	@mkdir -p $(OBJDIR)

@@ -1,9 +1,10 @@
 """oracle -- TEST INFRASTRUCTURE ONLY (parity checker + CPU baseline).
 
 ctypes binding over oracle/_build/liboracle.so, the CPU restatement of the
-reference's smoothing iteration (oracle/oracle.cpp).  PARITY UNPINNED: the
-reference cannot be built without OpenFOAM and ships no golden vectors; see the
-header of oracle.cpp.  Only tests/, __graft_entry__.smoke() and bench.py's
+reference's smoothing iteration (oracle/oracle.cpp).  Parity: bit-exact against the
+reference's own translation unit compiled against an OpenFOAM facade (oracle/_ref,
+tests/test_reference_build.py); the OpenFOAM semantics inside that facade are recalled,
+not verified -- see the header of oracle.cpp.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import this package.
 """
 from __future__ import annotations

@@ -1,0 +1,123 @@
+"""oracle.cpp against the reference's own code.
+
+oracle/_ref/smoothMesh_ref is the UNMODIFIED reference translation unit (/root/reference/src/smoothMesh.C
+with its two #included files), compiled where it lies against the OpenFOAM facade in oracle/of_facade
+(recipe: oracle/Makefile.ref; built by `make` / __graft_entry__.build() when /root/reference exists).  It runs
+the reference's main(): option handling, set-up, the smoothing loop, the log lines and the write rule.
+
+What the comparison proves: every line the reference authors wrote on this path (predictor, aspect-ratio
+blend, step clamp, the three constraints, the order-dependent worklist, the boundary layer treatment, the
+stop rule) is executed literally and oracle.cpp reproduces it bit for bit.  What it does not prove: the
+OpenFOAM semantics inside the facade (addressing row orders, face / cell centre formulas, Foam::min/max,
+vector ==), which are recalled, shared with oracle.cpp, and marked [OF-recalled] there.
+
+The binary uses libm's acos like the reference; positions never depend on acos, masks could in principle,
+so the masks are compared with both oracle builds.
+"""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import smoothmesh_b200 as sm
+from oracle import Oracle
+
+from meshes import CASES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/smoothMesh_ref not built "
+                                "(needs /root/reference; run `make -f oracle/Makefile.ref`)")
+
+
+def write_case(tmp_path, mesh):
+    case = tmp_path / "case"
+    mesh.write(case / "constant" / "polyMesh")
+    (case / "system").mkdir()
+    (case / "system" / "controlDict").write_text(
+        "FoamFile { version 2.0; format ascii; class dictionary; object controlDict; }\n"
+        "startFrom latestTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat binary;\nwritePrecision 12;\ntimePrecision 6;\n")
+    return case
+
+
+def run_reference(case, iters, cli):
+    r = subprocess.run([REF_BIN, "-case", str(case), "-centroidalIters", str(iters)] + cli,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    log = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    last = int(log[-1][0])
+    out = sm.Mesh.read(case / "constant" / "polyMesh")
+    out.read_points(case / str(last) / "polyMesh" / "points")
+    return np.array([int(b) for _, b, _ in log]), np.array([float(c) for _, _, c in log]), np.array(out.points), r.stdout
+
+
+def golden_mesh(name):
+    d = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    return sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"],
+                               int(d["n_cells"]), d["patch_start"], d["patch_size"], d["patch_kind"])
+
+
+# (mesh, oracle options, the same options on the reference's command line, iterations)
+RUNS = {
+    "hex_defaults": (CASES["hex6_j25"], dict(), [], 30),
+    "hex_tight_angles_total_freeze": (CASES["hex_8x6x5_j45"],
+                                      dict(rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0, total_min_freeze=1),
+                                      ["-relTol", "0", "-minAngle", "60", "-maxAngle", "120", "-totalMinFreeze", "true"], 12),
+    "hex_very_tight_angles": (CASES["hex_8x6x5_j45"], dict(rel_tol=0.0, min_angle_deg=80.0, max_angle_deg=100.0),
+                              ["-relTol", "0", "-minAngle", "80", "-maxAngle", "100"], 8),
+    "kelvin_polyhedral": (CASES["kelvin3_j20"], dict(rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0),
+                          ["-relTol", "0", "-minAngle", "60", "-maxAngle", "120"], 8),
+    "high_aspect_ratio": (CASES["layers_ar"], dict(rel_tol=0.0), ["-relTol", "0"], 10),
+    "constraints_off": (CASES["hex6_j25"], dict(rel_tol=1e-3, edge_angle_constraint=0, face_angle_constraint=0,
+                                                min_edge_length=0.02, max_step_length=0.004, rel_step_frac=0.8),
+                        ["-relTol", "1e-3", "-edgeAngleConstraint", "false", "-faceAngleConstraint", "false",
+                         "-minEdgeLength", "0.02", "-maxStepLength", "0.004", "-relStepFrac", "0.8"], 40),
+    "hex_layers_all_walls": (CASES["hex_8x6x5_j45"], dict(rel_tol=0.0, layer_patches=[1] * 6, max_layers=2),
+                             ["-relTol", "0", "-layerPatches", '(".*")', "-maxLayers", "2"], 10),
+    "hex_layers_options": (CASES["hex6_j25"],
+                           dict(rel_tol=0.0, layer_patches=[0, 1, 0, 0, 1, 1], max_layers=3, min_layers=2, layer_expansion_ratio=1.2,
+                                layer_edge_length=0.05, layer_max_blending_fraction=0.8, min_angle_deg=20.0),
+                           ["-relTol", "0", "-layerPatches", '(xMax "z.*")', "-maxLayers", "3", "-minLayers", "2",
+                            "-layerExpansionRatio", "1.2", "-layerEdgeLength", "0.05", "-layerMaxBlendingFraction", "0.8",
+                            "-minAngle", "20"], 10),
+    # BASELINE config 1 exactly as shipped (testcase/run_serial:18) on the committed restatement of its mesh
+    "testcase_as_shipped": (lambda: golden_mesh("testcase_layers"),
+                            dict(min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0, max_angle_deg=160.0,
+                                 layer_patches=[1, 0, 0, 0, 0, 0, 0]),
+                            ["-minEdgeLength", "0.01", "-maxStepLength", "0.002", "-minAngle", "15", "-maxAngle", "160",
+                             "-layerPatches", "(patch0)"], 100),
+    # BASELINE config 2 (testcase4 without boundary point smoothing)
+    "testcase4": (lambda: golden_mesh("testcase4"), dict(total_min_freeze=1), ["-totalMinFreeze", "true"], 200),
+}
+
+
+@pytest.mark.parametrize("name", list(RUNS))
+def test_oracle_reproduces_the_reference_translation_unit(name, tmp_path):
+    build, okw, cli, iters = RUNS[name]
+    mesh = build()
+    case = write_case(tmp_path, mesh)
+    nf_ref, res_ref, pts_ref, stdout = run_reference(case, iters, cli + ["-smoothingPatches", "()"])
+    for libm in (True, False):
+        o = Oracle(mesh.desc_arrays(), libm=libm, **okw)
+        n, nf, res = o.iterate(iters)
+        assert n == len(nf_ref), (n, len(nf_ref))                       # stop rule / iteration count
+        assert np.array_equal(nf, nf_ref)                               # the count printed at :2396
+        assert np.allclose(res, res_ref, rtol=1e-5, atol=0)             # printed with 6 significant digits
+        assert np.array_equal(o.get("points"), pts_ref)                 # binary writeFormat: bit for bit
+    if n < iters:
+        assert "Residual reached relTol, stopping." in stdout
+    else:
+        assert "Maximum centroidalIters reached, stopping." in stdout
+
+
+def test_golden_fixtures_equal_the_reference_translation_unit(tmp_path):
+    """The committed fixtures (tests/golden/*.npz) were produced by the oracle; the reference's own code gives
+    the same numbers."""
+    d = np.load(os.path.join(GOLDEN, "testcase4.npz"))
+    case = write_case(tmp_path, golden_mesh("testcase4"))
+    nf, res, pts, _ = run_reference(case, int(d["max_iters"]), ["-totalMinFreeze", "true", "-smoothingPatches", "()"])
+    assert np.array_equal(nf, d["n_frozen"]) and np.array_equal(pts, d["final_points"])
