@@ -154,6 +154,42 @@ def cpu_baseline(n_side, iters, threads):
     return mesh.n_points * n / dt, used, dt
 
 
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
+
+
+def reference_binary_rate(n_side=40, iters=(1, 5)):
+    """Serial rate of oracle/_ref/smoothMesh_ref, the reference's own translation unit compiled against the
+    OpenFOAM facade (prebuilt; nothing under /root/reference is read at run time): two runs with different
+    iteration counts on the same jittered block, the difference of their wall times is the loop alone.
+    Returns None when the binary is absent."""
+    if not os.path.exists(REF_BIN):
+        return None
+    import shutil
+    import subprocess
+    import tempfile
+    import smoothmesh_b200 as sm
+    mesh = sm.Mesh.hex_block(n_side, n_side, n_side).jitter(JITTER / n_side, SEED)
+    tmp = tempfile.mkdtemp(prefix="smref_")
+    try:
+        mesh.write(os.path.join(tmp, "constant", "polyMesh"))
+        os.makedirs(os.path.join(tmp, "system"))
+        with open(os.path.join(tmp, "system", "controlDict"), "w") as f:
+            f.write("startFrom startTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat binary;\n")
+        times = []
+        for k in iters:
+            t0 = time.perf_counter()
+            subprocess.run([REF_BIN, "-case", tmp, "-centroidalIters", str(k), "-relTol", "0", "-smoothingPatches", "()"],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+            times.append(time.perf_counter() - t0)
+        dt = times[1] - times[0]
+        if dt <= 0:
+            return None
+        return dict(value=mesh.n_points * (iters[1] - iters[0]) / dt, cores=1,
+                    sample=f"{iters[1] - iters[0]} iterations of a jittered {n_side}^3 hex block ({dt:.1f} s), serial")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be
     built here (OpenFOAM + wmake absent), so this times the oracle port with all host threads in
@@ -201,10 +237,12 @@ def run_reference(args, rank, world):
         "ms_per_step": 1e3 * dt / max(n, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"hex {n_side}^3 jittered block (bounded sample of the 200^3 config), all constraints on",
-                   "decomposition": "x".join(map(str, dims)), "note": "CPU oracle port in rank-emulation mode; the "
-                   "OpenFOAM-linked reference cannot be built in this image"},
+                   "decomposition": "x".join(map(str, dims)), "note": "CPU oracle port in rank-emulation mode on all host threads (bit-identical to "
+                   "the reference's translation unit, oracle/_ref, which is single-threaded without MPI and therefore the "
+                   "slower arm; its serial rate is in cpu_baseline.reference_tu)"},
         "cpu_baseline": {"value": value, "unit": "point-updates/s", "cores": p2, "kind": "port",
-                         "sample": f"{n} iterations of a jittered {n_side}^3 hex block, {p2} threads"},
+                         "sample": f"{n} iterations of a jittered {n_side}^3 hex block, {p2} threads",
+                         "reference_tu": reference_binary_rate()},
         "e2e": {"value": value, "unit": "point-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -376,6 +414,11 @@ def main():
                                           f"(same jitter rule/options), rank-emulation on {cN} threads ({dtN:.1f} s); "
                                           f"serial: {v1:.4g} point-updates/s ({dt1:.1f} s)",
                                 "serial_value": v1}
+        ref = reference_binary_rate()
+        if ref is not None:
+            # the reference's own translation unit (oracle/_ref, compiled against the OpenFOAM facade), serial
+            line["cpu_baseline"]["reference_tu"] = {"value": ref["value"], "unit": "point-updates/s", "cores": 1,
+                                                    "kind": "reference", "sample": ref["sample"]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
