@@ -13,8 +13,9 @@
 // counts, nFrozenPoints and final points agree bit for bit.  The caveat: what OpenFOAM itself computes
 // (geometry formulas, connectivity row orders, VSMALL-tolerant vector equality, Foam::min/max, syncTools)
 // is written from memory of OpenFOAM v2312/v12, marked [OF-recalled], and SHARED between this file and
-// the facade -- the comparison verifies the reading of the reference's code, not those recalled semantics,
-// and it is serial (the rank emulation below has no reference counterpart to run against).
+// the facade -- the comparison verifies the reading of the reference's code, not those recalled semantics.
+// The same binary run with -parallel (one forked process per processor directory, syncPointList /
+// returnReduce over shared memory) is reproduced bit for bit by the rank emulation below.
 // Further pins: the known-answer tests in tests/test_oracle_known_answers.py and an independent NumPy
 // restatement (oracle/oracle_np.py).  Every function cites the reference lines it follows (paths relative
 // to /root/reference).

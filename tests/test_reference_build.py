@@ -9,7 +9,8 @@ What the comparison proves: every line the reference authors wrote on this path 
 blend, step clamp, the three constraints, the order-dependent worklist, the boundary layer treatment, the
 stop rule) is executed literally and oracle.cpp reproduces it bit for bit.  What it does not prove: the
 OpenFOAM semantics inside the facade (addressing row orders, face / cell centre formulas, Foam::min/max,
-vector ==), which are recalled, shared with oracle.cpp, and marked [OF-recalled] there.
+vector ==, the order in which copies of a shared point are combined), which are recalled, shared with
+oracle.cpp, and marked [OF-recalled] there.
 
 The binary uses libm's acos like the reference; positions never depend on acos, masks could in principle,
 so the masks are compared with both oracle builds.
@@ -121,3 +122,51 @@ def test_golden_fixtures_equal_the_reference_translation_unit(tmp_path):
     case = write_case(tmp_path, golden_mesh("testcase4"))
     nf, res, pts, _ = run_reference(case, int(d["max_iters"]), ["-totalMinFreeze", "true", "-smoothingPatches", "()"])
     assert np.array_equal(nf, d["n_frozen"]) and np.array_equal(pts, d["final_points"])
+
+
+# ---- the reference's parallel code path -------------------------------------------------------------
+# `smoothMesh_ref -parallel` forks one process per processor<k> directory; each runs the reference's main()
+# on its processor mesh, and the facade implements returnReduce / syncTools::syncPointList over a
+# shared-memory all-gather (copies combined in ascending rank order, the same [OF-recalled] assumption as
+# the oracle's rank emulation and the product's exchange layer).  What is compared is therefore the
+# reference's own parallel logic -- the three-stage closest-point merge, the freeze-flag OR, the layer
+# treatment's five synchronisations -- against the oracle's emulation of it.
+PARALLEL_RUNS = {
+    "hex_2x2x1_tight_angles": (CASES["hex_8x6x5_j45"], ("bricks", (2, 2, 1)),
+                               dict(rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0, total_min_freeze=1),
+                               ["-relTol", "0", "-minAngle", "60", "-maxAngle", "120", "-totalMinFreeze", "true"], 10),
+    "kelvin_rcb3": (CASES["kelvin3_j20"], ("rcb", (3,)), dict(rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0),
+                    ["-relTol", "0", "-minAngle", "60", "-maxAngle", "120"], 8),
+    "high_aspect_ratio_2x1x1": (CASES["layers_ar"], ("bricks", (2, 1, 1)), dict(rel_tol=0.0), ["-relTol", "0"], 10),
+    "hex_layers_2x2x1": (lambda: CASES["hex_8x6x5_j45"](), ("bricks", (2, 2, 1)),
+                         dict(rel_tol=0.0, layer_patches=[1] * 6, max_layers=2),
+                         ["-relTol", "0", "-layerPatches", '("x.*" "y.*" "z.*")', "-maxLayers", "2"], 10),
+    # testcase/run_parallel:22 (mpirun -np 3, layer treatment on the hole walls) on the committed mesh
+    "testcase_run_parallel": (lambda: golden_mesh("testcase_layers"), ("rcb", (3,)),
+                              dict(min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0, max_angle_deg=160.0,
+                                   layer_patches=[1, 0, 0, 0, 0, 0, 0]),
+                              ["-minEdgeLength", "0.01", "-maxStepLength", "0.002", "-minAngle", "15", "-maxAngle", "160",
+                               "-layerPatches", "(patch0)"], 40),
+}
+
+
+@pytest.mark.parametrize("name", list(PARALLEL_RUNS))
+def test_rank_emulation_reproduces_the_reference_in_parallel(name, tmp_path):
+    build, (method, dims), okw, cli, iters = PARALLEL_RUNS[name]
+    mesh = build()
+    case = write_case(tmp_path, mesh)
+    parts = mesh.decompose(*dims) if method == "bricks" else mesh.decompose(dims[0], method="rcb")
+    sm.Mesh.write_decomposed(parts, case, binary=True)
+    r = subprocess.run([REF_BIN, "-case", str(case), "-parallel", "-centroidalIters", str(iters), "-smoothingPatches", "()"]
+                       + cli, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    log = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    parts = [sm.Mesh.read_processor(case, k) for k in range(len(parts))]
+    o = Oracle([p.desc_arrays() for p in parts], libm=True, **okw)
+    n, nf, res = o.iterate(iters)
+    assert n == len(log)
+    assert [int(b) for _, b, _ in log] == nf.tolist()
+    assert np.allclose([float(c) for _, _, c in log], res, rtol=1e-5, atol=0)
+    for k, p in enumerate(parts):
+        p.read_points(case / f"processor{k}" / str(n) / "polyMesh" / "points")
+        assert np.array_equal(p.points, o.get("points", rank=k)), f"processor {k}"
