@@ -21,6 +21,7 @@
 #include <dirent.h>
 #include <fstream>
 #include <condition_variable>
+#include <ctime>
 #include <map>
 #include <mutex>
 #include <thread>
@@ -208,6 +209,7 @@ struct RunOptions
     int writePrecision, timePrecision;
     std::string caseDir, startName;
     std::string layerPatches; // -layerPatches expression, empty = none
+    int logPrecision = 6;
 };
 
 namespace
@@ -373,7 +375,8 @@ static int runParallel(const RunOptions &ro)
             std::vector<double> pts(3 * nPoints);
             std::vector<int64_t> nFrozen(std::max(ro.centroidalIters, 1));
             std::vector<double> residual(std::max(ro.centroidalIters, 1));
-            int i = 0, logPrecision = 6;
+            int i = 0;
+            const int logPrecision = ro.logPrecision;
             bool stop = ro.centroidalIters <= 0;
             while (!stop && failure.empty())
             {
@@ -412,7 +415,6 @@ static int runParallel(const RunOptions &ro)
                 if (stop || (ro.writeInterval > 0 && ((last + 1) % ro.writeInterval) == 0 && last > 0))
                 {
                     const std::string tn = timeName(ro.startTime + i * ro.deltaT, ro.timePrecision);
-                    logPrecision = std::max(10, logPrecision);
                     if (k == 0)
                         printf("Writing new mesh to time %s\n\n", tn.c_str());
                     if (smgpu_get_points(h, pts.data()) != SMGPU_OK ||
@@ -435,6 +437,7 @@ static int runParallel(const RunOptions &ro)
 
 int main(int argc, char **argv)
 {
+    const time_t wallStart = time(nullptr);
     // ---- option table: name -> has value (src/smoothMesh.C:1642-1784 + OpenFOAM standard options)
     const char *valued[] = {"case",
                             "time",
@@ -504,6 +507,8 @@ int main(int argc, char **argv)
     const bool binary = control.count("writeFormat") && control["writeFormat"] == "binary";
     const int writePrecision = control.count("writePrecision") ? atoi(control["writePrecision"].c_str()) : 6;
     const int timePrecision = control.count("timePrecision") ? atoi(control["timePrecision"].c_str()) : 6;
+    // [OF-recalled] Time::readDict: a writePrecision entry also sets the precision of the log streams
+    const int lp = control.count("writePrecision") ? writePrecision : 6;
 
     // ---- start time (createTime.H + :1792-1803) and mesh instance lookup (createMesh.H)
     // -parallel looks the time directories up under processor0/ (the case root holds none after decomposePar)
@@ -584,6 +589,7 @@ int main(int argc, char **argv)
         if (has("layerPatches") && !patchSetEmpty(opt["layerPatches"]))
             ro.layerPatches = opt["layerPatches"];
         ro.prm = prm;
+        ro.logPrecision = lp;
         ro.centroidalIters = centroidalIters;
         ro.writeInterval = writeInterval;
         ro.deltaT = deltaT;
@@ -697,45 +703,75 @@ int main(int argc, char **argv)
     // parameter echo, :1933-1975
     printf("Applying following parameter values in smoothing:\n");
     printf("    centroidalIters        %d\n", centroidalIters);
-    printf("    relTol                 %g\n", prm.rel_tol);
-    printf("    minEdgeLength          %g\n", prm.min_edge_length);
-    printf("    maxStepLength          %g\n", prm.max_step_length);
-    printf("    relStepFrac            %g\n", prm.rel_step_frac);
+    printf("    relTol                 %.*g\n", lp, prm.rel_tol);
+    printf("    minEdgeLength          %.*g\n", lp, prm.min_edge_length);
+    printf("    maxStepLength          %.*g\n", lp, prm.max_step_length);
+    printf("    relStepFrac            %.*g\n", lp, prm.rel_step_frac);
     printf("    totalMinFreeze         %d\n", prm.total_min_freeze);
     if (prm.edge_angle_constraint)
-        printf("    edgeAngleConstraint    true\n    minAngle               %g\n", prm.min_angle_deg);
+        printf("    edgeAngleConstraint    true\n    minAngle               %.*g\n", lp, prm.min_angle_deg);
     else
         printf("    edgeAngleConstraint    false (edge min angle quality constraint is NOT applied)\n");
     if (prm.face_angle_constraint)
-        printf("    faceAngleConstraint    true\n    minAngle               %g\n    maxAngle               %g\n",
-               prm.min_angle_deg, prm.max_angle_deg);
+        printf("    faceAngleConstraint    true\n    minAngle               %.*g\n    maxAngle               %.*g\n", lp,
+               prm.min_angle_deg, lp, prm.max_angle_deg);
     else
         printf("    faceAngleConstraint    false (face angle quality constraints are NOT applied)\n");
     if (layerMaxBlendingFraction > 1e-15)
-        printf("    layerMaxBlendingFraction %g\n    layerEdgeLength          %g\n    layerExpansionRatio      %g\n"
+        printf("    layerMaxBlendingFraction %.*g\n    layerEdgeLength          %.*g\n    layerExpansionRatio      %.*g\n"
                "    minLayers                %d\n    maxLayers                %d\n\n",
-               prm.layer_max_blending_fraction, prm.layer_edge_length < 0 ? prm.min_edge_length : prm.layer_edge_length,
-               prm.layer_expansion_ratio, prm.min_layers, prm.max_layers);
+               lp, prm.layer_max_blending_fraction, lp,
+               prm.layer_edge_length < 0 ? prm.min_edge_length : prm.layer_edge_length, lp, prm.layer_expansion_ratio,
+               prm.min_layers, prm.max_layers);
     else
         printf("    layerMaxBlendingFraction 0 (boundary layer treatment is NOT applied)\n\n");
+    // the remaining set-up messages in the reference's order (:2010-2012, :2027-2098, :2181-2187 and
+    // src/boundaryPointSmoothing.C:432-438), so that logs of the two tools can be compared line by line
+    printf("Starting to build pointNeighPoints (this may take some time)\nDone building pointNeighPoints\n\n");
     if (doLayerTreatment)
-        printf("Enabled boundary layer treatment\n\nWARNING: Boundary layer treatment will be done without boundary "
-               "point smoothing. This can result in distorted boundary cells.\n\n");
+        printf("Enabled boundary layer treatment\n\n");
     else
         printf("Boundary layer treatment is disabled. Either no layerPatches were specified or "
                "boundaryMaxBlendingFraction is zero\n\n");
+    printf("Did not find corners and feature edges in isCornerPoint and isFeatureEdgePoint files\n\n");
     printf("Boundary point smoothing is disabled. Missing smoothingPatches, or one or both of files:\n"
            "constant/geometry/targetSurfaces.obj\nconstant/geometry/initEdges.obj\n\n");
+    if (doLayerTreatment)
+        printf("WARNING: Boundary layer treatment will be done without boundary point smoothing. This can result in "
+               "distorted boundary cells.\n\n");
+    const double layerEdgeLengthEcho = prm.layer_edge_length < 0 ? prm.min_edge_length : prm.layer_edge_length;
     printf("Mesh includes a total of %lld points:\n  - %lld internal (non-boundary) points\n  - %lld boundary points\n"
-           "Mesh minimum edge length = %g\nMesh maximum edge length = %g\n\n",
-           (long long)nPoints, (long long)nInternal, (long long)(nPoints - nInternal), meshMinEdge, meshMaxEdge);
+           "Mesh minimum edge length = %.*g\nMesh maximum edge length = %.*g\nDistance tolerance = %.*g\n\n",
+           (long long)nPoints, (long long)nInternal, (long long)(nPoints - nInternal), lp, meshMinEdge, lp, meshMaxEdge, lp,
+           1e-4 * std::min(meshMinEdge, layerEdgeLengthEcho)); // REL_TOL * min(...), :1921
+    {
+        // classifyBoundaryPoints' summary (src/boundaryPointSmoothing.C:301-438) for a run without boundary
+        // point smoothing: every boundary point is classified once, by the first patch that contains it
+        const int32_t *fo = smmesh_face_offsets(mesh), *fv = smmesh_face_verts(mesh);
+        std::vector<uint8_t> visited(nPoints, 0);
+        long long nLayerSurface = 0, nFrozenSurface = 0;
+        for (int pi = 0; pi < nPatches; ++pi)
+            for (int32_t f = pStart[pi]; f < pStart[pi] + pSize[pi]; ++f)
+                for (int32_t k = fo[f]; k < fo[f + 1]; ++k)
+                    if (!visited[fv[k]])
+                    {
+                        visited[fv[k]] = 1;
+                        nLayerSurface += layerSel[pi] ? 1 : 0;
+                        ++nFrozenSurface;
+                    }
+        printf("Boundary point classification summary:\n- Detected number of corner points: 0\n- Detected number of "
+               "feature edge points: 0\n- Detected number of layer surface points: %lld\n- Detected number of "
+               "smoothing surface points: 0\n- Detected number of frozen surface points: %lld\n\n",
+               nLayerSurface, nFrozenSurface);
+    }
 
     // ---- iteration loop, :2257-2437.  The library stops on relTol by itself; the loop here is
     // cut at write intervals so intermediate meshes can be written (:2416).
     std::vector<double> pts(3 * nPoints);
     std::vector<int64_t> nFrozen(std::max(centroidalIters, 1));
     std::vector<double> residual(std::max(centroidalIters, 1));
-    int i = 0, logPrecision = 6;
+    int i = 0;
+    const int logPrecision = lp;
     double totalMs = 0;
     bool stop = centroidalIters <= 0;
     while (!stop)
@@ -773,7 +809,7 @@ int main(int argc, char **argv)
         if (stop || (writeInterval > 0 && ((last + 1) % writeInterval) == 0 && last > 0))
         {
             const std::string tn = timeName(startTime + i * deltaT, timePrecision);
-            logPrecision = std::max(10, logPrecision); // :2425 raises the global stream precision
+            // :2425 raises IOstream::defaultPrecision for the points file; the log stream keeps its precision
             printf("Writing new mesh to time %s\n\n", tn.c_str());
             if (smgpu_get_points(h, pts.data()) != SMGPU_OK)
                 fatal(smgpu_last_error());
@@ -784,7 +820,7 @@ int main(int argc, char **argv)
     }
     printf("GPU iteration time = %.3f ms (%d iterations, %.4g point-updates/s)\n", totalMs, i,
            totalMs > 0 ? 1e3 * double(nPoints) * i / totalMs : 0.0);
-    printf("\nEnd\n");
+    printf("ClockTime = %lld s.\n\nEnd\n", (long long)(time(nullptr) - wallStart));
     smgpu_destroy(h);
     smmesh_free(mesh);
     return 0;

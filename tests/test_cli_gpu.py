@@ -1,4 +1,5 @@
 """The stand-alone `smoothMesh` executable (reference command-line surface + polyMesh I/O) on a GPU."""
+import os
 import re
 import subprocess
 
@@ -48,6 +49,38 @@ def test_cli_matches_oracle_and_writes_time_directories(tmp_path):
                          "-maxAngle", "120", "-totalMinFreeze", "true"], capture_output=True, text=True)
     assert r2.returncode == 0 and "Create mesh for time = 12" in r2.stdout
     assert (case / "15" / "polyMesh" / "points").exists()
+
+
+REF_BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "smoothMesh_ref")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/smoothMesh_ref not built")
+@pytest.mark.parametrize("layers", [False, True])
+def test_cli_log_equals_the_reference_translation_unit(tmp_path, layers):
+    """Drop-in check at the outermost boundary: the GPU executable and the reference's own main() (compiled
+    against the OpenFOAM facade, oracle/_ref) on copies of one case -- same command line, same standard output
+    line by line (set-up messages, parameter echo, every iteration line, write messages; only the banner, the
+    GPU timing line and ClockTime are the tools' own) and bit-identical points files."""
+    mesh = hex_jittered(7, 6, 5, 0.35, seed=21)
+    opts = ["-centroidalIters", "12", "-relTol", "0", "-minAngle", "50", "-maxAngle", "130", "-writeInterval", "5",
+            "-smoothingPatches", "()"]
+    if layers:
+        opts += ["-layerPatches", '("x.*" zMin)', "-maxLayers", "3", "-layerExpansionRatio", "1.25"]
+    outs = {}
+    for tool, binary in (("gpu", sm.CLI_PATH), ("ref", REF_BIN)):
+        case = make_case(tmp_path / tool, mesh)
+        r = subprocess.run([binary, "-case", str(case)] + opts, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        lines = [ln.rstrip() for ln in r.stdout.splitlines()]
+        lines = [ln for ln in lines if not ln.startswith(("smoothMesh (smoothmesh_b200", "GPU iteration time", "ClockTime"))]
+        while lines and lines[0] == "":
+            lines.pop(0)
+        outs[tool] = (lines, case)
+    assert outs["gpu"][0] == outs["ref"][0]
+    for t in ("5", "10", "12"):
+        a = (outs["gpu"][1] / t / "polyMesh" / "points").read_bytes()
+        b = (outs["ref"][1] / t / "polyMesh" / "points").read_bytes()
+        assert a == b, f"points file of time {t} differs"
 
 
 def test_cli_ascii_precision_and_reltol_stop(tmp_path):
