@@ -1,30 +1,11 @@
 // ref_main.cpp -- TEST INFRASTRUCTURE ONLY.  Compiles the UNMODIFIED reference translation unit
 // (/root/reference/src/smoothMesh.C, read where it lies; never copied) against the OpenFOAM facade in
-// this directory.  Output: oracle/_ref/smoothMesh_ref, a serial executable with the reference's own
-// main(), command line and log lines.  See OpenFOAMFacade.H for what the facade does and does not prove.
+// this directory.  Output: oracle/_ref/smoothMesh_ref, an executable with the reference's own main(),
+// command line and log lines.  See OpenFOAMFacade.H for what the facade does and does not prove, and
+// FacadeSupport.H for why nothing else of this repository is included here.
 //
 // Build recipe: oracle/Makefile.ref (only in the build container, where /root/reference exists).
-#include <algorithm>
-#include <array>
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <cstring>
 #include <dirent.h>
-#include <map>
-#include <stack>
-#include <string>
-#include <vector>
-
-#include "../../smoothmesh_b200/csrc/sm_math.h"
-
-// oracle.cpp's Rank supplies mesh addressing and geometry (the OpenFOAM-recalled part shared by oracle
-// and facade); its names stay inside namespace orc
-#define ORACLE_LIBM_ACOS 1
-namespace orc
-{
-#include "../oracle.cpp"
-}
 
 #include "FacadeMesh.H"
 

@@ -159,7 +159,85 @@ CASES = {
 }
 
 
+def read_obj(path):
+    """Vertices, polyline edges and (fan-triangulated) faces of a Wavefront OBJ file."""
+    v, e, t = [], [], []
+    for line in open(path):
+        w = line.split()
+        if not w:
+            continue
+        if w[0] == "v":
+            v.append([float(x) for x in w[1:4]])
+        elif w[0] == "l":
+            ids = [int(x) - 1 for x in w[1:]]
+            e += [[a, b] for a, b in zip(ids[:-1], ids[1:])]
+        elif w[0] == "f":
+            ids = [int(x.split("/")[0]) - 1 for x in w[1:]]
+            t += [[ids[0], a, b] for a, b in zip(ids[1:-1], ids[2:])]
+    return np.array(v), np.array(e, dtype=np.int32).reshape(-1, 2), np.array(t, dtype=np.int32).reshape(-1, 3)
+
+
+def write_obj(path, v, edges=None, tris=None, name="obj"):
+    with open(path, "w") as f:
+        f.write(f"o {name}\n")
+        for p in v:
+            f.write("v %.17g %.17g %.17g\n" % tuple(p))
+        for a, b in (edges if edges is not None else []):
+            f.write(f"l {a + 1} {b + 1}\n")
+        for a, b, c in (tris if tris is not None else []):
+            f.write(f"f {a + 1} {b + 1} {c + 1}\n")
+
+
+def boundary_fixture():
+    """SURVEY 8(f)-4 groundwork: testcase4 exactly as shipped (testcase4/run_serial: layer treatment on `walls`
+    plus boundary point smoothing onto constant/geometry/*.obj), run by the reference's own translation unit
+    under the OpenFOAM facade (oracle/_ref; its findLine is a brute-force segment/triangle search).  The fixture
+    holds the mesh, the geometry as arrays and the reference's log and final points: the target for the
+    boundary-point-smoothing restatement and CUDA path that this repository does not have yet."""
+    import shutil
+    import subprocess
+    import tempfile
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
+    mesh = testcase4_mesh()
+    geo = os.path.join(REF, "testcase4", "constant", "geometry")
+    tmp = tempfile.mkdtemp(prefix="golden_tc4_")
+    try:
+        mesh.write(os.path.join(tmp, "constant", "polyMesh"))
+        os.makedirs(os.path.join(tmp, "system"))
+        os.makedirs(os.path.join(tmp, "constant", "geometry"))
+        open(os.path.join(tmp, "system", "controlDict"), "w").write("startFrom startTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat binary;\n")
+        out = {}
+        for f, key in (("initEdges.obj", "init_edges"), ("targetEdges.obj", "target_edges"), ("targetSurfaces.obj", "target_surfaces")):
+            v, e, t = read_obj(os.path.join(geo, f))
+            out[key + "_points"], out[key + "_edges"], out[key + "_tris"] = v, e, t
+            # the binary reads the same arrays back from files written with full precision, so that the
+            # fixture can be replayed without /root/reference
+            write_obj(os.path.join(tmp, "constant", "geometry", f), v, e, t, key)
+        cli = ["-centroidalIters", "200", "-layerExpansionRatio", "1.2", "-layerEdgeLength", "0.05", "-maxLayers", "3",
+               "-layerPatches", "(walls)", "-smoothingPatches", '(".*")']
+        r = subprocess.run([ref_bin, "-case", tmp] + cli, capture_output=True, text=True, check=True)
+        log = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+        n = int(log[-1][0])
+        final = sm.Mesh.read(os.path.join(tmp, "constant", "polyMesh"))
+        final.read_points(os.path.join(tmp, str(n), "polyMesh", "points"))
+        a = mesh.desc_arrays()
+        out.update(points=a["points"], face_offsets=a["face_offsets"], face_verts=a["face_verts"], owner=a["owner"],
+                   neighbour=a["neighbour"], n_cells=np.int64(a["n_cells"]), patch_start=a["patch_start"],
+                   patch_size=a["patch_size"], patch_kind=a["patch_kind"], cli=np.array(cli),
+                   iterations=np.int64(n), n_frozen=np.array([int(b) for _, b, _ in log]),
+                   residual=np.array([float(c) for _, _, c in log]), final_points=np.array(final.points))
+        path = os.path.join(HERE, "testcase4_boundary.npz")
+        np.savez_compressed(path, **out)
+        rad = np.hypot(out["final_points"][:, 0], out["final_points"][:, 1]).max()
+        print(f"testcase4_boundary: {n} iterations by the reference translation unit, max radius {rad:.6f}; wrote {path} "
+              f"({os.path.getsize(path) / 1e3:.0f} kB)")
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
+    if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")):
+        boundary_fixture()
     for name, (build, kw, iters) in CASES.items():
         mesh = build()
         a = mesh.desc_arrays()

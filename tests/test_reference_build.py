@@ -170,3 +170,33 @@ def test_rank_emulation_reproduces_the_reference_in_parallel(name, tmp_path):
     for k, p in enumerate(parts):
         p.read_points(case / f"processor{k}" / str(n) / "polyMesh" / "points")
         assert np.array_equal(p.points, o.get("points", rank=k)), f"processor {k}"
+
+
+def test_boundary_smoothing_fixture_replays(tmp_path):
+    """SURVEY 8(f)-4 groundwork.  tests/golden/testcase4_boundary.npz is testcase4 exactly as shipped (layer
+    treatment plus boundary point smoothing onto constant/geometry/*.obj) run by the reference's own translation
+    unit under the facade.  The product has no boundary point smoothing yet (its executable refuses such
+    cases); the fixture is the target for that work and this test keeps it reproducible from its own arrays."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from make_golden import write_obj
+    d = np.load(os.path.join(GOLDEN, "testcase4_boundary.npz"))
+    m = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
+                            d["patch_start"], d["patch_size"], d["patch_kind"])
+    case = write_case(tmp_path, m)
+    (case / "constant" / "geometry").mkdir()
+    for f, key in (("initEdges.obj", "init_edges"), ("targetEdges.obj", "target_edges"), ("targetSurfaces.obj", "target_surfaces")):
+        write_obj(case / "constant" / "geometry" / f, d[key + "_points"], d[key + "_edges"], d[key + "_tris"], key)
+    cli = [str(x) for x in d["cli"]]
+    cli[cli.index("-layerPatches") + 1] = "(patch0)"   # from_arrays names patches patch<i>
+    r = subprocess.run([REF_BIN, "-case", str(case)] + cli, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Enabled boundary point smoothing" in r.stdout and "Detected number of feature edge points: 80" in r.stdout
+    log = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    assert [int(b) for _, b, _ in log] == d["n_frozen"].tolist()
+    out = sm.Mesh.read(case / "constant" / "polyMesh")
+    out.read_points(case / str(int(d["iterations"])) / "polyMesh" / "points")
+    assert np.array_equal(out.points, d["final_points"])
+    # the square box (half width 1.36) has been morphed onto the target surface, whose largest radius is 2
+    assert abs(np.hypot(d["final_points"][:, 0], d["final_points"][:, 1]).max() - 2.0) < 1e-3
+    assert np.hypot(d["points"][:, 0], d["points"][:, 1]).max() < 1.93
