@@ -48,6 +48,7 @@ class _OMesh(C.Structure):
         ("pStart", C.c_void_p), ("pSize", C.c_void_p), ("pKind", C.c_void_p),
         ("pointGlobalId", C.c_void_p),
         ("pLayer", C.c_void_p),
+        ("pSmooth", C.c_void_p),
     ]
 
 
@@ -71,6 +72,7 @@ def _lib(libm=False):
         L.orc_mesh_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_set_params.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_params.restype = C.c_int
+        L.orc_set_geometry.argtypes = [C.c_void_p] + [C.c_int64, C.c_void_p] * 6 + [C.c_double]
         L.orc_sizes.restype = C.c_int64
         L.orc_sizes.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int64]
@@ -107,8 +109,11 @@ class Oracle:
                  max_angle_deg=160.0, rel_tol=0.02, total_min_freeze=0, edge_angle_constraint=1,
                  face_angle_constraint=1, geometry_variant=0, libm=False, threads=1, layer_patches=None,
                  layer_max_blending_fraction=0.3, layer_edge_length=-1.0, layer_expansion_ratio=1.3, min_layers=1,
-                 max_layers=4):
-        """layer_patches: 0/1 flag per physical patch (-layerPatches)."""
+                 max_layers=4, smoothing_patches=None, geometry=None, internal_smoothing_blending_fraction=0.0):
+        """layer_patches / smoothing_patches: 0/1 flag per physical patch (-layerPatches / -smoothingPatches).
+        geometry: dict(init_edges=(points, edges), target_edges=(points, edges), surface=(points, tris)) --
+        the arrays of constant/geometry/*.obj; with it and a selected smoothing patch the run does boundary
+        point smoothing (oracle only, the CUDA path does not have it)."""
         self.L = _lib(libm)
         if isinstance(meshes, dict):
             meshes = [meshes]
@@ -142,6 +147,13 @@ class Oracle:
             o.pStart, o.pSize, o.pKind = _p(a["pStart"]), _p(a["pSize"]), _p(a["pKind"])
             o.pointGlobalId = _p(a["gid"])
             o.pLayer = _p(a["lay"])
+            a["smo"] = None
+            if smoothing_patches is not None:
+                smo = np.zeros(a["pStart"].size, dtype=np.int32)
+                k = min(smo.size, len(smoothing_patches))
+                smo[:k] = np.asarray(smoothing_patches, dtype=np.int32)[:k]
+                a["smo"] = smo
+            o.pSmooth = _p(a["smo"])
         self.prm = OParams(min_edge_length, max_step_length, rel_step_frac, min_angle_deg, max_angle_deg, rel_tol,
                            int(total_min_freeze), int(edge_angle_constraint), int(face_angle_constraint),
                            int(geometry_variant), layer_max_blending_fraction, layer_edge_length,
@@ -150,6 +162,15 @@ class Oracle:
         if not self.h:
             raise RuntimeError("oracle: " + self.L.orc_last_error().decode())
         self._keep = None
+        if geometry is not None:
+            g = []
+            for key, width in (("init_edges", 2), ("target_edges", 2), ("surface", 3)):
+                pts, idx = geometry[key]
+                pts = np.ascontiguousarray(pts, dtype=np.float64).reshape(-1, 3)
+                idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(-1, width)
+                g += [pts.shape[0], _p(pts), idx.shape[0], _p(idx)]
+                self.__dict__.setdefault("_geo_keep", []).extend([pts, idx])
+            self.L.orc_set_geometry(self.h, *g, float(internal_smoothing_blending_fraction))
         mn, mx = C.c_double(), C.c_double()
         self.L.orc_mesh_stats(self.h, C.byref(mn), C.byref(mx))
         self.min_edge, self.max_edge = mn.value, mx.value
