@@ -36,7 +36,7 @@ $(OBJDIR)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.h) $(
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 
-LIBOBJS := $(OBJDIR)/smgpu.o $(OBJDIR)/exchange.o $(OBJDIR)/polymesh.o $(OBJDIR)/topology.o $(OBJDIR)/smmesh_api.o
+LIBOBJS := $(OBJDIR)/smgpu.o $(OBJDIR)/exchange.o $(OBJDIR)/polymesh.o $(OBJDIR)/topology.o $(OBJDIR)/boundary.o $(OBJDIR)/smmesh_api.o
 
 $(LIB): $(LIBOBJS)
 	@mkdir -p $(LIBDIR)

@@ -77,6 +77,22 @@ extern "C"
      * face list, faces of the mesh, largest point list}.  Fails if an invariant the kernel relies on does not hold. */
     int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[5]);
 
+    /* One-time host set-up of boundary point smoothing (smoothmesh_b200/csrc/boundary.hpp; the reference's
+     * classifyBoundaryPoints, findEdgeMeshStrings, calculatePointHopsToBoundary(smoothingPatches),
+     * propagateInnerNeighInfo and the pointStrings loop, src/smoothMesh.C:2131-2250) for the mesh and the arrays
+     * of constant/geometry/initEdges.obj / targetEdges.obj (edges = point pairs).  patch_smoothing: 0/1 per
+     * patch.  Outputs (any may be NULL) are per point; corner_points is xyz.  Returns SMGPU_ERR_MESH with the
+     * reference's FatalError text where the reference aborts. */
+    int smmesh_boundary_setup(const smmesh *m, int64_t n_init_points, const double *init_points, int64_t n_init_edges,
+                              const int32_t *init_edges, int64_t n_target_points, const double *target_points,
+                              int64_t n_target_edges, const int32_t *target_edges, const int32_t *patch_smoothing,
+                              double layer_edge_length, uint8_t *is_corner, uint8_t *is_feature_edge,
+                              uint8_t *is_smoothing_surface, double *corner_points, int32_t *point_strings,
+                              int32_t *hops_to_smoothing, int32_t *point_to_inner, int32_t *target_edge_strings);
+    /* Wavefront OBJ reader used for constant/geometry: counts first (arrays NULL), then the data. */
+    int smmesh_read_obj(const char *file, int64_t *n_points, double *points, int64_t *n_edges, int32_t *edges,
+                        int64_t *n_tris, int32_t *tris);
+
     /* Morton (space-filling-curve) renumbering of points and cells, the renumberMesh stand-in: returns a new
      * valid polyMesh whose storage order keeps the smoothing kernels' gathers local.  The optional maps
      * receive the old label of every new point / cell.  Labels change, so label-order-dependent results are

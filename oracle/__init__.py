@@ -212,6 +212,10 @@ class Oracle:
         "snapCurMax": ("points", np.float64, 1), "edges": ("edges", np.int32, 2),
         "snapNormals": ("points", np.float64, 3), "snapLayerBlend": ("points", np.float64, 3),
         "hopsToLayer": ("points", np.int32, 1), "pointToOuter": ("points", np.int32, 1),
+        "isCorner": ("points", np.uint8, 1), "isFeatureEdge": ("points", np.uint8, 1),
+        "isSmoothingSurface": ("points", np.uint8, 1), "cornerPoints": ("points", np.float64, 3),
+        "pointStrings": ("points", np.int32, 1), "hopsToSmoothing": ("points", np.int32, 1),
+        "pointToInner": ("points", np.int32, 1),
     }
 
     def get(self, name, rank=0):

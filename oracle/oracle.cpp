@@ -2240,6 +2240,20 @@ extern "C"
             return copyOut(R.hopsToLayer, out, capBytes);
         if (n == "pointToOuter")
             return copyOut(R.pointToOuter, out, capBytes);
+        if (n == "isCorner")
+            return copyOut(R.isCorner, out, capBytes);
+        if (n == "isFeatureEdge")
+            return copyOut(R.isFeatureEdge, out, capBytes);
+        if (n == "isSmoothingSurface")
+            return copyOut(R.isSmoothingSurface, out, capBytes);
+        if (n == "cornerPoints")
+            return copyOut(R.cornerPoints, out, capBytes);
+        if (n == "pointStrings")
+            return copyOut(R.pointStrings, out, capBytes);
+        if (n == "hopsToSmoothing")
+            return copyOut(R.hopsToSmoothing, out, capBytes);
+        if (n == "pointToInner")
+            return copyOut(R.pointToInner, out, capBytes);
         if (n == "edges")
             return copyOut(R.edges, out, capBytes);
         return -1;

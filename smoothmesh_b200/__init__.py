@@ -126,6 +126,9 @@ def lib():
         L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
         L.smmesh_quality.argtypes = [C.c_void_p, C.c_void_p]
         L.smmesh_geom_tiles.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+        L.smmesh_boundary_setup.argtypes = ([C.c_void_p] + [C.c_int64, C.c_void_p] * 4 + [C.c_void_p, C.c_double]
+                                            + [C.c_void_p] * 8)
+        L.smmesh_read_obj.argtypes = [C.c_char_p] + [C.c_void_p] * 6
         L.smmesh_write_decomposed.argtypes = [C.c_void_p, C.c_int32, C.c_char_p, C.c_int32]
         L.smmesh_read_processor.restype = C.c_void_p
         L.smmesh_read_processor.argtypes = [C.c_char_p, C.c_int32]
@@ -325,6 +328,28 @@ class Mesh:
         pm = np.zeros(self.n_points, dtype=np.int32)
         cm = np.zeros(self.n_cells, dtype=np.int32)
         return Mesh(lib().smmesh_renumber(self._h, _ptr(pm), _ptr(cm))), pm, cm
+
+    def boundary_setup(self, init_edges, target_edges, patch_smoothing, layer_edge_length=-1.0):
+        """Host set-up of boundary point smoothing (include/smmesh.h: smmesh_boundary_setup); edges = (points, pairs)."""
+        P = self.n_points
+        ip, ie = (np.ascontiguousarray(init_edges[0], dtype=np.float64).reshape(-1, 3),
+                  np.ascontiguousarray(init_edges[1], dtype=np.int32).reshape(-1, 2))
+        tp, te = (np.ascontiguousarray(target_edges[0], dtype=np.float64).reshape(-1, 3),
+                  np.ascontiguousarray(target_edges[1], dtype=np.int32).reshape(-1, 2))
+        ps = np.zeros(self.n_patches, dtype=np.int32)
+        k = min(len(patch_smoothing), ps.size)
+        ps[:k] = np.asarray(patch_smoothing, dtype=np.int32)[:k]
+        out = dict(is_corner=np.zeros(P, np.uint8), is_feature_edge=np.zeros(P, np.uint8),
+                   is_smoothing_surface=np.zeros(P, np.uint8), corner_points=np.zeros((P, 3)),
+                   point_strings=np.zeros(P, np.int32), hops_to_smoothing=np.zeros(P, np.int32),
+                   point_to_inner=np.zeros(P, np.int32), target_edge_strings=np.zeros(len(te), np.int32))
+        rc = lib().smmesh_boundary_setup(self._h, len(ip), _ptr(ip), len(ie), _ptr(ie), len(tp), _ptr(tp), len(te), _ptr(te),
+                                         _ptr(ps), C.c_double(layer_edge_length), *[_ptr(out[k]) for k in
+                                         ("is_corner", "is_feature_edge", "is_smoothing_surface", "corner_points",
+                                          "point_strings", "hops_to_smoothing", "point_to_inner", "target_edge_strings")])
+        if rc != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+        return out
 
     def geom_tiles(self, max_cells=256, max_faces=1024, max_points=1024):
         """Host-side tiling of the fused geometry kernel, checked:

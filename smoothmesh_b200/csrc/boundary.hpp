@@ -1,0 +1,56 @@
+// boundary.hpp -- one-time host set-up of boundary point smoothing (src/boundaryPointSmoothing.C and the
+// calls around it in src/smoothMesh.C:2080-2250): inputs from constant/geometry/*.obj, sanity checks, edge
+// strings, classification of the boundary points, hop counts to the smoothing patches, inner-neighbour map.
+// Pure CPU code; the per-iteration projections run on the device (kernels.cuh: k_boundary_*).
+#pragma once
+#include "polymesh.hpp"
+#include "topology.hpp"
+
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace sm
+{
+
+// edgeMesh as OpenFOAM reads it from an OBJ file: points, edges, edges of every point in ascending edge order
+struct EdgeMesh
+{
+    std::vector<double> points; // xyz
+    std::vector<int32_t> edges; // pairs
+    std::vector<std::vector<int32_t>> pointEdges;
+    int64_t nPoints() const { return (int64_t)points.size() / 3; }
+    int64_t nEdges() const { return (int64_t)edges.size() / 2; }
+    void finish();
+};
+struct TriSurface
+{
+    std::vector<double> points; // xyz
+    std::vector<int32_t> tris;  // triples
+    int64_t nTris() const { return (int64_t)tris.size() / 3; }
+};
+// Wavefront OBJ: "v", "l" (polylines) and "f" (fan-triangulated) records
+void readObj(const std::string &file, std::vector<double> &points, std::vector<int32_t> &edges, std::vector<int32_t> &tris);
+
+struct BoundarySetup
+{
+    EdgeMesh targetEdges;
+    TriSurface surface;
+    std::vector<int32_t> targetEdgeStrings;                            // per target edge
+    std::vector<uint8_t> isCorner, isFeatureEdge, isSmoothingSurface;  // per point
+    std::vector<uint8_t> isConnectedToInternal;
+    std::vector<double> cornerPoints;                                  // xyz per point (corner points only)
+    std::vector<int32_t> pointStrings, hopsToSmoothing, pointToInner;  // per point, -1 = none
+    std::vector<int32_t> boundaryPoints;                               // non-internal points, ascending
+    double distanceTolerance = 0;
+    int64_t nCorners = 0, nFeatureEdgePoints = 0, nSmoothingSurfacePoints = 0;
+    int32_t nStrings = 0;
+};
+// Throws std::runtime_error with the reference's FatalError texts.  layerEdgeLength / minEdgeLength are
+// the resolved options (distanceTolerance = REL_TOL min(meshMinEdgeLength, layerEdgeLength), :1921).
+BoundarySetup buildBoundarySetup(const PolyMesh &patchesAndFaces, const Topology &t, const std::vector<double> &points,
+                                 const EdgeMesh &initEdges, const EdgeMesh &targetEdges, const TriSurface &surface,
+                                 const std::vector<int32_t> &patchSmoothing, double layerEdgeLength);
+
+} // namespace sm

@@ -3,6 +3,7 @@
 #include "../../include/smmesh.h"
 #include "polymesh.hpp"
 #include "topology.hpp"
+#include "boundary.hpp"
 
 #include <algorithm>
 #include <stdexcept>
@@ -310,6 +311,74 @@ extern "C"
             out[2] = maxFaces;
             out[3] = t.F;
             out[4] = maxPoints;
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
+    int smmesh_boundary_setup(const smmesh *m, int64_t n_init_points, const double *init_points, int64_t n_init_edges,
+                              const int32_t *init_edges, int64_t n_target_points, const double *target_points,
+                              int64_t n_target_edges, const int32_t *target_edges, const int32_t *patch_smoothing,
+                              double layer_edge_length, uint8_t *is_corner, uint8_t *is_feature_edge,
+                              uint8_t *is_smoothing_surface, double *corner_points, int32_t *point_strings,
+                              int32_t *hops_to_smoothing, int32_t *point_to_inner, int32_t *target_edge_strings)
+    {
+        try
+        {
+            const sm::Topology t = sm::buildTopology(m->m);
+            sm::EdgeMesh ie, te;
+            ie.points.assign(init_points, init_points + 3 * n_init_points);
+            ie.edges.assign(init_edges, init_edges + 2 * n_init_edges);
+            ie.finish();
+            te.points.assign(target_points, target_points + 3 * n_target_points);
+            te.edges.assign(target_edges, target_edges + 2 * n_target_edges);
+            te.finish();
+            std::vector<int32_t> ps(patch_smoothing, patch_smoothing + m->m.patches.size());
+            const double lel = layer_edge_length < 0 ? 0.5 * t.minEdgeLength : layer_edge_length;
+            const sm::BoundarySetup B = sm::buildBoundarySetup(m->m, t, m->m.points, ie, te, sm::TriSurface(), ps, lel);
+            auto put = [](auto *dst, const auto &src) {
+                if (dst)
+                    std::copy(src.begin(), src.end(), dst);
+            };
+            put(is_corner, B.isCorner);
+            put(is_feature_edge, B.isFeatureEdge);
+            put(is_smoothing_surface, B.isSmoothingSurface);
+            put(corner_points, B.cornerPoints);
+            put(point_strings, B.pointStrings);
+            put(hops_to_smoothing, B.hopsToSmoothing);
+            put(point_to_inner, B.pointToInner);
+            put(target_edge_strings, B.targetEdgeStrings);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
+    int smmesh_read_obj(const char *file, int64_t *n_points, double *points, int64_t *n_edges, int32_t *edges,
+                        int64_t *n_tris, int32_t *tris)
+    {
+        try
+        {
+            std::vector<double> p;
+            std::vector<int32_t> e, t;
+            sm::readObj(file, p, e, t);
+            if (n_points)
+                *n_points = (int64_t)p.size() / 3;
+            if (n_edges)
+                *n_edges = (int64_t)e.size() / 2;
+            if (n_tris)
+                *n_tris = (int64_t)t.size() / 3;
+            if (points)
+                std::copy(p.begin(), p.end(), points);
+            if (edges)
+                std::copy(e.begin(), e.end(), edges);
+            if (tris)
+                std::copy(t.begin(), t.end(), tris);
         }
         catch (const std::exception &e)
         {

@@ -150,3 +150,39 @@ def test_oracle_reproduces_testcase4_as_shipped():
         assert n == int(d["iterations"]) and np.array_equal(nf, d["n_frozen"])
         assert np.allclose(res, d["residual"], rtol=1e-5, atol=0)
         assert np.array_equal(o.get("points"), d["final_points"])
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_product_host_setup_matches_the_oracle(seed):
+    """smoothmesh_b200/csrc/boundary.cpp (the product's one-time set-up of boundary point smoothing: edge strings,
+    corner / feature-edge / smoothing-surface classes, corner targets, hop counts, inner-neighbour map) against the
+    oracle's restatement, on the same synthetic box cases and on testcase4 as shipped."""
+    rng = np.random.default_rng(1000 + seed)
+    if seed == 0:
+        d = np.load(os.path.join(ROOT, "tests", "golden", "testcase4_boundary.npz"))
+        mesh = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
+                                   d["patch_start"], d["patch_size"], d["patch_kind"])
+        init, target = (d["init_edges_points"], d["init_edges_edges"]), (d["target_edges_points"], d["target_edges_edges"])
+        surface, flags, lel = (d["target_surfaces_points"], d["target_surfaces_tris"]), [1], 0.05
+    else:
+        nx, ny, nz = rng.integers(3, 7, size=3)
+        hi = tuple(rng.uniform(0.8, 1.6, size=3))
+        mesh = sm.Mesh.hex_block(int(nx), int(ny), int(nz), hi=hi).jitter(0.1 * min(hi[0] / nx, hi[1] / ny, hi[2] / nz), int(seed))
+        seg = int(rng.integers(2, 6))
+        ip, ie, _, _ = box_geometry((0, 0, 0), hi, seg)
+        c, sc = np.array(hi) / 2, rng.uniform(0.9, 1.15, size=3)
+        tp, te, tc, tt = box_geometry(c - sc * c, c + sc * c, seg)
+        init, target, surface = (ip, ie), (tp, te), (tc, tt)
+        flags = [int(rng.random() < 0.8) for _ in range(6)]
+        flags[int(rng.integers(0, 6))] = 1
+        lel = -1.0
+    o = Oracle(mesh.desc_arrays(), smoothing_patches=flags, layer_edge_length=lel,
+               geometry=dict(init_edges=init, target_edges=target, surface=surface))
+    b = mesh.boundary_setup(init, target, flags, layer_edge_length=lel)
+    for mine, theirs in (("is_corner", "isCorner"), ("is_feature_edge", "isFeatureEdge"), ("is_smoothing_surface", "isSmoothingSurface"),
+                         ("point_strings", "pointStrings"), ("hops_to_smoothing", "hopsToSmoothing"), ("point_to_inner", "pointToInner")):
+        assert np.array_equal(b[mine], o.get(theirs)), mine
+    corners = b["is_corner"] == 1
+    assert np.array_equal(b["corner_points"][corners], o.get("cornerPoints")[corners])
+    if seed > 0:
+        assert corners.sum() == 8 and b["target_edge_strings"].max() == 11     # 8 box corners, 12 edge strings
