@@ -96,6 +96,32 @@ extern "C"
 
     void smgpu_default_params(smgpu_params *p);
     const char *smgpu_last_error(void);
+    /* Boundary point smoothing (src/boundaryPointSmoothing.C): the arrays of
+     * constant/geometry/initEdges.obj, targetEdges.obj (pass the initial edges again when that file is absent,
+     * src/smoothMesh.C:2148-2160) and targetSurfaces.obj.  Edges are point pairs, triangles point triples. */
+    typedef struct smgpu_boundary_geometry
+    {
+        int64_t n_init_points;
+        const double *init_points;
+        int64_t n_init_edges;
+        const int32_t *init_edges;
+        int64_t n_target_points;
+        const double *target_points;
+        int64_t n_target_edges;
+        const int32_t *target_edges;
+        int64_t n_surface_points;
+        const double *surface_points;
+        int64_t n_surface_tris;
+        const int32_t *surface_tris;
+    } smgpu_boundary_geometry;
+    /* Turns boundary point smoothing on for the patches with patch_smoothing[i] != 0 (-smoothingPatches): runs
+     * the reference's one-time set-up (sanity checks :20-82, edge strings :557-590, classification :269-440,
+     * hop counts and inner-neighbour map, point strings src/smoothMesh.C:2234-2250) on the mesh as it is now and
+     * makes smgpu_iterate do :2307-2356 and the restore rule of :2387.  Single-GPU handles only; the target
+     * surface is searched triangle by triangle (test-sized surfaces).  Call after smgpu_create (and again after
+     * smgpu_set_points).  Where the reference aborts the call returns SMGPU_ERR_MESH with its message. */
+    int smgpu_enable_boundary_smoothing(smgpu_handle *h, const smgpu_boundary_geometry *geometry,
+                                        const int32_t *patch_smoothing, double internal_smoothing_blending_fraction);
     const char *smgpu_version(void);
     int smgpu_device_count(int32_t *n); /* visible CUDA devices (0 and SMGPU_ERR_CUDA if none) */
 

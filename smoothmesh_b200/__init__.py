@@ -416,7 +416,7 @@ class Smoother:
         if rc != 0:
             raise SmoothMeshError(f"smgpu_create failed ({rc}): {L.smgpu_last_error().decode()}")
         self._h = h
-        self.n_points, self.n_cells = int(d.n_points), int(d.n_cells)
+        self.n_points, self.n_cells, self.n_patches = int(d.n_points), int(d.n_cells), int(d.n_patches)
         self._arrays = None
 
     def _ck(self, rc):
@@ -526,6 +526,35 @@ class Smoother:
         val = np.zeros(n.value, dtype=np.int32)
         self._ck(lib().smgpu_get_csr(self._h, name.encode(), _ptr(off), _ptr(val), C.byref(n)))
         return off, val
+
+    def enable_boundary_smoothing(self, geometry, smoothing_patches, internal_smoothing_blending_fraction=0.0):
+        """Boundary point smoothing (include/smgpu.h: smgpu_enable_boundary_smoothing).  geometry:
+        dict(init_edges=(points, pairs), target_edges=(points, pairs), surface=(points, triangles));
+        smoothing_patches: 0/1 per patch (shorter lists are padded with 0)."""
+        class _Geo(C.Structure):
+            _fields_ = [(n, t) for k in ("init", "target") for n, t in
+                        ((f"n_{k}_points", C.c_int64), (f"{k}_points", C.c_void_p), (f"n_{k}_edges", C.c_int64),
+                         (f"{k}_edges", C.c_void_p))] + [("n_surface_points", C.c_int64), ("surface_points", C.c_void_p),
+                                                         ("n_surface_tris", C.c_int64), ("surface_tris", C.c_void_p)]
+        keep = []
+
+        def arr(a, dt, w):
+            a = np.ascontiguousarray(a, dtype=dt).reshape(-1, w)
+            keep.append(a)
+            return a
+        g = _Geo()
+        ip, ie = arr(geometry["init_edges"][0], np.float64, 3), arr(geometry["init_edges"][1], np.int32, 2)
+        tp, te = arr(geometry["target_edges"][0], np.float64, 3), arr(geometry["target_edges"][1], np.int32, 2)
+        sp, st = arr(geometry["surface"][0], np.float64, 3), arr(geometry["surface"][1], np.int32, 3)
+        g.n_init_points, g.init_points, g.n_init_edges, g.init_edges = len(ip), _ptr(ip), len(ie), _ptr(ie)
+        g.n_target_points, g.target_points, g.n_target_edges, g.target_edges = len(tp), _ptr(tp), len(te), _ptr(te)
+        g.n_surface_points, g.surface_points, g.n_surface_tris, g.surface_tris = len(sp), _ptr(sp), len(st), _ptr(st)
+        flags = np.zeros(self.n_patches, dtype=np.int32)
+        k = min(len(smoothing_patches), flags.size)
+        flags[:k] = np.asarray(smoothing_patches, dtype=np.int32)[:k]
+        lib().smgpu_enable_boundary_smoothing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        self._ck(lib().smgpu_enable_boundary_smoothing(self._h, C.byref(g), _ptr(flags),
+                                                      float(internal_smoothing_blending_fraction)))
 
     def profile(self, enable=True):
         self._ck(lib().smgpu_profile(self._h, int(enable)))

@@ -6,6 +6,7 @@
 #include "kernels.cuh"
 #include "polymesh.hpp"
 #include "topology.hpp"
+#include "boundary.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -56,6 +57,8 @@ struct smgpu_handle
     // boundary layer treatment: one-time set-up data and per-hop tables
     sm::LayerSetup layer;
     int resolveBlocks = 1;
+    bool doBoundary = false;            // boundary point smoothing enabled (smgpu_enable_boundary_smoothing)
+    std::vector<sm::Patch> patches;     // patch table of the mesh (boundary set-up needs it after create)
     bool useTiles = false; // fused geometry kernel over sm::GeomTiles
     int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
     bool doLayers = false;
@@ -165,6 +168,8 @@ struct smgpu_handle
         // (blendWithOrthogonalPoints, src/orthogonalBoundaryBlending.C:547-555; its maxLayers is maxLayers + 1, :2300)
         doLayers = anyLayerPatch && prm.layer_max_blending_fraction > 1e-15; // :2025, SMALL
         d.layers = doLayers ? 1 : 0;
+        d.bsmooth = doBoundary ? 1 : 0;
+        d.normalsOn = (doLayers || doBoundary) ? 1 : 0;
         if (doLayers && dLayerLength)
         {
             const double maxLayers = prm.max_layers + 1, minLayers = prm.min_layers;
@@ -187,9 +192,11 @@ struct smgpu_handle
         d.cosLargeF = (float)std::cos(d.largeAngle);
         // the single-precision level is used when its error budget at the mesh's shortest edge is small
         // (64 epsAbs / (edge/4) + 5e-5 < 0.05); otherwise the FP64 filter (and its face-mean table) is
-        d.faceFilter32 = d.faceFilter && !getenv("SMGPU_NO_F32") &&
+        // (and only while the points stay inside the initial hull, which its error bound assumes: boundary
+        // point smoothing moves them out of it, so it runs on the FP64 filter)
+        d.faceFilter32 = d.faceFilter && !getenv("SMGPU_NO_F32") && !doBoundary &&
                          (64.0 * d.epsAbs / (0.25 * meshMinEdge) + 5e-5 < 0.05);
-        d.edgeFilter32 = d.edgeFilter && !getenv("SMGPU_NO_F32") &&
+        d.edgeFilter32 = d.edgeFilter && !getenv("SMGPU_NO_F32") && !doBoundary &&
                          (16.0 * d.epsAbs / (0.5 * meshMinEdge) + 2e-5 < 0.02);
         if (noFilters)
             d.edgeFilter = d.faceFilter = d.faceFilter32 = d.edgeFilter32 = 0;
@@ -295,12 +302,12 @@ struct smgpu_handle
         if (useTiles)
         {
             launchCellCentres();
-            if (doLayers)
+            if (doLayers || doBoundary)
                 launchLayerNormals();
             return;
         }
         launchFaceGeom();
-        if (doLayers)
+        if (doLayers || doBoundary)
             launchLayerNormals();
         launchCells();
     }
@@ -327,9 +334,35 @@ struct smgpu_handle
     }
     // set-up call of calculateBoundaryPointNormals + propagateOuterNeighInfo's normal copies
     // (src/smoothMesh.C:2219-2220) for the mesh currently on the device
+    // device tables of the boundary point normals / layer treatment for `layer`
+    void allocLayerTables()
+    {
+        d.normals = dalloc<P4>(topo.P);
+        normalsTmp = dalloc<P4>(topo.P);
+        d.hops = dHops = upload(layer.hops);
+        d.pointToOuter = dPointToOuter = upload(layer.pointToOuter);
+        d.normalSrc = upload(layer.normalSrc);
+        d.bfOff = upload(layer.bfOff);
+        d.bf = upload(layer.bf);
+        const int hopCap = std::max(layer.maxHop, prm.max_layers + 1) + 2;
+        dLayerLength = dalloc<double>(hopCap);
+        dLayerBlend = dalloc<double>(hopCap);
+        d.layerLength = dLayerLength;
+        d.layerBlend = dLayerBlend;
+    }
+    // :2312-2355: projection of the boundary points, prismatic projection, third step clamp
+    void launchBoundary()
+    {
+        profBegin(K_LAYER);
+        if (d.nBPoints > 0)
+            k_boundary_project<<<grid(d.nBPoints, 128), 128, 0, stream>>>(d);
+        k_boundary_finish<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        profEnd(2);
+        launches += 2;
+    }
     void initLayerNormals()
     {
-        if (!doLayers)
+        if (!doLayers && !doBoundary)
             return;
         if (layersParallel)
         {
@@ -755,6 +788,7 @@ extern "C"
             }
             tick("topology (total)");
             const sm::Topology &t = h->topo;
+            h->patches = m.patches;
             h->prm = *params;
             h->prmRequested = *params;
             h->meshMinEdge = t.minEdgeLength;
@@ -894,18 +928,7 @@ extern "C"
                     h->layerMesh.patches = m.patches;
                     h->patchLayerFlags = patchLayer;
                 }
-                d.normals = h->dalloc<P4>(t.P);
-                h->normalsTmp = h->dalloc<P4>(t.P);
-                d.hops = h->dHops = h->upload(h->layer.hops);
-                d.pointToOuter = h->dPointToOuter = h->upload(h->layer.pointToOuter);
-                d.normalSrc = h->upload(h->layer.normalSrc);
-                d.bfOff = h->upload(h->layer.bfOff);
-                d.bf = h->upload(h->layer.bf);
-                const int hopCap = std::max(h->layer.maxHop, params->max_layers + 1) + 2;
-                h->dLayerLength = h->dalloc<double>(hopCap);
-                h->dLayerBlend = h->dalloc<double>(hopCap);
-                d.layerLength = h->dLayerLength;
-                d.layerBlend = h->dLayerBlend;
+                h->allocLayerTables();
             }
             h->setPoints(md->points); // also fixes the single-precision mirror's origin and error bound
             h->resolveParams();
@@ -919,6 +942,111 @@ extern "C"
             return setErr(SMGPU_ERR_CUDA, e.what());
         }
         *out = h;
+        return SMGPU_OK;
+    }
+
+    int smgpu_enable_boundary_smoothing(smgpu_handle *h, const smgpu_boundary_geometry *g, const int32_t *patch_smoothing,
+                                        double internal_smoothing_blending_fraction)
+    {
+        if (!h || !g || !patch_smoothing)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (h->comm || !h->topo.procPoints.empty())
+            return setErr(SMGPU_ERR_ARG, "boundary point smoothing is single-GPU in this build (its four extra "
+                                         "synchronisations are not in the exchange layer yet)");
+        if (!h->pointOldOfNew.empty())
+            return setErr(SMGPU_ERR_ARG, "boundary point smoothing cannot be combined with params.renumber");
+        bool any = false;
+        for (size_t i = 0; i < h->patches.size(); ++i)
+            any = any || patch_smoothing[i] != 0;
+        if (!any)
+            return SMGPU_OK; // no smoothing patches: the feature stays off, like the reference (:2082-2086)
+        try
+        {
+            CK(cudaSetDevice(h->prm.device));
+            const sm::Topology &t = h->topo;
+            Dev &d = h->d;
+            // the classification works on the mesh as it is now
+            std::vector<P4> cur(t.P);
+            CK(cudaMemcpy(cur.data(), d.pts, t.P * sizeof(P4), cudaMemcpyDeviceToHost));
+            std::vector<double> points(3 * (size_t)t.P);
+            for (int64_t p = 0; p < t.P; ++p)
+                points[3 * p] = cur[p].x, points[3 * p + 1] = cur[p].y, points[3 * p + 2] = cur[p].z;
+            sm::PolyMesh pm; // patches only: the set-up reads faces from the topology tables
+            pm.patches = h->patches;
+            sm::EdgeMesh ie, te;
+            ie.points.assign(g->init_points, g->init_points + 3 * g->n_init_points);
+            ie.edges.assign(g->init_edges, g->init_edges + 2 * g->n_init_edges);
+            ie.finish();
+            te.points.assign(g->target_points, g->target_points + 3 * g->n_target_points);
+            te.edges.assign(g->target_edges, g->target_edges + 2 * g->n_target_edges);
+            te.finish();
+            sm::TriSurface surf;
+            surf.points.assign(g->surface_points, g->surface_points + 3 * g->n_surface_points);
+            surf.tris.assign(g->surface_tris, g->surface_tris + 3 * g->n_surface_tris);
+            std::vector<int32_t> ps(patch_smoothing, patch_smoothing + h->patches.size());
+            const double layerEdgeLength = h->prm.layer_edge_length < 0 ? h->prm.min_edge_length : h->prm.layer_edge_length;
+            sm::BoundarySetup B;
+            try
+            {
+                B = sm::buildBoundarySetup(pm, t, points, ie, te, surf, ps, layerEdgeLength);
+            }
+            catch (const std::exception &e)
+            {
+                return setErr(SMGPU_ERR_MESH, e.what());
+            }
+            if (!h->anyLayerPatch)
+            { // boundary point normals are needed without any layer patch too (:2215-2221)
+                sm::PolyMesh faces;
+                faces.patches = h->patches;
+                faces.faceOffsets = t.faceOff;
+                faces.faceVerts = t.faceVerts;
+                h->layer = sm::buildLayerSetup(faces, t, std::vector<int32_t>(h->patches.size(), 0), h->prm.max_layers);
+                h->allocLayerTables();
+            }
+            auto toP4 = [](const std::vector<double> &xyz) {
+                std::vector<P4> out(xyz.size() / 3);
+                for (size_t i = 0; i < out.size(); ++i)
+                    out[i] = P4{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.0};
+                return out;
+            };
+            std::vector<uint8_t> cls(t.P, 0);
+            for (int64_t p = 0; p < t.P; ++p)
+                cls[p] = (uint8_t)((B.isCorner[p] ? 1 : 0) | (B.isFeatureEdge[p] ? 2 : 0) | (B.isSmoothingSurface[p] ? 4 : 0) |
+                                   (B.isConnectedToInternal[p] ? 8 : 0));
+            std::vector<P4> corner(B.boundaryPoints.size());
+            std::vector<int32_t> bString(B.boundaryPoints.size());
+            for (size_t b = 0; b < B.boundaryPoints.size(); ++b)
+            {
+                const int32_t p = B.boundaryPoints[b];
+                corner[b] = P4{B.cornerPoints[3 * (size_t)p], B.cornerPoints[3 * (size_t)p + 1], B.cornerPoints[3 * (size_t)p + 2], 0.0};
+                bString[b] = B.pointStrings[p];
+            }
+            d.bClass = h->upload(cls);
+            d.sharp = h->dalloc<uint8_t>(t.P + 8);
+            CK(cudaMemset(d.sharp, 0, t.P + 8));
+            d.bPoints = h->upload(B.boundaryPoints);
+            d.nBPoints = (int)B.boundaryPoints.size();
+            d.cornerPts = h->upload(corner);
+            d.bString = h->upload(bString);
+            d.bInner = h->upload(B.pointToInner);
+            d.tePts = h->upload(toP4(B.targetEdges.points));
+            d.teEdges = h->upload(B.targetEdges.edges);
+            d.teString = h->upload(B.targetEdgeStrings);
+            d.nTargetEdges = (int)B.targetEdges.nEdges();
+            d.surfPts = h->upload(toP4(surf.points));
+            d.surfTris = h->upload(surf.tris);
+            d.nSurfTris = (int)surf.nTris();
+            d.distanceTolerance = B.distanceTolerance;
+            d.internalFraction = internal_smoothing_blending_fraction;
+            h->doBoundary = true;
+            h->applyParams();
+            h->initLayerNormals(); // the set-up call of calculateBoundaryPointNormals (:2219) with the sharp flags
+            CK(cudaDeviceSynchronize());
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
         return SMGPU_OK;
     }
 
@@ -1006,6 +1134,8 @@ extern "C"
                         h->launchPredict();
                         if (h->doLayers)
                             h->launchLayerBlend(); // :2283-2305
+                        if (h->doBoundary)
+                            h->launchBoundary(); // :2307-2356
                         h->launchEdgeConstraints();
                         if (h->prm.face_angle_constraint)
                             h->launchFaceAngle();
@@ -1032,8 +1162,17 @@ extern "C"
             CK(cudaMemcpy(&it, h->d.iter, sizeof(int), cudaMemcpyDeviceToHost));
             CK(cudaMemcpy(&errFlag, h->d.errFlag, sizeof(int), cudaMemcpyDeviceToHost));
             if (errFlag)
-                return setErr(SMGPU_ERR_MESH, "Sanity broken, outerNeighCoord is undefined for an interface point "
-                                              "(src/orthogonalBoundaryBlending.C:537)");
+            {
+                static const char *msg[] = {"", "Sanity broken, outerNeighCoord is undefined for an interface point "
+                                                "(src/orthogonalBoundaryBlending.C:537)",
+                                            "Internal sanity check failed: Did not find any edges with the required string index "
+                                            "(src/boundaryPointSmoothing.C:257)",
+                                            "pointNormal is zero for a smoothing surface point (src/boundaryPointSmoothing.C:691)",
+                                            "Did not find surface intersection for a boundary point (src/boundaryPointSmoothing.C:934)",
+                                            "A smoothing surface point has zero point normal (src/orthogonalBoundaryBlending.C:611)"};
+                CK(cudaMemset(h->d.errFlag, 0, sizeof(int)));
+                return setErr(SMGPU_ERR_MESH, msg[(errFlag >= 1 && errFlag <= 5) ? errFlag : 1]);
+            }
             if (iters_done)
                 *iters_done = it;
             if (it > 0 && residual)

@@ -1,0 +1,92 @@
+"""Boundary point smoothing on the GPU against the oracle, which is itself pinned to the
+reference's own translation unit (tests/test_boundary_smoothing_oracle.py): bit-exact iteration logs, freeze
+masks and points on synthetic box cases (corners, feature edge strings, surfaces, partial patch selections,
+with and without layer treatment) and on testcase4 exactly as shipped."""
+import os
+
+import numpy as np
+import pytest
+
+import smoothmesh_b200 as sm
+from oracle import Oracle
+
+from test_boundary_smoothing_oracle import box_geometry
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def synthetic(seed):
+    rng = np.random.default_rng(seed)
+    nx, ny, nz = rng.integers(3, 7, size=3)
+    hi = tuple(rng.uniform(0.8, 1.6, size=3))
+    h = min(hi[0] / nx, hi[1] / ny, hi[2] / nz)
+    mesh = sm.Mesh.hex_block(int(nx), int(ny), int(nz), hi=hi).jitter(float(rng.uniform(0.05, 0.3)) * h, int(rng.integers(1, 10 ** 6)))
+    seg = int(rng.integers(2, 6))
+    ip, ie, _, _ = box_geometry((0, 0, 0), hi, seg)
+    c, sc = np.array(hi) / 2, rng.uniform(0.9, 1.15, size=3)
+    tp, te, tc, tt = box_geometry(c - sc * c, c + sc * c, seg)
+    geo = dict(init_edges=(ip, ie), target_edges=(tp, te), surface=(tc, tt))
+    flags = [int(rng.random() < 0.8) for _ in range(6)]
+    flags[int(rng.integers(0, 6))] = 1
+    kw = dict(rel_tol=0.0)
+    layer = None
+    if rng.random() < 0.5:
+        layer = [int(rng.random() < 0.6) for _ in range(6)]
+        kw["max_layers"] = int(rng.integers(1, 4))
+    if rng.random() < 0.5:
+        kw["min_angle_deg"], kw["max_angle_deg"] = float(rng.uniform(10, 60)), float(rng.uniform(120, 175))
+    frac = float(rng.uniform(0.0, 0.5)) if rng.random() < 0.4 else 0.0
+    return mesh, geo, flags, layer, kw, frac, int(rng.integers(4, 10))
+
+
+def run_pair(mesh, geo, flags, layer, kw, frac, iters):
+    g = sm.Smoother(mesh, layer_patches=layer, **kw)
+    g.enable_boundary_smoothing(geo, flags, frac)
+    o = Oracle(mesh.desc_arrays(), layer_patches=layer, smoothing_patches=flags, geometry=geo,
+               internal_smoothing_blending_fraction=frac, **kw)
+    n, nf, res = o.iterate(iters)
+    log = g.iterate(iters)
+    assert log.iterations == n
+    assert np.array_equal(log.n_frozen, nf), (log.n_frozen, nf)
+    assert np.array_equal(log.residual, res)
+    assert np.array_equal(g.frozen(), o.get("frozen"))
+    assert np.array_equal(g.points(), o.get("points"))
+    return g, o
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_boundary_smoothing_matches_oracle_on_synthetic_boxes(seed):
+    mesh, geo, flags, layer, kw, frac, iters = synthetic(seed)
+    g, o = run_pair(mesh, geo, flags, layer, kw, frac, iters)
+    moved = np.abs(g.points() - np.asarray(mesh.points)).max(axis=1) > 0
+    assert moved[o.get("isInternal") == 0].any()            # boundary points do move
+
+
+def test_testcase4_as_shipped():
+    """testcase4/run_serial: layer treatment on `walls` + boundary point smoothing of every patch onto
+    constant/geometry/*.obj, 200 iterations; the fixture was produced by the reference's own translation unit."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", "testcase4_boundary.npz"))
+    mesh = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
+                               d["patch_start"], d["patch_size"], d["patch_kind"])
+    geo = dict(init_edges=(d["init_edges_points"], d["init_edges_edges"]),
+               target_edges=(d["target_edges_points"], d["target_edges_edges"]),
+               surface=(d["target_surfaces_points"], d["target_surfaces_tris"]))
+    g = sm.Smoother(mesh, layer_patches=[1], layer_expansion_ratio=1.2, layer_edge_length=0.05, max_layers=3)
+    g.enable_boundary_smoothing(geo, [1])
+    log = g.iterate(200)
+    assert log.iterations == int(d["iterations"]) and np.array_equal(log.n_frozen, d["n_frozen"])
+    assert np.array_equal(g.points(), d["final_points"])
+
+
+def test_boundary_smoothing_refusals():
+    mesh = sm.Mesh.hex_block(4, 4, 4).jitter(0.02, 1)
+    ip, ie, _, _ = box_geometry((0, 0, 0), (1, 1, 1), 2)
+    tp, te, tc, tt = box_geometry((-3, -3, -3), (4, 4, 4), 2)       # perimeter far off: the reference's sanity check
+    g = sm.Smoother(mesh)
+    with pytest.raises(sm.SmoothMeshError, match="Perimeter"):
+        g.enable_boundary_smoothing(dict(init_edges=(ip, ie), target_edges=(tp, te), surface=(tc, tt)), [1] * 6)
+    parts = mesh.decompose(2, 1, 1)
+    gp = sm.Smoother(parts[0])
+    with pytest.raises(sm.SmoothMeshError, match="single-GPU"):
+        gp.enable_boundary_smoothing(dict(init_edges=(ip, ie), target_edges=(ip, ie), surface=(tc, tt)), [1] * 6)
