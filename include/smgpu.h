@@ -122,6 +122,9 @@ extern "C"
      * smgpu_set_points).  Where the reference aborts the call returns SMGPU_ERR_MESH with its message. */
     int smgpu_enable_boundary_smoothing(smgpu_handle *h, const smgpu_boundary_geometry *geometry,
                                         const int32_t *patch_smoothing, double internal_smoothing_blending_fraction);
+    /* counts of the boundary point classification after smgpu_enable_boundary_smoothing:
+     * out = {corner points, feature edge points, smoothing surface points, target edge strings} */
+    int smgpu_boundary_counts(smgpu_handle *h, int64_t out[4]);
     const char *smgpu_version(void);
     int smgpu_device_count(int32_t *n); /* visible CUDA devices (0 and SMGPU_ERR_CUDA if none) */
 

@@ -58,6 +58,7 @@ struct smgpu_handle
     sm::LayerSetup layer;
     int resolveBlocks = 1;
     bool doBoundary = false;            // boundary point smoothing enabled (smgpu_enable_boundary_smoothing)
+    int64_t boundaryCounts[4] = {0, 0, 0, 0};
     std::vector<sm::Patch> patches;     // patch table of the mesh (boundary set-up needs it after create)
     bool useTiles = false; // fused geometry kernel over sm::GeomTiles
     int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
@@ -1038,6 +1039,10 @@ extern "C"
             d.nSurfTris = (int)surf.nTris();
             d.distanceTolerance = B.distanceTolerance;
             d.internalFraction = internal_smoothing_blending_fraction;
+            h->boundaryCounts[0] = B.nCorners;
+            h->boundaryCounts[1] = B.nFeatureEdgePoints;
+            h->boundaryCounts[2] = B.nSmoothingSurfacePoints;
+            h->boundaryCounts[3] = B.nStrings + 1;
             h->doBoundary = true;
             h->applyParams();
             h->initLayerNormals(); // the set-up call of calculateBoundaryPointNormals (:2219) with the sharp flags
@@ -1047,6 +1052,15 @@ extern "C"
         {
             return setErr(SMGPU_ERR_CUDA, e.what());
         }
+        return SMGPU_OK;
+    }
+
+    int smgpu_boundary_counts(smgpu_handle *h, int64_t out[4])
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        for (int i = 0; i < 4; ++i)
+            out[i] = h->boundaryCounts[i];
         return SMGPU_OK;
     }
 

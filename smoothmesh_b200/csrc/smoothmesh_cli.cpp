@@ -577,9 +577,11 @@ int main(int argc, char **argv)
     const bool smoothingPatchesEmpty = has("smoothingPatches") && patchSetEmpty(opt["smoothingPatches"]);
     const bool surfaces = fileExists(caseDir + "/constant/geometry/targetSurfaces.obj");
     const bool initEdges = fileExists(caseDir + "/constant/geometry/initEdges.obj");
-    if (!has("decompose") && surfaces && initEdges && !smoothingPatchesEmpty)
-        fatal("boundary point smoothing would be enabled (constant/geometry/*.obj present and smoothingPatches not "
-              "empty); it is outside the GPU hot path and there is no CPU fallback; pass -smoothingPatches '()'");
+    // :2080-2086 (the isCornerPoint / isFeatureEdgePoint label lists of earlier runs are not read)
+    const bool boundaryRequested = !has("decompose") && surfaces && initEdges && !smoothingPatchesEmpty;
+    if (boundaryRequested && parallel)
+        fatal("boundary point smoothing with -parallel: the feature is single-GPU in this build (its four extra "
+              "synchronisations are not in the exchange layer yet); pass -smoothingPatches '()' or run serially");
 
     if (parallel)
     {
@@ -668,8 +670,15 @@ int main(int argc, char **argv)
     else
         printf("Patches for boundary layer treatment: none\n");
     const bool doLayerTreatment = anyLayerPatch && layerMaxBlendingFraction > 1e-15; // :2025
-    printf("Patches for boundary point smoothing: %s\n",
-           smoothingPatchesEmpty ? "none" : (has("smoothingPatches") ? opt["smoothingPatches"].c_str() : "(\".*\")"));
+    {
+        // :1837-1854: the option defaults to '(".*")'; "none" is printed when no patch matches
+        bool anySmoothing = !has("smoothingPatches");
+        if (has("smoothingPatches"))
+            for (int32_t f : selectPatches(opt["smoothingPatches"], patchNames))
+                anySmoothing = anySmoothing || f;
+        printf("Patches for boundary point smoothing: %s\n",
+               !anySmoothing ? "none" : (has("smoothingPatches") ? opt["smoothingPatches"].c_str() : "(\".*\")"));
+    }
 
     // ---- GPU handle
     smgpu_mesh_desc md;
@@ -734,9 +743,69 @@ int main(int argc, char **argv)
         printf("Boundary layer treatment is disabled. Either no layerPatches were specified or "
                "boundaryMaxBlendingFraction is zero\n\n");
     printf("Did not find corners and feature edges in isCornerPoint and isFeatureEdgePoint files\n\n");
-    printf("Boundary point smoothing is disabled. Missing smoothingPatches, or one or both of files:\n"
-           "constant/geometry/targetSurfaces.obj\nconstant/geometry/initEdges.obj\n\n");
-    if (doLayerTreatment)
+    // boundary point smoothing, :2080-2171: inputs from constant/geometry, set-up inside the library
+    std::vector<int32_t> smoothSel(nPatches, 0);
+    if (boundaryRequested)
+        smoothSel = has("smoothingPatches") ? selectPatches(opt["smoothingPatches"], patchNames)
+                                            : std::vector<int32_t>(nPatches, 1); // default '(".*")', :1837-1840
+    bool doBoundarySmoothing = false;
+    for (int32_t f : smoothSel)
+        doBoundarySmoothing = doBoundarySmoothing || f;
+    if (doBoundarySmoothing)
+    {
+        printf("Enabled boundary point smoothing\n\n");
+        struct Obj
+        {
+            std::vector<double> p;
+            std::vector<int32_t> e, t;
+        };
+        auto load = [&](const std::string &rel) {
+            Obj o;
+            int64_t np = 0, ne = 0, nt = 0;
+            const std::string f = caseDir + "/" + rel;
+            if (smmesh_read_obj(f.c_str(), &np, nullptr, &ne, nullptr, &nt, nullptr) != SMGPU_OK)
+                fatal(smmesh_last_error());
+            o.p.resize(3 * np);
+            o.e.resize(2 * ne);
+            o.t.resize(3 * nt);
+            smmesh_read_obj(f.c_str(), nullptr, o.p.data(), nullptr, o.e.data(), nullptr, o.t.data());
+            return o;
+        };
+        // (the statistics lines are this tool's; OpenFOAM's triSurface / edgeMesh writeStats print more)
+        const Obj surf = load("constant/geometry/targetSurfaces.obj");
+        printf("Target surfaces file constant/geometry/targetSurfaces.obj stats:\nTriangles    : %lld\nVertices     : %lld\n\n",
+               (long long)(surf.t.size() / 3), (long long)(surf.p.size() / 3));
+        const Obj ie = load("constant/geometry/initEdges.obj");
+        printf("Initial feature edges file constant/geometry/initEdges.obj stats:\npoints      : %lld\nedges       : %lld\n\n",
+               (long long)(ie.p.size() / 3), (long long)(ie.e.size() / 2));
+        Obj te = ie;
+        if (fileExists(caseDir + "/constant/geometry/targetEdges.obj"))
+        {
+            te = load("constant/geometry/targetEdges.obj");
+            printf("Target feature edges file constant/geometry/targetEdges.obj stats:\npoints      : %lld\nedges       : %lld\n",
+                   (long long)(te.p.size() / 3), (long long)(te.e.size() / 2));
+        }
+        else
+            printf("WARNING: Initial feature edges will be used also as target edges, because\ndid not find file "
+                   "constant/geometry/targetEdges.obj.\n\n");
+        printf("Checking initial edge mesh sanity\nChecking target edge mesh sanity\n");
+        smgpu_boundary_geometry geo;
+        geo.n_init_points = (int64_t)ie.p.size() / 3, geo.init_points = ie.p.data();
+        geo.n_init_edges = (int64_t)ie.e.size() / 2, geo.init_edges = ie.e.data();
+        geo.n_target_points = (int64_t)te.p.size() / 3, geo.target_points = te.p.data();
+        geo.n_target_edges = (int64_t)te.e.size() / 2, geo.target_edges = te.e.data();
+        geo.n_surface_points = (int64_t)surf.p.size() / 3, geo.surface_points = surf.p.data();
+        geo.n_surface_tris = (int64_t)surf.t.size() / 3, geo.surface_tris = surf.t.data();
+        if (smgpu_enable_boundary_smoothing(h, &geo, smoothSel.data(), num("internalSmoothingBlendingFraction", 0.0)) != SMGPU_OK)
+            fatal(smgpu_last_error());
+        int64_t counts[4];
+        smgpu_boundary_counts(h, counts);
+        printf("\nStarting to build targetEdgeStrings\nDetected number of target edge mesh strings: %lld\n\n", (long long)counts[3]);
+    }
+    else
+        printf("Boundary point smoothing is disabled. Missing smoothingPatches, or one or both of files:\n"
+               "constant/geometry/targetSurfaces.obj\nconstant/geometry/initEdges.obj\n\n");
+    if (doLayerTreatment && !doBoundarySmoothing)
         printf("WARNING: Boundary layer treatment will be done without boundary point smoothing. This can result in "
                "distorted boundary cells.\n\n");
     const double layerEdgeLengthEcho = prm.layer_edge_length < 0 ? prm.min_edge_length : prm.layer_edge_length;
@@ -749,7 +818,7 @@ int main(int argc, char **argv)
         // point smoothing: every boundary point is classified once, by the first patch that contains it
         const int32_t *fo = smmesh_face_offsets(mesh), *fv = smmesh_face_verts(mesh);
         std::vector<uint8_t> visited(nPoints, 0);
-        long long nLayerSurface = 0, nFrozenSurface = 0;
+        long long nLayerSurface = 0, nSmoothingSurface = 0, nFrozenSurface = 0;
         for (int pi = 0; pi < nPatches; ++pi)
             for (int32_t f = pStart[pi]; f < pStart[pi] + pSize[pi]; ++f)
                 for (int32_t k = fo[f]; k < fo[f + 1]; ++k)
@@ -757,12 +826,18 @@ int main(int argc, char **argv)
                     {
                         visited[fv[k]] = 1;
                         nLayerSurface += layerSel[pi] ? 1 : 0;
-                        ++nFrozenSurface;
+                        if (doBoundarySmoothing && smoothSel[pi])
+                            ++nSmoothingSurface;
+                        else
+                            ++nFrozenSurface;
                     }
-        printf("Boundary point classification summary:\n- Detected number of corner points: 0\n- Detected number of "
-               "feature edge points: 0\n- Detected number of layer surface points: %lld\n- Detected number of "
-               "smoothing surface points: 0\n- Detected number of frozen surface points: %lld\n\n",
-               nLayerSurface, nFrozenSurface);
+        int64_t counts[4] = {0, 0, 0, 0};
+        if (doBoundarySmoothing)
+            smgpu_boundary_counts(h, counts);
+        printf("Boundary point classification summary:\n- Detected number of corner points: %lld\n- Detected number of "
+               "feature edge points: %lld\n- Detected number of layer surface points: %lld\n- Detected number of "
+               "smoothing surface points: %lld\n- Detected number of frozen surface points: %lld\n\n",
+               (long long)counts[0], (long long)counts[1], nLayerSurface, nSmoothingSurface, nFrozenSurface);
     }
 
     // ---- iteration loop, :2257-2437.  The library stops on relTol by itself; the loop here is

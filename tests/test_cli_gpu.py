@@ -136,3 +136,38 @@ def test_cli_parallel_on_processor_directories(tmp_path):
     for k in range(2):
         parts[k].read_points(case / f"processor{k}" / "6" / "polyMesh" / "points")
         assert np.array_equal(parts[k].points, o.get("points", rank=k))
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/smoothMesh_ref not built")
+def test_cli_boundary_point_smoothing_testcase4_as_shipped(tmp_path):
+    """testcase4/run_serial exactly as shipped -- layer treatment on the wall patch and boundary point smoothing
+    of every patch onto constant/geometry/*.obj -- through both executables: same log, bit-identical points."""
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    from make_golden import write_obj
+    d = np.load(os.path.join(golden, "testcase4_boundary.npz"))
+    mesh = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
+                               d["patch_start"], d["patch_size"], d["patch_kind"])
+    cli = [str(x) for x in d["cli"]]
+    cli[cli.index("-layerPatches") + 1] = "(patch0)"
+    cli[cli.index("-centroidalIters") + 1] = "60"
+    outs = {}
+    for tool, binary in (("gpu", sm.CLI_PATH), ("ref", REF_BIN)):
+        case = make_case(tmp_path / tool, mesh)
+        (case / "constant" / "geometry").mkdir()
+        for f, key in (("initEdges.obj", "init_edges"), ("targetEdges.obj", "target_edges"), ("targetSurfaces.obj", "target_surfaces")):
+            write_obj(case / "constant" / "geometry" / f, d[key + "_points"], d[key + "_edges"], d[key + "_tris"], key)
+        r = subprocess.run([binary, "-case", str(case)] + cli, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+        lines = [ln.rstrip() for ln in r.stdout.splitlines()]
+        lines = [ln for ln in lines if not ln.startswith(("smoothMesh (smoothmesh_b200", "GPU iteration time", "ClockTime"))]
+        while lines and lines[0] == "":
+            lines.pop(0)
+        outs[tool] = (lines, case)
+    assert "Enabled boundary point smoothing" in outs["gpu"][0]
+    assert "- Detected number of feature edge points: 80" in outs["gpu"][0]
+    assert outs["gpu"][0] == outs["ref"][0]
+    a = (outs["gpu"][1] / "60" / "polyMesh" / "points").read_bytes()
+    b = (outs["ref"][1] / "60" / "polyMesh" / "points").read_bytes()
+    assert a == b
