@@ -25,7 +25,7 @@ endif
 
 all: $(LIB) $(CLI) $(ORACLE) $(ORACLE_LM) $(REFBIN)
 
-oracle/_ref/smoothMesh_ref: oracle/of_facade/ref_main.cpp $(wildcard oracle/of_facade/*.H) oracle/oracle.cpp $(OBJDIR)/polymesh.o
+oracle/_ref/smoothMesh_ref: oracle/of_facade/ref_main.cpp oracle/of_facade/of_support.cpp $(wildcard oracle/of_facade/*.H) oracle/oracle.cpp $(OBJDIR)/polymesh.o
 	$(MAKE) -f oracle/Makefile.ref
 
 $(OBJDIR)/%.o: $(CSRC)/%.cpp $(wildcard $(CSRC)/*.hpp) $(wildcard $(CSRC)/*.h) $(wildcard include/*.h)

@@ -113,6 +113,11 @@ extern "C"
         const double *surface_points;
         int64_t n_surface_tris;
         const int32_t *surface_tris;
+        /* isCornerPoint / isFeatureEdgePoint label lists written by an earlier run (src/smoothMesh.C:2039-2078),
+         * one entry per point, or NULL: when either holds a 1 the classes come from them instead of from the
+         * initial edges, so a restart does not need init_edges to match the moved mesh */
+        const int32_t *is_corner_point;
+        const int32_t *is_feature_edge_point;
     } smgpu_boundary_geometry;
     /* Turns boundary point smoothing on for the patches with patch_smoothing[i] != 0 (-smoothingPatches): runs
      * the reference's one-time set-up (sanity checks :20-82, edge strings :557-590, classification :269-440,
@@ -125,6 +130,8 @@ extern "C"
     /* counts of the boundary point classification after smgpu_enable_boundary_smoothing:
      * out = {corner points, feature edge points, smoothing surface points, target edge strings} */
     int smgpu_boundary_counts(smgpu_handle *h, int64_t out[4]);
+    /* the classification as the two label lists the reference writes with the mesh (1 / 0 per point) */
+    int smgpu_get_boundary_classes(smgpu_handle *h, int32_t *is_corner_point, int32_t *is_feature_edge_point);
     const char *smgpu_version(void);
     int smgpu_device_count(int32_t *n); /* visible CUDA devices (0 and SMGPU_ERR_CUDA if none) */
 

@@ -89,6 +89,12 @@ extern "C"
                               double layer_edge_length, uint8_t *is_corner, uint8_t *is_feature_edge,
                               uint8_t *is_smoothing_surface, double *corner_points, int32_t *point_strings,
                               int32_t *hops_to_smoothing, int32_t *point_to_inner, int32_t *target_edge_strings);
+    /* labelIOList files next to the mesh (the isCornerPoint / isFeatureEdgePoint lists the reference keeps
+     * between runs, src/smoothMesh.C:2039-2065): read returns the length (or -1 when the file is absent /
+     * unreadable) and fills `data` when it is non-NULL; write emits OpenFOAM's `N{v}` form for uniform lists. */
+    int64_t smmesh_read_label_list(const char *file, int32_t *data, int64_t capacity);
+    int smmesh_write_label_list(const char *file, const char *object, const char *location, const int32_t *data,
+                                int64_t n, int32_t binary);
     /* Wavefront OBJ reader used for constant/geometry: counts first (arrays NULL), then the data. */
     int smmesh_read_obj(const char *file, int64_t *n_points, double *points, int64_t *n_edges, int32_t *edges,
                         int64_t *n_tris, int32_t *tris);

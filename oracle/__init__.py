@@ -73,6 +73,7 @@ def _lib(libm=False):
         L.orc_set_params.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_params.restype = C.c_int
         L.orc_set_geometry.argtypes = [C.c_void_p] + [C.c_int64, C.c_void_p] * 6 + [C.c_double]
+        L.orc_set_label_lists.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_sizes.restype = C.c_int64
         L.orc_sizes.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_get.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_int64]
@@ -171,6 +172,10 @@ class Oracle:
                 g += [pts.shape[0], _p(pts), idx.shape[0], _p(idx)]
                 self.__dict__.setdefault("_geo_keep", []).extend([pts, idx])
             self.L.orc_set_geometry(self.h, *g, float(internal_smoothing_blending_fraction))
+            if geometry.get("is_corner_point") is not None:   # label lists of an earlier run (serial restart)
+                a = np.ascontiguousarray(geometry["is_corner_point"], dtype=np.int32)
+                b = np.ascontiguousarray(geometry["is_feature_edge_point"], dtype=np.int32)
+                self.L.orc_set_label_lists(self.h, 0, a.size, _p(a), _p(b))
         mn, mx = C.c_double(), C.c_double()
         self.L.orc_mesh_stats(self.h, C.byref(mn), C.byref(mx))
         self.min_edge, self.max_edge = mn.value, mx.value

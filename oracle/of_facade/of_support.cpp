@@ -63,7 +63,7 @@ std::string facadeLoadMesh(const std::string &topoDir, const std::string &points
             A.patchName.push_back(p.name);
             A.patchType.push_back(p.type);
         }
-        orc::MeshIn in;
+        orc::MeshIn in = {};
         in.P = pm.nPoints();
         in.C = pm.nCells;
         in.F = pm.nFaces();
@@ -129,3 +129,29 @@ void facadeWritePoints(const FacadeAddressing &A, const std::string &dir, bool b
 {
     sm::writePoints(A.points.data(), A.P, dir, binary, precision, location);
 }
+
+namespace Foam
+{
+bool facadeReadLabels(const std::string &file, std::vector<int> &out)
+{
+    FILE *f = fopen(file.c_str(), "rb");
+    if (!f)
+        return false;
+    fclose(f);
+    try
+    {
+        const std::vector<int32_t> v = sm::readLabelIOList(file);
+        out.assign(v.begin(), v.end());
+    }
+    catch (const std::exception &)
+    {
+        return false;
+    }
+    return true;
+}
+void facadeWriteLabels(const std::string &file, const std::string &object, const std::string &location, const std::vector<int> &v,
+                       bool binary)
+{
+    sm::writeLabelIOList(file, object, location, std::vector<int32_t>(v.begin(), v.end()), binary);
+}
+} // namespace Foam

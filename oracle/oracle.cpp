@@ -145,6 +145,7 @@ struct Rank
     EdgeMesh initEdges, targetEdges;
     TriSurface surf;
     std::vector<int> pSmooth;                   // patch selected by -smoothingPatches
+    std::vector<int> cornerIO, featureIO;       // isCornerPoint / isFeatureEdgePoint lists of an earlier run (may be empty)
     double internalSmoothingBlendingFraction = 0.0;
     double distanceTolerance = 0.0, meshPerimeter = 0.0;
     V3 bbMin = {0, 0, 0}, bbMax = {0, 0, 0};
@@ -549,14 +550,28 @@ void Rank::classifyBoundaryPoints()
                 if (!initEdges.points.empty() && !targetEdges.points.empty())
                 {
                     const V3 pt = pts[pointI];
-                    V3 projPoint;
-                    int dummy, dummy2, closestEdgePointI = UNDEF_LABEL;
-                    findClosestEdgeInfo(pt, initEdges, -1, targetEdgeStrings, distanceTolerance, projPoint, dummy, dummy2,
-                                        closestEdgePointI);
-                    if (closestEdgePointI >= 0 && initEdges.pointEdges[closestEdgePointI].size() != 2)
-                        isCorner[pointI] = 1;
-                    else if (mag(pt - projPoint) < distanceTolerance)
-                        isFeatureEdge[pointI] = 1;
+                    // src/smoothMesh.C:2067-2078 + :336-340: classes from the label lists of an earlier run
+                    bool labelIOListsHaveData = false;
+                    for (int v : cornerIO)
+                        labelIOListsHaveData = labelIOListsHaveData || v == 1;
+                    for (int v : featureIO)
+                        labelIOListsHaveData = labelIOListsHaveData || v == 1;
+                    if (labelIOListsHaveData)
+                    {
+                        isCorner[pointI] = (pointI < (int)cornerIO.size() && cornerIO[pointI] == 1) ? 1 : 0;
+                        isFeatureEdge[pointI] = (pointI < (int)featureIO.size() && featureIO[pointI] == 1) ? 1 : 0;
+                    }
+                    else
+                    {
+                        V3 projPoint;
+                        int dummy, dummy2, closestEdgePointI = UNDEF_LABEL;
+                        findClosestEdgeInfo(pt, initEdges, -1, targetEdgeStrings, distanceTolerance, projPoint, dummy, dummy2,
+                                            closestEdgePointI);
+                        if (closestEdgePointI >= 0 && initEdges.pointEdges[closestEdgePointI].size() != 2)
+                            isCorner[pointI] = 1;
+                        else if (mag(pt - projPoint) < distanceTolerance)
+                            isFeatureEdge[pointI] = 1;
+                    }
                     if (isCorner[pointI])
                     {
                         const int c = findClosestEdgeMeshCornerPointIndex(pt, targetEdges);
@@ -2082,6 +2097,13 @@ extern "C"
     }
 
     void orc_destroy(void *h) { delete (Group *)h; }
+    // isCornerPoint / isFeatureEdgePoint label lists of an earlier run for one rank (restart); before orc_set_params
+    void orc_set_label_lists(void *h, int rank, int64_t n, const int32_t *isCornerPoint, const int32_t *isFeatureEdgePoint)
+    {
+        Rank &R = ((Group *)h)->ranks[rank];
+        R.cornerIO.assign(isCornerPoint, isCornerPoint + n);
+        R.featureIO.assign(isFeatureEdgePoint, isFeatureEdgePoint + n);
+    }
 
     // Inputs of boundary point smoothing (constant/geometry/initEdges.obj, targetEdges.obj -- the initial
     // edges again when that file is absent, src/smoothMesh.C:2148-2160 --, targetSurfaces.obj) as arrays,

@@ -535,7 +535,8 @@ class Smoother:
             _fields_ = [(n, t) for k in ("init", "target") for n, t in
                         ((f"n_{k}_points", C.c_int64), (f"{k}_points", C.c_void_p), (f"n_{k}_edges", C.c_int64),
                          (f"{k}_edges", C.c_void_p))] + [("n_surface_points", C.c_int64), ("surface_points", C.c_void_p),
-                                                         ("n_surface_tris", C.c_int64), ("surface_tris", C.c_void_p)]
+                                                         ("n_surface_tris", C.c_int64), ("surface_tris", C.c_void_p),
+                                                         ("is_corner_point", C.c_void_p), ("is_feature_edge_point", C.c_void_p)]
         keep = []
 
         def arr(a, dt, w):
@@ -549,12 +550,24 @@ class Smoother:
         g.n_init_points, g.init_points, g.n_init_edges, g.init_edges = len(ip), _ptr(ip), len(ie), _ptr(ie)
         g.n_target_points, g.target_points, g.n_target_edges, g.target_edges = len(tp), _ptr(tp), len(te), _ptr(te)
         g.n_surface_points, g.surface_points, g.n_surface_tris, g.surface_tris = len(sp), _ptr(sp), len(st), _ptr(st)
+        for key in ("is_corner_point", "is_feature_edge_point"):   # label lists of an earlier run (restart)
+            if geometry.get(key) is not None:
+                a = np.ascontiguousarray(geometry[key], dtype=np.int32)
+                keep.append(a)
+                setattr(g, key, _ptr(a))
         flags = np.zeros(self.n_patches, dtype=np.int32)
         k = min(len(smoothing_patches), flags.size)
         flags[:k] = np.asarray(smoothing_patches, dtype=np.int32)[:k]
         lib().smgpu_enable_boundary_smoothing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
         self._ck(lib().smgpu_enable_boundary_smoothing(self._h, C.byref(g), _ptr(flags),
                                                       float(internal_smoothing_blending_fraction)))
+
+    def boundary_classes(self):
+        """(isCornerPoint, isFeatureEdgePoint) label lists, as the reference writes them with the mesh."""
+        a, b = np.zeros(self.n_points, dtype=np.int32), np.zeros(self.n_points, dtype=np.int32)
+        lib().smgpu_get_boundary_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        self._ck(lib().smgpu_get_boundary_classes(self._h, _ptr(a), _ptr(b)))
+        return a, b
 
     def profile(self, enable=True):
         self._ck(lib().smgpu_profile(self._h, int(enable)))

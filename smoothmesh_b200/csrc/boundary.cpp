@@ -206,9 +206,15 @@ void readObj(const std::string &file, std::vector<double> &points, std::vector<i
 
 BoundarySetup buildBoundarySetup(const PolyMesh &m, const Topology &t, const std::vector<double> &points, const EdgeMesh &initEdges,
                                  const EdgeMesh &targetEdgesIn, const TriSurface &surface, const std::vector<int32_t> &patchSmoothing,
-                                 double layerEdgeLength)
+                                 double layerEdgeLength, const std::vector<int32_t> &cornerIO, const std::vector<int32_t> &featureIO)
 {
     BoundarySetup B;
+    // src/smoothMesh.C:2067-2078: do the label lists of an earlier run hold classification data
+    bool labelIOListsHaveData = false;
+    for (int32_t v : cornerIO)
+        labelIOListsHaveData = labelIOListsHaveData || v == 1;
+    for (int32_t v : featureIO)
+        labelIOListsHaveData = labelIOListsHaveData || v == 1;
     const int64_t P = t.P;
     B.targetEdges = targetEdgesIn;
     B.surface = surface;
@@ -262,14 +268,22 @@ BoundarySetup buildBoundarySetup(const PolyMesh &m, const Topology &t, const std
                 if (initEdges.nPoints() > 0 && B.targetEdges.nPoints() > 0)
                 {
                     const V pt = at(points, p);
-                    V projPoint;
-                    int32_t stringI, closestEdgePointI;
-                    findClosestEdgeInfo(pt, initEdges, -1, B.targetEdgeStrings, B.distanceTolerance, projPoint, stringI,
-                                        closestEdgePointI);
-                    if (closestEdgePointI >= 0 && initEdges.pointEdges[closestEdgePointI].size() != 2)
-                        B.isCorner[p] = 1;
-                    else if (mag(pt - projPoint) < B.distanceTolerance)
-                        B.isFeatureEdge[p] = 1;
+                    if (labelIOListsHaveData)
+                    { // :336-340
+                        B.isCorner[p] = (p < (int32_t)cornerIO.size() && cornerIO[p] == 1) ? 1 : 0;
+                        B.isFeatureEdge[p] = (p < (int32_t)featureIO.size() && featureIO[p] == 1) ? 1 : 0;
+                    }
+                    else
+                    {
+                        V projPoint;
+                        int32_t stringI, closestEdgePointI;
+                        findClosestEdgeInfo(pt, initEdges, -1, B.targetEdgeStrings, B.distanceTolerance, projPoint, stringI,
+                                            closestEdgePointI);
+                        if (closestEdgePointI >= 0 && initEdges.pointEdges[closestEdgePointI].size() != 2)
+                            B.isCorner[p] = 1;
+                        else if (mag(pt - projPoint) < B.distanceTolerance)
+                            B.isFeatureEdge[p] = 1;
+                    }
                     if (B.isCorner[p])
                     { // findClosestEdgeMeshCornerPointIndex, :151-186
                         double distance = SM_GREAT;

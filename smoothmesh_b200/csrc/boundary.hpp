@@ -49,8 +49,11 @@ struct BoundarySetup
 };
 // Throws std::runtime_error with the reference's FatalError texts.  layerEdgeLength / minEdgeLength are
 // the resolved options (distanceTolerance = REL_TOL min(meshMinEdgeLength, layerEdgeLength), :1921).
+// cornerIO / featureIO: the isCornerPoint / isFeatureEdgePoint label lists of an earlier run (empty = none).
+// When either holds a 1 the classes are taken from them instead of from the initial edges (:336-340).
 BoundarySetup buildBoundarySetup(const PolyMesh &patchesAndFaces, const Topology &t, const std::vector<double> &points,
                                  const EdgeMesh &initEdges, const EdgeMesh &targetEdges, const TriSurface &surface,
-                                 const std::vector<int32_t> &patchSmoothing, double layerEdgeLength);
+                                 const std::vector<int32_t> &patchSmoothing, double layerEdgeLength,
+                                 const std::vector<int32_t> &cornerIO = {}, const std::vector<int32_t> &featureIO = {});
 
 } // namespace sm

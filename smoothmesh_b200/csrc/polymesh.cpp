@@ -1460,6 +1460,14 @@ void writeLabelListFile(const std::string &file, const std::string &object, cons
     if (!o)
         fail("cannot write " + file);
     o << foamHeader("labelIOList", location, object, binary);
+    bool uniform = v.size() > 1;
+    for (size_t i = 1; i < v.size() && uniform; ++i)
+        uniform = v[i] == v[0];
+    if (uniform && !binary)
+    { // [OF-recalled] List<T>::writeList: uniform contiguous lists are written as N{value}
+        o << v.size() << "{" << v[0] << "}\n";
+        return;
+    }
     o << v.size() << "\n(";
     if (binary)
     {
@@ -1509,5 +1517,19 @@ PolyMesh readProcessorMesh(const std::string &caseDir, int k)
     if (probe.good())
         m.cellGlobalId = readIds(dir + "/cellProcAddressing");
     return m;
+}
+
+// labelIOList files next to the mesh (isCornerPoint / isFeatureEdgePoint, src/smoothMesh.C:2039-2065)
+void writeLabelIOList(const std::string &file, const std::string &object, const std::string &location,
+                      const std::vector<int32_t> &v, bool binary)
+{
+    writeLabelListFile(file, object, location, std::vector<int64_t>(v.begin(), v.end()), binary);
+}
+std::vector<int32_t> readLabelIOList(const std::string &file)
+{
+    Lexer lx;
+    lx.s = slurp(file);
+    const Header h = readHeader(lx);
+    return readLabelList(lx, h.binary);
 }
 } // namespace sm

@@ -112,6 +112,10 @@ void writePolyMesh(const PolyMesh &m, const std::string &dir, bool binary = fals
 void writePoints(const double *pts, int64_t nPoints, const std::string &dir, bool binary, int precision,
                  const std::string &location);
 std::vector<double> readPoints(const std::string &file);
+// labelIOList files written next to the mesh (isCornerPoint / isFeatureEdgePoint)
+void writeLabelIOList(const std::string &file, const std::string &object, const std::string &location,
+                      const std::vector<int32_t> &v, bool binary);
+std::vector<int32_t> readLabelIOList(const std::string &file);
 // decomposed cases: processor<k>/constant/polyMesh with pointProcAddressing / cellProcAddressing
 void writeDecomposedCase(const std::vector<PolyMesh> &parts, const std::string &caseDir, bool binary);
 PolyMesh readProcessorMesh(const std::string &caseDir, int k);

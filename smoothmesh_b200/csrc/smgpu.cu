@@ -59,6 +59,7 @@ struct smgpu_handle
     int resolveBlocks = 1;
     bool doBoundary = false;            // boundary point smoothing enabled (smgpu_enable_boundary_smoothing)
     int64_t boundaryCounts[4] = {0, 0, 0, 0};
+    std::vector<uint8_t> boundaryClass; // per point, bits as Dev::bClass
     std::vector<sm::Patch> patches;     // patch table of the mesh (boundary set-up needs it after create)
     bool useTiles = false; // fused geometry kernel over sm::GeomTiles
     int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
@@ -989,7 +990,12 @@ extern "C"
             sm::BoundarySetup B;
             try
             {
-                B = sm::buildBoundarySetup(pm, t, points, ie, te, surf, ps, layerEdgeLength);
+                std::vector<int32_t> cornerIO, featureIO;
+                if (g->is_corner_point)
+                    cornerIO.assign(g->is_corner_point, g->is_corner_point + t.P);
+                if (g->is_feature_edge_point)
+                    featureIO.assign(g->is_feature_edge_point, g->is_feature_edge_point + t.P);
+                B = sm::buildBoundarySetup(pm, t, points, ie, te, surf, ps, layerEdgeLength, cornerIO, featureIO);
             }
             catch (const std::exception &e)
             {
@@ -1023,6 +1029,7 @@ extern "C"
                 bString[b] = B.pointStrings[p];
             }
             d.bClass = h->upload(cls);
+            h->boundaryClass = cls;
             d.sharp = h->dalloc<uint8_t>(t.P + 8);
             CK(cudaMemset(d.sharp, 0, t.P + 8));
             d.bPoints = h->upload(B.boundaryPoints);
@@ -1051,6 +1058,22 @@ extern "C"
         catch (const std::exception &e)
         {
             return setErr(SMGPU_ERR_CUDA, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_get_boundary_classes(smgpu_handle *h, int32_t *is_corner_point, int32_t *is_feature_edge_point)
+    {
+        if (!h)
+            return setErr(SMGPU_ERR_ARG, "null handle");
+        if (h->boundaryClass.empty())
+            return setErr(SMGPU_ERR_ARG, "boundary point smoothing is not enabled");
+        for (int64_t p = 0; p < h->topo.P; ++p)
+        {
+            if (is_corner_point)
+                is_corner_point[p] = (h->boundaryClass[p] & 1) ? 1 : 0;
+            if (is_feature_edge_point)
+                is_feature_edge_point[p] = (h->boundaryClass[p] & 2) ? 1 : 0;
         }
         return SMGPU_OK;
     }

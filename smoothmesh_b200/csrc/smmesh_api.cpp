@@ -359,6 +359,35 @@ extern "C"
         }
         return SMGPU_OK;
     }
+    int64_t smmesh_read_label_list(const char *file, int32_t *data, int64_t capacity)
+    {
+        try
+        {
+            const std::vector<int32_t> v = sm::readLabelIOList(file);
+            if (data)
+                std::copy(v.begin(), v.begin() + std::min<int64_t>(capacity, (int64_t)v.size()), data);
+            return (int64_t)v.size();
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return -1;
+        }
+    }
+    int smmesh_write_label_list(const char *file, const char *object, const char *location, const int32_t *data, int64_t n,
+                                int32_t binary)
+    {
+        try
+        {
+            sm::writeLabelIOList(file, object, location, std::vector<int32_t>(data, data + n), binary != 0);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
     int smmesh_read_obj(const char *file, int64_t *n_points, double *points, int64_t *n_edges, int32_t *edges,
                         int64_t *n_tris, int32_t *tris)
     {

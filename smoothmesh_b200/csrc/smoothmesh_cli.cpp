@@ -578,7 +578,25 @@ int main(int argc, char **argv)
     const bool surfaces = fileExists(caseDir + "/constant/geometry/targetSurfaces.obj");
     const bool initEdges = fileExists(caseDir + "/constant/geometry/initEdges.obj");
     // :2080-2086 (the isCornerPoint / isFeatureEdgePoint label lists of earlier runs are not read)
-    const bool boundaryRequested = !has("decompose") && surfaces && initEdges && !smoothingPatchesEmpty;
+    // :2039-2078: the classification lists an earlier run left in the start time directory
+    auto readList = [&](const std::string &name) {
+        std::vector<int32_t> v;
+        const std::string f = caseDir + "/" + startName + "/" + name;
+        if (!parallel && fileExists(f))
+        {
+            const int64_t n = smmesh_read_label_list(f.c_str(), nullptr, 0);
+            if (n > 0)
+            {
+                v.resize(n);
+                smmesh_read_label_list(f.c_str(), v.data(), n);
+            }
+        }
+        return v;
+    };
+    const std::vector<int32_t> cornerIO = readList("isCornerPoint"), featureIO = readList("isFeatureEdgePoint");
+    const bool labelIOListsHaveData = std::find(cornerIO.begin(), cornerIO.end(), 1) != cornerIO.end() ||
+                                      std::find(featureIO.begin(), featureIO.end(), 1) != featureIO.end();
+    const bool boundaryRequested = !has("decompose") && surfaces && (initEdges || labelIOListsHaveData) && !smoothingPatchesEmpty;
     if (boundaryRequested && parallel)
         fatal("boundary point smoothing with -parallel: the feature is single-GPU in this build (its four extra "
               "synchronisations are not in the exchange layer yet); pass -smoothingPatches '()' or run serially");
@@ -742,7 +760,10 @@ int main(int argc, char **argv)
     else
         printf("Boundary layer treatment is disabled. Either no layerPatches were specified or "
                "boundaryMaxBlendingFraction is zero\n\n");
-    printf("Did not find corners and feature edges in isCornerPoint and isFeatureEdgePoint files\n\n");
+    if (labelIOListsHaveData)
+        printf("Found corners and feature edges in isCornerPoint and isFeatureEdgePoint files\n\n");
+    else
+        printf("Did not find corners and feature edges in isCornerPoint and isFeatureEdgePoint files\n\n");
     // boundary point smoothing, :2080-2171: inputs from constant/geometry, set-up inside the library
     std::vector<int32_t> smoothSel(nPatches, 0);
     if (boundaryRequested)
@@ -790,6 +811,12 @@ int main(int argc, char **argv)
                    "constant/geometry/targetEdges.obj.\n\n");
         printf("Checking initial edge mesh sanity\nChecking target edge mesh sanity\n");
         smgpu_boundary_geometry geo;
+        memset(&geo, 0, sizeof geo);
+        if (labelIOListsHaveData && (int64_t)cornerIO.size() == nPoints && (int64_t)featureIO.size() == nPoints)
+        {
+            geo.is_corner_point = cornerIO.data();
+            geo.is_feature_edge_point = featureIO.data();
+        }
         geo.n_init_points = (int64_t)ie.p.size() / 3, geo.init_points = ie.p.data();
         geo.n_init_edges = (int64_t)ie.e.size() / 2, geo.init_edges = ie.e.data();
         geo.n_target_points = (int64_t)te.p.size() / 3, geo.target_points = te.p.data();
@@ -839,6 +866,12 @@ int main(int argc, char **argv)
                "smoothing surface points: %lld\n- Detected number of frozen surface points: %lld\n\n",
                (long long)counts[0], (long long)counts[1], nLayerSurface, nSmoothingSurface, nFrozenSurface);
     }
+
+    // the two label lists are AUTO_WRITE objects of the mesh: the reference writes them with every mesh.write(),
+    // all zeros when boundary point smoothing is off (:2039-2065)
+    std::vector<int32_t> isCornerOut(nPoints, 0), isFeatureOut(nPoints, 0);
+    if (doBoundarySmoothing)
+        smgpu_get_boundary_classes(h, isCornerOut.data(), isFeatureOut.data());
 
     // ---- iteration loop, :2257-2437.  The library stops on relTol by itself; the loop here is
     // cut at write intervals so intermediate meshes can be written (:2416).
@@ -890,6 +923,11 @@ int main(int argc, char **argv)
                 fatal(smgpu_last_error());
             if (smmesh_write_points(pts.data(), nPoints, (caseDir + "/" + tn + "/polyMesh").c_str(), binary,
                                     std::max(10, writePrecision), (tn + "/polyMesh").c_str()) != SMGPU_OK)
+                fatal(smmesh_last_error());
+            if (smmesh_write_label_list((caseDir + "/" + tn + "/isCornerPoint").c_str(), "isCornerPoint", tn.c_str(),
+                                        isCornerOut.data(), nPoints, binary) != SMGPU_OK ||
+                smmesh_write_label_list((caseDir + "/" + tn + "/isFeatureEdgePoint").c_str(), "isFeatureEdgePoint", tn.c_str(),
+                                        isFeatureOut.data(), nPoints, binary) != SMGPU_OK)
                 fatal(smmesh_last_error());
         }
     }

@@ -186,3 +186,49 @@ def test_product_host_setup_matches_the_oracle(seed):
     assert np.array_equal(b["corner_points"][corners], o.get("cornerPoints")[corners])
     if seed > 0:
         assert corners.sum() == 8 and b["target_edge_strings"].max() == 11     # 8 box corners, 12 edge strings
+
+
+def _restart_case(tmp, binary=True):
+    hi = (1.0, 1.2, 0.9)
+    mesh = sm.Mesh.hex_block(5, 4, 4, hi=hi).jitter(0.02, 3)
+    ip, ie, _, _ = box_geometry((0, 0, 0), hi, 3)
+    tp, te, tc, tt = box_geometry((-0.06, -0.05, -0.04), (1.07, 1.26, 0.95), 3)
+    mesh.write(os.path.join(tmp, "constant", "polyMesh"))
+    os.makedirs(os.path.join(tmp, "system"))
+    os.makedirs(os.path.join(tmp, "constant", "geometry"))
+    open(os.path.join(tmp, "system", "controlDict"), "w").write(
+        "startFrom latestTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat %s;\nwritePrecision 16;\n" % ("binary" if binary else "ascii"))
+    write_obj(os.path.join(tmp, "constant", "geometry", "initEdges.obj"), ip, ie, None)
+    write_obj(os.path.join(tmp, "constant", "geometry", "targetEdges.obj"), tp, te, None)
+    write_obj(os.path.join(tmp, "constant", "geometry", "targetSurfaces.obj"), tc, None, tt)
+    return mesh, dict(init_edges=(ip, ie), target_edges=(tp, te), surface=(tc, tt))
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/smoothMesh_ref not built")
+def test_restart_uses_the_classification_lists_of_the_first_run(tmp_path):
+    """The reference keeps isCornerPoint / isFeatureEdgePoint label lists with the mesh (src/smoothMesh.C:2039-2078)
+    so that a second invocation -- testcase8/run_serial runs the tool twice -- classifies the moved boundary
+    points as the first one did.  Two runs of the reference translation unit against two oracle runs."""
+    tmp = str(tmp_path)
+    mesh, geo = _restart_case(tmp)
+    for run in (1, 2):
+        r = subprocess.run([REF, "-case", tmp, "-centroidalIters", "6", "-relTol", "0"], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert ("Found corners and feature edges" in r.stdout) == (run == 2)
+        assert "- Detected number of corner points: 8" in r.stdout
+    assert sorted(os.listdir(os.path.join(tmp, "6"))) == ["isCornerPoint", "isFeatureEdgePoint", "polyMesh"]
+    o1 = Oracle(mesh.desc_arrays(), libm=True, rel_tol=0.0, smoothing_patches=[1] * 6, geometry=geo)
+    o1.iterate(6)
+    out = sm.Mesh.read(os.path.join(tmp, "constant", "polyMesh"))
+    out.read_points(os.path.join(tmp, "6", "polyMesh", "points"))
+    assert np.array_equal(out.points, o1.get("points"))
+    moved = sm.Mesh.read(os.path.join(tmp, "constant", "polyMesh"))
+    moved.read_points(os.path.join(tmp, "6", "polyMesh", "points"))
+    lists = dict(geo, is_corner_point=o1.get("isCorner").astype(np.int32), is_feature_edge_point=o1.get("isFeatureEdge").astype(np.int32))
+    o2 = Oracle(moved.desc_arrays(), libm=True, rel_tol=0.0, smoothing_patches=[1] * 6, geometry=lists)
+    o2.iterate(6)
+    out.read_points(os.path.join(tmp, "12", "polyMesh", "points"))
+    assert np.array_equal(out.points, o2.get("points"))
+    # without the lists the moved corners would no longer be recognised
+    o3 = Oracle(moved.desc_arrays(), libm=True, rel_tol=0.0, smoothing_patches=[1] * 6, geometry=geo)
+    assert int(o3.get("isCorner").sum()) == 0 and int(o2.get("isCorner").sum()) == 8

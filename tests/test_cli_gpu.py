@@ -171,3 +171,32 @@ def test_cli_boundary_point_smoothing_testcase4_as_shipped(tmp_path):
     a = (outs["gpu"][1] / "60" / "polyMesh" / "points").read_bytes()
     b = (outs["ref"][1] / "60" / "polyMesh" / "points").read_bytes()
     assert a == b
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/smoothMesh_ref not built")
+def test_cli_restart_with_classification_lists(tmp_path):
+    """Two invocations in a row (testcase8/run_serial:17-19) with boundary point smoothing: the second one starts
+    from latestTime and takes the corner / feature-edge classes from the isCornerPoint / isFeatureEdgePoint lists the
+    first one wrote.  Same logs and bit-identical points as two invocations of the reference's own main()."""
+    from test_boundary_smoothing_oracle import _restart_case
+    res = {}
+    for tool, binary in (("gpu", sm.CLI_PATH), ("ref", REF_BIN)):
+        d = tmp_path / tool
+        d.mkdir()
+        _restart_case(str(d))
+        logs = []
+        for run in (1, 2):
+            r = subprocess.run([binary, "-case", str(d), "-centroidalIters", "6", "-relTol", "0"], capture_output=True, text=True, timeout=300)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            lines = [ln.rstrip() for ln in r.stdout.splitlines()]
+            lines = [ln for ln in lines if not ln.startswith(("smoothMesh (smoothmesh_b200", "GPU iteration time", "ClockTime"))]
+            while lines and lines[0] == "":
+                lines.pop(0)
+            logs.append(lines)
+        res[tool] = (logs, d)
+    assert "Found corners and feature edges in isCornerPoint and isFeatureEdgePoint files" in res["gpu"][0][1]
+    assert res["gpu"][0] == res["ref"][0]
+    for t in ("6", "12"):
+        assert (res["gpu"][1] / t / "polyMesh" / "points").read_bytes() == (res["ref"][1] / t / "polyMesh" / "points").read_bytes()
+        for f in ("isCornerPoint", "isFeatureEdgePoint"):
+            assert (res["gpu"][1] / t / f).read_bytes() == (res["ref"][1] / t / f).read_bytes()
