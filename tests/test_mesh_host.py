@@ -209,3 +209,36 @@ def test_geometry_tiles_cover_the_mesh():
     k = sm.Mesh.kelvin(3, 1.0).geom_tiles()                    # 14-faced cells: fewer cells per tile
     assert k["tiles"] >= 1 and k["max_faces"] <= 1024
     assert sm.Mesh.kelvin(2, 1.0).geom_tiles(max_cells=8, max_faces=10)["tiles"] == 0   # a cell does not fit
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_label_list_and_obj_files(tmp_path, binary):
+    """labelIOList files (isCornerPoint / isFeatureEdgePoint, src/smoothMesh.C:2039-2065) and the OBJ reader used for
+    constant/geometry."""
+    import ctypes as C
+    L = sm.lib()
+    L.smmesh_read_label_list.restype = C.c_int64
+    L.smmesh_read_label_list.argtypes = [C.c_char_p, C.c_void_p, C.c_int64]
+    L.smmesh_write_label_list.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int32]
+    for name, data in (("mixed", np.array([0, 1, 0, 0, 1, 1, 0], dtype=np.int32)), ("uniform", np.zeros(9, dtype=np.int32))):
+        f = str(tmp_path / name).encode()
+        assert L.smmesh_write_label_list(f, name.encode(), b"7", data.ctypes.data_as(C.c_void_p), data.size, int(binary)) == 0
+        n = L.smmesh_read_label_list(f, None, 0)
+        assert n == data.size
+        back = np.full(n, -1, dtype=np.int32)
+        L.smmesh_read_label_list(f, back.ctypes.data_as(C.c_void_p), n)
+        assert np.array_equal(back, data)
+        txt = open(f, "rb").read()
+        assert b"object" in txt and name.encode() in txt
+        if name == "uniform" and not binary:
+            assert b"9{0}" in txt                      # OpenFOAM's compact form for uniform lists
+    assert L.smmesh_read_label_list(str(tmp_path / "absent").encode(), None, 0) == -1
+    obj = tmp_path / "g.obj"
+    obj.write_text("# comment\no thing\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nl 1 2 3\nl 4 1\nf 1/1/1 2/2/1 3/3/1 4/4/1\n")
+    L.smmesh_read_obj.argtypes = [C.c_char_p] + [C.c_void_p] * 6
+    np_, ne, nt = C.c_int64(), C.c_int64(), C.c_int64()
+    assert L.smmesh_read_obj(str(obj).encode(), C.byref(np_), None, C.byref(ne), None, C.byref(nt), None) == 0
+    assert (np_.value, ne.value, nt.value) == (4, 3, 2)           # polyline -> 2 edges, +1; quad -> 2 triangles
+    e, t = np.zeros((3, 2), np.int32), np.zeros((2, 3), np.int32)
+    L.smmesh_read_obj(str(obj).encode(), None, None, None, e.ctypes.data_as(C.c_void_p), None, t.ctypes.data_as(C.c_void_p))
+    assert e.tolist() == [[0, 1], [1, 2], [3, 0]] and t.tolist() == [[0, 1, 2], [0, 2, 3]]
