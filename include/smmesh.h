@@ -89,6 +89,13 @@ extern "C"
                               double layer_edge_length, uint8_t *is_corner, uint8_t *is_feature_edge,
                               uint8_t *is_smoothing_surface, double *corner_points, int32_t *point_strings,
                               int32_t *hops_to_smoothing, int32_t *point_to_inner, int32_t *target_edge_strings);
+    /* One-time host set-up of the boundary layer treatment for a serial mesh (topology.hpp: buildLayerSetup;
+     * calculatePointHopsToBoundary and propagateOuterNeighInfo, src/orthogonalBoundaryBlending.C:52-134, :244-391):
+     * hop counts (-1 = none), the point-to-outer-point map (-1 = none) and, per point, the boundary point whose
+     * set-up normal it carries (-1 = zero normal).  patch_layer: 0/1 per patch. */
+    int smmesh_layer_setup(const smmesh *m, const int32_t *patch_layer, int32_t max_layers, int32_t *hops,
+                           int32_t *point_to_outer, int32_t *normal_source);
+
     /* labelIOList files next to the mesh (the isCornerPoint / isFeatureEdgePoint lists the reference keeps
      * between runs, src/smoothMesh.C:2039-2065): read returns the length (or -1 when the file is absent /
      * unreadable) and fills `data` when it is non-NULL; write emits OpenFOAM's `N{v}` form for uniform lists. */

@@ -329,6 +329,17 @@ class Mesh:
         cm = np.zeros(self.n_cells, dtype=np.int32)
         return Mesh(lib().smmesh_renumber(self._h, _ptr(pm), _ptr(cm))), pm, cm
 
+    def layer_setup(self, patch_layer, max_layers=4):
+        """Host set-up of the boundary layer treatment (include/smmesh.h: smmesh_layer_setup)."""
+        flags = np.zeros(self.n_patches, dtype=np.int32)
+        k = min(len(patch_layer), flags.size)
+        flags[:k] = np.asarray(patch_layer, dtype=np.int32)[:k]
+        out = [np.zeros(self.n_points, dtype=np.int32) for _ in range(3)]
+        lib().smmesh_layer_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        if lib().smmesh_layer_setup(self._h, _ptr(flags), int(max_layers), *[_ptr(a) for a in out]) != 0:
+            raise SmoothMeshError(lib().smmesh_last_error().decode())
+        return dict(hops=out[0], point_to_outer=out[1], normal_source=out[2])
+
     def boundary_setup(self, init_edges, target_edges, patch_smoothing, layer_edge_length=-1.0):
         """Host set-up of boundary point smoothing (include/smmesh.h: smmesh_boundary_setup); edges = (points, pairs)."""
         P = self.n_points

@@ -359,6 +359,28 @@ extern "C"
         }
         return SMGPU_OK;
     }
+    int smmesh_layer_setup(const smmesh *m, const int32_t *patch_layer, int32_t max_layers, int32_t *hops,
+                           int32_t *point_to_outer, int32_t *normal_source)
+    {
+        try
+        {
+            const sm::Topology t = sm::buildTopology(m->m);
+            const std::vector<int32_t> flags(patch_layer, patch_layer + m->m.patches.size());
+            const sm::LayerSetup L = sm::buildLayerSetup(m->m, t, flags, max_layers);
+            if (hops)
+                std::copy(L.hops.begin(), L.hops.end(), hops);
+            if (point_to_outer)
+                std::copy(L.pointToOuter.begin(), L.pointToOuter.end(), point_to_outer);
+            if (normal_source)
+                std::copy(L.normalSrc.begin(), L.normalSrc.end(), normal_source);
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
     int64_t smmesh_read_label_list(const char *file, int32_t *data, int64_t capacity)
     {
         try

@@ -242,3 +242,29 @@ def test_label_list_and_obj_files(tmp_path, binary):
     e, t = np.zeros((3, 2), np.int32), np.zeros((2, 3), np.int32)
     L.smmesh_read_obj(str(obj).encode(), None, None, None, e.ctypes.data_as(C.c_void_p), None, t.ctypes.data_as(C.c_void_p))
     assert e.tolist() == [[0, 1], [1, 2], [3, 0]] and t.tolist() == [[0, 1, 2], [0, 2, 3]]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_layer_setup_matches_the_oracle(seed):
+    """topology.cpp: buildLayerSetup (the product's one-time set-up of the boundary layer treatment) against the
+    oracle's calculatePointHopsToBoundary / propagateOuterNeighInfo on random meshes and patch selections: hop
+    counts, point-to-outer map, and which internal points end up with a propagated normal."""
+    from oracle import Oracle
+    rng = np.random.default_rng(500 + seed)
+    if seed % 4 == 3:
+        mesh = sm.Mesh.kelvin(3, 1.0).jitter(0.02, seed)
+    else:
+        nx, ny, nz = rng.integers(3, 9, size=3)
+        mesh = hex_jittered(int(nx), int(ny), int(nz), float(rng.uniform(0.05, 0.4)), seed=int(seed))
+    flags = [int(rng.random() < 0.6) for _ in range(mesh.n_patches)]
+    flags[int(rng.integers(0, mesh.n_patches))] = 1
+    max_layers = int(rng.integers(1, 6))
+    L = mesh.layer_setup(flags, max_layers)
+    o = Oracle(mesh.desc_arrays(), layer_patches=flags, max_layers=max_layers)
+    assert np.array_equal(L["hops"], o.get("hopsToLayer"))
+    assert np.array_equal(L["point_to_outer"], o.get("pointToOuter"))
+    # the oracle's set-up normals are non-zero exactly where the product copies a boundary point's normal
+    internal = o.get("isInternal").astype(bool)
+    o.iterate(1)
+    has_normal = np.abs(o.get("snapNormals")).sum(axis=1) > 0
+    assert np.array_equal(has_normal[internal], (L["normal_source"] >= 0)[internal])
