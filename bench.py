@@ -157,11 +157,13 @@ def cpu_baseline(n_side, iters, threads):
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
 
 
-def reference_binary_rate(n_side=40, iters=(1, 5)):
-    """Serial rate of oracle/_ref/smoothMesh_ref, the reference's own translation unit compiled against the
-    OpenFOAM facade (prebuilt; nothing under /root/reference is read at run time): two runs with different
-    iteration counts on the same jittered block, the difference of their wall times is the loop alone.
-    Returns None when the binary is absent."""
+def reference_binary_rate(n_side=40, iters=(1, 5), procs=1):
+    """Rate of oracle/_ref/smoothMesh_ref, the reference's own translation unit compiled against the OpenFOAM
+    facade (prebuilt; nothing under /root/reference is read at run time): two runs with different iteration counts
+    on the same jittered block, the difference of their wall times is the loop alone.  procs > 1 runs it the way
+    the reference scales on a CPU -- `-parallel`, one process per processor directory of a brick decomposition
+    (the facade forks them and combines interface points through shared memory).  Returns None when the binary is
+    absent."""
     if not os.path.exists(REF_BIN):
         return None
     import shutil
@@ -175,17 +177,29 @@ def reference_binary_rate(n_side=40, iters=(1, 5)):
         os.makedirs(os.path.join(tmp, "system"))
         with open(os.path.join(tmp, "system", "controlDict"), "w") as f:
             f.write("startFrom startTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat binary;\n")
+        extra = []
+        dims = [1, 1, 1]
+        if procs > 1:
+            t, i = procs, 0
+            while t % 2 == 0 and t > 1:
+                dims[i % 3] *= 2
+                t //= 2
+                i += 1
+            sm.Mesh.write_decomposed(mesh.decompose(*dims), tmp, binary=True)
+            extra = ["-parallel"]
         times = []
         for k in iters:
             t0 = time.perf_counter()
-            subprocess.run([REF_BIN, "-case", tmp, "-centroidalIters", str(k), "-relTol", "0", "-smoothingPatches", "()"],
-                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+            subprocess.run([REF_BIN, "-case", tmp] + extra + ["-centroidalIters", str(k), "-relTol", "0", "-smoothingPatches", "()"],
+                           check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
             times.append(time.perf_counter() - t0)
         dt = times[1] - times[0]
         if dt <= 0:
             return None
-        return dict(value=mesh.n_points * (iters[1] - iters[0]) / dt, cores=1,
-                    sample=f"{iters[1] - iters[0]} iterations of a jittered {n_side}^3 hex block ({dt:.1f} s), serial")
+        used = dims[0] * dims[1] * dims[2]
+        how = "serial" if used == 1 else f"-parallel, {used} processes ({'x'.join(map(str, dims))} bricks)"
+        return dict(value=mesh.n_points * (iters[1] - iters[0]) / dt, cores=used,
+                    sample=f"{iters[1] - iters[0]} iterations of a jittered {n_side}^3 hex block ({dt:.1f} s), {how}")
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -242,7 +256,8 @@ def run_reference(args, rank, world):
                    "slower arm; its serial rate is in cpu_baseline.reference_tu)"},
         "cpu_baseline": {"value": value, "unit": "point-updates/s", "cores": p2, "kind": "port",
                          "sample": f"{n} iterations of a jittered {n_side}^3 hex block, {p2} threads",
-                         "reference_tu": reference_binary_rate()},
+                         "reference_tu": reference_binary_rate(),
+                         "reference_tu_parallel": reference_binary_rate(n_side=64, iters=(1, 4), procs=p2)},
         "e2e": {"value": value, "unit": "point-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -416,9 +431,18 @@ def main():
                                 "serial_value": v1}
         ref = reference_binary_rate()
         if ref is not None:
-            # the reference's own translation unit (oracle/_ref, compiled against the OpenFOAM facade), serial
+            # the reference's own translation unit (oracle/_ref, compiled against the OpenFOAM facade), serial and
+            # as one process per host core (power of two)
             line["cpu_baseline"]["reference_tu"] = {"value": ref["value"], "unit": "point-updates/s", "cores": 1,
                                                     "kind": "reference", "sample": ref["sample"]}
+            try:
+                refp = reference_binary_rate(n_side=64, iters=(1, 4), procs=cN)
+                if refp is not None:
+                    line["cpu_baseline"]["reference_tu_parallel"] = {"value": refp["value"], "unit": "point-updates/s",
+                                                                     "cores": refp["cores"], "kind": "reference",
+                                                                     "sample": refp["sample"]}
+            except Exception as e:  # a failing baseline sample must not take the GPU line down
+                line["cpu_baseline"]["reference_tu_parallel"] = {"error": str(e)[:200]}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
