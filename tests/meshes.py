@@ -29,3 +29,37 @@ CASES = {
     "kelvin3_j20": lambda: kelvin_jittered(3, 0.20),
     "layers_ar": lambda: prism_layers(),
 }
+
+
+def tet_block(n=3, frac=0.15, seed=5):
+    """Conforming tetrahedral mesh: every cube of an n^3 lattice split into six tetrahedra around its main
+    diagonal (Kuhn triangulation), interior points jittered.  Triangular faces, four-faced cells, points of
+    valence up to 14: the generic (non-record) paths of the kernels and of the oracle."""
+    import itertools
+    idx = lambda i, j, k: i + (n + 1) * (j + (n + 1) * k)
+    pts = np.array([[i / n, j / n, k / n] for k in range(n + 1) for j in range(n + 1) for i in range(n + 1)], dtype=float)
+    cells = []
+    for k in range(n):
+        for j in range(n):
+            for i in range(n):
+                for perm in itertools.permutations(range(3)):
+                    v = [np.array([i, j, k])]
+                    for ax in perm:
+                        step = np.zeros(3, dtype=int)
+                        step[ax] = 1
+                        v.append(v[-1] + step)
+                    a, b, c, d = [idx(*map(int, q)) for q in v]
+                    faces = [[a, b, c], [a, b, d], [a, c, d], [b, c, d]]
+                    cc = pts[[a, b, c, d]].mean(axis=0)
+                    out = []
+                    for f in faces:
+                        p = pts[f]
+                        nrm = np.cross(p[1] - p[0], p[2] - p[0])
+                        out.append(f if np.dot(nrm, p.mean(axis=0) - cc) > 0 else f[::-1])
+                    cells.append(out)
+    m = sm.Mesh.from_cells(pts, cells)
+    return m.jitter(frac / n, seed)
+
+
+# CPU-only for now (oracle against the reference translation unit): not yet part of the GPU parity matrix
+EXTRA_CASES = {"tets3_j15": lambda: tet_block()}

@@ -25,7 +25,7 @@ import pytest
 import smoothmesh_b200 as sm
 from oracle import Oracle
 
-from meshes import CASES
+from meshes import CASES, EXTRA_CASES
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
@@ -73,6 +73,11 @@ RUNS = {
     "kelvin_polyhedral": (CASES["kelvin3_j20"], dict(rel_tol=0.0, min_angle_deg=60.0, max_angle_deg=120.0),
                           ["-relTol", "0", "-minAngle", "60", "-maxAngle", "120"], 8),
     "high_aspect_ratio": (CASES["layers_ar"], dict(rel_tol=0.0), ["-relTol", "0"], 10),
+    # tetrahedra: triangular faces, four-faced cells, point valence up to 14
+    "tetrahedra": (EXTRA_CASES["tets3_j15"], dict(rel_tol=0.0, min_angle_deg=20.0, max_angle_deg=150.0),
+                   ["-relTol", "0", "-minAngle", "20", "-maxAngle", "150"], 12),
+    "tetrahedra_layers": (EXTRA_CASES["tets3_j15"], dict(rel_tol=0.0, min_angle_deg=10.0, layer_patches=[1], max_layers=2),
+                          ["-relTol", "0", "-minAngle", "10", "-layerPatches", "(walls)", "-maxLayers", "2"], 8),
     "constraints_off": (CASES["hex6_j25"], dict(rel_tol=1e-3, edge_angle_constraint=0, face_angle_constraint=0,
                                                 min_edge_length=0.02, max_step_length=0.004, rel_step_frac=0.8),
                         ["-relTol", "1e-3", "-edgeAngleConstraint", "false", "-faceAngleConstraint", "false",
