@@ -61,5 +61,5 @@ def tet_block(n=3, frac=0.15, seed=5):
     return m.jitter(frac / n, seed)
 
 
-# CPU-only for now (oracle against the reference translation unit): not yet part of the GPU parity matrix
-EXTRA_CASES = {"tets3_j15": lambda: tet_block()}
+CASES["tets3_j15"] = lambda: tet_block()
+EXTRA_CASES = {"tets3_j15": CASES["tets3_j15"]}
