@@ -23,15 +23,22 @@ REF = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
 pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/smoothMesh_ref not built")
 
 
-def one(seed, verbose=False):
+def one(seed, verbose=False, force_kind=None):
     rng=np.random.default_rng(seed)
     kind = rng.choice(["hex","hex","hex","kelvin","flat"])
+    if force_kind:
+        kind = force_kind
     if kind=="hex":
         nx,ny,nz = rng.integers(3,8,size=3)
         hi = tuple(rng.uniform(0.5,2.0,size=3))
         m = sm.Mesh.hex_block(int(nx),int(ny),int(nz),hi=hi)
         h = min(hi[0]/nx,hi[1]/ny,hi[2]/nz)
         m = m.jitter(float(rng.uniform(0.05,0.49))*h, int(rng.integers(1,10**6)))
+    elif kind=="tets":
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from meshes import tet_block
+        m = tet_block(int(rng.integers(2,5)), float(rng.uniform(0.05,0.25)), int(rng.integers(1,10**6)))
     elif kind=="kelvin":
         m = sm.Mesh.kelvin(int(rng.integers(2,4)),1.0).jitter(float(rng.uniform(0.05,0.3))*(2**0.5)/4, int(rng.integers(1,10**6)))
     else:
@@ -62,15 +69,15 @@ def one(seed, verbose=False):
     iters=int(rng.integers(3,12))
     par = None
     if rng.random()<0.5:
-        par = (int(rng.integers(1,3)), int(rng.integers(1,3)), int(rng.integers(1,3))) if kind!="kelvin" else (int(rng.integers(2,5)),)
-        if kind!="kelvin" and par==(1,1,1): par=(2,1,1)
+        par = (int(rng.integers(1,3)), int(rng.integers(1,3)), int(rng.integers(1,3))) if kind not in ("kelvin","tets") else (int(rng.integers(2,5)),)
+        if kind not in ("kelvin","tets") and par==(1,1,1): par=(2,1,1)
     tmp=tempfile.mkdtemp(prefix="fz_")
     try:
         m.write(tmp+"/constant/polyMesh"); os.makedirs(tmp+"/system")
         open(tmp+"/system/controlDict","w").write("startFrom startTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat binary;\n")
         args=[REF,"-case",tmp,"-centroidalIters",str(iters),"-smoothingPatches","()"]+cli
         if par:
-            parts = m.decompose(*par) if kind!="kelvin" else m.decompose(par[0],method="rcb")
+            parts = m.decompose(*par) if kind not in ("kelvin","tets") else m.decompose(par[0],method="rcb")
             sm.Mesh.write_decomposed(parts,tmp,binary=True); args.insert(3,"-parallel")
         r=subprocess.run(args,capture_output=True,text=True,timeout=120)
         log=re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
@@ -103,4 +110,11 @@ def one(seed, verbose=False):
 def test_random_configurations_agree_with_the_reference_translation_unit(block):
     for seed in range(10 * block, 10 * block + 10):
         ok, msg = one(seed)
+        assert ok, msg
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_random_tetrahedral_configurations_agree_with_the_reference_translation_unit(block):
+    for seed in range(5000 + 10 * block, 5000 + 10 * block + 10):
+        ok, msg = one(seed, force_kind="tets")
         assert ok, msg
