@@ -159,6 +159,67 @@ CASES = {
 }
 
 
+def block_mesh(case):
+    """blockMesh restated for the SwiftBlock-generated dictionaries of the reference's test cases: straight
+    edges, uniform grading (every edgeGrading section is (1 n 1)), old-style `patches` list with named patches.
+    Numbering is this builder's, not blockMesh's.  Returns (mesh, patch names)."""
+    txt=open(os.path.join(REF,case,"system","blockMeshDict")).read()
+    sc=re.search(r"(?:scale|convertToMeters)\s+([\d.eE+-]+)\s*;",txt)
+    scale=float(sc.group(1)) if sc else 1.0
+    vtxt=txt[txt.index("vertices"):txt.index("edges")]
+    verts=scale*np.array([[float(x) for x in m] for m in re.findall(r"\(\s*(-?[\d.eE+-]+)\s+(-?[\d.eE+-]+)\s+(-?[\d.eE+-]+)\s*\)", vtxt)])
+    blocks=[([int(x) for x in a.split()],[int(x) for x in b.split()]) for a,b in re.findall(r"hex\s*\(([\d\s]+)\)\s*\(([\d\s]+)\)", txt)]
+    ptxt=txt[txt.index("patches"):]
+    patches=[]
+    for m in re.finditer(r"(\w+)\s+(\w+)\s*\(\s*((?:\(\s*\d+\s+\d+\s+\d+\s+\d+\s*\)\s*)+)\)", ptxt):
+        quads=[tuple(int(x) for x in q.split()) for q in re.findall(r"\(\s*(\d+\s+\d+\s+\d+\s+\d+)\s*\)", m.group(3))]
+        patches.append((m.group(2), m.group(1), quads))
+    key2id, pts = {}, []
+    def pid(x):
+        k=tuple(np.round(x/1e-9).astype(np.int64))
+        if k not in key2id:
+            key2id[k]=len(pts); pts.append(x)
+        return key2id[k]
+    side_sets={0:(0,3,7,4),1:(1,2,6,5),2:(0,1,5,4),3:(3,2,6,7),4:(0,1,2,3),5:(4,5,6,7)}  # u-,u+,v-,v+,w-,w+
+    quad_patch={}
+    for pi,(name,typ,quads) in enumerate(patches):
+        for q in quads:
+            quad_patch[frozenset(q)]=pi
+    cells=[]; face_patch={}
+    for b,(nx,ny,nz) in blocks:
+        c=verts[b]
+        ids=np.zeros((nx+1,ny+1,nz+1),dtype=np.int64)
+        for k in range(nz+1):
+            for j in range(ny+1):
+                for i in range(nx+1):
+                    u,v,w=i/nx,j/ny,k/nz
+                    x=((1-u)*(1-v)*(1-w)*c[0]+u*(1-v)*(1-w)*c[1]+u*v*(1-w)*c[2]+(1-u)*v*(1-w)*c[3]
+                       +(1-u)*(1-v)*w*c[4]+u*(1-v)*w*c[5]+u*v*w*c[6]+(1-u)*v*w*c[7])
+                    ids[i,j,k]=pid(x)
+        side_of={s:quad_patch.get(frozenset(b[v] for v in side_sets[s])) for s in range(6)}
+        for k in range(nz):
+            for j in range(ny):
+                for i in range(nx):
+                    q=lambda a,b_,c_: int(ids[i+a,j+b_,k+c_])
+                    faces=[[q(0,0,0),q(0,0,1),q(0,1,1),q(0,1,0)],[q(1,0,0),q(1,1,0),q(1,1,1),q(1,0,1)],
+                           [q(0,0,0),q(1,0,0),q(1,0,1),q(0,0,1)],[q(0,1,0),q(0,1,1),q(1,1,1),q(1,1,0)],
+                           [q(0,0,0),q(0,1,0),q(1,1,0),q(1,0,0)],[q(0,0,1),q(1,0,1),q(1,1,1),q(0,1,1)]]
+                    onside=[i==0,i==nx-1,j==0,j==ny-1,k==0,k==nz-1]
+                    ci=len(cells)
+                    for s in range(6):
+                        if onside[s] and side_of[s] is not None:
+                            face_patch[(ci,frozenset(faces[s]))]=side_of[s]
+                    cells.append(faces)
+    points=np.array(pts)
+    cells=[orient_outward(points,c) for c in cells]
+    names=[p[0] for p in patches]; types=[p[1] for p in patches]
+    def patch_of(ci,fi,f):
+        return face_patch.get((ci,frozenset(f)), len(names)-1)
+    m=sm.Mesh.from_cells(points,cells,patch_of_face=patch_of,patch_names=names,patch_types=types)
+    return m, names
+
+
+
 def read_obj(path):
     """Vertices, polyline edges and (fan-triangulated) faces of a Wavefront OBJ file."""
     v, e, t = [], [], []
@@ -235,9 +296,85 @@ def boundary_fixture():
         shutil.rmtree(tmp, ignore_errors=True)
 
 
+# The other test cases of the reference that run boundary point smoothing, exactly as their run_serial scripts
+# invoke the tool (blockMesh restated by block_mesh(); testcase6 needs createBaffles / extrudeMesh and is not
+# restated).  (command line, the same options for the oracle, iteration cap, keep as committed fixture?)
+SHIPPED = {
+    # testcase3 (-relTol 1e-8 -centroidalIters 200 -minAngle 15; 39 711 points, 7 200 target triangles) does not run
+    # under the facade: the visit-every-triangle findLine stand-in has no tolerance at triangle edges and one ray
+    # through a seam of the target surface finds no intersection in the first iteration (OpenFOAM's octree search
+    # is tolerant there).
+    "testcase5": (["-centroidalIters", "500", "-minAngle", "15", "-layerExpansionRatio", "1.2", "-layerEdgeLength", "0.05",
+                   "-maxLayers", "3", "-layerPatches", '("top")', "-smoothingPatches", '(".*")'],
+                  dict(min_angle_deg=15.0, layer_expansion_ratio=1.2, layer_edge_length=0.05, max_layers=3), 500, True),
+    "testcase7": (["-centroidalIters", "100", "-layerPatches", "(walls)"], dict(), 100, False),
+    "testcase8": (["-centroidalIters", "50"], dict(), 50, True),
+}
+
+
+def shipped_boundary_cases(which=None):
+    """Runs every case of SHIPPED through the reference's translation unit (oracle/_ref) and through the oracle and
+    insists on identical logs and points; the small ones are committed as fixtures (<case>_boundary.npz) so that the
+    comparison can be repeated without /root/reference, the large one (testcase7: 31 361 points)
+    is only checked here."""
+    import shutil
+    import subprocess
+    import tempfile
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")
+    for case, (cli, okw, iters, keep) in SHIPPED.items():
+        if which and case not in which:
+            continue
+        mesh, names = block_mesh(case)
+        tmp = tempfile.mkdtemp(prefix="golden_" + case + "_")
+        try:
+            mesh.write(os.path.join(tmp, "constant", "polyMesh"))
+            os.makedirs(os.path.join(tmp, "system"))
+            os.makedirs(os.path.join(tmp, "constant", "geometry"))
+            open(os.path.join(tmp, "system", "controlDict"), "w").write("startFrom startTime;\nstartTime 0;\ndeltaT 1;\nwriteFormat binary;\n")
+            geo, out = {}, {}
+            for f, key in (("initEdges.obj", "init_edges"), ("targetEdges.obj", "target_edges"), ("targetSurfaces.obj", "target_surfaces")):
+                path = os.path.join(REF, case, "constant", "geometry", f)
+                if not os.path.exists(path):
+                    continue
+                v, e, t = read_obj(path)
+                write_obj(os.path.join(tmp, "constant", "geometry", f), v, e, t, key)
+                out[key + "_points"], out[key + "_edges"], out[key + "_tris"] = v, e, t
+                geo["surface" if key == "target_surfaces" else key] = (v, t if key == "target_surfaces" else e)
+            geo.setdefault("target_edges", geo["init_edges"])
+            r = subprocess.run([ref_bin, "-case", tmp] + cli, capture_output=True, text=True, check=True)
+            log = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+            n = int(log[-1][0])
+            final = sm.Mesh.read(os.path.join(tmp, "constant", "polyMesh"))
+            final.read_points(os.path.join(tmp, str(n), "polyMesh", "points"))
+            layer = None
+            if "-layerPatches" in cli:
+                expr = cli[cli.index("-layerPatches") + 1]
+                layer = [1 if nm in expr else 0 for nm in names]
+            o = Oracle(mesh.desc_arrays(), libm=True, layer_patches=layer, smoothing_patches=[1] * len(names), geometry=geo, **okw)
+            on, onf, _ = o.iterate(iters)
+            assert on == n and [int(b) for _, b, _ in log] == onf.tolist(), case
+            assert np.array_equal(np.array(final.points), o.get("points")), case
+            print(f"{case}: {mesh.n_points} points, {n} iterations, oracle == reference translation unit (log and points)")
+            if keep:
+                a = mesh.desc_arrays()
+                out.update(points=a["points"], face_offsets=a["face_offsets"], face_verts=a["face_verts"], owner=a["owner"],
+                           neighbour=a["neighbour"], n_cells=np.int64(a["n_cells"]), patch_start=a["patch_start"],
+                           patch_size=a["patch_size"], patch_kind=a["patch_kind"], patch_names=np.array(names), cli=np.array(cli),
+                           layer_patches=np.array(layer if layer else [], dtype=np.int32),
+                           opt_keys=np.array(sorted(okw)), opt_vals=np.array([float(okw[k]) for k in sorted(okw)]),
+                           iterations=np.int64(n), n_frozen=np.array([int(b) for _, b, _ in log]),
+                           residual=np.array([float(c) for _, _, c in log]), final_points=np.array(final.points))
+                path = os.path.join(HERE, f"{case}_boundary.npz")
+                np.savez_compressed(path, **out)
+                print(f"    wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
 def main():
     if os.path.exists(os.path.join(ROOT, "oracle", "_ref", "smoothMesh_ref")):
         boundary_fixture()
+        shipped_boundary_cases()
     for name, (build, kw, iters) in CASES.items():
         mesh = build()
         a = mesh.desc_arrays()
