@@ -90,3 +90,25 @@ def test_boundary_smoothing_refusals():
     gp = sm.Smoother(parts[0])
     with pytest.raises(sm.SmoothMeshError, match="single-GPU"):
         gp.enable_boundary_smoothing(dict(init_edges=(ip, ie), target_edges=(ip, ie), surface=(tc, tt)), [1] * 6)
+
+
+@pytest.mark.parametrize("case", ["testcase5", "testcase8"])
+def test_shipped_boundary_cases(case):
+    """testcase5/run_serial (500 iterations: layer treatment on `top`, boundary point smoothing with eight corner
+    points) and testcase8/run_serial exactly as shipped; fixtures produced by the reference's own translation unit."""
+    d = np.load(os.path.join(ROOT, "tests", "golden", f"{case}_boundary.npz"))
+    mesh = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
+                               d["patch_start"], d["patch_size"], d["patch_kind"])
+    target = "target_edges" if "target_edges_points" in d.files else "init_edges"
+    geo = dict(init_edges=(d["init_edges_points"], d["init_edges_edges"]),
+               target_edges=(d[target + "_points"], d[target + "_edges"]),
+               surface=(d["target_surfaces_points"], d["target_surfaces_tris"]))
+    okw = {str(k): float(v) for k, v in zip(d["opt_keys"], d["opt_vals"])}
+    for k in ("max_layers", "min_layers"):
+        if k in okw:
+            okw[k] = int(okw[k])
+    g = sm.Smoother(mesh, layer_patches=d["layer_patches"].tolist() or None, **okw)
+    g.enable_boundary_smoothing(geo, [1] * len(d["patch_start"]))
+    log = g.iterate(int(d["cli"][list(d["cli"]).index("-centroidalIters") + 1]))
+    assert log.iterations == int(d["iterations"]) and np.array_equal(log.n_frozen, d["n_frozen"])
+    assert np.array_equal(g.points(), d["final_points"])
