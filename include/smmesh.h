@@ -96,6 +96,13 @@ extern "C"
     int smmesh_layer_setup(const smmesh *m, const int32_t *patch_layer, int32_t max_layers, int32_t *hops,
                            int32_t *point_to_outer, int32_t *normal_source);
 
+    /* Surface ray casts (the findLine of boundary point smoothing): nearest intersection of each segment
+     * start[i] -> end[i] with the triangles, by visiting every triangle (use_bvh = 0, the reference definition
+     * shared with the device kernel and the oracle) or through the bounding volume hierarchy of boundary.hpp
+     * (use_bvh = 1), which must return the same triangle and the same point.  hit_tri[i] = -1 when there is none. */
+    int smmesh_ray_cast(int64_t n_points, const double *points, int64_t n_tris, const int32_t *tris, int64_t n_rays,
+                        const double *start, const double *end, int32_t use_bvh, int32_t *hit_tri, double *hit_point);
+
     /* labelIOList files next to the mesh (the isCornerPoint / isFeatureEdgePoint lists the reference keeps
      * between runs, src/smoothMesh.C:2039-2065): read returns the length (or -1 when the file is absent /
      * unreadable) and fills `data` when it is non-NULL; write emits OpenFOAM's `N{v}` form for uniform lists. */

@@ -379,4 +379,177 @@ BoundarySetup buildBoundarySetup(const PolyMesh &m, const Topology &t, const std
     return B;
 }
 
+
+// ------------------------------------------------------------------ surface ray casts ----
+namespace
+{
+inline V crossV(V a, V b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+// Moeller-Trumbore segment / triangle test, the operation order shared with the device kernel and the oracle
+inline bool triangleHit(const TriSurface &s, int32_t i, V start, V dir, double &t)
+{
+    const V p0 = at(s.points, s.tris[3 * i]), p1 = at(s.points, s.tris[3 * i + 1]), p2 = at(s.points, s.tris[3 * i + 2]);
+    const V e1 = p1 - p0, e2 = p2 - p0;
+    const V h = crossV(dir, e2);
+    const double det = dot(e1, h);
+    if (std::fabs(det) < SM_VSMALL)
+        return false;
+    const double inv = 1.0 / det;
+    const V sv = start - p0;
+    const double u = inv * dot(sv, h);
+    if (u < 0.0 || u > 1.0)
+        return false;
+    const V q = crossV(sv, e1);
+    const double v = inv * dot(dir, q);
+    if (v < 0.0 || u + v > 1.0)
+        return false;
+    t = inv * dot(e2, q);
+    return !(t < 0.0 || t > 1.0);
+}
+} // namespace
+
+TriangleBvh buildTriangleBvh(const TriSurface &s, int leafSize)
+{
+    TriangleBvh B;
+    const int32_t n = (int32_t)s.nTris();
+    B.order.resize(n);
+    for (int32_t i = 0; i < n; ++i)
+        B.order[i] = i;
+    std::vector<double> lo(3 * (size_t)n), hi(3 * (size_t)n), ctr(3 * (size_t)n);
+    for (int32_t i = 0; i < n; ++i)
+        for (int d = 0; d < 3; ++d)
+        {
+            const double a = s.points[3 * (size_t)s.tris[3 * i] + d], b = s.points[3 * (size_t)s.tris[3 * i + 1] + d],
+                         c = s.points[3 * (size_t)s.tris[3 * i + 2] + d];
+            lo[3 * (size_t)i + d] = std::min(a, std::min(b, c));
+            hi[3 * (size_t)i + d] = std::max(a, std::max(b, c));
+            ctr[3 * (size_t)i + d] = (a + b + c) / 3.0;
+        }
+    struct Job
+    {
+        int32_t node, first, count;
+    };
+    std::vector<Job> stack;
+    auto newNode = [&]() {
+        B.box.resize(B.box.size() + 6);
+        B.left.push_back(-1);
+        B.right.push_back(-1);
+        B.first.push_back(0);
+        B.count.push_back(0);
+        return (int32_t)B.right.size() - 1;
+    };
+    if (n == 0)
+        return B;
+    stack.push_back({newNode(), 0, n});
+    while (!stack.empty())
+    {
+        const Job j = stack.back();
+        stack.pop_back();
+        double blo[3] = {SM_VGREAT, SM_VGREAT, SM_VGREAT}, bhi[3] = {-SM_VGREAT, -SM_VGREAT, -SM_VGREAT};
+        double clo[3] = {SM_VGREAT, SM_VGREAT, SM_VGREAT}, chi[3] = {-SM_VGREAT, -SM_VGREAT, -SM_VGREAT};
+        for (int32_t k = j.first; k < j.first + j.count; ++k)
+            for (int d = 0; d < 3; ++d)
+            {
+                const size_t q = 3 * (size_t)B.order[k] + d;
+                blo[d] = std::min(blo[d], lo[q]);
+                bhi[d] = std::max(bhi[d], hi[q]);
+                clo[d] = std::min(clo[d], ctr[q]);
+                chi[d] = std::max(chi[d], ctr[q]);
+            }
+        for (int d = 0; d < 3; ++d)
+        { // inflate: the slab test must never reject a segment that a triangle test would accept
+            const double pad = 1e-9 * (std::fabs(blo[d]) + std::fabs(bhi[d]) + (bhi[d] - blo[d])) + 1e-300;
+            B.box[6 * (size_t)j.node + d] = blo[d] - pad;
+            B.box[6 * (size_t)j.node + 3 + d] = bhi[d] + pad;
+        }
+        int axis = 0;
+        for (int d = 1; d < 3; ++d)
+            if (chi[d] - clo[d] > chi[axis] - clo[axis])
+                axis = d;
+        if (j.count <= leafSize || !(chi[axis] > clo[axis]))
+        {
+            B.first[j.node] = j.first;
+            B.count[j.node] = j.count;
+            continue;
+        }
+        const int32_t mid = j.first + j.count / 2;
+        std::nth_element(B.order.begin() + j.first, B.order.begin() + mid, B.order.begin() + j.first + j.count,
+                         [&](int32_t a, int32_t b) {
+                             const double ca = ctr[3 * (size_t)a + axis], cb = ctr[3 * (size_t)b + axis];
+                             return ca < cb || (ca == cb && a < b);
+                         });
+        const int32_t left = newNode();
+        const int32_t right = newNode();
+        B.left[j.node] = left;
+        B.right[j.node] = right;
+        stack.push_back({right, mid, j.first + j.count - mid});
+        stack.push_back({left, j.first, mid - j.first});
+    }
+    return B;
+}
+
+int32_t segmentSurfaceHit(const TriSurface &s, const TriangleBvh *bvh, const double startA[3], const double endA[3], double hit[3])
+{
+    const V start = {startA[0], startA[1], startA[2]}, end = {endA[0], endA[1], endA[2]};
+    const V dir = end - start;
+    double best = 2.0;
+    int32_t bestI = -1;
+    auto consider = [&](int32_t i) {
+        double t;
+        if (triangleHit(s, i, start, dir, t) && (t < best || (t == best && i < bestI)))
+        {
+            best = t;
+            bestI = i;
+        }
+    };
+    if (!bvh)
+        for (int32_t i = 0; i < (int32_t)s.nTris(); ++i)
+            consider(i);
+    else if (!bvh->right.empty())
+    {
+        const double o[3] = {start.x, start.y, start.z}, dv[3] = {dir.x, dir.y, dir.z};
+        std::vector<int32_t> stack(1, 0);
+        while (!stack.empty())
+        {
+            const int32_t node = stack.back();
+            stack.pop_back();
+            // slab test of the segment parameter range [0, min(1, best)] against the inflated box
+            double t0 = 0.0, t1 = best < 1.0 ? best : 1.0;
+            bool miss = false;
+            for (int d = 0; d < 3 && !miss; ++d)
+            {
+                const double lo = bvh->box[6 * (size_t)node + d], hi = bvh->box[6 * (size_t)node + 3 + d];
+                if (dv[d] == 0.0)
+                    miss = o[d] < lo || o[d] > hi;
+                else
+                {
+                    double a = (lo - o[d]) / dv[d], b = (hi - o[d]) / dv[d];
+                    if (a > b)
+                        std::swap(a, b);
+                    // one ulp-scale slack on the parametric bounds keeps the test conservative
+                    a -= 1e-12 * (1.0 + std::fabs(a));
+                    b += 1e-12 * (1.0 + std::fabs(b));
+                    t0 = a > t0 ? a : t0;
+                    t1 = b < t1 ? b : t1;
+                    miss = t0 > t1;
+                }
+            }
+            if (miss)
+                continue;
+            if (bvh->right[node] < 0)
+                for (int32_t k = bvh->first[node]; k < bvh->first[node] + bvh->count[node]; ++k)
+                    consider(bvh->order[k]);
+            else
+            {
+                stack.push_back(bvh->right[node]);
+                stack.push_back(bvh->left[node]);
+            }
+        }
+    }
+    if (bestI < 0)
+        return -1;
+    const V p = start + best * dir;
+    hit[0] = p.x, hit[1] = p.y, hit[2] = p.z;
+    return bestI;
+}
+
 } // namespace sm

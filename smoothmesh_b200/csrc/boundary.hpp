@@ -33,6 +33,24 @@ struct TriSurface
 // Wavefront OBJ: "v", "l" (polylines) and "f" (fan-triangulated) records
 void readObj(const std::string &file, std::vector<double> &points, std::vector<int32_t> &edges, std::vector<int32_t> &tris);
 
+// Bounding volume hierarchy over the target triangles: the acceleration structure for the surface ray casts
+// (findLine).  It changes which triangles are tested, never the arithmetic of a test nor the choice among hits
+// (smallest parameter, lower triangle label on ties), so a traversal returns exactly what the visit-every-triangle
+// search returns.  Host builder and host traversal (the device kernel still visits every triangle; porting the
+// traversal is the next step for large surfaces).
+struct TriangleBvh
+{
+    // node i: box lo/hi (6 doubles, slightly inflated), then either two children or a leaf
+    std::vector<double> box;           // 6 per node
+    std::vector<int32_t> left, right;  // internal node: child nodes; leaf: -1
+    std::vector<int32_t> first, count; // leaf: range in `order`
+    std::vector<int32_t> order;  // triangle labels, leaf ranges are contiguous
+};
+TriangleBvh buildTriangleBvh(const TriSurface &s, int leafSize = 4);
+// the intersection of the segment start -> end with the surface that is nearest to start: returns the triangle
+// label (-1 = none) and the hit point; `useBvh = false` visits every triangle (the reference definition)
+int32_t segmentSurfaceHit(const TriSurface &s, const TriangleBvh *bvh, const double start[3], const double end[3], double hit[3]);
+
 struct BoundarySetup
 {
     EdgeMesh targetEdges;

@@ -381,6 +381,30 @@ extern "C"
         }
         return SMGPU_OK;
     }
+    int smmesh_ray_cast(int64_t n_points, const double *points, int64_t n_tris, const int32_t *tris, int64_t n_rays,
+                        const double *start, const double *end, int32_t use_bvh, int32_t *hit_tri, double *hit_point)
+    {
+        try
+        {
+            sm::TriSurface s;
+            s.points.assign(points, points + 3 * n_points);
+            s.tris.assign(tris, tris + 3 * n_tris);
+            const sm::TriangleBvh bvh = use_bvh ? sm::buildTriangleBvh(s) : sm::TriangleBvh();
+#pragma omp parallel for schedule(dynamic, 64)
+            for (int64_t i = 0; i < n_rays; ++i)
+            {
+                double h[3] = {0, 0, 0};
+                hit_tri[i] = sm::segmentSurfaceHit(s, use_bvh ? &bvh : nullptr, start + 3 * i, end + 3 * i, h);
+                hit_point[3 * i] = h[0], hit_point[3 * i + 1] = h[1], hit_point[3 * i + 2] = h[2];
+            }
+        }
+        catch (const std::exception &e)
+        {
+            g_merr = e.what();
+            return SMGPU_ERR_MESH;
+        }
+        return SMGPU_OK;
+    }
     int64_t smmesh_read_label_list(const char *file, int32_t *data, int64_t capacity)
     {
         try

@@ -268,3 +268,51 @@ def test_layer_setup_matches_the_oracle(seed):
     o.iterate(1)
     has_normal = np.abs(o.get("snapNormals")).sum(axis=1) > 0
     assert np.array_equal(has_normal[internal], (L["normal_source"] >= 0)[internal])
+
+
+def test_bvh_ray_casts_equal_the_visit_every_triangle_search():
+    """The triangle BVH of boundary.cpp (acceleration structure for the surface ray casts of boundary point
+    smoothing) must return exactly what the reference definition returns -- same triangle, same hit point, bit for
+    bit -- on random segments against a random triangle soup, a closed sphere-like surface (rays through shared
+    edges and vertices included) and the target surface of testcase4."""
+    import ctypes as C
+    L = sm.lib()
+    L.smmesh_ray_cast.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(7)
+
+    def cast(pts, tris, a, b, use_bvh):
+        pts, tris = np.ascontiguousarray(pts, np.float64), np.ascontiguousarray(tris, np.int32)
+        a, b = np.ascontiguousarray(a, np.float64), np.ascontiguousarray(b, np.float64)
+        ht, hp = np.zeros(len(a), np.int32), np.zeros((len(a), 3))
+        p = lambda x: x.ctypes.data_as(C.c_void_p)
+        assert L.smmesh_ray_cast(len(pts), p(pts), len(tris), p(tris), len(a), p(a), p(b), use_bvh, p(ht), p(hp)) == 0
+        return ht, hp
+
+    surfaces = []
+    soup = rng.uniform(-1, 1, size=(900, 3))
+    surfaces.append((soup, np.arange(900).reshape(-1, 3)))
+    # lat-long sphere: many triangles share vertices and edges
+    nu, nv = 24, 12
+    sp = np.array([[np.cos(2 * np.pi * i / nu) * np.sin(np.pi * j / nv), np.sin(2 * np.pi * i / nu) * np.sin(np.pi * j / nv),
+                    np.cos(np.pi * j / nv)] for j in range(nv + 1) for i in range(nu)])
+    st = []
+    for j in range(nv):
+        for i in range(nu):
+            a, b = j * nu + i, j * nu + (i + 1) % nu
+            st += [[a, b, a + nu], [b, b + nu, a + nu]]
+    surfaces.append((sp, np.array(st)))
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "testcase4_boundary.npz"))
+    surfaces.append((d["target_surfaces_points"], d["target_surfaces_tris"]))
+    for pts, tris in surfaces:
+        lo, hi = pts.min(axis=0) - 0.2, pts.max(axis=0) + 0.2
+        a = rng.uniform(lo, hi, size=(4000, 3))
+        b = rng.uniform(lo, hi, size=(4000, 3))
+        # segments that start on mesh vertices / pass through vertices and edge midpoints: ties between triangles
+        v = pts[rng.integers(0, len(pts), size=500)]
+        a = np.concatenate([a, v - 0.3 * (v - pts.mean(axis=0)), v])
+        b = np.concatenate([b, v + 0.3 * (v - pts.mean(axis=0)), v + rng.normal(size=(500, 3))])
+        t0, p0 = cast(pts, tris, a, b, 0)
+        t1, p1 = cast(pts, tris, a, b, 1)
+        assert (t0 >= 0).sum() > 100
+        assert np.array_equal(t0, t1) and np.array_equal(p0, p1)
