@@ -205,9 +205,12 @@ def reference_binary_rate(n_side=40, iters=(1, 5), procs=1):
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be
-    built here (OpenFOAM + wmake absent), so this times the oracle port with all host threads in
-    rank-emulation mode (the reference's `mpirun` strategy) on bounded samples of the workload."""
+    """--impl reference: the reference's CPU implementation of the path.  A real build of the reference needs
+    OpenFOAM + wmake; its translation unit compiled against the OpenFOAM facade (oracle/_ref) is bit-identical to
+    the oracle port but slower (single-threaded containers, one process per rank), so the line's value is the
+    faster, hence conservative, arm: the oracle port with all host threads in rank-emulation mode (the reference's
+    `mpirun` strategy) on bounded samples of the workload.  The rates of oracle/_ref itself, serial and as rank
+    processes, are reported next to it in cpu_baseline."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
