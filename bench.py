@@ -207,10 +207,10 @@ def reference_binary_rate(n_side=40, iters=(1, 5), procs=1):
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path.  A real build of the reference needs
     OpenFOAM + wmake; its translation unit compiled against the OpenFOAM facade (oracle/_ref) is bit-identical to
-    the oracle port but slower (single-threaded containers, one process per rank), so the line's value is the
-    faster, hence conservative, arm: the oracle port with all host threads in rank-emulation mode (the reference's
-    `mpirun` strategy) on bounded samples of the workload.  The rates of oracle/_ref itself, serial and as rank
-    processes, are reported next to it in cpu_baseline."""
+    the oracle port.  When that binary exists it is what this arm times: `-parallel` with one process per host core
+    (the reference's `mpirun` strategy), loop time = difference of two runs; the (faster) oracle port's rate is
+    reported next to it in cpu_baseline.port.  Without the binary the oracle port is timed in rank-emulation mode
+    with all host threads on a bounded sample."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
@@ -231,6 +231,37 @@ def run_reference(args, rank, world):
         mesh = sm.Mesh.hex_block(n_side, n_side, n_side).jitter(JITTER / n_side, SEED)
         parts = mesh.decompose(*dims) if p2 > 1 else [mesh]
         return mesh, Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, threads=p2)
+
+    # the reference's own translation unit (oracle/_ref) as one process per host core, when it was built
+    if os.path.exists(REF_BIN) and not os.environ.get("SMBENCH_REFERENCE_PORT"):
+        n_ref = args.ref_n if args.ref_n > 0 else 64
+        warm = max(args.warmup, 1)
+        ref = reference_binary_rate(n_side=n_ref, iters=(warm, warm + args.steps), procs=p2)
+        if ref is not None:
+            mesh, o = build(32)
+            t0 = time.perf_counter()
+            o.iterate(4)
+            port_rate = mesh.n_points * 4 / (time.perf_counter() - t0)
+            value = ref["value"]
+            pts_ref = (n_ref + 1) ** 3
+            line = {
+                "impl": "reference", "metric": "mesh point-updates/s per smoothing iteration", "value": value,
+                "unit": "point-updates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
+                "ms_per_step": 1e3 * pts_ref / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"hex {n_ref}^3 jittered block (bounded sample of the 200^3 config), all constraints on",
+                           "decomposition": ref["sample"].split("(")[-1].rstrip(")") if "bricks" in ref["sample"] else "1x1x1",
+                           "note": "the reference's own translation unit (src/smoothMesh.C compiled in place against the OpenFOAM "
+                                   "facade, oracle/_ref) run as `-parallel` rank processes; the loop time is the difference of two "
+                                   "runs (warm-up only / warm-up + steps), which cancels mesh reading and set-up"},
+                "cpu_baseline": {"value": value, "unit": "point-updates/s", "cores": ref["cores"], "kind": "reference",
+                                 "sample": ref["sample"],
+                                 "port": {"value": port_rate, "unit": "point-updates/s", "cores": p2, "kind": "port",
+                                          "sample": "4 iterations of a jittered 32^3 hex block, oracle port in rank emulation"}},
+                "e2e": {"value": value, "unit": "point-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }
+            print(json.dumps(line), flush=True)
+            return
 
     # bounded sample: size the block so that warmup + steps iterations take about args.ref_budget
     # seconds at the rate calibrated on a 32^3 block (per-point cost is size independent)
