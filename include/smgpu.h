@@ -186,7 +186,10 @@ extern "C"
     int smgpu_op_face_angle_constraint(smgpu_handle *h, uint8_t *frozen_out /* or NULL */);
     /* restore + count + calculateResidual + movePoints (:2384-2399) */
     int smgpu_op_commit(smgpu_handle *h, int64_t *n_frozen, double *residual);
-    /* calculateBoundaryPointNormals (src/orthogonalBoundaryBlending.C:141-233), the call at :2266 */
+    /* calculateBoundaryPointNormals (src/orthogonalBoundaryBlending.C:141-233), the call at :2266.  The reference
+     * accumulates onto the previous call's normals (:178); this probe returns what the next call would produce and
+     * leaves the handle's normals untouched.  The other smgpu_op_* entry points work on the handle's live state
+     * (newPoints, isFrozenPoint, the face-angle work space) like the reference functions they stand for. */
     int smgpu_op_layer_normals(smgpu_handle *h, double *normals_out /* [3*n_points] or NULL */);
     /* updateNeighCoords + blendWithOrthogonalPoints + constrainMaxStepLength (:2283-2305) */
     int smgpu_op_layer_blend(smgpu_handle *h, double *new_points_out /* [3*n_points] or NULL */);
@@ -213,6 +216,31 @@ extern "C"
     int smgpu_comm_local_shared(smgpu_handle *h, int64_t *n, int64_t *gids_out /* or NULL */);
     int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t nccl_unique_id[128],
                         const int64_t *counts, const int64_t *all_gids);
+
+    /* Two-step form of the start-up for hosts that can agree on the outcome before anything collective runs:
+     * smgpu_comm_prepare is purely local (exchange plan, buffers; fails on a mesh without point_global_id or on a
+     * point shared by too many ranks), so the host can all-reduce its status and skip smgpu_comm_init on every
+     * rank when any rank failed -- a rank that fails inside a one-step smgpu_comm_init would leave the others
+     * waiting in ncclCommInitRank.  smgpu_comm_init after a successful prepare only does the collective half
+     * (its counts / all_gids arguments are then ignored). */
+    int smgpu_comm_prepare(smgpu_handle *h, int32_t rank, int32_t n_ranks, const int64_t *counts, const int64_t *all_gids);
+    /* ncclCommAbort on this handle's communicator: releases kernels that wait for a peer which failed.  The
+     * handle can only be destroyed afterwards. */
+    int smgpu_comm_abort(smgpu_handle *h);
+
+    /* ---- in-process group: several processor meshes on ONE device ----------------------
+     * The same decomposed-case semantics (every member is one of the reference's MPI ranks) without NCCL: the
+     * members are handles of this process on one device, driven by one host thread; the interface exchanges are
+     * stream-ordered device copies between the members' buffers and the two reductions one small kernel.  Use:
+     * a decomposed case with more processor directories than GPUs (the CLI's -parallel falls back to it), and
+     * the parity tests of the exchange kernels on a single-GPU box.  handles[r] is rank r; every handle must be
+     * freshly created from a processor mesh (with point_global_id) on the same device.  The group does not own
+     * the handles: destroy the group first, then the handles.  Results per member through smgpu_get_points /
+     * smgpu_get_frozen; smgpu_iterate on a member is refused. */
+    typedef struct smgpu_group smgpu_group;
+    int smgpu_group_create(smgpu_handle **handles, int32_t n, smgpu_group **out);
+    int smgpu_group_iterate(smgpu_group *g, int32_t max_iters, int64_t *n_frozen, double *residual, int32_t *iters_done);
+    int smgpu_group_destroy(smgpu_group *g);
 
     /* Host-only helper (no GPU needed): the exchange plan smgpu_comm_init would build, as
      * flat arrays, so that host-side logic can be tested without devices.  local[i] / gids[i]

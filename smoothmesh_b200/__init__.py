@@ -122,6 +122,11 @@ def lib():
         L.smgpu_comm_unique_id.argtypes = [C.c_void_p]
         L.smgpu_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_comm_local_shared.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_comm_prepare.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.smgpu_comm_abort.argtypes = [C.c_void_p]
+        L.smgpu_group_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.smgpu_group_iterate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_group_destroy.argtypes = [C.c_void_p]
         L.smgpu_exchange_plan.restype = C.c_int64
         L.smgpu_exchange_plan.argtypes = [C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 6
         L.smmesh_quality.argtypes = [C.c_void_p, C.c_void_p]
@@ -608,6 +613,14 @@ class Smoother:
         self._ck(lib().smgpu_comm_local_shared(self._h, C.byref(n), _ptr(g)))
         return g[:n.value]
 
+    def comm_prepare(self, rank, n_ranks, counts, all_gids):
+        """Local half of the start-up (exchange plan, buffers); raises without touching any other rank."""
+        counts = np.ascontiguousarray(counts, dtype=np.int64)
+        all_gids = np.ascontiguousarray(all_gids, dtype=np.int64)
+        if all_gids.size == 0:
+            all_gids = np.zeros(1, dtype=np.int64)
+        self._ck(lib().smgpu_comm_prepare(self._h, rank, n_ranks, _ptr(counts), _ptr(all_gids)))
+
     def comm_init(self, rank, n_ranks, unique_id: bytes, counts, all_gids):
         buf = (C.c_uint8 * 128)(*unique_id)
         counts = np.ascontiguousarray(counts, dtype=np.int64)
@@ -615,6 +628,42 @@ class Smoother:
         if all_gids.size == 0:
             all_gids = np.zeros(1, dtype=np.int64)
         self._ck(lib().smgpu_comm_init(self._h, rank, n_ranks, buf, _ptr(counts), _ptr(all_gids)))
+
+    def comm_abort(self):
+        self._ck(lib().smgpu_comm_abort(self._h))
+
+
+class Group:
+    """In-process group (include/smgpu.h: smgpu_group_*): the processor meshes of one decomposed case as
+    Smoothers on ONE device, rank = position in the list; the reference's `mpirun -np N` semantics without NCCL."""
+
+    def __init__(self, smoothers):
+        self.members = list(smoothers)
+        arr = (C.c_void_p * len(self.members))(*[s._h for s in self.members])
+        h = C.c_void_p()
+        rc = lib().smgpu_group_create(arr, len(self.members), C.byref(h))
+        if rc != 0:
+            raise SmoothMeshError(f"smgpu_group_create failed ({rc}): {lib().smgpu_last_error().decode()}")
+        self._h = h
+
+    def iterate(self, max_iters) -> IterationLog:
+        nf = np.zeros(max(max_iters, 1), dtype=np.int64)
+        res = np.zeros(max(max_iters, 1), dtype=np.float64)
+        done = C.c_int32()
+        rc = lib().smgpu_group_iterate(self._h, int(max_iters), _ptr(nf), _ptr(res), C.byref(done))
+        if rc != 0:
+            raise SmoothMeshError(f"libsmgpu error {rc}: {lib().smgpu_last_error().decode()}")
+        ms, ln = C.c_double(), C.c_int64()
+        lib().smgpu_last_timing(self.members[0]._h, C.byref(ms), C.byref(ln))
+        n = done.value
+        return IterationLog(n, nf[:n].copy(), res[:n].copy(), ms.value, ln.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().smgpu_group_destroy(self._h)
+            self._h = None
+
+    __del__ = close
 
 
 def exchange_plan(rank, n_ranks, local, gids, counts, all_gids):

@@ -48,7 +48,10 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
     const bool internal = self.w != 0.0;
     PointLocal L;
     pointLocal(d, p, x, internal, L);
-    const bool hc = shareCell(d, L.n1, L.n2);
+    // topology.cpp refuses meshes with a point that has fewer than two eligible neighbours (the reference's
+    // "Failed to find cLabel" abort, src/smoothMesh.C:354-362), so n1/n2 are labels here; the guard keeps
+    // the walk inside the table even if that invariant were ever broken
+    const bool hc = (L.n1 >= 0 && L.n2 >= 0) && shareCell(d, L.n1, L.n2);
     double *r = c.sendBuf + (size_t)i * c.tuple;
     r[0] = L.sum.x, r[1] = L.sum.y, r[2] = L.sum.z;
     r[3] = (double)L.nCells;
@@ -279,11 +282,15 @@ __global__ void k_finish_iter(Dev d, CommDev c)
 namespace sm
 {
 
+struct LocalGroup;
 struct Comm
 {
     ncclComm_t nccl = nullptr;
     ExchangePlan plan;
     smk::CommDev c;
+    // in-process group (smgpu_group_*): the ranks are handles of this process driven by one host thread on one
+    // stream; exchanges are stream-ordered device copies between the members' buffers instead of NCCL calls
+    LocalGroup *group = nullptr;
     // the predictor exchange runs on its own stream, fenced by these events, so that kernels that do not
     // need its result keep the GPU busy meanwhile
     cudaStream_t xStream = nullptr;
@@ -301,6 +308,8 @@ struct Comm
 static void haloExchange(Comm *cm, cudaStream_t stream, const void *send, void *recv, size_t elemBytes)
 {
     const ExchangePlan &pl = cm->plan;
+    if (cm->group)
+        throw std::runtime_error("internal: NCCL exchange requested for a member of an in-process group");
     NCK(nccl().GroupStart());
     for (size_t j = 0; j < pl.nbrRank.size(); ++j)
     {

@@ -24,6 +24,7 @@ namespace sm
 {
 struct Comm;
 static void commSetupLayers(Comm *cm, struct ::smgpu_handle *h);
+static bool commIsGroupMember(const Comm *cm);
 }
 
 static thread_local std::string g_err;
@@ -369,6 +370,9 @@ struct smgpu_handle
         if (layersParallel)
         {
             // processor mesh: the set-up synchronises with the other ranks (sm::commSetupLayers)
+            if (comm && sm::commIsGroupMember(comm))
+                throw std::runtime_error("the layer set-up of an in-process group is collective: re-create the group "
+                                         "instead of calling smgpu_set_points on one member");
             if (comm)
                 sm::commSetupLayers(comm, this);
             return;
@@ -436,16 +440,92 @@ struct smgpu_handle
         CK(cudaMemsetAsync(d.done, 0, sizeof(int), stream));
         CK(cudaMemsetAsync(d.iter, 0, sizeof(int), stream));
     }
+    // conditions on which the reference aborts inside the loop, raised by a kernel through d.errFlag
+    int checkErrFlag()
+    {
+        int errFlag = 0;
+        CK(cudaMemcpy(&errFlag, d.errFlag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (!errFlag)
+            return SMGPU_OK;
+        static const char *msg[] = {"", "Sanity broken, outerNeighCoord is undefined for an interface point "
+                                        "(src/orthogonalBoundaryBlending.C:537)",
+                                    "Internal sanity check failed: Did not find any edges with the required string index "
+                                    "(src/boundaryPointSmoothing.C:257)",
+                                    "pointNormal is zero for a smoothing surface point (src/boundaryPointSmoothing.C:691)",
+                                    "Did not find surface intersection for a boundary point (src/boundaryPointSmoothing.C:934)",
+                                    "A smoothing surface point has zero point normal (src/orthogonalBoundaryBlending.C:611)"};
+        CK(cudaMemset(d.errFlag, 0, sizeof(int)));
+        return setErr(SMGPU_ERR_MESH, msg[(errFlag >= 1 && errFlag <= 5) ? errFlag : 1]);
+    }
+    // per-iteration log of the last run (what the reference prints at src/smoothMesh.C:2396)
+    int fetchStats(int64_t *n_frozen, double *residual, int32_t *iters_done)
+    {
+        int it = 0;
+        CK(cudaMemcpy(&it, d.iter, sizeof(int), cudaMemcpyDeviceToHost));
+        if (iters_done)
+            *iters_done = it;
+        if (it > 0 && residual)
+            CK(cudaMemcpy(residual, d.statRes, it * sizeof(double), cudaMemcpyDeviceToHost));
+        if (it > 0 && n_frozen)
+        {
+            std::vector<long long> tmp(it);
+            CK(cudaMemcpy(tmp.data(), d.statFrozen, it * sizeof(long long), cudaMemcpyDeviceToHost));
+            for (int i = 0; i < it; ++i)
+                n_frozen[i] = tmp[i];
+        }
+        return SMGPU_OK;
+    }
 };
 
 #include "comm_impl.cuh"
 
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+
 namespace sm
 {
 
-static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[128], const int64_t *counts,
-                        const int64_t *allGids)
+struct HostBarrier
 {
+    std::mutex m;
+    std::condition_variable cv;
+    int n = 1, count = 0, gen = 0;
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const int g = gen;
+        if (++count == n)
+        {
+            count = 0;
+            ++gen;
+            cv.notify_all();
+        }
+        else
+            cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+// In-process group (smgpu_group_*): the processor meshes of one decomposed case as handles of this process,
+// all on one device and one stream, driven by one host thread.  The exchanges of an iteration become
+// stream-ordered device copies between the members' buffers and one small reduction kernel; the collective
+// host steps of the one-time layer set-up run on one short-lived host thread per member.
+struct LocalGroup
+{
+    std::vector<smgpu_handle *> members; // rank order
+    cudaStream_t stream = nullptr;
+    HostBarrier bar;
+    std::vector<const void *> posted; // hostSync: the send array of every member
+    double **dRes = nullptr;          // device arrays of the members' redRes / redFrozen pointers
+    long long **dFrozen = nullptr;
+    std::vector<cudaStream_t> ownStreams; // the members' own streams, restored when the group is destroyed
+};
+
+// this rank's half of the plan: no communication, so a failure here cannot leave other ranks waiting
+static Comm *commPrepare(smgpu_handle *h, int rank, int nRanks, const int64_t *counts, const int64_t *allGids)
+{
+    if (h->gid.empty() && !h->topo.procPoints.empty())
+        throw std::runtime_error("mesh has processor patches but was created without point_global_id");
     Comm *cm = new Comm;
     try
     {
@@ -462,13 +542,6 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         if (pl.maxCopies > SMK_MAXCOPIES)
             throw std::runtime_error("an interface point is shared by more ranks than the exchange layer supports");
         CK(cudaSetDevice(h->prm.device));
-        ncclUniqueId uid;
-        static_assert(sizeof(uid) == 128, "ncclUniqueId size");
-        memcpy(&uid, id, 128);
-        NCK(nccl().CommInitRank(&cm->nccl, nRanks, uid, rank));
-        CK(cudaStreamCreateWithFlags(&cm->xStream, cudaStreamNonBlocking));
-        CK(cudaEventCreateWithFlags(&cm->evPacked, cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&cm->evExchanged, cudaEventDisableTiming));
         smk::CommDev &c = cm->c;
         c.rank = rank;
         c.nSlots = (int)pl.sendPoint.size();
@@ -486,50 +559,89 @@ static Comm *commCreate(smgpu_handle *h, int rank, int nRanks, const uint8_t id[
         c.recvFz = h->dalloc<uint8_t>(c.nSlots);
         c.redRes = h->dalloc<double>(1);
         c.redFrozen = h->dalloc<long long>(1);
-        h->d.multiRank = 1;
-        h->d.locRes = c.redRes;
-        h->d.locFrozen = c.redFrozen;
-        // getMeshStats' returnReduce(min/max) (src/smoothMesh.C:1527-1528): the option defaults
-        // must come from the global edge-length extrema, not this rank's
-        double mm[2] = {-h->topo.minEdgeLength, h->topo.maxEdgeLength};
-        double *dmm = h->dalloc<double>(2);
-        CK(cudaMemcpy(dmm, mm, sizeof mm, cudaMemcpyHostToDevice));
-        NCK(nccl().AllReduce(dmm, dmm, 2, ncclDouble, ncclMax, cm->nccl, h->stream));
-        CK(cudaStreamSynchronize(h->stream));
-        CK(cudaMemcpy(mm, dmm, sizeof mm, cudaMemcpyDeviceToHost));
-        h->meshMinEdge = -mm[0];
-        h->meshMaxEdge = mm[1];
-        h->resolveParams();
-        commSetupLayers(cm, h);
     }
     catch (...)
     {
-        if (cm->nccl)
-            nccl().CommDestroy(cm->nccl);
         delete cm;
         throw;
     }
     return cm;
 }
 
+static bool commIsGroupMember(const Comm *cm) { return cm && cm->group; }
+
+static void commAttach(Comm *cm, smgpu_handle *h)
+{
+    h->d.multiRank = 1;
+    h->d.locRes = cm->c.redRes;
+    h->d.locFrozen = cm->c.redFrozen;
+}
+
+// the collective half over NCCL: communicator, global edge-length extrema, layer set-up
+static void commConnectNccl(Comm *cm, smgpu_handle *h, int rank, int nRanks, const uint8_t id[128])
+{
+    CK(cudaSetDevice(h->prm.device));
+    ncclUniqueId uid;
+    static_assert(sizeof(uid) == 128, "ncclUniqueId size");
+    memcpy(&uid, id, 128);
+    NCK(nccl().CommInitRank(&cm->nccl, nRanks, uid, rank));
+    CK(cudaStreamCreateWithFlags(&cm->xStream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&cm->evPacked, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&cm->evExchanged, cudaEventDisableTiming));
+    commAttach(cm, h);
+    // getMeshStats' returnReduce(min/max) (src/smoothMesh.C:1527-1528): the option defaults
+    // must come from the global edge-length extrema, not this rank's
+    double mm[2] = {-h->topo.minEdgeLength, h->topo.maxEdgeLength};
+    double *dmm = h->dalloc<double>(2);
+    CK(cudaMemcpy(dmm, mm, sizeof mm, cudaMemcpyHostToDevice));
+    NCK(nccl().AllReduce(dmm, dmm, 2, ncclDouble, ncclMax, cm->nccl, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpy(mm, dmm, sizeof mm, cudaMemcpyDeviceToHost));
+    h->meshMinEdge = -mm[0];
+    h->meshMaxEdge = mm[1];
+    h->resolveParams();
+    commSetupLayers(cm, h);
+}
+
 // syncTools::syncPointList for a host field with N values of T per point (set-up only): the copies of
-// every interface point travel through the iteration's exchange buffers and are combined in ascending
-// rank order, like the device-side merge.
+// every interface point are combined in ascending rank order, like the device-side merge.  NCCL ranks move
+// them through the iteration's exchange buffers; the members of an in-process group (one host thread each
+// during the set-up) read each other's send arrays between two barriers.
 template <class T, int N, class Op> static void hostSync(Comm *cm, smgpu_handle *h, std::vector<T> &field, Op combine)
 {
     const ExchangePlan &pl = cm->plan;
     const smk::CommDev &c = cm->c;
-    if (c.nSlots == 0)
+    if (c.nSlots == 0 && !cm->group)
         return;
     static_assert(sizeof(T) * N <= SMK_TUPLE * sizeof(double), "record larger than the exchange buffers");
     std::vector<T> send((size_t)c.nSlots * N), recv((size_t)c.nSlots * N);
     for (int i = 0; i < c.nSlots; ++i)
         for (int k = 0; k < N; ++k)
             send[(size_t)i * N + k] = field[(size_t)pl.sendPoint[i] * N + k];
-    CK(cudaMemcpyAsync(c.sendBuf, send.data(), send.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    haloExchange(cm, h->stream, c.sendBuf, c.recvBuf, N * sizeof(T));
-    CK(cudaMemcpyAsync(recv.data(), c.recvBuf, recv.size() * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
+    if (cm->group)
+    {
+        LocalGroup *g = cm->group;
+        g->posted[pl.rank] = send.data();
+        g->bar.wait();
+        for (size_t j = 0; j < pl.nbrRank.size(); ++j)
+        {
+            const ExchangePlan &ql = g->members[pl.nbrRank[j]]->comm->plan;
+            const size_t jj = std::find(ql.nbrRank.begin(), ql.nbrRank.end(), pl.rank) - ql.nbrRank.begin();
+            const size_t cnt = (size_t)(pl.nbrOff[j + 1] - pl.nbrOff[j]) * N;
+            if (jj >= ql.nbrRank.size() || (size_t)(ql.nbrOff[jj + 1] - ql.nbrOff[jj]) * N != cnt)
+                throw std::runtime_error("internal: exchange plans of two group members disagree");
+            memcpy(recv.data() + (size_t)pl.nbrOff[j] * N, (const T *)g->posted[pl.nbrRank[j]] + (size_t)ql.nbrOff[jj] * N,
+                   cnt * sizeof(T));
+        }
+        g->bar.wait(); // every member has read before any send array goes away
+    }
+    else
+    {
+        CK(cudaMemcpyAsync(c.sendBuf, send.data(), send.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+        haloExchange(cm, h->stream, c.sendBuf, c.recvBuf, N * sizeof(T));
+        CK(cudaMemcpyAsync(recv.data(), c.recvBuf, recv.size() * sizeof(T), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
     for (size_t s = 0; s < pl.sharedPoint.size(); ++s)
     {
         const int32_t p = pl.sharedPoint[s];
@@ -564,10 +676,13 @@ template <class T, int N, class Op> static void hostSync(Comm *cm, smgpu_handle 
 // Collective: every rank of the communicator calls it (smgpu_comm_init, smgpu_set_points).
 static void commSetupLayers(Comm *cm, smgpu_handle *h)
 {
-    if (!h->doLayers || !h->layersParallel)
+    // whenever a layer patch exists (not only while the blending fraction is positive), so that raising
+    // layer_max_blending_fraction later through smgpu_set_params finds the set-up done
+    if (!h->anyLayerPatch || !h->layersParallel)
         return;
     Dev &d = h->d;
     const int64_t P = h->topo.P;
+    CK(cudaSetDevice(h->prm.device));
     // this rank's share of the set-up call of calculateBoundaryPointNormals on the current mesh
     CK(cudaMemsetAsync(d.normals, 0, P * sizeof(P4), h->stream));
     CK(cudaMemsetAsync(d.done, 0, sizeof(int), h->stream));
@@ -626,64 +741,165 @@ static void commDestroy(Comm *cm)
     delete cm;
 }
 
-// One iteration with the interface exchanges (src/smoothMesh.C:2257-2399 under -parallel).
-// Returns the stop flag.
-static int commIterate(Comm *cm, smgpu_handle *h)
+// ---- one iteration with the interface exchanges (src/smoothMesh.C:2257-2399 under -parallel), in the
+// phases between which the copies of the interface points travel ----
+// A: geometry, then the local predictor tuple of every interface point.  With layer treatment the interface
+// records carry the normals of the previous iteration, so they are packed before k_layer_normals replaces
+// those; interface points get their normal, blend and second clamp in k_shared_merge, which overwrites
+// whatever the point-wise kernels wrote for them.
+static void commPhasePack(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
-    const int gs = smgpu_handle::grid(c.nSlots, 128);
-    // with layer treatment the interface records carry the normals of the previous iteration, so they
-    // are packed before k_layer_normals replaces those; interface points get their normal, blend and
-    // second clamp in k_shared_merge, which overwrites whatever the point-wise kernels wrote for them
     h->launchCellCentres();
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
-        k_shared_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
-    CK(cudaEventRecord(cm->evPacked, h->stream));
-    CK(cudaStreamWaitEvent(cm->xStream, cm->evPacked, 0));
-    haloExchange(cm, cm->xStream, c.sendBuf, c.recvBuf, c.tuple * sizeof(double));
-    CK(cudaEventRecord(cm->evExchanged, cm->xStream));
+        k_shared_pack<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
+    h->launches += 1;
+}
+// B1: everything that needs nothing from the exchange (it runs while the tuples are in flight)
+static void commPhaseLocal(Comm *cm, smgpu_handle *h)
+{
     if (h->doLayers)
         h->launchLayerNormals();
     h->launchPredict();
     if (h->doLayers)
         h->launchLayerBlend();
-    // (the exchange was enqueued on its own stream right after the pack, see above)
     if (h->prm.face_angle_constraint)
-        h->launchFaceCurrent(); // current-mesh half of the face-angle constraint: needs nothing from the exchange
+        h->launchFaceCurrent(); // current-mesh half of the face-angle constraint
+}
+// B2: merge of the copies, constraints, this rank's freeze flags of the interface points
+static void commPhaseConstrain(Comm *cm, smgpu_handle *h)
+{
+    const smk::CommDev &c = cm->c;
     h->profBegin(smgpu_handle::K_EXCHANGE);
-    CK(cudaStreamWaitEvent(h->stream, cm->evExchanged, 0));
     if (c.nShared > 0)
         k_shared_merge<<<smgpu_handle::grid(c.nShared, 64), 64, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
-    h->launches += 2;
+    h->launches += 1;
     h->launchEdgeConstraints();
     if (h->prm.face_angle_constraint)
         h->launchFaceResolve();
     h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
-        k_frozen_pack<<<gs, 128, 0, h->stream>>>(h->d, c);
-    haloExchange(cm, h->stream, c.sendFz, c.recvFz, 1);
+        k_frozen_pack<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
+    h->profEnd(1);
+    h->launches += 1;
+}
+// C: OR of the freeze flags (:2374), restore + residual + movePoints
+static void commPhaseCommit(Comm *cm, smgpu_handle *h)
+{
+    const smk::CommDev &c = cm->c;
+    h->profBegin(smgpu_handle::K_EXCHANGE);
     if (c.nSlots > 0)
-        k_frozen_or<<<gs, 128, 0, h->stream>>>(h->d, c);
-    h->profEnd(2);
-    h->launches += 2;
+        k_frozen_or<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
+    h->profEnd(1);
+    h->launches += 1;
     h->launchCommit();
+}
+// D: statistics and stop flag from the reduced residual / count (:2396-2405)
+static void commPhaseFinish(Comm *cm, smgpu_handle *h)
+{
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    k_finish_iter<<<1, 32, 0, h->stream>>>(h->d, cm->c);
+    h->profEnd(1);
+    h->launches += 1;
+}
+
+static void commIterate(Comm *cm, smgpu_handle *h)
+{
+    const smk::CommDev &c = cm->c;
+    commPhasePack(cm, h);
+    // the predictor exchange runs on its own stream while the main stream works on what does not need it
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    CK(cudaEventRecord(cm->evPacked, h->stream));
+    CK(cudaStreamWaitEvent(cm->xStream, cm->evPacked, 0));
+    haloExchange(cm, cm->xStream, c.sendBuf, c.recvBuf, c.tuple * sizeof(double));
+    CK(cudaEventRecord(cm->evExchanged, cm->xStream));
+    h->profEnd(0);
+    commPhaseLocal(cm, h);
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    CK(cudaStreamWaitEvent(h->stream, cm->evExchanged, 0));
+    h->profEnd(0);
+    commPhaseConstrain(cm, h);
+    h->profBegin(smgpu_handle::K_EXCHANGE);
+    haloExchange(cm, h->stream, c.sendFz, c.recvFz, 1);
+    h->profEnd(0);
+    commPhaseCommit(cm, h);
     h->profBegin(smgpu_handle::K_EXCHANGE);
     NCK(nccl().GroupStart());
     NCK(nccl().AllReduce(c.redRes, c.redRes, 1, ncclDouble, ncclMax, cm->nccl, h->stream));
     NCK(nccl().AllReduce(c.redFrozen, c.redFrozen, 1, ncclInt64, ncclSum, cm->nccl, h->stream));
     NCK(nccl().GroupEnd());
-    k_finish_iter<<<1, 32, 0, h->stream>>>(h->d, c);
-    h->profEnd(1);
-    h->launches += 1;
+    h->profEnd(0);
+    commPhaseFinish(cm, h);
     // no host round trip: the stop flag is global (it comes from the all-reduced residual), so every
     // rank keeps launching the same sequence and the kernels turn into no-ops once it is raised
-    return 0;
+}
+
+// ---- in-process group ----
+__global__ void k_group_reduce(int n, double *const *res, long long *const *frz)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0)
+        return;
+    double m = *res[0];
+    long long s = *frz[0];
+    for (int r = 1; r < n; ++r)
+    {
+        const double v = *res[r];
+        m = (v > m) ? v : m; // returnReduce(maxOp), :1567
+        s += *frz[r];        // returnReduce(sumOp), :2396
+    }
+    for (int r = 0; r < n; ++r)
+    {
+        *res[r] = m;
+        *frz[r] = s;
+    }
+}
+// which = 0: predictor tuples, 1: freeze flags
+static void groupExchange(LocalGroup *g, int which)
+{
+    for (smgpu_handle *h : g->members)
+    {
+        const Comm *cm = h->comm;
+        const ExchangePlan &pl = cm->plan;
+        const size_t eb = which == 0 ? cm->c.tuple * sizeof(double) : 1;
+        char *recv = which == 0 ? (char *)cm->c.recvBuf : (char *)cm->c.recvFz;
+        for (size_t j = 0; j < pl.nbrRank.size(); ++j)
+        {
+            const Comm *qm = g->members[pl.nbrRank[j]]->comm;
+            const ExchangePlan &ql = qm->plan;
+            const size_t jj = std::find(ql.nbrRank.begin(), ql.nbrRank.end(), pl.rank) - ql.nbrRank.begin();
+            const char *send = which == 0 ? (const char *)qm->c.sendBuf : (const char *)qm->c.sendFz;
+            CK(cudaMemcpyAsync(recv + (size_t)pl.nbrOff[j] * eb, send + (size_t)ql.nbrOff[jj] * eb,
+                               (size_t)(pl.nbrOff[j + 1] - pl.nbrOff[j]) * eb, cudaMemcpyDeviceToDevice, g->stream));
+        }
+    }
+}
+static void groupIterate(LocalGroup *g)
+{
+    for (smgpu_handle *h : g->members)
+        commPhasePack(h->comm, h);
+    groupExchange(g, 0);
+    for (smgpu_handle *h : g->members)
+    {
+        commPhaseLocal(h->comm, h);
+        commPhaseConstrain(h->comm, h);
+    }
+    groupExchange(g, 1);
+    for (smgpu_handle *h : g->members)
+        commPhaseCommit(h->comm, h);
+    k_group_reduce<<<1, 32, 0, g->stream>>>((int)g->members.size(), g->dRes, g->dFrozen);
+    for (smgpu_handle *h : g->members)
+        commPhaseFinish(h->comm, h);
 }
 
 } // namespace sm
+
+struct smgpu_group
+{
+    sm::LocalGroup g;
+};
 
 extern "C"
 {
@@ -1091,10 +1307,15 @@ extern "C"
     {
         if (!h)
             return SMGPU_OK;
-        if (h->comm)
+        cudaSetDevice(h->prm.device); // the frees below must hit this handle's context in multi-GPU processes
+        if (h->comm && !h->comm->group) // members of an in-process group are detached by smgpu_group_destroy
             sm::commDestroy(h->comm);
         for (void *p : h->allocs)
             cudaFree(p);
+        if (h->staging)
+            cudaFreeHost(h->staging);
+        for (cudaEvent_t e : h->evPool)
+            cudaEventDestroy(e);
         if (h->ev0)
             cudaEventDestroy(h->ev0);
         if (h->ev1)
@@ -1147,6 +1368,10 @@ extern "C"
         if (h->doLayers && h->layersParallel && !h->layersReady)
             return setErr(SMGPU_ERR_ARG, "boundary layer treatment on a processor mesh: call smgpu_comm_init first "
                                          "(its set-up synchronises hop counts and normals between the ranks)");
+        if (h->comm && h->comm->group)
+            return setErr(SMGPU_ERR_ARG, "this handle is a member of an in-process group: call smgpu_group_iterate");
+        if (h->comm && !h->comm->nccl)
+            return setErr(SMGPU_ERR_COMM, "the communicator of this handle was prepared but never connected, or was aborted");
         try
         {
             CK(cudaSetDevice(h->prm.device));
@@ -1195,32 +1420,10 @@ extern "C"
             h->lastLaunches = h->launches;
             if (h->profiling)
                 h->profCollect();
-            int it = 0, errFlag = 0;
-            CK(cudaMemcpy(&it, h->d.iter, sizeof(int), cudaMemcpyDeviceToHost));
-            CK(cudaMemcpy(&errFlag, h->d.errFlag, sizeof(int), cudaMemcpyDeviceToHost));
-            if (errFlag)
-            {
-                static const char *msg[] = {"", "Sanity broken, outerNeighCoord is undefined for an interface point "
-                                                "(src/orthogonalBoundaryBlending.C:537)",
-                                            "Internal sanity check failed: Did not find any edges with the required string index "
-                                            "(src/boundaryPointSmoothing.C:257)",
-                                            "pointNormal is zero for a smoothing surface point (src/boundaryPointSmoothing.C:691)",
-                                            "Did not find surface intersection for a boundary point (src/boundaryPointSmoothing.C:934)",
-                                            "A smoothing surface point has zero point normal (src/orthogonalBoundaryBlending.C:611)"};
-                CK(cudaMemset(h->d.errFlag, 0, sizeof(int)));
-                return setErr(SMGPU_ERR_MESH, msg[(errFlag >= 1 && errFlag <= 5) ? errFlag : 1]);
-            }
-            if (iters_done)
-                *iters_done = it;
-            if (it > 0 && residual)
-                CK(cudaMemcpy(residual, h->d.statRes, it * sizeof(double), cudaMemcpyDeviceToHost));
-            if (it > 0 && n_frozen)
-            {
-                std::vector<long long> tmp(it);
-                CK(cudaMemcpy(tmp.data(), h->d.statFrozen, it * sizeof(long long), cudaMemcpyDeviceToHost));
-                for (int i = 0; i < it; ++i)
-                    n_frozen[i] = tmp[i];
-            }
+            const int rc = h->checkErrFlag();
+            if (rc != SMGPU_OK)
+                return rc;
+            return h->fetchStats(n_frozen, residual, iters_done);
         }
         catch (const std::exception &e)
         {
@@ -1350,11 +1553,27 @@ extern "C"
             return setErr(SMGPU_ERR_ARG, "boundary layer treatment is not enabled for this handle");
         cudaSetDevice(h->prm.device);
         h->resetControl();
+        // calculateBoundaryPointNormals accumulates onto the normals of the previous call (:178), so this probe
+        // works on a copy: the handle's normals (and sharp flags) are what they were, and a later smgpu_iterate
+        // still follows the reference's call sequence
+        const size_t P = (size_t)h->topo.P;
+        std::vector<uint8_t> sharpKeep;
+        if (cudaMemcpyAsync(h->normalsTmp, h->d.normals, P * sizeof(P4), cudaMemcpyDeviceToDevice, h->stream) != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, "copy failed");
+        if (h->d.sharp)
+        {
+            sharpKeep.resize(P);
+            cudaStreamSynchronize(h->stream);
+            cudaMemcpy(sharpKeep.data(), h->d.sharp, P, cudaMemcpyDeviceToHost);
+        }
         h->launchFaceGeom();
         h->launchLayerNormals();
         int rc = finishOp(h);
         if (rc == SMGPU_OK && out)
             rc = downloadP4(h, h->d.normals, h->topo.P, out, h->pointOldOfNew);
+        cudaMemcpy(h->d.normals, h->normalsTmp, P * sizeof(P4), cudaMemcpyDeviceToDevice);
+        if (h->d.sharp)
+            cudaMemcpy(h->d.sharp, sharpKeep.data(), P, cudaMemcpyHostToDevice);
         return rc;
     }
 
@@ -1542,22 +1761,253 @@ extern "C"
         return SMGPU_OK;
     }
 
-    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t id[128], const int64_t *counts,
-                        const int64_t *all_gids)
+    int smgpu_comm_prepare(smgpu_handle *h, int32_t rank, int32_t n_ranks, const int64_t *counts, const int64_t *all_gids)
     {
-        if (!h || !id || !counts || (!all_gids && n_ranks > 1))
-            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (!h || !counts || (!all_gids && n_ranks > 1) || rank < 0 || rank >= n_ranks)
+            return setErr(SMGPU_ERR_ARG, "bad argument");
         if (h->comm)
             return setErr(SMGPU_ERR_ARG, "communicator already initialised");
+        if (h->doBoundary)
+            return setErr(SMGPU_ERR_ARG, "boundary point smoothing is single-GPU in this build");
         try
         {
-            h->comm = sm::commCreate(h, rank, n_ranks, id, counts, all_gids);
+            h->comm = sm::commPrepare(h, rank, n_ranks, counts, all_gids);
         }
         catch (const std::exception &e)
         {
             return setErr(SMGPU_ERR_COMM, e.what());
         }
         return SMGPU_OK;
+    }
+
+    int smgpu_comm_init(smgpu_handle *h, int32_t rank, int32_t n_ranks, const uint8_t id[128], const int64_t *counts,
+                        const int64_t *all_gids)
+    {
+        if (!h || !id)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (h->comm && (h->comm->nccl || h->comm->group))
+            return setErr(SMGPU_ERR_ARG, "communicator already initialised");
+        if (!h->comm)
+        { // one-step use: a local failure here leaves the other ranks waiting in ncclCommInitRank; hosts that can
+          // agree on the outcome first call smgpu_comm_prepare, compare notes, and only then come here
+            const int rc = smgpu_comm_prepare(h, rank, n_ranks, counts, all_gids);
+            if (rc != SMGPU_OK)
+                return rc;
+        }
+        try
+        {
+            sm::commConnectNccl(h->comm, h, rank, n_ranks, id);
+        }
+        catch (const std::exception &e)
+        {
+            if (h->comm->nccl)
+                sm::nccl().CommAbort(h->comm->nccl);
+            h->comm->nccl = nullptr;
+            return setErr(SMGPU_ERR_COMM, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_abort(smgpu_handle *h)
+    {
+        if (!h || !h->comm || !h->comm->nccl)
+            return SMGPU_OK;
+        try
+        {
+            sm::nccl().CommAbort(h->comm->nccl); // releases kernels of this rank that wait for a peer
+            h->comm->nccl = nullptr;
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_COMM, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_group_create(smgpu_handle **handles, int32_t n, smgpu_group **out)
+    {
+        if (!handles || n < 1 || !out)
+            return setErr(SMGPU_ERR_ARG, "bad argument");
+        *out = nullptr;
+        for (int r = 0; r < n; ++r)
+        {
+            if (!handles[r] || handles[r]->comm)
+                return setErr(SMGPU_ERR_ARG, "group members must be fresh handles without a communicator");
+            if (handles[r]->prm.device != handles[0]->prm.device)
+                return setErr(SMGPU_ERR_ARG, "the members of an in-process group share one device");
+            if (handles[r]->doBoundary)
+                return setErr(SMGPU_ERR_ARG, "boundary point smoothing is single-GPU in this build");
+            if (handles[r]->gid.empty() && !handles[r]->topo.procPoints.empty())
+                return setErr(SMGPU_ERR_ARG, "mesh has processor patches but was created without point_global_id");
+        }
+        smgpu_group *grp = new smgpu_group;
+        sm::LocalGroup &g = grp->g;
+        try
+        {
+            CK(cudaSetDevice(handles[0]->prm.device));
+            g.members.assign(handles, handles + n);
+            g.stream = handles[0]->stream;
+            g.bar.n = n;
+            g.posted.assign(n, nullptr);
+            // the all-gather of the processor-point lists a multi-process host does itself (smgpu_comm_local_shared)
+            std::vector<int64_t> counts(n), all;
+            for (int r = 0; r < n; ++r)
+            {
+                counts[r] = (int64_t)handles[r]->topo.procPoints.size();
+                for (int32_t p : handles[r]->topo.procPoints)
+                    all.push_back(handles[r]->gid[p]);
+            }
+            if (all.empty())
+                all.push_back(0);
+            double mn = 1e300, mx = 0;
+            for (int r = 0; r < n; ++r)
+            {
+                smgpu_handle *h = handles[r];
+                h->comm = sm::commPrepare(h, r, n, counts.data(), all.data());
+                h->comm->group = &g;
+                sm::commAttach(h->comm, h);
+                CK(cudaStreamSynchronize(h->stream));
+                g.ownStreams.push_back(h->stream);
+                h->stream = g.stream; // one stream orders the members' kernels and the copies between them
+                mn = std::min(mn, h->topo.minEdgeLength);
+                mx = std::max(mx, h->topo.maxEdgeLength);
+            }
+            std::vector<double *> res(n);
+            std::vector<long long *> frz(n);
+            for (int r = 0; r < n; ++r)
+            {
+                res[r] = handles[r]->comm->c.redRes;
+                frz[r] = handles[r]->comm->c.redFrozen;
+            }
+            g.dRes = (double **)handles[0]->upload(res);
+            g.dFrozen = (long long **)handles[0]->upload(frz);
+            for (int r = 0; r < n; ++r)
+            { // getMeshStats' returnReduce(min/max), src/smoothMesh.C:1527-1528
+                handles[r]->meshMinEdge = mn;
+                handles[r]->meshMaxEdge = mx;
+                handles[r]->resolveParams();
+            }
+            // the collective host steps of the layer set-up: one short-lived thread per member
+            std::vector<std::string> errs(n);
+            std::vector<std::thread> th;
+            bool anyLayers = false;
+            for (int r = 0; r < n; ++r)
+                anyLayers = anyLayers || (handles[r]->anyLayerPatch && handles[r]->layersParallel);
+            if (anyLayers)
+            {
+                for (int r = 0; r < n; ++r)
+                    if (!(handles[r]->anyLayerPatch && handles[r]->layersParallel))
+                        throw std::runtime_error("boundary layer treatment must be selected on every member of a group "
+                                                 "(the reference evaluates -layerPatches on every rank)");
+                for (int r = 0; r < n; ++r)
+                    th.emplace_back([&, r] {
+                        try
+                        {
+                            sm::commSetupLayers(handles[r]->comm, handles[r]);
+                        }
+                        catch (const std::exception &e)
+                        {
+                            errs[r] = e.what();
+                        }
+                    });
+                for (auto &t : th)
+                    t.join();
+                for (int r = 0; r < n; ++r)
+                    if (!errs[r].empty())
+                        throw std::runtime_error(errs[r]);
+            }
+        }
+        catch (const std::exception &e)
+        {
+            smgpu_group_destroy(grp);
+            return setErr(SMGPU_ERR_COMM, e.what());
+        }
+        *out = grp;
+        return SMGPU_OK;
+    }
+
+    int smgpu_group_destroy(smgpu_group *grp)
+    {
+        if (!grp)
+            return SMGPU_OK;
+        sm::LocalGroup &g = grp->g;
+        if (g.stream)
+            cudaStreamSynchronize(g.stream);
+        for (size_t r = 0; r < g.members.size(); ++r)
+        {
+            smgpu_handle *h = g.members[r];
+            if (r < g.ownStreams.size())
+                h->stream = g.ownStreams[r];
+            if (h->comm)
+            {
+                sm::commDestroy(h->comm);
+                h->comm = nullptr;
+                h->d.multiRank = 0;
+            }
+        }
+        delete grp;
+        return SMGPU_OK;
+    }
+
+    int smgpu_group_iterate(smgpu_group *grp, int32_t max_iters, int64_t *n_frozen, double *residual, int32_t *iters_done)
+    {
+        if (!grp || max_iters < 0)
+            return setErr(SMGPU_ERR_ARG, "bad argument");
+        sm::LocalGroup &g = grp->g;
+        smgpu_handle *h0 = g.members[0];
+        for (smgpu_handle *h : g.members)
+            if (h->doLayers && h->layersParallel && !h->layersReady)
+                return setErr(SMGPU_ERR_ARG, "boundary layer treatment: the group's layer set-up has not run");
+        try
+        {
+            CK(cudaSetDevice(h0->prm.device));
+            for (smgpu_handle *h : g.members)
+            {
+                h->ensureStats(max_iters);
+                h->launches = 0;
+                h->resetControl();
+            }
+            CK(cudaEventRecord(h0->ev0, g.stream));
+            int done = 0, launched = 0;
+            const int chunk = 16;
+            while (launched < max_iters && !done)
+            {
+                const int n = std::min(chunk, max_iters - launched);
+                for (int i = 0; i < n; ++i)
+                    sm::groupIterate(&g);
+                launched += n;
+                if (launched < max_iters)
+                {
+                    CK(cudaMemcpyAsync(&done, h0->d.done, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+                    CK(cudaStreamSynchronize(g.stream));
+                }
+            }
+            CK(cudaEventRecord(h0->ev1, g.stream));
+            CK(cudaStreamSynchronize(g.stream));
+            CK(cudaGetLastError());
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, h0->ev0, h0->ev1));
+            int64_t launches = 1;
+            for (smgpu_handle *h : g.members)
+            {
+                launches += h->launches;
+                if (h->profiling)
+                    h->profCollect();
+            }
+            h0->lastMs = ms;
+            h0->lastLaunches = launches;
+            for (smgpu_handle *h : g.members)
+            {
+                const int rc = h->checkErrFlag();
+                if (rc != SMGPU_OK)
+                    return rc;
+            }
+            return h0->fetchStats(n_frozen, residual, iters_done);
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
     }
 
 } // extern "C"

@@ -14,6 +14,7 @@
 #include "../../include/smmesh.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -248,10 +249,16 @@ static int runParallel(const RunOptions &ro)
         fatal("-parallel: no processor directories found in " + ro.caseDir + " (decompose the case first, e.g. -decompose '(2 1 1)')");
     int32_t nDev = 0;
     smgpu_device_count(&nDev);
-    if (nDev < nProcs)
-        fatal("-parallel: " + std::to_string(nProcs) + " processor directories but only " + std::to_string(nDev) +
-              " CUDA devices (one GPU per processor mesh is required)");
-    printf("Running on %d GPUs (one per processor directory)\n\nCreate mesh for time = %s\n\n", nProcs, ro.startName.c_str());
+    if (nDev < 1)
+        fatal("-parallel: no CUDA device available (there is no CPU fallback)");
+    // fewer GPUs than processor directories: all processor meshes become an in-process group on one device
+    // (smgpu_group_*: same rank semantics, device copies instead of NCCL)
+    const bool groupMode = nDev < nProcs;
+    if (groupMode)
+        printf("Running %d processor meshes as an in-process group on GPU %d\n\nCreate mesh for time = %s\n\n", nProcs,
+               ro.prm.device, ro.startName.c_str());
+    else
+        printf("Running on %d GPUs (one per processor directory)\n\nCreate mesh for time = %s\n\n", nProcs, ro.startName.c_str());
 
     std::vector<std::vector<int64_t>> shared(nProcs);
     std::vector<int64_t> counts(nProcs), allGids;
@@ -259,11 +266,22 @@ static int runParallel(const RunOptions &ro)
     Barrier bar(nProcs);
     std::mutex failMutex;
     std::string failure;
+    std::atomic<bool> failed{false}; // what the worker threads poll; `failure` itself is only touched under the mutex
+    std::vector<smgpu_handle *> handles(nProcs, nullptr);
     auto failAll = [&](const std::string &msg) {
         std::lock_guard<std::mutex> lk(failMutex);
         if (failure.empty())
             failure = msg;
+        if (!failed.exchange(true) && !groupMode)
+            for (smgpu_handle *q : handles) // peers may sit in an NCCL kernel waiting for the rank that failed
+                if (q)
+                    smgpu_comm_abort(q);
     };
+    smgpu_group *group = nullptr;
+    int sharedDone = 0;
+    bool sharedOk = true;
+    std::vector<int64_t> sharedFrozen(std::max(ro.centroidalIters, 1));
+    std::vector<double> sharedResidual(std::max(ro.centroidalIters, 1));
     int64_t totalPoints = 0, totalInternal = 0;
     std::vector<std::thread> threads;
     for (int k = 0; k < nProcs; ++k)
@@ -315,22 +333,29 @@ static int runParallel(const RunOptions &ro)
                 md.point_global_id = smmesh_point_global_id(mesh);
                 md.patch_layer = layerSel.data();
                 smgpu_params prm = ro.prm;
-                prm.device = k;
+                prm.device = groupMode ? ro.prm.device : k;
                 if (smgpu_create(&md, &prm, &h) != SMGPU_OK)
                 {
                     ok = false;
                     failAll(smgpu_last_error());
                 }
+                handles[k] = h;
             }
             if (ok)
             {
                 int64_t n = 0;
-                smgpu_comm_local_shared(h, &n, nullptr);
+                if (smgpu_comm_local_shared(h, &n, nullptr) != SMGPU_OK)
+                    failAll(smgpu_last_error());
                 shared[k].resize(n);
                 smgpu_comm_local_shared(h, &n, shared[k].data());
             }
             bar.wait();
-            if (k == 0 && failure.empty())
+            if (k == 0 && !failed && groupMode)
+            {
+                if (smgpu_group_create(handles.data(), nProcs, &group) != SMGPU_OK)
+                    failAll(smgpu_last_error());
+            }
+            else if (k == 0 && !failed)
             {
                 for (int r = 0; r < nProcs; ++r)
                 {
@@ -343,12 +368,21 @@ static int runParallel(const RunOptions &ro)
                     failAll(smgpu_last_error());
             }
             bar.wait();
-            if (!failure.empty())
+            if (failed)
                 return;
-            if (smgpu_comm_init(h, k, nProcs, uid, counts.data(), allGids.data()) != SMGPU_OK)
-                failAll(smgpu_last_error());
+            if (!groupMode)
+            {
+                // local half first, so that a rank whose plan fails does not leave the others in ncclCommInitRank
+                if (smgpu_comm_prepare(h, k, nProcs, counts.data(), allGids.data()) != SMGPU_OK)
+                    failAll(smgpu_last_error());
+                bar.wait();
+                if (failed)
+                    return;
+                if (smgpu_comm_init(h, k, nProcs, uid, counts.data(), allGids.data()) != SMGPU_OK)
+                    failAll(smgpu_last_error());
+            }
             bar.wait();
-            if (!failure.empty())
+            if (failed)
                 return;
             double mn, mx;
             int64_t nInternal, nEdges;
@@ -378,7 +412,7 @@ static int runParallel(const RunOptions &ro)
             int i = 0;
             const int logPrecision = ro.logPrecision;
             bool stop = ro.centroidalIters <= 0;
-            while (!stop && failure.empty())
+            while (!stop && (groupMode || !failed))
             {
                 int chunk = ro.centroidalIters - i;
                 if (ro.writeInterval > 0)
@@ -389,7 +423,24 @@ static int runParallel(const RunOptions &ro)
                     chunk = std::min(chunk, toWrite);
                 }
                 int done = 0;
-                if (smgpu_iterate(h, chunk, nFrozen.data(), residual.data(), &done) != SMGPU_OK)
+                if (groupMode)
+                { // one thread drives the whole group, the others take its log (the chunk is the same on every thread)
+                    if (k == 0)
+                    {
+                        sharedOk = smgpu_group_iterate(group, chunk, sharedFrozen.data(), sharedResidual.data(), &sharedDone) == SMGPU_OK;
+                        if (!sharedOk)
+                            failAll(smgpu_last_error());
+                    }
+                    bar.wait();
+                    const bool okNow = sharedOk;
+                    done = sharedDone;
+                    std::copy(sharedFrozen.begin(), sharedFrozen.begin() + done, nFrozen.begin());
+                    std::copy(sharedResidual.begin(), sharedResidual.begin() + done, residual.begin());
+                    bar.wait();
+                    if (!okNow)
+                        break;
+                }
+                else if (smgpu_iterate(h, chunk, nFrozen.data(), residual.data(), &done) != SMGPU_OK)
                 {
                     failAll(smgpu_last_error());
                     break;
@@ -424,6 +475,12 @@ static int runParallel(const RunOptions &ro)
                 }
             }
             bar.wait(); // nobody tears its communicator down while others still iterate
+            if (groupMode)
+            {
+                if (k == 0)
+                    smgpu_group_destroy(group);
+                bar.wait();
+            }
             smgpu_destroy(h);
             smmesh_free(mesh);
         });

@@ -58,6 +58,18 @@ def init_comm(smoother, rank, world, dist):
     counts, allg = gather_shared(smoother.comm_local_shared(), dist)
     backend = dist.get_backend()
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    # local half first; the ranks agree on its outcome before anything collective inside the library runs, so
+    # a rank that fails here (mesh without point_global_id, a point shared by too many ranks) cannot leave the
+    # others waiting in ncclCommInitRank
+    err = None
+    try:
+        smoother.comm_prepare(rank, world, counts, allg)
+    except sm.SmoothMeshError as e:
+        err = e
+    bad = torch.tensor([1 if err else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(bad, op=dist.ReduceOp.MAX)
+    if int(bad.item()):
+        raise err if err else sm.SmoothMeshError("smgpu_comm_prepare failed on another rank")
     uid = torch.zeros(128, dtype=torch.uint8, device=dev)
     if rank == 0:
         uid = torch.tensor(list(sm.Smoother.comm_unique_id()), dtype=torch.uint8, device=dev)

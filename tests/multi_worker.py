@@ -38,6 +38,16 @@ def make_parts(world, kind):
     raise ValueError(kind)
 
 
+def options(kind):
+    """(Smoother / Oracle keyword options, iterations) of a multi-rank parity case."""
+    if kind == "hexlayers":
+        return dict(rel_tol=0.0, layer_patches=[1, 1, 1, 0, 1, 1], max_layers=3, layer_expansion_ratio=1.2), 12
+    if kind == "prismlayers":  # testcase/run_parallel:22
+        return dict(rel_tol=0.0, min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0, max_angle_deg=160.0,
+                    layer_patches=[1, 0, 0, 0, 0, 0, 0]), 12
+    return dict(rel_tol=1e-3, min_angle_deg=70.0, max_angle_deg=110.0, total_min_freeze=0), 25
+
+
 def proc_points(part):
     s, z, k = part.patches
     off, verts = part.face_offsets, part.face_verts
@@ -91,15 +101,7 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    kw = dict(rel_tol=1e-3, min_angle_deg=70.0, max_angle_deg=110.0, total_min_freeze=0)
-    iters = 25
-    if kind == "hexlayers":
-        kw = dict(rel_tol=0.0, layer_patches=[1, 1, 1, 0, 1, 1], max_layers=3, layer_expansion_ratio=1.2)
-        iters = 12
-    if kind == "prismlayers":  # testcase/run_parallel:22
-        kw = dict(rel_tol=0.0, min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0, max_angle_deg=160.0,
-                  layer_patches=[1, 0, 0, 0, 0, 0, 0])
-        iters = 12
+    kw, iters = options(kind)
     g = sm.Smoother(mine, device=local_rank, **kw)
     multi.init_comm(g, rank, world, dist)
     if mode == "debug":

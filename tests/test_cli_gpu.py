@@ -99,10 +99,9 @@ def test_cli_ascii_precision_and_reltol_stop(tmp_path):
 
 def test_cli_parallel_on_processor_directories(tmp_path):
     """`smoothMesh -parallel` on a decomposed case (testcase/run_parallel:19-22: decomposePar, then
-    mpirun -np N smoothMesh -parallel): one GPU per processor directory, points written per processor."""
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    mpirun -np N smoothMesh -parallel): one GPU per processor directory (NCCL between host threads), or -- on a
+    box with fewer GPUs than directories -- all processor meshes as an in-process group on one GPU; points written
+    per processor."""
     mesh = hex_jittered(8, 6, 5, 0.35, seed=33)
     case = make_case(tmp_path, mesh)
     r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-decompose", "(2 1 1)"], capture_output=True, text=True)

@@ -192,9 +192,11 @@ def test_cli_decompose_utility_and_parallel_refusals(tmp_path):
         assert np.array_equal(q.points, expect[k].points)
     r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-decompose", "2"], capture_output=True, text=True)
     assert r.returncode != 0 and "(nx ny nz)" in r.stderr
-    # -parallel without processor directories / without enough GPUs fails loudly (no serial fallback)
-    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel"], capture_output=True, text=True)
-    assert r.returncode != 0 and "CUDA devices" in r.stderr
+    # -parallel without a GPU fails loudly (no CPU fallback); with fewer GPUs than processor directories the
+    # processor meshes run as an in-process group on one device (tests/test_cli_gpu.py)
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel"], capture_output=True, text=True,
+                       env=dict(os.environ, CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode != 0 and "no CUDA device" in r.stderr
 
 
 def test_geometry_tiles_cover_the_mesh():
