@@ -163,6 +163,18 @@ extern "C"
      * milliseconds, and the number of kernels it launched. */
     int smgpu_last_timing(smgpu_handle *h, double *ms, int64_t *launches);
 
+    /* Filter diagnostics of the last executed iteration: out = {1 if the face-angle filter runs
+     * fused into the geometry tiles, points marked suspect by it (end points of edges it could not certify; they
+     * take the literal evaluation), points active in the face-angle constraint (src/smoothMesh.C:1367-1368),
+     * bit set: 1 geometry tiles, 2 second-generation tile kernel, 4 uniform hex fast path, 8 / 16 per-edge /
+     * per-point single-precision filter level in use}. */
+    int smgpu_filter_stats(smgpu_handle *h, int64_t out[4]);
+
+    /* Self-test of the shared-reciprocal division the geometry kernels use (one reciprocal for the three
+     * components of a vector, the quotients bit-identical to IEEE division): about n random and structured
+     * (a, d) triples on the device, *mismatches = components that differ from a / d (must be 0). */
+    int smgpu_selftest_division(int32_t device, uint64_t seed, int64_t n, int64_t *mismatches);
+
     /* Optional per-kernel timing: when enabled, every kernel (group) launched by
      * smgpu_iterate is bracketed by CUDA events on the launch stream and the elapsed
      * times are accumulated per kernel name.  smgpu_profile() also clears the counters.

@@ -29,6 +29,9 @@ extern "C"
     smmesh *smmesh_gen_hex_block_part(int32_t nx, int32_t ny, int32_t nz, int32_t px, int32_t py, int32_t pz,
                                       int32_t rank, const double lo[3], const double hi[3]);
     smmesh *smmesh_gen_kelvin(int32_t n, double h);
+    /* brick `rank` (= ix + px*(iy + py*iz)) of that mesh as a processor mesh with point_global_id, generated
+     * locally (BASELINE config 4 at its stated size is never materialised on one host) */
+    smmesh *smmesh_gen_kelvin_part(int32_t n, double h, int32_t px, int32_t py, int32_t pz, int32_t rank);
     smmesh *smmesh_from_cells(int64_t n_points, const double *points, int32_t n_cells, const int32_t *cell_face_offsets,
                               const int32_t *cf_vert_offsets, const int32_t *cf_verts, const int32_t *cf_patch,
                               int32_t n_patches, const char *const *patch_names, const char *const *patch_types);
@@ -74,8 +77,10 @@ extern "C"
     /* Tiling of the fused geometry kernel (cells grouped along a space-filling curve, each tile with the list
      * of faces its cells touch; see smoothmesh_b200/csrc/topology.hpp GeomTiles), built and checked on the
      * host: out = {tiles (0 = a cell does not fit: two-kernel path), listed faces summed over tiles, largest
-     * face list, faces of the mesh, largest point list}.  Fails if an invariant the kernel relies on does not hold. */
-    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[5]);
+     * face list, faces of the mesh, largest point list, (edge, cell) pairs listed for the fused face-angle filter
+     * (0 = some cell is not closed: per-edge kernel), edges per cell if uniform else 0}.  Fails if an invariant
+     * the kernel relies on does not hold. */
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[7]);
 
     /* One-time host set-up of boundary point smoothing (smoothmesh_b200/csrc/boundary.hpp; the reference's
      * classifyBoundaryPoints, findEdgeMeshStrings, calculatePointHopsToBoundary(smoothingPatches),

@@ -83,7 +83,8 @@ def lib():
         L.smgpu_version.restype = C.c_char_p
         L.smmesh_last_error.restype = C.c_char_p
         L.smmesh_patch_name.restype = C.c_char_p
-        for f in ("smmesh_gen_hex_block", "smmesh_gen_kelvin", "smmesh_from_cells", "smmesh_from_arrays", "smmesh_read"):
+        for f in ("smmesh_gen_hex_block", "smmesh_gen_kelvin", "smmesh_gen_kelvin_part", "smmesh_from_cells",
+                  "smmesh_from_arrays", "smmesh_read"):
             getattr(L, f).restype = C.c_void_p
         for f in ("smmesh_points", "smmesh_points_mut", "smmesh_face_offsets", "smmesh_face_verts", "smmesh_owner",
                   "smmesh_neighbour", "smmesh_point_global_id", "smmesh_cell_global_id"):
@@ -101,6 +102,7 @@ def lib():
         L.smmesh_write_points.argtypes = [C.c_void_p, C.c_int64, C.c_char_p, C.c_int32, C.c_int32, C.c_char_p]
         L.smmesh_gen_hex_block.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.smmesh_gen_kelvin.argtypes = [C.c_int32, C.c_double]
+        L.smmesh_gen_kelvin_part.argtypes = [C.c_int32, C.c_double] + [C.c_int32] * 4
         L.smmesh_decompose.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.smmesh_from_cells.argtypes = [C.c_int64, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_int32, C.c_void_p, C.c_void_p]
@@ -202,6 +204,11 @@ class Mesh:
     @staticmethod
     def kelvin(n, h=1.0) -> "Mesh":
         return Mesh(lib().smmesh_gen_kelvin(n, h))
+
+    @staticmethod
+    def kelvin_part(n, h, px, py, pz, rank) -> "Mesh":
+        """Brick `rank` of the Kelvin mesh as a processor mesh, generated locally (point_global_id = lattice slot)."""
+        return Mesh(lib().smmesh_gen_kelvin_part(n, float(h), px, py, pz, rank))
 
     @staticmethod
     def read_processor(case_dir, k) -> "Mesh":
@@ -370,10 +377,11 @@ class Mesh:
     def geom_tiles(self, max_cells=256, max_faces=1024, max_points=1024):
         """Host-side tiling of the fused geometry kernel, checked:
         dict(tiles, listed_faces, max_faces, faces, max_points)."""
-        out = (C.c_int64 * 5)()
+        out = (C.c_int64 * 7)()
         if lib().smmesh_geom_tiles(self._h, int(max_cells), int(max_faces), int(max_points), out) != 0:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
-        return dict(tiles=out[0], listed_faces=out[1], max_faces=out[2], faces=out[3], max_points=out[4])
+        return dict(tiles=out[0], listed_faces=out[1], max_faces=out[2], faces=out[3], max_points=out[4],
+                    edge_cell_pairs=out[5], uniform_cell_edges=out[6])
 
     def decompose(self, px, py=1, pz=1, method="bricks"):
         n = px * py * pz if method == "bricks" else px
@@ -584,6 +592,12 @@ class Smoother:
         lib().smgpu_get_boundary_classes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         self._ck(lib().smgpu_get_boundary_classes(self._h, _ptr(a), _ptr(b)))
         return a, b
+
+    def filter_stats(self):
+        out = (C.c_int64 * 4)()
+        lib().smgpu_filter_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(lib().smgpu_filter_stats(self._h, out))
+        return dict(fused=bool(out[0]), suspect_points=int(out[1]), active_points=int(out[2]), paths=int(out[3]))
 
     def profile(self, enable=True):
         self._ck(lib().smgpu_profile(self._h, int(enable)))

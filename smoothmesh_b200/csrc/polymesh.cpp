@@ -279,25 +279,10 @@ PolyMesh buildFromCells(const std::vector<double> &points, const std::vector<int
 }
 
 // ------------------------------------------------------------- Kelvin mesh ----
-PolyMesh genKelvin(int n, double h)
+// face templates of a truncated octahedron relative to its centre (integer lattice units): 6 squares + 8
+// hexagons, outward oriented
+static std::vector<std::vector<std::array<int, 3>>> kelvinFaceTemplates()
 {
-    // BCC lattice with lattice constant 4 in integer units (vertex coordinates are
-    // integers); cell centres at (4i,4j,4k) and (4i+2,4j+2,4k+2).  A truncated
-    // octahedron around c has the 24 vertices c + perm(0,+-1,+-2).
-    if (n < 1)
-        fail("genKelvin: n < 1");
-    std::vector<std::array<int, 3>> centres;
-    for (int k = 0; k < n; ++k)
-        for (int j = 0; j < n; ++j)
-            for (int i = 0; i < n; ++i)
-            {
-                centres.push_back({4 * i, 4 * j, 4 * k});
-                centres.push_back({4 * i + 2, 4 * j + 2, 4 * k + 2});
-            }
-    std::sort(centres.begin(), centres.end(), [](const std::array<int, 3> &a, const std::array<int, 3> &b) {
-        return a[2] != b[2] ? a[2] < b[2] : (a[1] != b[1] ? a[1] < b[1] : a[0] < b[0]);
-    });
-    // face templates relative to the centre: 6 squares + 8 hexagons, outward oriented
     std::vector<std::vector<std::array<int, 3>>> tmpl;
     auto orient = [&](std::vector<std::array<int, 3>> loop) {
         // order by angle around the centroid, then make the normal point away from the origin
@@ -353,6 +338,28 @@ PolyMesh genKelvin(int n, double h)
                 while (std::next_permutation(perm, perm + 3));
                 tmpl.push_back(orient(loop));
             }
+    return tmpl;
+}
+
+PolyMesh genKelvin(int n, double h)
+{
+    // BCC lattice with lattice constant 4 in integer units (vertex coordinates are
+    // integers); cell centres at (4i,4j,4k) and (4i+2,4j+2,4k+2).  A truncated
+    // octahedron around c has the 24 vertices c + perm(0,+-1,+-2).
+    if (n < 1)
+        fail("genKelvin: n < 1");
+    std::vector<std::array<int, 3>> centres;
+    for (int k = 0; k < n; ++k)
+        for (int j = 0; j < n; ++j)
+            for (int i = 0; i < n; ++i)
+            {
+                centres.push_back({4 * i, 4 * j, 4 * k});
+                centres.push_back({4 * i + 2, 4 * j + 2, 4 * k + 2});
+            }
+    std::sort(centres.begin(), centres.end(), [](const std::array<int, 3> &a, const std::array<int, 3> &b) {
+        return a[2] != b[2] ? a[2] < b[2] : (a[1] != b[1] ? a[1] < b[1] : a[0] < b[0]);
+    });
+    const std::vector<std::vector<std::array<int, 3>>> tmpl = kelvinFaceTemplates();
     // vertices: integer triples -> ids in lexicographic (z,y,x) order, through a dense lattice index
     const int64_t G = 4 * (int64_t)n + 6; // coordinates lie in [-2, 4n+3]
     auto slot = [&](int x, int y, int z) { return ((int64_t)(z + 2) * G + (y + 2)) * G + (x + 2); };
@@ -390,6 +397,150 @@ PolyMesh genKelvin(int n, double h)
         cfo.push_back((int32_t)cvo.size() - 1);
     }
     return buildFromCells(pts, cfo, cvo, cv, cp, {"walls"}, {"wall"});
+}
+
+// One brick of the Kelvin mesh in processor-mesh form, generated locally: the lattice cells
+// [i0,i1) x [j0,j1) x [k0,k1) of an n^3 lattice split px x py x pz ways (both truncated octahedra of a
+// lattice cell belong to it).  Faces towards cells of other bricks become processor patches (one per
+// neighbour rank, ascending); pointGlobalId is the vertex's slot in the global integer lattice, which every
+// rank computes alike, so shared points match and the jitter (keyed on it) is identical on all copies.
+PolyMesh genKelvinPart(int n, double h, int px, int py, int pz, int rank)
+{
+    if (n < 1 || px < 1 || py < 1 || pz < 1 || rank < 0 || rank >= px * py * pz)
+        fail("genKelvinPart: bad arguments");
+    const int parts[3] = {px, py, pz};
+    const int mine[3] = {rank % px, (rank / px) % py, rank / (px * py)};
+    auto lower = [&](int d, int q) { return (int)((int64_t)n * q / parts[d]); };
+    int lo[3], hi[3];
+    for (int d = 0; d < 3; ++d)
+    {
+        lo[d] = lower(d, mine[d]);
+        hi[d] = lower(d, mine[d] + 1);
+        if (hi[d] <= lo[d])
+            fail("genKelvinPart: more bricks than lattice cells along an axis");
+    }
+    auto brickOf = [&](int d, int i) { // brick index along axis d of lattice cell i
+        int q = (int)(((int64_t)i * parts[d]) / n);
+        while (q + 1 < parts[d] && lower(d, q + 1) <= i)
+            ++q;
+        while (q > 0 && lower(d, q) > i)
+            --q;
+        return q;
+    };
+    // rank of the cell with centre c, -1 if there is no such cell
+    auto rankOfCentre = [&](const int c[3]) {
+        const int r0 = ((c[0] % 4) + 4) % 4;
+        if ((r0 != 0 && r0 != 2) || ((c[1] % 4) + 4) % 4 != r0 || ((c[2] % 4) + 4) % 4 != r0)
+            return -1;
+        int q[3];
+        for (int d = 0; d < 3; ++d)
+        {
+            if (c[d] - r0 < 0)
+                return -1;
+            const int i = (c[d] - r0) / 4;
+            if (i >= n)
+                return -1;
+            q[d] = brickOf(d, i);
+        }
+        return q[0] + px * (q[1] + py * q[2]);
+    };
+    std::vector<std::array<int, 3>> centres;
+    for (int k = lo[2]; k < hi[2]; ++k)
+        for (int j = lo[1]; j < hi[1]; ++j)
+            for (int i = lo[0]; i < hi[0]; ++i)
+            {
+                centres.push_back({4 * i, 4 * j, 4 * k});
+                centres.push_back({4 * i + 2, 4 * j + 2, 4 * k + 2});
+            }
+    std::sort(centres.begin(), centres.end(), [](const std::array<int, 3> &a, const std::array<int, 3> &b) {
+        return a[2] != b[2] ? a[2] < b[2] : (a[1] != b[1] ? a[1] < b[1] : a[0] < b[0]);
+    });
+    const std::vector<std::vector<std::array<int, 3>>> tmpl = kelvinFaceTemplates();
+    // local dense lattice over the brick's bounding box
+    int64_t base[3], ext[3];
+    for (int d = 0; d < 3; ++d)
+    {
+        base[d] = 4 * (int64_t)lo[d] - 2;
+        ext[d] = 4 * (int64_t)(hi[d] - lo[d]) + 6;
+    }
+    auto slot = [&](int x, int y, int z) { return ((z - base[2]) * ext[1] + (y - base[1])) * ext[0] + (x - base[0]); };
+    std::vector<int32_t> vid((size_t)(ext[0] * ext[1] * ext[2]), -1);
+    for (auto &c : centres)
+        for (auto &f : tmpl)
+            for (auto &v : f)
+                vid[slot(c[0] + v[0], c[1] + v[1], c[2] + v[2])] = 0;
+    const int64_t G = 4 * (int64_t)n + 6;
+    int32_t nv = 0;
+    std::vector<double> pts;
+    std::vector<int64_t> gid;
+    for (int64_t z = 0; z < ext[2]; ++z)
+        for (int64_t y = 0; y < ext[1]; ++y)
+            for (int64_t x = 0; x < ext[0]; ++x)
+            {
+                int32_t &id = vid[(size_t)((z * ext[1] + y) * ext[0] + x)];
+                if (id == 0)
+                {
+                    id = nv++;
+                    const int64_t gx = x + base[0], gy = y + base[1], gz = z + base[2];
+                    pts.push_back(gx * h / 4.0);
+                    pts.push_back(gy * h / 4.0);
+                    pts.push_back(gz * h / 4.0);
+                    gid.push_back(((gz + 2) * G + (gy + 2)) * G + (gx + 2));
+                }
+            }
+    // neighbour ranks -> patch ids (0 = walls, then ascending neighbour rank)
+    std::map<int, int> patchOfRank;
+    std::vector<int32_t> cfo{0}, cvo{0}, cv, cp;
+    std::vector<int> cpRank; // per cell face: -1 wall, own rank = internal candidate, else neighbour rank
+    cv.reserve(centres.size() * 72);
+    for (auto &c : centres)
+    {
+        for (auto &f : tmpl)
+        {
+            int sum[3] = {0, 0, 0};
+            for (auto &v : f)
+            {
+                cv.push_back(vid[slot(c[0] + v[0], c[1] + v[1], c[2] + v[2])]);
+                for (int d = 0; d < 3; ++d)
+                    sum[d] += v[d];
+            }
+            cvo.push_back((int32_t)cv.size());
+            // the face centroid is half way to the neighbour's centre
+            const int nb[3] = {c[0] + 2 * sum[0] / (int)f.size(), c[1] + 2 * sum[1] / (int)f.size(), c[2] + 2 * sum[2] / (int)f.size()};
+            const int r = rankOfCentre(nb);
+            cpRank.push_back(r);
+            if (r >= 0 && r != rank)
+                patchOfRank[r] = 0;
+        }
+        cfo.push_back((int32_t)cvo.size() - 1);
+    }
+    std::vector<std::string> names{"walls"}, types{"wall"};
+    for (auto &kv : patchOfRank)
+    {
+        kv.second = (int)names.size();
+        names.push_back("procBoundary" + std::to_string(rank) + "to" + std::to_string(kv.first));
+        types.push_back("processor");
+    }
+    cp.resize(cpRank.size());
+    for (size_t i = 0; i < cpRank.size(); ++i)
+        cp[i] = (cpRank[i] < 0 || cpRank[i] == rank) ? 0 : patchOfRank[cpRank[i]];
+    PolyMesh m = buildFromCells(pts, cfo, cvo, cv, cp, names, types);
+    // a face towards a cell of this brick must have been paired: a wall patch face whose neighbour exists here
+    // would mean the templates and the neighbour rule disagree
+    for (auto &kv : patchOfRank)
+    {
+        m.patches[kv.second].myProc = rank;
+        m.patches[kv.second].nbrProc = kv.first;
+    }
+    m.pointGlobalId = gid;
+    m.cellGlobalId.resize(centres.size());
+    for (size_t i = 0; i < centres.size(); ++i)
+    {
+        const int b = centres[i][0] % 4 == 0 ? 0 : 1;
+        const int64_t ci = (centres[i][0] - 2 * b) / 4, cj = (centres[i][1] - 2 * b) / 4, ck = (centres[i][2] - 2 * b) / 4;
+        m.cellGlobalId[i] = 2 * ((ck * n + cj) * n + ci) + b;
+    }
+    return m;
 }
 
 // ------------------------------------------------------------------ jitter ----

@@ -61,6 +61,9 @@ PolyMesh genHexBlockPart(int nx, int ny, int nz, int px, int py, int pz, int ran
 // Kelvin-cell (truncated octahedron, BCC Voronoi) polyhedral mesh clipped to the
 // box [0,n]^3*h: stand-in for polyDualMesh output.
 PolyMesh genKelvin(int n, double h);
+// One brick of that mesh (rank = ix + px*(iy + py*iz) of a px x py x pz split of the lattice) in processor-mesh
+// form, generated locally (config 4 at its stated size never exists on one host).
+PolyMesh genKelvinPart(int n, double h, int px, int py, int pz, int rank);
 
 // Generic builder: cells given as lists of outward-oriented faces (vertex
 // loops).  cellFaceOffsets[C+1] indexes faces; cfVertOffsets[NF+1] / cfVerts

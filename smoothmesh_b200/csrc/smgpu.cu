@@ -63,6 +63,9 @@ struct smgpu_handle
     std::vector<uint8_t> boundaryClass; // per point, bits as Dev::bClass
     std::vector<sm::Patch> patches;     // patch table of the mesh (boundary set-up needs it after create)
     bool useTiles = false; // fused geometry kernel over sm::GeomTiles
+    bool tilesF = false;   // its second generation (k_geom_tiles_f: run-time strides, fused face-angle filter)
+    bool tilesUniform = false, tilesHavePairs = false;
+    size_t tileSmem = 0;
     int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
     bool doLayers = false;
     bool anyLayerPatch = false;
@@ -203,6 +206,19 @@ struct smgpu_handle
                          (16.0 * d.epsAbs / (0.5 * meshMinEdge) + 2e-5 < 0.02);
         if (noFilters)
             d.edgeFilter = d.faceFilter = d.faceFilter32 = d.edgeFilter32 = 0;
+        // Fused face-angle filter of k_geom_tiles_f: single precision relative to a tile-local origin, its error
+        // budget evaluated per cell at run time, so it has no precondition on the size of the mesh.  Off with
+        // boundary point smoothing (kept on the FP64 filter like the other single-precision level, to keep that
+        // feature's validated configuration unchanged) and under SMGPU_NO_F32 / SMGPU_NO_FUSED_FILTER.
+        d.fusedFaceFilter = (tilesF && tilesHavePairs && d.faceFilter && !getenv("SMGPU_NO_F32") && !doBoundary &&
+                             !(getenv("SMGPU_NO_FUSED_FILTER") && atoi(getenv("SMGPU_NO_FUSED_FILTER")) != 0))
+                                ? 1
+                                : 0;
+        if (d.fusedFaceFilter)
+            d.faceFilter32 = 0; // the per-edge single-precision level is not used (smgpu_op_edge_face_angles is literal)
+        d.faceMirrors = d.faceFilter32;
+        d.faceMean64 = (!d.fusedFaceFilter && d.faceFilter && !d.faceFilter32) ? 1 : 0;
+        d.pointMirrors = (d.edgeFilter32 || d.faceFilter32) ? 1 : 0;
     }
     bool noFilters = false; // SMGPU_NO_FILTERS=1: always take the literal path (testing aid)
     void ensureStats(int n)
@@ -284,6 +300,19 @@ struct smgpu_handle
     // (SMGPU_NO_TILES=1, or a mesh with a cell too large for a tile)
     void launchCellCentres()
     {
+        if (useTiles && tilesF)
+        {
+            profBegin(K_GEOM_TILES);
+            if (d.fusedFaceFilter)
+                CK(cudaMemsetAsync(d.suspect, 0, (size_t)d.P, stream));
+            if (tilesUniform)
+                k_geom_tiles_f<true><<<d.nTiles, SMK_TILE_CELLS, tileSmem, stream>>>(d);
+            else
+                k_geom_tiles_f<false><<<d.nTiles, SMK_TILE_CELLS, tileSmem, stream>>>(d);
+            profEnd(1);
+            ++launches;
+            return;
+        }
         if (useTiles)
         {
             profBegin(K_GEOM_TILES);
@@ -404,7 +433,10 @@ struct smgpu_handle
     {
         const int nChunks = grid(d.P, SMK_CHUNK);
         profBegin(K_FACE_CUR);
-        k_face_current<<<grid(d.E, 128), 128, 0, stream>>>(d, dbgMin, dbgMax);
+        if (d.fusedFaceFilter && !dbgMin)
+            k_face_suspects<<<grid(d.P, 128), 128, 0, stream>>>(d); // the pairs k_geom_tiles_f did not certify
+        else
+            k_face_current<<<grid(d.E, 128), 128, 0, stream>>>(d, dbgMin, dbgMax);
         profEnd(1);
         profBegin(K_COMPACT);
         k_active_count<<<nChunks, 256, 0, stream>>>(d);
@@ -1124,6 +1156,36 @@ extern "C"
                     d.tilePoints = h->upload(G.tilePoints);
                     d.faceRefOff = h->upload(G.faceRefOff);
                     d.faceRef = h->upload(G.faceRef);
+                    const bool oldTiles = getenv("SMGPU_OLD_TILES") && atoi(getenv("SMGPU_OLD_TILES")) != 0;
+                    h->tilesUniform = d.uniformFaceSize == 4 && d.uniformCellFaces == 6 && (G.cellEdgeRef.empty() || !G.hexRec.empty());
+                    h->tilesHavePairs = !G.cellEdgeRef.empty();
+                    d.uniformCellEdges = G.uniformCellEdges;
+                    d.tileSF = (G.maxTileFaces + 31) / 32 * 32;
+                    d.tileSP = (G.maxTilePoints + 31) / 32 * 32;
+                    d.tileSE = h->tilesUniform && h->tilesHavePairs ? 4 * G.maxTileCells : 0; // 32-byte record per cell
+                    h->tileSmem = tileSmemBytes(d.tileSF, d.tileSP, d.tileSE);
+                    if (h->tilesHavePairs)
+                    {
+                        if (!h->tilesUniform)
+                            d.cellEdgeOff = h->upload(G.cellEdgeOff);
+                        if (h->tilesUniform)
+                            d.hexRec = (const uint2 *)h->upload(G.hexRec); // the pair lists stay on the host
+                        else
+                            d.cellEdgeRef = (const uint2 *)h->upload(G.cellEdgeRef);
+                    }
+                    d.suspect = h->dalloc<uint8_t>(t.P + 8);
+                    CK(cudaMemset(d.suspect, 0, t.P + 8));
+                    h->tilesF = !oldTiles && h->tileSmem <= 110 * 1024;
+                    {
+                        int perSm = 0, sms = 0;
+                        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, params->device));
+                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_geom_tiles_f<true>, SMK_TILE_CELLS, h->tileSmem));
+                        d.tilePrefetch = std::max(1, perSm) * sms; // one generation of resident blocks ahead
+                        if (getenv("SMGPU_TILE_PREFETCH"))
+                            d.tilePrefetch = atoi(getenv("SMGPU_TILE_PREFETCH"));
+                    }
+                    CK(cudaFuncSetAttribute(k_geom_tiles_f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(h->tileSmem, 220 * 1024)));
+                    CK(cudaFuncSetAttribute(k_geom_tiles_f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(h->tileSmem, 220 * 1024)));
                     CK(cudaFuncSetAttribute(k_geom_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     CK(cudaFuncSetAttribute(k_geom_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     if (getenv("SMGPU_TILE_MINB"))
@@ -1494,6 +1556,56 @@ extern "C"
             for (int64_t i = 0; i < h->topo.P; ++i)
                 out[h->pointOldOfNew[i]] = tmp[i];
         }
+        return SMGPU_OK;
+    }
+
+    int smgpu_filter_stats(smgpu_handle *h, int64_t out[4])
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        try
+        {
+            CK(cudaSetDevice(h->prm.device));
+            const size_t P = (size_t)h->topo.P;
+            std::vector<uint8_t> buf(P);
+            out[0] = h->d.fusedFaceFilter;
+            out[1] = 0;
+            if (h->d.suspect && h->d.fusedFaceFilter)
+            {
+                CK(cudaMemcpy(buf.data(), h->d.suspect, P, cudaMemcpyDeviceToHost));
+                for (uint8_t b : buf)
+                    out[1] += b != 0;
+            }
+            CK(cudaMemcpy(buf.data(), h->d.activeFlag, P, cudaMemcpyDeviceToHost));
+            out[2] = 0;
+            for (uint8_t b : buf)
+                out[2] += b != 0;
+            out[3] = (h->useTiles ? 1 : 0) | (h->tilesF ? 2 : 0) | (h->tilesUniform ? 4 : 0) | (h->d.faceFilter32 ? 8 : 0) |
+                     (h->d.edgeFilter32 ? 16 : 0);
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_CUDA, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_selftest_division(int32_t device, uint64_t seed, int64_t n, int64_t *mismatches)
+    {
+        if (!mismatches || n < 1)
+            return setErr(SMGPU_ERR_ARG, "bad argument");
+        unsigned long long *dbad = nullptr;
+        if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&dbad, 8) != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, "no CUDA device");
+        cudaMemset(dbad, 0, 8);
+        const int blocks = 1184, threads = 256, per = (int)std::min<int64_t>(1 << 20, (n + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads));
+        k_selftest_division<<<blocks, threads>>>(seed, per, dbad);
+        unsigned long long bad = 0;
+        const cudaError_t e = cudaMemcpy(&bad, dbad, 8, cudaMemcpyDeviceToHost);
+        cudaFree(dbad);
+        if (e != cudaSuccess)
+            return setErr(SMGPU_ERR_CUDA, cudaGetErrorString(e));
+        *mismatches = (int64_t)bad;
         return SMGPU_OK;
     }
 

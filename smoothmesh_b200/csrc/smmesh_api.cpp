@@ -59,6 +59,10 @@ extern "C"
     {
         return guarded([&] { return sm::genKelvin(n, h); });
     }
+    smmesh *smmesh_gen_kelvin_part(int32_t n, double h, int32_t px, int32_t py, int32_t pz, int32_t rank)
+    {
+        return guarded([&] { return sm::genKelvinPart(n, h, px, py, pz, rank); });
+    }
     smmesh *smmesh_from_cells(int64_t n_points, const double *points, int32_t n_cells, const int32_t *cfo,
                               const int32_t *cvo, const int32_t *cv, const int32_t *cp, int32_t n_patches,
                               const char *const *names, const char *const *types)
@@ -243,7 +247,7 @@ extern "C"
         }
         return SMGPU_OK;
     }
-    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[5])
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[7])
     {
         try
         {
@@ -297,6 +301,48 @@ extern "C"
                     }
                 }
             }
+            // the (edge, cell) pairs of the fused face-angle filter: every pair names an edge of the mesh, one of
+            // its cells, and the two faces findCellFacePair (src/smoothMesh.C:1042-1097) returns for them; all
+            // pairs of the mesh are listed exactly once
+            if (G.nTiles > 0 && !G.cellEdgeOff.empty())
+            {
+                int64_t listed = 0;
+                for (int32_t k = 0; k < G.nTiles; ++k)
+                {
+                    const int32_t fb = G.tileFaceOff[k], pb = G.tilePointOff[k], cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
+                    for (int32_t i = 0; i < nc; ++i)
+                    {
+                        const int32_t slot = cb + i, c = G.tileCells[slot];
+                        const int32_t n = G.cellEdgeOff[slot + 1] - G.cellEdgeOff[slot];
+                        for (int32_t j = 0; j < n; ++j)
+                        {
+                            const size_t at = G.uniformCellEdges ? (size_t)G.uniformCellEdges * cb + (size_t)j * nc + i
+                                                                 : (size_t)G.cellEdgeOff[slot] + j;
+                            const uint16_t *r = &G.cellEdgeRef[4 * at];
+                            const int32_t p0 = G.tilePoints[pb + r[0]], p1 = G.tilePoints[pb + r[1]];
+                            const int32_t f0 = G.tileFaces[fb + r[2]] & 0x7fffffff, f1 = G.tileFaces[fb + r[3]] & 0x7fffffff;
+                            int32_t e = -1;
+                            for (int32_t q = t.ppOff[p0]; q < t.ppOff[p0 + 1]; ++q)
+                                if (t.pp[q] == p1)
+                                    e = t.pe[q];
+                            if (e < 0 || p0 >= p1)
+                                throw std::runtime_error("(edge, cell) pair does not name an edge");
+                            bool found = false;
+                            for (int32_t q = t.ecOff[e]; q < t.ecOff[e + 1]; ++q)
+                                if (t.ecCell[q] == c)
+                                {
+                                    const int32_t g0 = t.ef[t.efOff[e] + (t.ecPair[q] & 0xffff)], g1 = t.ef[t.efOff[e] + ((t.ecPair[q] >> 16) & 0xffff)];
+                                    found = (g0 == f0 && g1 == f1) || (g0 == f1 && g1 == f0);
+                                }
+                            if (!found)
+                                throw std::runtime_error("(edge, cell) pair does not match the cell's face pair at that edge");
+                            ++listed;
+                        }
+                    }
+                }
+                if (listed != (int64_t)t.ecCell.size())
+                    throw std::runtime_error("(edge, cell) pairs do not cover the mesh exactly once");
+            }
             if (G.nTiles > 0)
             {
                 for (int32_t c = 0; c < t.C; ++c)
@@ -311,6 +357,8 @@ extern "C"
             out[2] = maxFaces;
             out[3] = t.F;
             out[4] = maxPoints;
+            out[5] = (int64_t)G.cellEdgeRef.size() / 4;
+            out[6] = G.uniformCellEdges;
         }
         catch (const std::exception &e)
         {

@@ -3,6 +3,7 @@
 #include "sm_math.h"
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -939,6 +940,211 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         }
     }
     tick("tiles: references");
+    // ---- (edge, cell) pairs of the fused face-angle filter: the edges of a cell are the vertex pairs that two
+    //      of its faces share; both faces and both end points are already tile-local references ----
+    {
+        std::vector<int32_t> nPairs(C + 1, 0);
+        bool closed = true;
+        struct Half
+        {
+            uint16_t a, b, f;
+        };
+        auto cellPairs = [&](int32_t k, int32_t slot, std::vector<Half> &hs, uint16_t *out) -> int32_t {
+            // half edges of the cell's faces, sorted by end points; a closed cell has every edge exactly twice
+            hs.clear();
+            const int32_t fb = G.tileFaceOff[k];
+            for (int32_t q = G.slotOff[slot]; q < G.slotOff[slot + 1]; ++q)
+            {
+                const uint16_t li = G.slotRef[q] & 0x7fff;
+                const int32_t rb = G.faceRefOff[fb + li], nv = G.faceRefOff[fb + li + 1] - rb;
+                for (int32_t v = 0; v < nv; ++v)
+                {
+                    const uint16_t a = G.faceRef[rb + v], b = G.faceRef[rb + (v + 1 == nv ? 0 : v + 1)];
+                    hs.push_back({std::min(a, b), std::max(a, b), li});
+                }
+            }
+            std::sort(hs.begin(), hs.end(), [](const Half &x, const Half &y) {
+                return x.a != y.a ? x.a < y.a : (x.b != y.b ? x.b < y.b : x.f < y.f);
+            });
+            if (hs.size() % 2)
+                return -1;
+            int32_t n = 0;
+            for (size_t i = 0; i < hs.size(); i += 2)
+            {
+                if (hs[i].a != hs[i + 1].a || hs[i].b != hs[i + 1].b || hs[i].a == hs[i].b ||
+                    (i + 2 < hs.size() && hs[i + 2].a == hs[i].a && hs[i + 2].b == hs[i].b))
+                    return -1;
+                if (out)
+                {
+                    out[4 * n] = hs[i].a, out[4 * n + 1] = hs[i].b;
+                    out[4 * n + 2] = hs[i].f, out[4 * n + 3] = hs[i + 1].f;
+                }
+                ++n;
+            }
+            return n;
+        };
+#pragma omp parallel
+        {
+            std::vector<Half> hs;
+#pragma omp for schedule(dynamic, 16)
+            for (int32_t k = 0; k < G.nTiles; ++k)
+                for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
+                {
+                    const int32_t n = cellPairs(k, slot, hs, nullptr);
+                    if (n < 0)
+                    {
+#pragma omp atomic write
+                        closed = false;
+                    }
+                    nPairs[slot + 1] = std::max(n, 0);
+                }
+        }
+        for (int32_t k = 0; k < G.nTiles; ++k)
+        {
+            G.maxTileCells = std::max(G.maxTileCells, G.tileCellOff[k + 1] - G.tileCellOff[k]);
+            G.maxTileFaces = std::max(G.maxTileFaces, G.tileFaceOff[k + 1] - G.tileFaceOff[k]);
+            G.maxTilePoints = std::max(G.maxTilePoints, G.tilePointOff[k + 1] - G.tilePointOff[k]);
+        }
+        if (closed)
+        {
+            G.uniformCellEdges = C ? nPairs[1] : 0;
+            for (int64_t c = 0; c < C && G.uniformCellEdges; ++c)
+                if (nPairs[c + 1] != G.uniformCellEdges)
+                    G.uniformCellEdges = 0;
+            int64_t total = 0;
+            for (int64_t c = 0; c < C; ++c)
+                total += nPairs[c + 1];
+            if (total < (int64_t)INT32_MAX / 2)
+            {
+                G.cellEdgeOff.assign(C + 1, 0);
+                for (int64_t c = 0; c < C; ++c)
+                    G.cellEdgeOff[c + 1] = G.cellEdgeOff[c] + nPairs[c + 1];
+                G.cellEdgeRef.resize(4 * (size_t)total);
+                for (int32_t k = 0; k < G.nTiles; ++k)
+                    G.maxTileEdgePairs = std::max(G.maxTileEdgePairs, G.cellEdgeOff[G.tileCellOff[k + 1]] - G.cellEdgeOff[G.tileCellOff[k]]);
+#pragma omp parallel
+                {
+                    std::vector<Half> hs;
+                    std::vector<uint16_t> tmp;
+#pragma omp for schedule(dynamic, 16)
+                    for (int32_t k = 0; k < G.nTiles; ++k)
+                    {
+                        const int32_t cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
+                        for (int32_t i = 0; i < nc; ++i)
+                        {
+                            const int32_t slot = cb + i;
+                            if (!G.uniformCellEdges)
+                            {
+                                cellPairs(k, slot, hs, G.cellEdgeRef.data() + 4 * (size_t)G.cellEdgeOff[slot]);
+                                continue;
+                            }
+                            tmp.resize(4 * (size_t)G.uniformCellEdges);
+                            cellPairs(k, slot, hs, tmp.data());
+                            for (int32_t j = 0; j < G.uniformCellEdges; ++j) // pair-major inside the tile
+                                for (int q = 0; q < 4; ++q)
+                                    G.cellEdgeRef[4 * ((size_t)G.uniformCellEdges * cb + (size_t)j * nc + i) + q] = tmp[4 * j + q];
+                        }
+                    }
+                }
+            }
+        }
+        // canonical hexahedron records (see topology.hpp), checked against the pair lists above
+        if (closed && G.uniformCellEdges == 12 && !G.cellEdgeRef.empty())
+        {
+            bool allHex = true;
+            for (int64_t f = 0; f < F && allHex; ++f)
+                allHex = m.faceOffsets[f + 1] - m.faceOffsets[f] == 4;
+            for (int64_t c = 0; c < C && allHex; ++c)
+                allHex = t.cfOff[c + 1] - t.cfOff[c] == 6;
+            if (allHex)
+            {
+                G.hexRec.assign(16 * (size_t)C, 0);
+                bool ok = true;
+#pragma omp parallel for schedule(dynamic, 16)
+                for (int32_t k = 0; k < G.nTiles; ++k)
+                {
+                    const int32_t cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb, fb = G.tileFaceOff[k];
+                    for (int32_t i = 0; i < nc; ++i)
+                    {
+                        const int32_t slot = cb + i;
+                        uint16_t fl[6], fv[6][4];
+                        for (int q = 0; q < 6; ++q)
+                        {
+                            fl[q] = G.slotRef[G.slotOff[slot] + q] & 0x7fff;
+                            const int32_t rb = G.faceRefOff[fb + fl[q]];
+                            for (int v = 0; v < 4; ++v)
+                                fv[q][v] = G.faceRef[rb + v];
+                        }
+                        auto has = [&](int q, uint16_t p) { return fv[q][0] == p || fv[q][1] == p || fv[q][2] == p || fv[q][3] == p; };
+                        uint16_t rec[16] = {0};
+                        bool good = true;
+                        int B = -1;
+                        for (int q = 1; q < 6; ++q)
+                            if (!has(q, fv[0][0]) && !has(q, fv[0][1]) && !has(q, fv[0][2]) && !has(q, fv[0][3]))
+                                B = (B < 0) ? q : 99;
+                        good = B >= 1 && B < 6;
+                        for (int e = 0; e < 4 && good; ++e)
+                        {
+                            const uint16_t a = fv[0][e], b = fv[0][(e + 1) & 3];
+                            int S = -1;
+                            for (int q = 1; q < 6; ++q)
+                                if (q != B && has(q, a) && has(q, b))
+                                    S = (S < 0) ? q : 99;
+                            if (S < 1 || S > 5)
+                            {
+                                good = false;
+                                break;
+                            }
+                            // w_e: the neighbour of a in S's loop that is not b
+                            int at = 0;
+                            while (fv[S][at] != a)
+                                ++at;
+                            const uint16_t n1 = fv[S][(at + 1) & 3], n2 = fv[S][(at + 3) & 3];
+                            const uint16_t w = (n1 == b) ? n2 : n1;
+                            good = (n1 == b || n2 == b) && has(B, w);
+                            rec[e] = a;
+                            rec[4 + e] = w;
+                            rec[10 + e] = fl[S];
+                        }
+                        rec[8] = fl[0];
+                        rec[9] = good ? fl[B] : 0;
+                        if (good)
+                        { // the pattern must reproduce the cell's pair list
+                            std::vector<std::array<uint16_t, 4>> want, got;
+                            for (int j = 0; j < 12; ++j)
+                            {
+                                const uint16_t *r = &G.cellEdgeRef[4 * ((size_t)12 * cb + (size_t)j * nc + i)];
+                                want.push_back({r[0], r[1], std::min(r[2], r[3]), std::max(r[2], r[3])});
+                            }
+                            auto add = [&](uint16_t p0, uint16_t p1, uint16_t f0, uint16_t f1) {
+                                got.push_back({std::min(p0, p1), std::max(p0, p1), std::min(f0, f1), std::max(f0, f1)});
+                            };
+                            for (int e = 0; e < 4; ++e)
+                            {
+                                add(rec[e], rec[(e + 1) & 3], rec[8], rec[10 + e]);
+                                add(rec[4 + e], rec[4 + ((e + 1) & 3)], rec[9], rec[10 + e]);
+                                add(rec[e], rec[4 + e], rec[10 + ((e + 3) & 3)], rec[10 + e]);
+                            }
+                            std::sort(want.begin(), want.end());
+                            std::sort(got.begin(), got.end());
+                            good = want == got;
+                        }
+                        if (!good)
+                        {
+#pragma omp atomic write
+                            ok = false;
+                        }
+                        uint16_t *o1 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)i], *o2 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)nc + 8 * (size_t)i];
+                        for (int q = 0; q < 8; ++q)
+                            o1[q] = rec[q], o2[q] = rec[8 + q];
+                    }
+                }
+                if (!ok)
+                    G.hexRec.clear();
+            }
+        }
+        tick("tiles: (edge, cell) pairs");
+    }
     return G;
 }
 } // namespace sm

@@ -95,6 +95,25 @@ struct GeomTiles
     std::vector<int32_t> tilePointOff, tilePoints; // ascending point labels
     std::vector<int32_t> faceRefOff;               // per listed face (position in tileFaces) + 1: offsets into faceRef
     std::vector<uint16_t> faceRef;
+    // The (edge, cell) pairs of the fused face-angle filter: for every cell slot, each edge of the cell with its
+    // end points (indices into the tile's point list) and the two faces of the cell that meet at it (indices
+    // into the tile's face list) -- what calcMinMaxFaceAngleForEdge (src/smoothMesh.C:1135-1231) visits for this
+    // cell of the edge.  4 x uint16 per pair: p0, p1, f0, f1.  Uniform meshes (every cell has `uniformCellEdges`
+    // edges): the pairs of tile k start at uniformCellEdges * tileCellOff[k], stored pair-major (pair j of the
+    // tile's i-th cell at j * nCellsOfTile + i) so that a warp reads consecutive records; otherwise cell-major
+    // through cellEdgeOff (per slot + 1).  Empty when some cell is not closed (an edge not shared by exactly two
+    // of its faces): the caller then keeps the per-edge kernel.
+    std::vector<int32_t> cellEdgeOff;
+    std::vector<uint16_t> cellEdgeRef;
+    // All-hexahedra meshes: the same pairs as a canonical record per cell slot, 16 x uint16:
+    //   v0..v3 (vertex loop of one face A), w0..w3 (w_i = the vertex joined to v_i by an edge, on the opposite
+    //   face B), A, B, S0..S3 (S_i = the side face through v_i, v_i+1, w_i+1, w_i), 2 x padding.
+    // The twelve (edge, cell) pairs are then a fixed pattern: (v_i, v_i+1 | A, S_i), (w_i, w_i+1 | B, S_i),
+    // (v_i, w_i | S_i-1, S_i).  Per tile: the first 8 entries of all its cells, then the second 8 (two
+    // conflict-free 16-byte reads per thread).  Empty unless every cell matched.
+    std::vector<uint16_t> hexRec;
+    int32_t uniformCellEdges = 0;
+    int32_t maxTileCells = 0, maxTileFaces = 0, maxTilePoints = 0, maxTileEdgePairs = 0;
 };
 GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints);
 

@@ -23,6 +23,8 @@ def test_full_size_filtered_path_equals_literal_path(mesh, monkeypatch):
     g = sm.Smoother(mesh, rel_tol=0.0)
     log = g.iterate(iters)
     pts, fz = g.points(), g.frozen()
+    st = g.filter_stats()
+    assert st["fused"] and st["suspect_points"] <= 0.001 * mesh.n_points, st   # the fast path is the one measured
     g.close()
     monkeypatch.setenv("SMGPU_NO_FILTERS", "1")
     monkeypatch.setenv("SMGPU_NO_TILES", "1")  # and the two-kernel geometry instead of the fused tile kernel

@@ -133,12 +133,15 @@ def test_no_gpu_fallback_message():
 
 
 @pytest.mark.parametrize("case", ["hex_8x6x5_j45", "kelvin3_j20"])
-@pytest.mark.parametrize("env", ["SMGPU_NO_FILTERS", "SMGPU_NO_F32", "SMGPU_NO_TILES", "SMGPU_FORCE_TILES"])
+@pytest.mark.parametrize("env", ["SMGPU_NO_FILTERS", "SMGPU_NO_F32", "SMGPU_NO_TILES", "SMGPU_FORCE_TILES",
+                                 "SMGPU_NO_FUSED_FILTER", "SMGPU_OLD_TILES"])
 def test_literal_path_without_filters(case, env, monkeypatch):
     # SMGPU_NO_FILTERS=1 disables the guard-banded cosine-space filters so that every point /
     # edge takes the literal evaluation; SMGPU_NO_F32=1 disables only the single-precision first
     # level; SMGPU_NO_TILES=1 replaces the fused geometry kernel by the per-face + per-cell pair and
     # SMGPU_FORCE_TILES=1 uses it on polyhedral meshes too (default: all-quad / all-hex meshes only).
+    # SMGPU_NO_FUSED_FILTER=1 keeps the per-edge face-angle filter (k_face_current) instead of the per-cell one
+    # fused into the geometry tiles, SMGPU_OLD_TILES=1 the first-generation tile kernel.
     # Every combination must reproduce the oracle bit for bit.
     monkeypatch.setenv(env, "1")
     mesh = CASES[case]()
@@ -181,3 +184,37 @@ def test_mesh_quality_acceptance_after_smoothing():
     for k in ("max_non_ortho", "max_skewness", "min_edge_angle"):
         assert abs(qa[k] - qb[k]) <= 1e-6 * max(abs(qb[k]), 1e-30), k
     assert qa["max_non_ortho"] < 0.2 * before["max_non_ortho"] and qa["min_edge_angle"] > before["min_edge_angle"]
+
+
+@pytest.mark.parametrize("case,opts", [("slab", "default"), ("slab", "tight_angles"), ("far", "default"), ("far", "tight_angles")])
+def test_fused_face_filter_is_size_independent(case, opts):
+    """The fused face-angle filter works in single precision relative to a tile-local origin: its error budget
+    must not depend on how large the mesh is relative to its cells, or on where the mesh lies.  A long thin slab
+    (bounding box 250 cells long) and a block far from the coordinate origin: bit-exact against the oracle, and
+    at the default angle limits the filter certifies (almost) everything."""
+    if case == "slab":
+        mesh = sm.Mesh.hex_block(250, 4, 4, hi=(250.0, 4.0, 4.0)).jitter(0.25, 7)
+    else:
+        mesh = sm.Mesh.hex_block(12, 10, 9, lo=(4000.0, -7000.0, 9000.0), hi=(4001.2, -6999.0, 9000.9)).jitter(0.025, 8)
+    kw = dict(OPTION_SETS[opts], rel_tol=0.0)
+    g, o = _pair(mesh, **kw)
+    n, nf, res = o.iterate(8)
+    log = g.iterate(8)
+    assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
+    assert np.array_equal(g.frozen(), o.get("frozen")) and np.array_equal(g.points(), o.get("points"))
+    st = g.filter_stats()
+    assert st["fused"]
+    if opts == "default":
+        assert st["suspect_points"] <= 0.02 * mesh.n_points, st
+
+
+def test_shared_reciprocal_division_is_ieee_division():
+    """The geometry kernels divide the three components of a vector by one scalar with a single reciprocal
+    (kernels.cuh divShared); every quotient must be the IEEE quotient bit for bit: 3 x 10^9 components."""
+    import ctypes as C
+    bad = C.c_int64(-1)
+    L = sm.lib()
+    L.smgpu_selftest_division.argtypes = [C.c_int32, C.c_uint64, C.c_int64, C.c_void_p]
+    for seed in (1, 20261017):
+        assert L.smgpu_selftest_division(0, seed, 500_000_000, C.byref(bad)) == 0
+        assert bad.value == 0

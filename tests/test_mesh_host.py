@@ -8,6 +8,7 @@ import pytest
 import smoothmesh_b200 as sm
 
 from meshes import hex_jittered
+from oracle import Oracle
 
 
 def test_hex_block_counts_and_numbering():
@@ -318,3 +319,44 @@ def test_bvh_ray_casts_equal_the_visit_every_triangle_search():
         t1, p1 = cast(pts, tris, a, b, 1)
         assert (t0 >= 0).sum() > 100
         assert np.array_equal(t0, t1) and np.array_equal(p0, p1)
+
+
+@pytest.mark.parametrize("n,dims", [(3, (2, 1, 1)), (4, (2, 2, 1)), (4, (2, 2, 2)), (5, (3, 1, 2))])
+def test_kelvin_bricks_generated_per_rank_form_the_global_mesh(n, dims):
+    """BASELINE config 4 at its stated size is generated per rank (smmesh_gen_kelvin_part): the bricks must tile
+    the global Kelvin mesh -- same cells, same points (matched through point_global_id, identical coordinates
+    on every copy), every inter-brick face listed once by each side, and the same jitter on every copy."""
+    px, py, pz = dims
+    whole = sm.Mesh.kelvin(n, 1.0)
+    parts = [sm.Mesh.kelvin_part(n, 1.0, px, py, pz, r) for r in range(px * py * pz)]
+    assert sum(p.n_cells for p in parts) == whole.n_cells == 2 * n ** 3
+    coords = {}
+    for p in parts:
+        for g, x in zip(p.point_global_id.tolist(), np.asarray(p.points).tolist()):
+            assert coords.setdefault(g, x) == x
+    assert len(coords) == whole.n_points
+    assert sorted(map(tuple, coords.values())) == sorted(map(tuple, np.asarray(whole.points).tolist()))
+    # faces: internal faces of the bricks + half the processor faces + wall faces = faces of the whole mesh
+    n_int = sum(p.n_internal_faces for p in parts)
+    n_proc = n_wall = 0
+    pair = {}
+    for r, p in enumerate(parts):
+        s, z, k = p.patches
+        for name, size, kind in zip(p.patch_names, z, k):
+            if kind == sm.PATCH_PROCESSOR:
+                n_proc += size
+                other = int(name.split("to")[1])
+                pair[(r, other)] = size
+            else:
+                n_wall += size
+    assert all(pair[(b, a)] == v for (a, b), v in pair.items())
+    assert n_int + n_proc // 2 + n_wall == whole.n_faces and n_wall == whole.n_faces - whole.n_internal_faces
+    for p in parts:
+        p.jitter(0.05, 11)
+    moved = {}
+    for p in parts:
+        for g, x in zip(p.point_global_id.tolist(), np.asarray(p.points).tolist()):
+            assert moved.setdefault(g, x) == x
+    # the rank-emulating oracle accepts the bricks (interface points found through point_global_id)
+    o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0)
+    assert o.iterate(2)[0] == 2
