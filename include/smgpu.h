@@ -170,6 +170,10 @@ extern "C"
      * per-point single-precision filter level in use}. */
     int smgpu_filter_stats(smgpu_handle *h, int64_t out[4]);
 
+    /* Geometry tiles of this handle: out = {tiles (0 = two-kernel geometry), faces listed over all tiles (border
+     * faces are listed by both tiles), points listed over all tiles, dynamic shared memory per block [bytes]}. */
+    int smgpu_tile_stats(smgpu_handle *h, int64_t out[4]);
+
     /* Self-test of the shared-reciprocal division the geometry kernels use (one reciprocal for the three
      * components of a vector, the quotients bit-identical to IEEE division): about n random and structured
      * (a, d) triples on the device, *mismatches = components that differ from a / d (must be 0). */

@@ -593,6 +593,12 @@ class Smoother:
         self._ck(lib().smgpu_get_boundary_classes(self._h, _ptr(a), _ptr(b)))
         return a, b
 
+    def tile_stats(self):
+        out = (C.c_int64 * 4)()
+        lib().smgpu_tile_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._ck(lib().smgpu_tile_stats(self._h, out))
+        return dict(tiles=int(out[0]), listed_faces=int(out[1]), listed_points=int(out[2]), smem_bytes=int(out[3]))
+
     def filter_stats(self):
         out = (C.c_int64 * 4)()
         lib().smgpu_filter_stats.argtypes = [C.c_void_p, C.c_void_p]

@@ -65,6 +65,7 @@ struct smgpu_handle
     bool useTiles = false; // fused geometry kernel over sm::GeomTiles
     bool tilesF = false;   // its second generation (k_geom_tiles_f: run-time strides, fused face-angle filter)
     bool tilesUniform = false, tilesHavePairs = false;
+    int64_t tileListedFaces = 0, tileListedPoints = 0;
     size_t tileSmem = 0;
     int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
     bool doLayers = false;
@@ -219,6 +220,39 @@ struct smgpu_handle
         d.faceMirrors = d.faceFilter32;
         d.faceMean64 = (!d.fusedFaceFilter && d.faceFilter && !d.faceFilter32) ? 1 : 0;
         d.pointMirrors = (d.edgeFilter32 || d.faceFilter32) ? 1 : 0;
+        ensureBuffers();
+    }
+    // Buffers only some configurations touch, allocated when a configuration that needs them is selected:
+    // the 64-byte face records (two-kernel geometry; boundary face areas for the point normals), the FP64 /
+    // fp32 face-mean and cell-centre tables and the 48-byte edge records of the per-edge face-angle filter,
+    // the fp32 point mirrors of the single-precision filter levels.  At 368^3 they would add 27 GB.
+    void ensureBuffers()
+    {
+        if (!d.pts)
+            return; // smgpu_create has not allocated the state yet
+        const bool perEdgeFilter = !d.fusedFaceFilter && d.faceFilter;
+        if (!d.faceGeo && (!useTiles || anyLayerPatch || doBoundary))
+            d.faceGeo = dalloc<P4>(2 * topo.F);
+        if (!d.faceMean && d.faceMean64)
+            d.faceMean = dalloc<P4>(topo.F);
+        if (!d.faceMeanF && d.faceMirrors)
+        {
+            d.faceMeanF = dalloc<float4>(topo.F);
+            d.cellCtrF = dalloc<float4>(topo.C);
+        }
+        if (!d.ptsF && d.pointMirrors)
+        {
+            d.ptsF = dalloc<float4>(topo.P);
+            d.newPtsF = dalloc<float4>(topo.P);
+            CK(cudaMemsetAsync(d.newPtsF, 0, topo.P * sizeof(float4), stream));
+            k_mirror_points<<<grid(d.P, 256), 256, 0, stream>>>(d);
+        }
+        if (!d.edgeRec && perEdgeFilter)
+        {
+            sm::buildEdgeRecords(topo);
+            d.edgeRec = (const int4 *)upload(topo.edgeRec);
+            std::vector<int32_t>().swap(topo.edgeRec);
+        }
     }
     bool noFilters = false; // SMGPU_NO_FILTERS=1: always take the literal path (testing aid)
     void ensureStats(int n)
@@ -274,7 +308,8 @@ struct smgpu_handle
         const double R = 0.5 * std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) +
                                          (hi[2] - lo[2]) * (hi[2] - lo[2]));
         d.epsAbs = (float)(8.0 * 5.9604644775390625e-08 * (1.01 * R + 4.0 * topo.maxEdgeLength)); // 8 x 2^-24 x R
-        k_mirror_points<<<grid(d.P, 256), 256, 0, stream>>>(d);
+        if (d.ptsF)
+            k_mirror_points<<<grid(d.P, 256), 256, 0, stream>>>(d);
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -1057,13 +1092,7 @@ extern "C"
             d.E = (int)t.E;
             d.F = (int)t.F;
             tick("CUDA context, stream");
-            d.faceGeo = h->dalloc<P4>(2 * t.F);
-            d.faceMean = h->dalloc<P4>(t.F);
-            d.ptsF = h->dalloc<float4>(t.P);
-            d.newPtsF = h->dalloc<float4>(t.P);
-            d.cellCtrF = h->dalloc<float4>(t.C);
-            d.faceMeanF = h->dalloc<float4>(t.F);
-
+            // face records, mirrors and edge records are allocated on first need (ensureBuffers)
             d.pts = h->dalloc<P4>(t.P);
             d.newPts = h->dalloc<P4>(t.P);
             d.cellCtr = h->dalloc<P4>(t.C);
@@ -1095,7 +1124,6 @@ extern "C"
                 if (t.cfOff[c + 1] - t.cfOff[c] != d.uniformCellFaces)
                     d.uniformCellFaces = 0;
             d.pointRec = (const int4 *)h->upload(t.pointRec);
-            d.edgeRec = (const int4 *)h->upload(t.edgeRec);
             d.curMin = h->dalloc<unsigned long long>(t.P);
             d.curMax = h->dalloc<unsigned long long>(t.P);
             d.activeFlag = h->dalloc<uint8_t>(t.P + 8);
@@ -1157,8 +1185,10 @@ extern "C"
                     d.faceRefOff = h->upload(G.faceRefOff);
                     d.faceRef = h->upload(G.faceRef);
                     const bool oldTiles = getenv("SMGPU_OLD_TILES") && atoi(getenv("SMGPU_OLD_TILES")) != 0;
-                    h->tilesUniform = d.uniformFaceSize == 4 && d.uniformCellFaces == 6 && (G.cellEdgeRef.empty() || !G.hexRec.empty());
-                    h->tilesHavePairs = !G.cellEdgeRef.empty();
+                    h->tilesHavePairs = !G.cellEdgeRef.empty() || !G.hexRec.empty();
+                    h->tilesUniform = d.uniformFaceSize == 4 && d.uniformCellFaces == 6 && (!h->tilesHavePairs || !G.hexRec.empty());
+                    h->tileListedFaces = (int64_t)G.tileFaces.size();
+                    h->tileListedPoints = (int64_t)G.tilePoints.size();
                     d.uniformCellEdges = G.uniformCellEdges;
                     d.tileSF = (G.maxTileFaces + 31) / 32 * 32;
                     d.tileSP = (G.maxTilePoints + 31) / 32 * 32;
@@ -1556,6 +1586,17 @@ extern "C"
             for (int64_t i = 0; i < h->topo.P; ++i)
                 out[h->pointOldOfNew[i]] = tmp[i];
         }
+        return SMGPU_OK;
+    }
+
+    int smgpu_tile_stats(smgpu_handle *h, int64_t out[4])
+    {
+        if (!h || !out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        out[0] = h->useTiles ? h->d.nTiles : 0;
+        out[1] = h->tileListedFaces;
+        out[2] = h->tileListedPoints;
+        out[3] = (int64_t)h->tileSmem;
         return SMGPU_OK;
     }
 

@@ -252,7 +252,7 @@ extern "C"
         try
         {
             const sm::Topology t = sm::buildTopology(m->m);
-            const sm::GeomTiles G = sm::buildGeomTiles(m->m, t, max_cells, max_faces, max_points);
+            const sm::GeomTiles G = sm::buildGeomTiles(m->m, t, max_cells, max_faces, max_points, true);
             // invariants the fused geometry kernel relies on
             std::vector<int32_t> cellSeen(t.C, 0), faceStored(t.F, 0);
             int64_t maxFaces = 0, maxPoints = 0;
@@ -316,8 +316,7 @@ extern "C"
                         const int32_t n = G.cellEdgeOff[slot + 1] - G.cellEdgeOff[slot];
                         for (int32_t j = 0; j < n; ++j)
                         {
-                            const size_t at = G.uniformCellEdges ? (size_t)G.uniformCellEdges * cb + (size_t)j * nc + i
-                                                                 : (size_t)G.cellEdgeOff[slot] + j;
+                            const size_t at = (size_t)G.cellEdgeOff[slot] + j;
                             const uint16_t *r = &G.cellEdgeRef[4 * at];
                             const int32_t p0 = G.tilePoints[pb + r[0]], p1 = G.tilePoints[pb + r[1]];
                             const int32_t f0 = G.tileFaces[fb + r[2]] & 0x7fffffff, f1 = G.tileFaces[fb + r[3]] & 0x7fffffff;

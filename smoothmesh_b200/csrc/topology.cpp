@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <array>
+#include <parallel/algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -378,6 +379,19 @@ Topology buildTopology(const PolyMesh &m)
             r[15] = mask;
         }
     }
+    tick("point records");
+    return t;
+}
+
+} // namespace sm
+
+namespace sm
+{
+void buildEdgeRecords(Topology &t)
+{
+    const int64_t E = t.E;
+    if (!t.edgeRec.empty())
+        return;
     t.edgeRec.assign(12 * E, 0);
 #pragma omp parallel for schedule(static)
     for (int64_t e = 0; e < E; ++e)
@@ -457,10 +471,7 @@ Topology buildTopology(const PolyMesh &m)
         const int32_t meta = nf | (nc << 4) | (fan ? 0 : (int32_t)0x80000000u);
         r[10] = meta;
     }
-    tick("point / edge records");
-    return t;
 }
-
 } // namespace sm
 
 // ------------------------------------------------- boundary layer treatment ----
@@ -741,7 +752,7 @@ inline uint64_t spreadBits21(uint64_t v)
 }
 } // namespace
 
-GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints)
+GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints, bool keepPairs)
 {
     GeomTiles G;
     const int64_t C = t.C, F = t.F, P = t.P;
@@ -802,7 +813,7 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         keys[c] = {key, (int32_t)c};
     }
     tick("tiles: cell keys");
-    std::sort(keys.begin(), keys.end());
+    __gnu_parallel::sort(keys.begin(), keys.end());
     tick("tiles: sort");
     if (maxFaces > 0x7fff || maxPoints > 0xffff)
         return GeomTiles();
@@ -983,27 +994,129 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
             }
             return n;
         };
+        // canonical hexahedron record of a cell (see topology.hpp), checked against its pair list
+        auto hexRecord = [&](int32_t k, int32_t slot, const uint16_t *pairs, uint16_t rec[16]) -> bool {
+            const int32_t fb = G.tileFaceOff[k];
+            if (G.slotOff[slot + 1] - G.slotOff[slot] != 6)
+                return false;
+            uint16_t fl[6], fv[6][4];
+            for (int q = 0; q < 6; ++q)
+            {
+                fl[q] = G.slotRef[G.slotOff[slot] + q] & 0x7fff;
+                const int32_t rb = G.faceRefOff[fb + fl[q]];
+                if (G.faceRefOff[fb + fl[q] + 1] - rb != 4)
+                    return false;
+                for (int v = 0; v < 4; ++v)
+                    fv[q][v] = G.faceRef[rb + v];
+            }
+            auto has = [&](int q, uint16_t p) { return fv[q][0] == p || fv[q][1] == p || fv[q][2] == p || fv[q][3] == p; };
+            for (int q = 0; q < 16; ++q)
+                rec[q] = 0;
+            int B = -1;
+            for (int q = 1; q < 6; ++q)
+                if (!has(q, fv[0][0]) && !has(q, fv[0][1]) && !has(q, fv[0][2]) && !has(q, fv[0][3]))
+                    B = (B < 0) ? q : 99;
+            if (B < 1 || B > 5)
+                return false;
+            for (int e = 0; e < 4; ++e)
+            {
+                const uint16_t a = fv[0][e], b = fv[0][(e + 1) & 3];
+                int S = -1;
+                for (int q = 1; q < 6; ++q)
+                    if (q != B && has(q, a) && has(q, b))
+                        S = (S < 0) ? q : 99;
+                if (S < 1 || S > 5)
+                    return false;
+                int at = 0;
+                while (fv[S][at] != a)
+                    ++at;
+                // w_e: the neighbour of a in S's loop that is not b
+                const uint16_t n1 = fv[S][(at + 1) & 3], n2 = fv[S][(at + 3) & 3];
+                const uint16_t w = (n1 == b) ? n2 : n1;
+                if (!((n1 == b || n2 == b) && has(B, w)))
+                    return false;
+                rec[e] = a;
+                rec[4 + e] = w;
+                rec[10 + e] = fl[S];
+            }
+            rec[8] = fl[0];
+            rec[9] = fl[B];
+            // the fixed pattern must reproduce the cell's pair list
+            std::array<std::array<uint16_t, 4>, 12> want, got;
+            for (int j = 0; j < 12; ++j)
+                want[j] = {pairs[4 * j], pairs[4 * j + 1], std::min(pairs[4 * j + 2], pairs[4 * j + 3]), std::max(pairs[4 * j + 2], pairs[4 * j + 3])};
+            int ng = 0;
+            auto add = [&](uint16_t p0, uint16_t p1, uint16_t f0, uint16_t f1) {
+                got[ng++] = {std::min(p0, p1), std::max(p0, p1), std::min(f0, f1), std::max(f0, f1)};
+            };
+            for (int e = 0; e < 4; ++e)
+            {
+                add(rec[e], rec[(e + 1) & 3], rec[8], rec[10 + e]);
+                add(rec[4 + e], rec[4 + ((e + 1) & 3)], rec[9], rec[10 + e]);
+                add(rec[e], rec[4 + e], rec[10 + ((e + 3) & 3)], rec[10 + e]);
+            }
+            std::sort(want.begin(), want.end());
+            std::sort(got.begin(), got.end());
+            return want == got;
+        };
+        for (int32_t k = 0; k < G.nTiles; ++k)
+        {
+            G.maxTileCells = std::max(G.maxTileCells, G.tileCellOff[k + 1] - G.tileCellOff[k]);
+            G.maxTileFaces = std::max(G.maxTileFaces, G.tileFaceOff[k + 1] - G.tileFaceOff[k]);
+            G.maxTilePoints = std::max(G.maxTilePoints, G.tilePointOff[k + 1] - G.tilePointOff[k]);
+        }
+        // one pass: pair counts, closedness, and -- while every cell so far is a topological hexahedron -- the
+        // canonical records; the pair lists themselves are only materialised when some cell is not a hexahedron
+        // (or the caller wants them for checking)
+        bool allHex = true;
+        G.hexRec.assign(16 * (size_t)C, 0);
 #pragma omp parallel
         {
             std::vector<Half> hs;
+            std::vector<uint16_t> tmp;
 #pragma omp for schedule(dynamic, 16)
             for (int32_t k = 0; k < G.nTiles; ++k)
-                for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
+            {
+                const int32_t cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
+                for (int32_t i = 0; i < nc; ++i)
                 {
-                    const int32_t n = cellPairs(k, slot, hs, nullptr);
+                    const int32_t slot = cb + i;
+                    int32_t nHalf = 0;
+                    for (int32_t q = G.slotOff[slot]; q < G.slotOff[slot + 1]; ++q)
+                    {
+                        const int32_t at = G.tileFaceOff[k] + (G.slotRef[q] & 0x7fff);
+                        nHalf += G.faceRefOff[at + 1] - G.faceRefOff[at];
+                    }
+                    tmp.resize(2 * (size_t)nHalf + 4);
+                    const int32_t n = cellPairs(k, slot, hs, tmp.data());
                     if (n < 0)
                     {
 #pragma omp atomic write
                         closed = false;
                     }
                     nPairs[slot + 1] = std::max(n, 0);
+                    bool hexOk = false;
+                    uint16_t rec[16];
+                    if (n == 12)
+                        hexOk = hexRecord(k, slot, tmp.data(), rec);
+                    if (hexOk)
+                    {
+                        uint16_t *o1 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)i], *o2 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)nc + 8 * (size_t)i];
+                        for (int q = 0; q < 8; ++q)
+                            o1[q] = rec[q], o2[q] = rec[8 + q];
+                    }
+                    else
+                    {
+#pragma omp atomic write
+                        allHex = false;
+                    }
                 }
+            }
         }
-        for (int32_t k = 0; k < G.nTiles; ++k)
+        if (!closed || !allHex)
         {
-            G.maxTileCells = std::max(G.maxTileCells, G.tileCellOff[k + 1] - G.tileCellOff[k]);
-            G.maxTileFaces = std::max(G.maxTileFaces, G.tileFaceOff[k + 1] - G.tileFaceOff[k]);
-            G.maxTilePoints = std::max(G.maxTilePoints, G.tilePointOff[k + 1] - G.tilePointOff[k]);
+            G.hexRec.clear();
+            G.hexRec.shrink_to_fit();
         }
         if (closed)
         {
@@ -1014,7 +1127,7 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
             int64_t total = 0;
             for (int64_t c = 0; c < C; ++c)
                 total += nPairs[c + 1];
-            if (total < (int64_t)INT32_MAX / 2)
+            if ((G.hexRec.empty() || keepPairs) && total < (int64_t)INT32_MAX / 2)
             {
                 G.cellEdgeOff.assign(C + 1, 0);
                 for (int64_t c = 0; c < C; ++c)
@@ -1025,122 +1138,11 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
 #pragma omp parallel
                 {
                     std::vector<Half> hs;
-                    std::vector<uint16_t> tmp;
 #pragma omp for schedule(dynamic, 16)
                     for (int32_t k = 0; k < G.nTiles; ++k)
-                    {
-                        const int32_t cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
-                        for (int32_t i = 0; i < nc; ++i)
-                        {
-                            const int32_t slot = cb + i;
-                            if (!G.uniformCellEdges)
-                            {
-                                cellPairs(k, slot, hs, G.cellEdgeRef.data() + 4 * (size_t)G.cellEdgeOff[slot]);
-                                continue;
-                            }
-                            tmp.resize(4 * (size_t)G.uniformCellEdges);
-                            cellPairs(k, slot, hs, tmp.data());
-                            for (int32_t j = 0; j < G.uniformCellEdges; ++j) // pair-major inside the tile
-                                for (int q = 0; q < 4; ++q)
-                                    G.cellEdgeRef[4 * ((size_t)G.uniformCellEdges * cb + (size_t)j * nc + i) + q] = tmp[4 * j + q];
-                        }
-                    }
+                        for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
+                            cellPairs(k, slot, hs, G.cellEdgeRef.data() + 4 * (size_t)G.cellEdgeOff[slot]);
                 }
-            }
-        }
-        // canonical hexahedron records (see topology.hpp), checked against the pair lists above
-        if (closed && G.uniformCellEdges == 12 && !G.cellEdgeRef.empty())
-        {
-            bool allHex = true;
-            for (int64_t f = 0; f < F && allHex; ++f)
-                allHex = m.faceOffsets[f + 1] - m.faceOffsets[f] == 4;
-            for (int64_t c = 0; c < C && allHex; ++c)
-                allHex = t.cfOff[c + 1] - t.cfOff[c] == 6;
-            if (allHex)
-            {
-                G.hexRec.assign(16 * (size_t)C, 0);
-                bool ok = true;
-#pragma omp parallel for schedule(dynamic, 16)
-                for (int32_t k = 0; k < G.nTiles; ++k)
-                {
-                    const int32_t cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb, fb = G.tileFaceOff[k];
-                    for (int32_t i = 0; i < nc; ++i)
-                    {
-                        const int32_t slot = cb + i;
-                        uint16_t fl[6], fv[6][4];
-                        for (int q = 0; q < 6; ++q)
-                        {
-                            fl[q] = G.slotRef[G.slotOff[slot] + q] & 0x7fff;
-                            const int32_t rb = G.faceRefOff[fb + fl[q]];
-                            for (int v = 0; v < 4; ++v)
-                                fv[q][v] = G.faceRef[rb + v];
-                        }
-                        auto has = [&](int q, uint16_t p) { return fv[q][0] == p || fv[q][1] == p || fv[q][2] == p || fv[q][3] == p; };
-                        uint16_t rec[16] = {0};
-                        bool good = true;
-                        int B = -1;
-                        for (int q = 1; q < 6; ++q)
-                            if (!has(q, fv[0][0]) && !has(q, fv[0][1]) && !has(q, fv[0][2]) && !has(q, fv[0][3]))
-                                B = (B < 0) ? q : 99;
-                        good = B >= 1 && B < 6;
-                        for (int e = 0; e < 4 && good; ++e)
-                        {
-                            const uint16_t a = fv[0][e], b = fv[0][(e + 1) & 3];
-                            int S = -1;
-                            for (int q = 1; q < 6; ++q)
-                                if (q != B && has(q, a) && has(q, b))
-                                    S = (S < 0) ? q : 99;
-                            if (S < 1 || S > 5)
-                            {
-                                good = false;
-                                break;
-                            }
-                            // w_e: the neighbour of a in S's loop that is not b
-                            int at = 0;
-                            while (fv[S][at] != a)
-                                ++at;
-                            const uint16_t n1 = fv[S][(at + 1) & 3], n2 = fv[S][(at + 3) & 3];
-                            const uint16_t w = (n1 == b) ? n2 : n1;
-                            good = (n1 == b || n2 == b) && has(B, w);
-                            rec[e] = a;
-                            rec[4 + e] = w;
-                            rec[10 + e] = fl[S];
-                        }
-                        rec[8] = fl[0];
-                        rec[9] = good ? fl[B] : 0;
-                        if (good)
-                        { // the pattern must reproduce the cell's pair list
-                            std::vector<std::array<uint16_t, 4>> want, got;
-                            for (int j = 0; j < 12; ++j)
-                            {
-                                const uint16_t *r = &G.cellEdgeRef[4 * ((size_t)12 * cb + (size_t)j * nc + i)];
-                                want.push_back({r[0], r[1], std::min(r[2], r[3]), std::max(r[2], r[3])});
-                            }
-                            auto add = [&](uint16_t p0, uint16_t p1, uint16_t f0, uint16_t f1) {
-                                got.push_back({std::min(p0, p1), std::max(p0, p1), std::min(f0, f1), std::max(f0, f1)});
-                            };
-                            for (int e = 0; e < 4; ++e)
-                            {
-                                add(rec[e], rec[(e + 1) & 3], rec[8], rec[10 + e]);
-                                add(rec[4 + e], rec[4 + ((e + 1) & 3)], rec[9], rec[10 + e]);
-                                add(rec[e], rec[4 + e], rec[10 + ((e + 3) & 3)], rec[10 + e]);
-                            }
-                            std::sort(want.begin(), want.end());
-                            std::sort(got.begin(), got.end());
-                            good = want == got;
-                        }
-                        if (!good)
-                        {
-#pragma omp atomic write
-                            ok = false;
-                        }
-                        uint16_t *o1 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)i], *o2 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)nc + 8 * (size_t)i];
-                        for (int q = 0; q < 8; ++q)
-                            o1[q] = rec[q], o2[q] = rec[8 + q];
-                    }
-                }
-                if (!ok)
-                    G.hexRec.clear();
             }
         }
         tick("tiles: (edge, cell) pairs");

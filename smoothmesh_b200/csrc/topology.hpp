@@ -98,11 +98,10 @@ struct GeomTiles
     // The (edge, cell) pairs of the fused face-angle filter: for every cell slot, each edge of the cell with its
     // end points (indices into the tile's point list) and the two faces of the cell that meet at it (indices
     // into the tile's face list) -- what calcMinMaxFaceAngleForEdge (src/smoothMesh.C:1135-1231) visits for this
-    // cell of the edge.  4 x uint16 per pair: p0, p1, f0, f1.  Uniform meshes (every cell has `uniformCellEdges`
-    // edges): the pairs of tile k start at uniformCellEdges * tileCellOff[k], stored pair-major (pair j of the
-    // tile's i-th cell at j * nCellsOfTile + i) so that a warp reads consecutive records; otherwise cell-major
-    // through cellEdgeOff (per slot + 1).  Empty when some cell is not closed (an edge not shared by exactly two
-    // of its faces): the caller then keeps the per-edge kernel.
+    // cell of the edge.  4 x uint16 per pair: p0, p1, f0, f1, cell-major through cellEdgeOff (per slot + 1);
+    // uniformCellEdges > 0 when every cell has that many.  Empty when some cell is not closed (an edge not shared
+    // by exactly two of its faces: the caller then keeps the per-edge kernel) and, unless asked for, on
+    // all-hexahedra meshes, where hexRec replaces them.
     std::vector<int32_t> cellEdgeOff;
     std::vector<uint16_t> cellEdgeRef;
     // All-hexahedra meshes: the same pairs as a canonical record per cell slot, 16 x uint16:
@@ -115,11 +114,15 @@ struct GeomTiles
     int32_t uniformCellEdges = 0;
     int32_t maxTileCells = 0, maxTileFaces = 0, maxTilePoints = 0, maxTileEdgePairs = 0;
 };
-GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints);
+// keepPairs: also materialise the pair lists of an all-hexahedra mesh (the kernel only reads hexRec there)
+GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints, bool keepPairs = false);
 
 // Throws std::runtime_error with the reference's FatalError texts where the
 // reference would abort (empty patches :61-66, <2 eligible closest points
 // :354-362, edge/cell face-pair sanity :1073,:1087).
 Topology buildTopology(const PolyMesh &m);
+// The 48-byte edge records (Topology::edgeRec) are only read by the per-edge face-angle filter, which the fused
+// per-cell filter replaces on tiled meshes: built on first use.
+void buildEdgeRecords(Topology &t);
 
 } // namespace sm
