@@ -167,12 +167,15 @@ extern "C"
      * fused into the geometry tiles, points marked suspect by it (end points of edges it could not certify; they
      * take the literal evaluation), points active in the face-angle constraint (src/smoothMesh.C:1367-1368),
      * bit set: 1 geometry tiles, 2 second-generation tile kernel, 4 uniform hex fast path, 8 / 16 per-edge /
-     * per-point single-precision filter level in use}. */
+     * per-point single-precision filter level (global mirrors) in use, 32 per-point kernels on point tiles, 64 their
+     * tile-local single-precision level}. */
     int smgpu_filter_stats(smgpu_handle *h, int64_t out[4]);
 
     /* Geometry tiles of this handle: out = {tiles (0 = two-kernel geometry), faces listed over all tiles (border
-     * faces are listed by both tiles), points listed over all tiles, dynamic shared memory per block [bytes]}. */
-    int smgpu_tile_stats(smgpu_handle *h, int64_t out[4]);
+     * faces are listed by both tiles), points listed over all tiles, dynamic shared memory per block [bytes],
+     * point tiles of the per-point kernels (0 = per-point kernels without tiles), points / cells listed over all
+     * point tiles, dynamic shared memory of the edge-constraint tile kernel [bytes]}. */
+    int smgpu_tile_stats(smgpu_handle *h, int64_t out[8]);
 
     /* Self-test of the shared-reciprocal division the geometry kernels use (one reciprocal for the three
      * components of a vector, the quotients bit-identical to IEEE division): about n random and structured

@@ -594,10 +594,12 @@ class Smoother:
         return a, b
 
     def tile_stats(self):
-        out = (C.c_int64 * 4)()
+        out = (C.c_int64 * 8)()
         lib().smgpu_tile_stats.argtypes = [C.c_void_p, C.c_void_p]
         self._ck(lib().smgpu_tile_stats(self._h, out))
-        return dict(tiles=int(out[0]), listed_faces=int(out[1]), listed_points=int(out[2]), smem_bytes=int(out[3]))
+        return dict(tiles=int(out[0]), listed_faces=int(out[1]), listed_points=int(out[2]), smem_bytes=int(out[3]),
+                    point_tiles=int(out[4]), pt_listed_points=int(out[5]), pt_listed_cells=int(out[6]),
+                    edge_tile_smem_bytes=int(out[7]))
 
     def filter_stats(self):
         out = (C.c_int64 * 4)()

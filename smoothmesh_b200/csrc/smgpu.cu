@@ -66,6 +66,9 @@ struct smgpu_handle
     bool tilesF = false;   // its second generation (k_geom_tiles_f: run-time strides, fused face-angle filter)
     bool tilesUniform = false, tilesHavePairs = false;
     int64_t tileListedFaces = 0, tileListedPoints = 0;
+    bool usePointTiles = false; // k_predict_tiles / k_edge_tiles over sm::PointTiles
+    size_t predictSmem = 0, edgeSmem = 0;
+    int64_t ptListedPoints = 0, ptListedCells = 0;
     size_t tileSmem = 0;
     int tileMinBlocks = 2; // resident blocks per SM the kernel variant is compiled for (register budget)
     bool doLayers = false;
@@ -217,6 +220,11 @@ struct smgpu_handle
                                 : 0;
         if (d.fusedFaceFilter)
             d.faceFilter32 = 0; // the per-edge single-precision level is not used (smgpu_op_edge_face_angles is literal)
+        // per-point kernels on tiles: their single-precision level works relative to a tile-local origin with a
+        // run-time error budget, the global mirrors are not needed
+        d.edgeTile32 = (usePointTiles && d.edgeFilter && !getenv("SMGPU_NO_F32") && !doBoundary) ? 1 : 0;
+        if (usePointTiles)
+            d.edgeFilter32 = 0;
         d.faceMirrors = d.faceFilter32;
         d.faceMean64 = (!d.fusedFaceFilter && d.faceFilter && !d.faceFilter32) ? 1 : 0;
         d.pointMirrors = (d.edgeFilter32 || d.faceFilter32) ? 1 : 0;
@@ -381,7 +389,10 @@ struct smgpu_handle
     void launchPredict()
     {
         profBegin(K_PREDICT);
-        k_predict<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        if (usePointTiles)
+            k_predict_tiles<<<d.nPointTiles, SMK_PT_THREADS, predictSmem, stream>>>(d);
+        else
+            k_predict<<<grid(d.P, 128), 128, 0, stream>>>(d);
         profEnd(1);
         ++launches;
     }
@@ -452,7 +463,10 @@ struct smgpu_handle
     void launchEdgeConstraints()
     {
         profBegin(K_EDGE);
-        k_edge_constraints<<<grid(d.P, 128), 128, 0, stream>>>(d);
+        if (usePointTiles)
+            k_edge_tiles<<<d.nPointTiles, SMK_PT_THREADS, edgeSmem, stream>>>(d);
+        else
+            k_edge_constraints<<<grid(d.P, 128), 128, 0, stream>>>(d);
         profEnd(1);
         ++launches;
     }
@@ -1210,16 +1224,52 @@ extern "C"
                         int perSm = 0, sms = 0;
                         CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, params->device));
                         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_geom_tiles_f<true>, SMK_TILE_CELLS, h->tileSmem));
-                        d.tilePrefetch = std::max(1, perSm) * sms; // one generation of resident blocks ahead
+                        // L2 warm-up one generation of resident blocks ahead: measured slower at 200^3 (1.31 vs 1.23 ms,
+                        // the extra loads cost more than the colder prologue), so it stays an experiment switch
+                        d.tilePrefetch = 0;
                         if (getenv("SMGPU_TILE_PREFETCH"))
-                            d.tilePrefetch = atoi(getenv("SMGPU_TILE_PREFETCH"));
+                            d.tilePrefetch = atoi(getenv("SMGPU_TILE_PREFETCH")) * std::max(1, perSm) * sms;
                     }
-                    CK(cudaFuncSetAttribute(k_geom_tiles_f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(h->tileSmem, 220 * 1024)));
-                    CK(cudaFuncSetAttribute(k_geom_tiles_f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::min<size_t>(h->tileSmem, 220 * 1024)));
+                    // the attribute belongs to the function, not to this handle: always the device's opt-in maximum,
+                    // so that a later handle with smaller tiles does not lower it under an earlier handle's launches
+                    int smemOptin = 0;
+                    CK(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, params->device));
+                    CK(cudaFuncSetAttribute(k_geom_tiles_f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+                    CK(cudaFuncSetAttribute(k_geom_tiles_f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
                     CK(cudaFuncSetAttribute(k_geom_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     CK(cudaFuncSetAttribute(k_geom_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     if (getenv("SMGPU_TILE_MINB"))
                         h->tileMinBlocks = atoi(getenv("SMGPU_TILE_MINB")) == 3 ? 3 : 2;
+                }
+            }
+            // Per-point kernels on point tiles (k_predict_tiles / k_edge_tiles): built to the same parity bar, but at
+            // 200^3 they measured slower than the per-point gather kernels (0.51 / 0.56 ms against 0.50 / 0.46 ms;
+            // profiles/r2_ncu_point_tiles_n200.txt: a third of their time is the label -> point gather chain ahead of
+            // the first barrier, the rest is issue-bound on ~1000 instructions per point either way), so they are an
+            // option (SMGPU_POINT_TILES=1), not the default.
+            if (!noTiles && getenv("SMGPU_POINT_TILES") && atoi(getenv("SMGPU_POINT_TILES")) != 0)
+            {
+                const sm::PointTiles T = sm::buildPointTiles(m, t, SMK_PT_THREADS, SMK_PT_ROUNDS * SMK_PT_THREADS, SMK_PT_ROUNDS * SMK_PT_THREADS);
+                if (T.nTiles > 0)
+                {
+                    d.nPointTiles = T.nTiles;
+                    d.ptOwnOff = h->upload(T.ownOff);
+                    d.ptHaloOff = h->upload(T.haloOff);
+                    d.ptHalo = h->upload(T.halo);
+                    d.ptCellOff = h->upload(T.cellOff);
+                    d.ptCell = h->upload(T.cell);
+                    d.ptRec = (const uint4 *)h->upload(T.rec);
+                    d.ptSH = (T.maxHalo + 31) / 32 * 32;
+                    d.ptSC = (T.maxCells + 31) / 32 * 32;
+                    h->predictSmem = predictTileSmem(d.ptSH, d.ptSC);
+                    h->edgeSmem = edgeTileSmem(d.ptSH);
+                    h->ptListedPoints = (int64_t)T.halo.size();
+                    h->ptListedCells = (int64_t)T.cell.size();
+                    int smemOptin = 0;
+                    CK(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, params->device));
+                    CK(cudaFuncSetAttribute(k_predict_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+                    CK(cudaFuncSetAttribute(k_edge_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+                    h->usePointTiles = true;
                 }
             }
             tick("records, work space, tiles");
@@ -1589,7 +1639,7 @@ extern "C"
         return SMGPU_OK;
     }
 
-    int smgpu_tile_stats(smgpu_handle *h, int64_t out[4])
+    int smgpu_tile_stats(smgpu_handle *h, int64_t out[8])
     {
         if (!h || !out)
             return setErr(SMGPU_ERR_ARG, "null argument");
@@ -1597,6 +1647,10 @@ extern "C"
         out[1] = h->tileListedFaces;
         out[2] = h->tileListedPoints;
         out[3] = (int64_t)h->tileSmem;
+        out[4] = h->usePointTiles ? h->d.nPointTiles : 0;
+        out[5] = h->ptListedPoints;
+        out[6] = h->ptListedCells;
+        out[7] = (int64_t)h->edgeSmem;
         return SMGPU_OK;
     }
 
@@ -1622,7 +1676,7 @@ extern "C"
             for (uint8_t b : buf)
                 out[2] += b != 0;
             out[3] = (h->useTiles ? 1 : 0) | (h->tilesF ? 2 : 0) | (h->tilesUniform ? 4 : 0) | (h->d.faceFilter32 ? 8 : 0) |
-                     (h->d.edgeFilter32 ? 16 : 0);
+                     (h->d.edgeFilter32 ? 16 : 0) | (h->usePointTiles ? 32 : 0) | (h->d.edgeTile32 ? 64 : 0);
         }
         catch (const std::exception &e)
         {

@@ -843,14 +843,27 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         std::sort(T.points.begin(), T.points.end());
         T.points.erase(std::unique(T.points.begin(), T.points.end()), T.points.end());
     };
-    const int64_t nRuns = (C + maxCells - 1) / maxCells;
+    // runs are closed at maxCells cells and at every aligned block of 2^8 keys (an 8 x 8 x 4 brick of a
+    // block-structured mesh), so that a brick cut short by the mesh boundary does not shift all later tiles
+    // off the brick grid (271^3: 33 full bricks and one of 7 cells per row)
+    std::vector<std::pair<int32_t, int32_t>> runs;
+    for (int64_t i = 0; i < C;)
+    {
+        int64_t j = i;
+        const uint64_t block = keys[i].first >> 8;
+        while (j < C && j - i < maxCells && (maxCells < 256 || (keys[j].first >> 8) == block))
+            ++j;
+        runs.push_back({(int32_t)i, (int32_t)j});
+        i = j;
+    }
+    const int64_t nRuns = (int64_t)runs.size();
     std::vector<std::vector<Tile>> perRun(nRuns);
     bool cellTooLarge = false;
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t r = 0; r < nRuns; ++r)
     {
         std::vector<Tile> todo, done;
-        todo.push_back({(int32_t)(r * maxCells), (int32_t)std::min<int64_t>(C, (r + 1) * maxCells), {}, {}});
+        todo.push_back({runs[r].first, runs[r].second, {}, {}});
         while (!todo.empty())
         {
             Tile T = std::move(todo.back());
@@ -1148,5 +1161,182 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         tick("tiles: (edge, cell) pairs");
     }
     return G;
+}
+
+PointTiles buildPointTiles(const PolyMesh &m, const Topology &t, int maxOwn, int maxHalo, int maxCells)
+{
+    PointTiles T;
+    const int64_t P = t.P;
+    if (P == 0 || maxHalo > 0xffff || maxCells > 0xffff)
+        return T;
+    const bool timing = getenv("SMGPU_TIMING") && atoi(getenv("SMGPU_TIMING")) != 0;
+    auto clock = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tPrev = clock();
+    auto tick = [&](const char *what) {
+        if (!timing)
+            return;
+        const double tNow = clock();
+        fprintf(stderr, "[smgpu set-up] %-28s %.3f s\n", what, tNow - tPrev);
+        tPrev = tNow;
+    };
+    // Morton order over the points, quantised (round to nearest) by the mean point spacing: on block-structured
+    // meshes 2^8 consecutive keys are an 8 x 8 x 4 brick of lattice positions, jitter below half a spacing
+    // does not move a point to another position
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t p = 0; p < P; ++p)
+        for (int d = 0; d < 3; ++d)
+        {
+            lo[d] = std::min(lo[d], m.points[3 * p + d]);
+            hi[d] = std::max(hi[d], m.points[3 * p + d]);
+        }
+    double vol = 1.0;
+    int dims = 0;
+    for (int d = 0; d < 3; ++d)
+        if (hi[d] - lo[d] > 0)
+        {
+            vol *= hi[d] - lo[d];
+            ++dims;
+        }
+    const double h = dims ? std::pow(vol / double(std::max<int64_t>(t.C, 1)), 1.0 / dims) : 1.0;
+    const double invH = h > 0 ? 1.0 / h : 0.0;
+    std::vector<std::pair<uint64_t, int32_t>> keys(P);
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < P; ++p)
+    {
+        uint64_t key = 0;
+        for (int d = 0; d < 3; ++d)
+        {
+            double q = (m.points[3 * p + d] - lo[d]) * invH + 0.5;
+            q = q < 0 ? 0 : (q > 2097151.0 ? 2097151.0 : q);
+            key |= spreadBits21((uint64_t)q) << d;
+        }
+        keys[p] = {key, (int32_t)p};
+    }
+    __gnu_parallel::sort(keys.begin(), keys.end());
+    tick("point tiles: keys, sort");
+    // runs: closed at every aligned 2^8 block of keys and at maxOwn points
+    std::vector<std::pair<int32_t, int32_t>> runs;
+    for (int64_t i = 0; i < P;)
+    {
+        int64_t j = i;
+        const uint64_t block = keys[i].first >> 8;
+        while (j < P && j - i < maxOwn && (keys[j].first >> 8) == block)
+            ++j;
+        runs.push_back({(int32_t)i, (int32_t)j});
+        i = j;
+    }
+    struct Tile
+    {
+        int32_t a, b;
+        std::vector<int32_t> own, halo, cells;
+    };
+    auto collect = [&](Tile &X) {
+        X.own.clear();
+        X.halo.clear();
+        X.cells.clear();
+        for (int32_t i = X.a; i < X.b; ++i)
+            X.own.push_back(keys[i].second);
+        std::sort(X.own.begin(), X.own.end());
+        for (int32_t p : X.own)
+        {
+            for (int32_t k = t.ppOff[p]; k < t.ppOff[p + 1]; ++k)
+                if (!std::binary_search(X.own.begin(), X.own.end(), t.pp[k]))
+                    X.halo.push_back(t.pp[k]);
+            for (int32_t k = t.pcOff[p]; k < t.pcOff[p + 1]; ++k)
+                X.cells.push_back(t.pc[k]);
+        }
+        std::sort(X.halo.begin(), X.halo.end());
+        X.halo.erase(std::unique(X.halo.begin(), X.halo.end()), X.halo.end());
+        std::sort(X.cells.begin(), X.cells.end());
+        X.cells.erase(std::unique(X.cells.begin(), X.cells.end()), X.cells.end());
+    };
+    std::vector<std::vector<Tile>> perRun(runs.size());
+    bool tooLarge = false;
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t r = 0; r < (int64_t)runs.size(); ++r)
+    {
+        std::vector<Tile> todo, done;
+        todo.push_back({runs[r].first, runs[r].second, {}, {}, {}});
+        while (!todo.empty())
+        {
+            Tile X = std::move(todo.back());
+            todo.pop_back();
+            collect(X);
+            if ((int)(X.own.size() + X.halo.size()) <= maxHalo && (int)X.cells.size() <= maxCells)
+                done.push_back(std::move(X));
+            else if (X.b - X.a == 1)
+            {
+#pragma omp atomic write
+                tooLarge = true;
+            }
+            else
+            {
+                const int32_t mid = X.a + (X.b - X.a) / 2;
+                todo.push_back({mid, X.b, {}, {}, {}});
+                todo.push_back({X.a, mid, {}, {}, {}});
+            }
+        }
+        perRun[r] = std::move(done);
+    }
+    tick("point tiles: lists");
+    if (tooLarge)
+        return PointTiles(); // a point whose stencil does not fit a tile: the caller keeps the per-point kernels
+    std::vector<Tile *> tiles;
+    for (auto &v : perRun)
+        for (Tile &X : v)
+            tiles.push_back(&X);
+    T.nTiles = (int32_t)tiles.size();
+    T.ownOff.assign(T.nTiles + 1, 0);
+    T.haloOff.assign(T.nTiles + 1, 0);
+    T.cellOff.assign(T.nTiles + 1, 0);
+    for (int32_t k = 0; k < T.nTiles; ++k)
+    {
+        const Tile &X = *tiles[k];
+        T.ownOff[k + 1] = T.ownOff[k] + (int32_t)X.own.size();
+        T.haloOff[k + 1] = T.haloOff[k] + (int32_t)(X.own.size() + X.halo.size());
+        T.cellOff[k + 1] = T.cellOff[k] + (int32_t)X.cells.size();
+        T.maxOwn = std::max(T.maxOwn, (int32_t)X.own.size());
+        T.maxHalo = std::max(T.maxHalo, (int32_t)(X.own.size() + X.halo.size()));
+        T.maxCells = std::max(T.maxCells, (int32_t)X.cells.size());
+    }
+    T.halo.resize(T.haloOff[T.nTiles]);
+    T.cell.resize(T.cellOff[T.nTiles]);
+    T.rec.assign(16 * (size_t)P, 0);
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int32_t k = 0; k < T.nTiles; ++k)
+    {
+        const Tile &X = *tiles[k];
+        const int32_t no = (int32_t)X.own.size();
+        std::copy(X.own.begin(), X.own.end(), T.halo.begin() + T.haloOff[k]);
+        std::copy(X.halo.begin(), X.halo.end(), T.halo.begin() + T.haloOff[k] + no);
+        std::copy(X.cells.begin(), X.cells.end(), T.cell.begin() + T.cellOff[k]);
+        auto pointRef = [&](int32_t q) -> uint16_t {
+            auto it = std::lower_bound(X.own.begin(), X.own.end(), q);
+            if (it != X.own.end() && *it == q)
+                return (uint16_t)(it - X.own.begin());
+            return (uint16_t)(no + (std::lower_bound(X.halo.begin(), X.halo.end(), q) - X.halo.begin()));
+        };
+        for (int32_t i = 0; i < no; ++i)
+        {
+            const int32_t p = X.own[i];
+            uint16_t *r = &T.rec[16 * (size_t)(T.ownOff[k] + i)];
+            const int32_t *src = &t.pointRec[16 * (size_t)p];
+            const int32_t meta = src[14];
+            const int32_t npc = meta & 0xff, npp = (meta >> 8) & 0xff;
+            if (meta < 0)
+            {
+                r[14] = 0x8000;
+                continue;
+            }
+            for (int32_t j = 0; j < npc; ++j)
+                r[j] = (uint16_t)(std::lower_bound(X.cells.begin(), X.cells.end(), src[j]) - X.cells.begin());
+            for (int32_t j = 0; j < npp; ++j)
+                r[8 + j] = pointRef(src[8 + j]);
+            r[14] = (uint16_t)(npc | (npp << 4));
+            r[15] = (uint16_t)src[15];
+        }
+    }
+    tick("point tiles: records");
+    return T;
 }
 } // namespace sm

@@ -117,6 +117,25 @@ struct GeomTiles
 // keepPairs: also materialise the pair lists of an all-hexahedra mesh (the kernel only reads hexRec there)
 GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints, bool keepPairs = false);
 
+// Tiles of the per-point kernels (k_predict_tiles, k_edge_tiles): compact groups of points (aligned bricks of a
+// space-filling-curve order) with the list of the points their stencils read -- the tile's own points first,
+// then their edge neighbours outside the tile -- and the list of the cells around them.  A thread block
+// stages the positions of the listed points and the centres of the listed cells in shared memory once; the
+// per-point rows become 16-bit references into those lists.
+struct PointTiles
+{
+    int32_t nTiles = 0;
+    std::vector<int32_t> ownOff;           // per tile + 1: its own points are slots ownOff[t] .. ownOff[t+1]
+    std::vector<int32_t> haloOff, halo;    // per tile + 1; point labels: the tile's own points (ascending), then the halo (ascending)
+    std::vector<int32_t> cellOff, cell;    // per tile + 1; cell labels, ascending
+    // per own-point slot, 16 x uint16: cells[8] (pointCells row order), nbrs[6] (pointPoints row order), both as
+    // indices into the tile's lists; [14] = nCells | nNbrs << 4 | generic << 15; [15] = corner-pair mask (as
+    // Topology::pointRec[15]).  generic: the point takes the CSR path (valence above the record's capacity).
+    std::vector<uint16_t> rec;
+    int32_t maxOwn = 0, maxHalo = 0, maxCells = 0;
+};
+PointTiles buildPointTiles(const PolyMesh &m, const Topology &t, int maxOwn, int maxHalo, int maxCells);
+
 // Throws std::runtime_error with the reference's FatalError texts where the
 // reference would abort (empty patches :61-66, <2 eligible closest points
 // :354-362, edge/cell face-pair sanity :1073,:1087).

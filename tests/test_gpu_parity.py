@@ -134,7 +134,7 @@ def test_no_gpu_fallback_message():
 
 @pytest.mark.parametrize("case", ["hex_8x6x5_j45", "kelvin3_j20"])
 @pytest.mark.parametrize("env", ["SMGPU_NO_FILTERS", "SMGPU_NO_F32", "SMGPU_NO_TILES", "SMGPU_FORCE_TILES",
-                                 "SMGPU_NO_FUSED_FILTER", "SMGPU_OLD_TILES"])
+                                 "SMGPU_NO_FUSED_FILTER", "SMGPU_OLD_TILES", "SMGPU_POINT_TILES"])
 def test_literal_path_without_filters(case, env, monkeypatch):
     # SMGPU_NO_FILTERS=1 disables the guard-banded cosine-space filters so that every point /
     # edge takes the literal evaluation; SMGPU_NO_F32=1 disables only the single-precision first
@@ -142,6 +142,8 @@ def test_literal_path_without_filters(case, env, monkeypatch):
     # SMGPU_FORCE_TILES=1 uses it on polyhedral meshes too (default: all-quad / all-hex meshes only).
     # SMGPU_NO_FUSED_FILTER=1 keeps the per-edge face-angle filter (k_face_current) instead of the per-cell one
     # fused into the geometry tiles, SMGPU_OLD_TILES=1 the first-generation tile kernel.
+    # SMGPU_POINT_TILES=1 runs the predictor / edge constraints on point tiles (shared-memory staging) instead of
+    # the per-point gather kernels.
     # Every combination must reproduce the oracle bit for bit.
     monkeypatch.setenv(env, "1")
     mesh = CASES[case]()
@@ -218,3 +220,18 @@ def test_shared_reciprocal_division_is_ieee_division():
     for seed in (1, 20261017):
         assert L.smgpu_selftest_division(0, seed, 500_000_000, C.byref(bad)) == 0
         assert bad.value == 0
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_point_tile_kernels_loop_parity(case, monkeypatch):
+    """The tiled forms of the predictor and the edge constraints (k_predict_tiles / k_edge_tiles, opt-in through
+    SMGPU_POINT_TILES=1): same device functions behind shared-memory staging, bit-exact on every mesh kind."""
+    monkeypatch.setenv("SMGPU_POINT_TILES", "1")
+    mesh = CASES[case]()
+    kw = dict(OPTION_SETS["tight_angles"], rel_tol=1e-3)
+    g, o = _pair(mesh, **kw)
+    assert g.tile_stats()["point_tiles"] > 0
+    n, nf, res = o.iterate(25)
+    log = g.iterate(25)
+    assert log.iterations == n and np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
+    assert np.array_equal(g.frozen(), o.get("frozen")) and np.array_equal(g.points(), o.get("points"))
