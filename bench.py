@@ -148,7 +148,7 @@ def kernel_bytes(P, C, F, Fi, E, FV, PC, EC, tiles):
         "k_active_compact": 2 * P,
         "k_face_tests": 0,
         "k_face_resolve": 0,
-        "halo_exchange": 0,
+        "halo_exchange": 0, "x_pack": 0, "x_merge": 0, "x_frozen": 0, "x_finish": 0,
         # points + newPoints + mask read, points written
         "k_commit": 24 * P + 24 * P + P + 24 * P,
     }
@@ -190,7 +190,10 @@ def parity_check(args, world, rank, local_rank, dist):
         multi.init_comm(g, rank, world, dist)
     log = g.iterate(iters)
     res = dict(n=log.iterations, nf=log.n_frozen, res=log.residual, pts=g.points(), fz=g.frozen(), mesh=mine.desc_arrays())
-    g.close()
+    if world > 1:
+        multi.shutdown_comm(g, dist)
+    else:
+        g.close()
     allres = [res]
     if world > 1:
         allres = [None] * world
@@ -423,9 +426,10 @@ def main():
     t0 = time.perf_counter()
     g = sm.Smoother(mesh, rel_tol=0.0, device=local_rank, renumber=args.renumber, min_angle_deg=args.min_angle,
                     max_angle_deg=args.max_angle)
+    exchange = None
     if world > 1:
         from smoothmesh_b200 import multi
-        multi.init_comm(g, rank, world, dist)
+        exchange = "peer-memory (NVLink stores from the producer kernels)" if multi.init_comm(g, rank, world, dist) else "nccl"
     t_setup = time.perf_counter() - t0
     stats = g.mesh_stats()
     tiles = g.tile_stats()
@@ -489,6 +493,9 @@ def main():
     assert np.array_equal(log2.n_frozen, log.n_frozen)
     assert np.isfinite(out_pts).all()
 
+    if dist is not None:
+        from smoothmesh_b200 import multi
+        multi.shutdown_comm(g, dist)
     if rank != 0:
         dist.barrier()
         dist.destroy_process_group()
@@ -525,7 +532,7 @@ def main():
                    "renumber": args.renumber, "min_angle": args.min_angle, "max_angle": args.max_angle,
                    "l2": "working set (>= 4 GB per iteration) exceeds the 126 MB L2",
                    "setup_s": {"mesh_generation": t_gen_max, "create_upload": t_setup_max},
-                   "hbm_resident_gb": hbm_gb,
+                   "hbm_resident_gb": hbm_gb, "exchange": exchange,
                    "filter": fstats},
         "clocks": clocks,
         "parity": parity,

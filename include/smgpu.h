@@ -243,6 +243,21 @@ extern "C"
      * waiting in ncclCommInitRank.  smgpu_comm_init after a successful prepare only does the collective half
      * (its counts / all_gids arguments are then ignored). */
     int smgpu_comm_prepare(smgpu_handle *h, int32_t rank, int32_t n_ranks, const int64_t *counts, const int64_t *all_gids);
+    /* ---- peer-memory exchange (optional, after smgpu_comm_init) ----------------------------
+     * Replaces the per-iteration NCCL calls (two grouped send/recv exchanges, two all-reduces) by stores into
+     * peer memory issued from the kernels that produce the data, over NVLink: every rank owns one exchange block
+     * (receive buffers, a flag word per neighbour and exchange, a statistics slot per rank); its peers map it --
+     * CUDA IPC between processes, peer access between handles of one process -- and the producer kernels write
+     * their records and then the flag with release semantics; the consumer kernels wait for the flags with
+     * acquire loads.  Start-up: smgpu_comm_p2p_export on every rank, all-gather the 64-byte handles, then
+     * smgpu_comm_p2p_connect with all of them (all_handles[64 * r] = rank r's; local_peers[r] non-NULL for ranks
+     * that are handles of this process, which are then addressed directly; either argument may be NULL when the
+     * other covers every rank).  All ranks must end up in the same mode: if connect fails anywhere, call
+     * smgpu_comm_p2p_disable everywhere and the NCCL exchanges stay in use.  Results are identical in both modes. */
+    int smgpu_comm_p2p_export(smgpu_handle *h, uint8_t handle_out[64]);
+    int smgpu_comm_p2p_connect(smgpu_handle *h, const uint8_t *all_handles, smgpu_handle *const *local_peers);
+    int smgpu_comm_p2p_disable(smgpu_handle *h);
+
     /* ncclCommAbort on this handle's communicator: releases kernels that wait for a peer which failed.  The
      * handle can only be destroyed afterwards. */
     int smgpu_comm_abort(smgpu_handle *h);

@@ -126,6 +126,9 @@ def lib():
         L.smgpu_comm_local_shared.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_comm_prepare.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.smgpu_comm_abort.argtypes = [C.c_void_p]
+        L.smgpu_comm_p2p_export.argtypes = [C.c_void_p, C.c_void_p]
+        L.smgpu_comm_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.smgpu_comm_p2p_disable.argtypes = [C.c_void_p]
         L.smgpu_group_create.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
         L.smgpu_group_iterate.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.smgpu_group_destroy.argtypes = [C.c_void_p]
@@ -653,6 +656,19 @@ class Smoother:
 
     def comm_abort(self):
         self._ck(lib().smgpu_comm_abort(self._h))
+
+    def comm_p2p_export(self) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._ck(lib().smgpu_comm_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def comm_p2p_connect(self, all_handles: bytes):
+        """all_handles: the 64-byte IPC handles of all ranks, concatenated in rank order."""
+        buf = (C.c_uint8 * len(all_handles))(*all_handles)
+        self._ck(lib().smgpu_comm_p2p_connect(self._h, buf, None))
+
+    def comm_p2p_disable(self):
+        self._ck(lib().smgpu_comm_p2p_disable(self._h))
 
 
 class Group:

@@ -23,9 +23,64 @@ namespace smk
 #define SMK_TUPLE_LAYERS 24 /* with boundary layer treatment: + accumulated normal, face count, outer neighbour */
 #define SMK_MAXCOPIES 16
 
+#define SMK_MAXNBR 32   /* neighbour ranks of one rank the peer-memory exchange supports */
+#define SMK_MAXRANKS 64 /* ranks of a run it supports */
+
+// Peer-memory exchange (smgpu_comm_p2p_*): every rank owns one exchange block -- receive buffers, one flag
+// word per neighbour and exchange, one statistics slot per rank and parity -- that its peers map (CUDA IPC
+// between processes, peer access inside one process) and WRITE into directly from the kernels that produce
+// the data; a flag written with release semantics after the data tells the consumer kernel, which waits for
+// it with acquire loads, that the iteration's records have landed.  No collective call, no extra launch.
+struct P2PStat
+{
+    double res;
+    long long nf;
+    unsigned long long epoch, pad;
+};
+struct P2PDev
+{
+    int nNbr, nRanks, rank, pad;
+    const unsigned char *slotNbr; // per send slot: index of its neighbour
+    int nbrOff[SMK_MAXNBR + 1];
+    double *peerRecv[SMK_MAXNBR];     // where this rank's records for neighbour j go (in j's block)
+    uint8_t *peerRecvFz[SMK_MAXNBR];
+    unsigned long long *peerFlagT[SMK_MAXNBR], *peerFlagF[SMK_MAXNBR]; // j's flag words for this rank
+    unsigned long long *flagT, *flagF; // this rank's flag words, one per neighbour, written by the neighbours
+    P2PStat *peerStat[SMK_MAXRANKS];   // every rank's slot array [2][nRanks]
+    P2PStat *stat;                     // this rank's
+    unsigned long long *epoch;         // iteration counter of the exchange (never reset)
+    unsigned int *packDone, *fzDone;   // last-block counters of the two producer kernels
+};
+__device__ __forceinline__ void stReleaseSys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// waits until *p >= want (want == exact for the parity-buffered statistics); a peer that never arrives raises
+// errFlag 6 after about ten seconds instead of hanging the device
+__device__ __forceinline__ void spinUntil(const unsigned long long *p, unsigned long long want, int *errFlag)
+{
+    const long long t0 = clock64();
+    while (ldAcquireSys(p) < want)
+    {
+        __nanosleep(64);
+        if (clock64() - t0 > 20000000000ll)
+        {
+            *errFlag = 6;
+            break;
+        }
+    }
+}
+
 struct CommDev
 {
     int nSlots, nShared, rank;
+    const P2PDev *p2p; // non-null: the exchanges go through peer memory
     int tuple; // doubles per record: SMK_TUPLE, or SMK_TUPLE_LAYERS with boundary layer treatment
     const int *sendPoint, *sharedPoint, *selfSlot, *copyOff, *copyRank, *copySlot;
     double *sendBuf, *recvBuf;
@@ -40,46 +95,79 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
     if (*d.done)
         return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c.nSlots)
-        return;
-    const int p = c.sendPoint[i];
-    const P4 self = ld4(d.pts + p);
-    const D3 x = {self.x, self.y, self.z};
-    const bool internal = self.w != 0.0;
-    PointLocal L;
-    pointLocal(d, p, x, internal, L);
-    // topology.cpp refuses meshes with a point that has fewer than two eligible neighbours (the reference's
-    // "Failed to find cLabel" abort, src/smoothMesh.C:354-362), so n1/n2 are labels here; the guard keeps
-    // the walk inside the table even if that invariant were ever broken
-    const bool hc = (L.n1 >= 0 && L.n2 >= 0) && shareCell(d, L.n1, L.n2);
-    double *r = c.sendBuf + (size_t)i * c.tuple;
-    r[0] = L.sum.x, r[1] = L.sum.y, r[2] = L.sum.z;
-    r[3] = (double)L.nCells;
-    r[4] = L.r1.x, r[5] = L.r1.y, r[6] = L.r1.z;
-    r[7] = L.r2.x, r[8] = L.r2.y, r[9] = L.r2.z;
-    r[10] = L.r3.x, r[11] = L.r3.y, r[12] = L.r3.z;
-    r[13] = hc ? 1.0 : 0.0;
-    r[14] = r[15] = 0.0;
-    if (d.layers)
+    if (i < c.nSlots)
     {
-        // calculateBoundaryPointNormals up to its synchronisation (orthogonalBoundaryBlending.C:151-182):
-        // this copy's previous normal minus the unit normals of its boundary faces, and the face count
-        D3 n = ld3(d.normals, p);
-        const int b = d.bfOff[p], e = d.bfOff[p + 1];
-        for (int k = b; k < e; ++k)
+        const int p = c.sendPoint[i];
+        const P4 self = ld4(d.pts + p);
+        const D3 x = {self.x, self.y, self.z};
+        const bool internal = self.w != 0.0;
+        PointLocal L;
+        pointLocal(d, p, x, internal, L);
+        // topology.cpp refuses meshes with a point that has fewer than two eligible neighbours (the reference's
+        // "Failed to find cLabel" abort, src/smoothMesh.C:354-362), so n1/n2 are labels here; the guard keeps
+        // the walk inside the table even if that invariant were ever broken
+        const bool hc = (L.n1 >= 0 && L.n2 >= 0) && shareCell(d, L.n1, L.n2);
+        double *r = c.sendBuf + (size_t)i * c.tuple;
+        r[0] = L.sum.x, r[1] = L.sum.y, r[2] = L.sum.z;
+        r[3] = (double)L.nCells;
+        r[4] = L.r1.x, r[5] = L.r1.y, r[6] = L.r1.z;
+        r[7] = L.r2.x, r[8] = L.r2.y, r[9] = L.r2.z;
+        r[10] = L.r3.x, r[11] = L.r3.y, r[12] = L.r3.z;
+        r[13] = hc ? 1.0 : 0.0;
+        r[14] = r[15] = 0.0;
+        if (d.layers)
         {
-            const D3 Sf = ld3(d.faceGeo, 2 * d.bf[k] + 1);
-            n = n - Sf / mag(Sf);
+            // calculateBoundaryPointNormals up to its synchronisation (orthogonalBoundaryBlending.C:151-182):
+            // this copy's previous normal minus the unit normals of its boundary faces, and the face count
+            D3 n = ld3(d.normals, p);
+            const int b = d.bfOff[p], e = d.bfOff[p + 1];
+            for (int k = b; k < e; ++k)
+            {
+                const D3 Sf = ld3(d.faceGeo, 2 * d.bf[k] + 1);
+                n = n - Sf / mag(Sf);
+            }
+            r[16] = n.x, r[17] = n.y, r[18] = n.z;
+            r[19] = (double)(e - b);
+            // updateNeighCoords before its synchronisation (:472-487)
+            const int o = d.pointToOuter[p];
+            D3 oc = {SM_GREAT, SM_GREAT, SM_GREAT};
+            if (o >= 0)
+                oc = ld3(d.pts, o);
+            r[20] = oc.x, r[21] = oc.y, r[22] = oc.z;
+            r[23] = 0.0;
         }
-        r[16] = n.x, r[17] = n.y, r[18] = n.z;
-        r[19] = (double)(e - b);
-        // updateNeighCoords before its synchronisation (:472-487)
-        const int o = d.pointToOuter[p];
-        D3 oc = {SM_GREAT, SM_GREAT, SM_GREAT};
-        if (o >= 0)
-            oc = ld3(d.pts, o);
-        r[20] = oc.x, r[21] = oc.y, r[22] = oc.z;
-        r[23] = 0.0;
+    }
+    if (c.p2p)
+    {
+        // The block's records go straight into the neighbours' receive buffers over NVLink: the block copies its
+        // contiguous piece of the send buffer 16 bytes per lane, consecutive lanes to consecutive addresses, so a
+        // warp instruction is one 512-byte write (a neighbour boundary inside the piece only splits one of them).
+        const P2PDev *x2 = c.p2p;
+        __syncthreads(); // the records the threads of this block have just written
+        const int s0 = blockIdx.x * blockDim.x, s1 = min(s0 + (int)blockDim.x, c.nSlots);
+        const int perSlot = c.tuple / 2, pieces = (s1 - s0) * perSlot;
+        for (int q = threadIdx.x; q < pieces; q += blockDim.x)
+        {
+            const int slot = s0 + q / perSlot, k = 2 * (q % perSlot);
+            const int j = x2->slotNbr[slot];
+            const double2 v = *reinterpret_cast<const double2 *>(c.sendBuf + (size_t)slot * c.tuple + k);
+            *reinterpret_cast<double2 *>(x2->peerRecv[j] + (size_t)(slot - x2->nbrOff[j]) * c.tuple + k) = v;
+        }
+        // the last block to finish tells every neighbour that this iteration's records are complete
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned int t = atomicAdd(x2->packDone, 1u);
+            if (t == gridDim.x - 1)
+            {
+                *x2->packDone = 0;
+                __threadfence_system();
+                const unsigned long long e = *x2->epoch;
+                for (int j = 0; j < x2->nNbr; ++j)
+                    stReleaseSys(x2->peerFlagT[j], e);
+            }
+        }
     }
 }
 
@@ -113,6 +201,12 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
 {
     if (*d.done)
         return;
+    if (c.p2p)
+    { // the neighbours' records of this iteration have landed in this rank's receive buffer
+        if (threadIdx.x < c.p2p->nNbr)
+            spinUntil(c.p2p->flagT + threadIdx.x, *c.p2p->epoch, d.errFlag);
+        __syncthreads();
+    }
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= c.nShared)
         return;
@@ -250,21 +344,100 @@ __global__ void __launch_bounds__(128) k_frozen_pack(Dev d, CommDev c)
         return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c.nSlots)
-        c.sendFz[i] = d.frozen[c.sendPoint[i]];
+    {
+        const uint8_t f = d.frozen[c.sendPoint[i]];
+        c.sendFz[i] = f;
+        if (c.p2p)
+        {
+            const int j = c.p2p->slotNbr[i];
+            c.p2p->peerRecvFz[j][i - c.p2p->nbrOff[j]] = f;
+        }
+    }
+    if (c.p2p)
+    {
+        const P2PDev *x2 = c.p2p;
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            const unsigned int t = atomicAdd(x2->fzDone, 1u);
+            if (t == gridDim.x - 1)
+            {
+                *x2->fzDone = 0;
+                __threadfence_system();
+                const unsigned long long e = *x2->epoch;
+                for (int j = 0; j < x2->nNbr; ++j)
+                    stReleaseSys(x2->peerFlagF[j], e);
+            }
+        }
+    }
 }
 // orEqOp<bool> on isFrozenPoint, :2374
 __global__ void __launch_bounds__(128) k_frozen_or(Dev d, CommDev c)
 {
     if (*d.done)
         return;
+    if (c.p2p)
+    {
+        if (threadIdx.x < c.p2p->nNbr)
+            spinUntil(c.p2p->flagF + threadIdx.x, *c.p2p->epoch, d.errFlag);
+        __syncthreads();
+    }
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < c.nSlots && c.recvFz[i])
         d.frozen[c.sendPoint[i]] = 1;
 }
-// publishes the all-reduced statistics of the iteration and the stop flag (:2396-2405)
-__global__ void k_finish_iter(Dev d, CommDev c)
+// publishes the all-reduced statistics of the iteration and the stop flag (:2396-2405).  Peer-memory mode: this
+// rank's (residual, nFrozen) goes into every rank's slot array first (one lane per rank), then the kernel waits
+// for all slots of this iteration and reduces them in rank order (max / exact integer sum), which replaces the
+// two returnReduce calls (:1567, :2396); the slots are double-buffered by iteration parity because a rank that is
+// not a neighbour may already be one iteration ahead.
+__global__ void __launch_bounds__(SMK_MAXRANKS) k_finish_iter(Dev d, CommDev c)
 {
-    if (*d.done || threadIdx.x != 0 || blockIdx.x != 0)
+    if (*d.done)
+        return;
+    if (c.p2p)
+    {
+        const P2PDev *x2 = c.p2p;
+        const unsigned long long e = *x2->epoch;
+        const int par = (int)(e & 1), r = threadIdx.x;
+        if (r < x2->nRanks)
+        {
+            P2PStat *dst = x2->peerStat[r] + par * x2->nRanks + x2->rank;
+            dst->res = *c.redRes;
+            dst->nf = *c.redFrozen;
+            __threadfence_system();
+            stReleaseSys(&dst->epoch, e);
+            // exact match: the slot of this parity still holds iteration e - 2 until the peer has written
+            const long long t0 = clock64();
+            while (ldAcquireSys(&x2->stat[par * x2->nRanks + r].epoch) != e)
+            {
+                __nanosleep(64);
+                if (clock64() - t0 > 20000000000ll)
+                {
+                    *d.errFlag = 6;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+        {
+            double m = x2->stat[par * x2->nRanks].res;
+            long long sum = x2->stat[par * x2->nRanks].nf;
+            for (int q = 1; q < x2->nRanks; ++q)
+            {
+                const double v = x2->stat[par * x2->nRanks + q].res;
+                m = (v > m) ? v : m;
+                sum += x2->stat[par * x2->nRanks + q].nf;
+            }
+            *c.redRes = m;
+            *c.redFrozen = sum;
+            *x2->epoch = e + 1;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0 || blockIdx.x != 0)
         return;
     const double res = *c.redRes;
     const int it = *d.iter;
@@ -292,6 +465,11 @@ struct Comm
     // in-process group (smgpu_group_*): the ranks are handles of this process driven by one host thread on one
     // stream; exchanges are stream-ordered device copies between the members' buffers instead of NCCL calls
     LocalGroup *group = nullptr;
+    // peer-memory exchange: this rank's exchange block (what the peers map) and the mapped blocks of the peers
+    unsigned char *xblock = nullptr;
+    size_t xblockBytes = 0;
+    std::vector<void *> ipcMapped;
+    bool p2p = false;
     // the predictor exchange runs on its own stream, fenced by these events, so that kernels that do not
     // need its result keep the GPU busy meanwhile
     cudaStream_t xStream = nullptr;

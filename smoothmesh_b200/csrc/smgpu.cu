@@ -97,7 +97,7 @@ struct smgpu_handle
     }
 
     // optional per-kernel timing (CUDA events on the launch stream)
-    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_LAYER, K_GEOM_TILES, K_NUM };
+    enum { K_FACE_GEOM, K_CELL, K_PREDICT, K_EDGE, K_FACE_CUR, K_COMPACT, K_FACE_TESTS, K_FACE_RESOLVE, K_COMMIT, K_EXCHANGE, K_LAYER, K_GEOM_TILES, K_X_PACK, K_X_MERGE, K_X_FROZEN, K_X_FINISH, K_NUM };
     bool profiling = false;
     std::vector<cudaEvent_t> evPool;
     std::vector<std::pair<int, size_t>> evUse; // (kernel id, index of start event)
@@ -536,6 +536,9 @@ struct smgpu_handle
                                     "Did not find surface intersection for a boundary point (src/boundaryPointSmoothing.C:934)",
                                     "A smoothing surface point has zero point normal (src/orthogonalBoundaryBlending.C:611)"};
         CK(cudaMemset(d.errFlag, 0, sizeof(int)));
+        if (errFlag == 6)
+            return setErr(SMGPU_ERR_COMM, "peer-memory exchange: a rank did not deliver its records within ten seconds "
+                                          "(did every rank call smgpu_iterate with the same arguments?)");
         return setErr(SMGPU_ERR_MESH, msg[(errFlag >= 1 && errFlag <= 5) ? errFlag : 1]);
     }
     // per-iteration log of the last run (what the reference prints at src/smoothMesh.C:2396)
@@ -602,6 +605,14 @@ struct LocalGroup
     std::vector<cudaStream_t> ownStreams; // the members' own streams, restored when the group is destroyed
 };
 
+// what the peers of a rank need to know to write into its exchange block; sits at the start of the block
+struct XHeader
+{
+    int magic, rank, nRanks, tuple, nSlots, nNbr;
+    int nbrRank[SMK_MAXNBR], nbrOff[SMK_MAXNBR + 1];
+    long long offFlagT, offFlagF, offStat, offRecv, offFz;
+};
+
 // this rank's half of the plan: no communication, so a failure here cannot leave other ranks waiting
 static Comm *commPrepare(smgpu_handle *h, int rank, int nRanks, const int64_t *counts, const int64_t *allGids)
 {
@@ -635,9 +646,37 @@ static Comm *commPrepare(smgpu_handle *h, int rank, int nRanks, const int64_t *c
         c.copySlot = h->upload(pl.copySlot);
         c.tuple = h->anyLayerPatch ? SMK_TUPLE_LAYERS : SMK_TUPLE;
         c.sendBuf = h->dalloc<double>((size_t)c.nSlots * c.tuple);
-        c.recvBuf = h->dalloc<double>((size_t)c.nSlots * c.tuple);
         c.sendFz = h->dalloc<uint8_t>(c.nSlots);
-        c.recvFz = h->dalloc<uint8_t>(c.nSlots);
+        // the receive side lives in one exchange block that peers can map (smgpu_comm_p2p_*): header (who this
+        // rank's neighbours are and where their records go), flag words, statistics slots, receive buffers
+        XHeader hdr;
+        memset(&hdr, 0, sizeof hdr);
+        hdr.magic = 0x534d5832; // "SMX2"
+        hdr.rank = rank;
+        hdr.nRanks = nRanks;
+        hdr.tuple = c.tuple;
+        hdr.nSlots = c.nSlots;
+        hdr.nNbr = (int)pl.nbrRank.size();
+        for (int j = 0; j < hdr.nNbr && j < SMK_MAXNBR; ++j)
+        {
+            hdr.nbrRank[j] = pl.nbrRank[j];
+            hdr.nbrOff[j] = pl.nbrOff[j];
+        }
+        if (hdr.nNbr <= SMK_MAXNBR)
+            hdr.nbrOff[hdr.nNbr] = pl.nbrOff[hdr.nNbr];
+        hdr.offFlagT = 512;
+        hdr.offFlagF = hdr.offFlagT + SMK_MAXNBR * 8;
+        hdr.offStat = hdr.offFlagF + SMK_MAXNBR * 8;
+        hdr.offRecv = hdr.offStat + 2 * SMK_MAXRANKS * (long long)sizeof(smk::P2PStat);
+        hdr.offFz = hdr.offRecv + (((long long)c.nSlots * c.tuple * 8 + 255) / 256) * 256;
+        cm->xblockBytes = (size_t)hdr.offFz + (size_t)c.nSlots + 256;
+        static_assert(sizeof(XHeader) <= 512, "exchange block header");
+        cm->xblock = h->dalloc<unsigned char>(cm->xblockBytes);
+        CK(cudaMemset(cm->xblock, 0, cm->xblockBytes));
+        CK(cudaMemcpy(cm->xblock, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
+        c.recvBuf = reinterpret_cast<double *>(cm->xblock + hdr.offRecv);
+        c.recvFz = cm->xblock + hdr.offFz;
+        c.p2p = nullptr;
         c.redRes = h->dalloc<double>(1);
         c.redFrozen = h->dalloc<long long>(1);
     }
@@ -819,7 +858,72 @@ static void commDestroy(Comm *cm)
         cudaEventDestroy(cm->evExchanged);
     if (cm->nccl)
         nccl().CommDestroy(cm->nccl);
+    for (void *p : cm->ipcMapped)
+        cudaIpcCloseMemHandle(p);
     delete cm;
+}
+
+// Maps the peers' exchange blocks and fills the device-side table of the peer-memory exchange.  bases[r]:
+// device pointer to rank r's block as seen from this process (own block for r == rank).
+static void commConnectPeers(Comm *cm, smgpu_handle *h, const std::vector<unsigned char *> &bases)
+{
+    const ExchangePlan &pl = cm->plan;
+    const int nRanks = pl.nRanks, nNbr = (int)pl.nbrRank.size();
+    if (nNbr > SMK_MAXNBR || nRanks > SMK_MAXRANKS)
+        throw std::runtime_error("peer-memory exchange: more neighbour ranks / ranks than its tables hold");
+    smk::P2PDev x;
+    memset(&x, 0, sizeof x);
+    x.nNbr = nNbr;
+    x.nRanks = nRanks;
+    x.rank = pl.rank;
+    XHeader mine;
+    CK(cudaMemcpy(&mine, cm->xblock, sizeof mine, cudaMemcpyDeviceToHost));
+    x.flagT = reinterpret_cast<unsigned long long *>(cm->xblock + mine.offFlagT);
+    x.flagF = reinterpret_cast<unsigned long long *>(cm->xblock + mine.offFlagF);
+    x.stat = reinterpret_cast<smk::P2PStat *>(cm->xblock + mine.offStat);
+    std::vector<unsigned char> slotNbr(pl.sendPoint.size());
+    for (int j = 0; j < nNbr; ++j)
+    {
+        x.nbrOff[j] = pl.nbrOff[j];
+        for (int32_t i = pl.nbrOff[j]; i < pl.nbrOff[j + 1]; ++i)
+            slotNbr[i] = (unsigned char)j;
+    }
+    x.nbrOff[nNbr] = pl.nbrOff[nNbr];
+    for (int r = 0; r < nRanks; ++r)
+    {
+        XHeader ph;
+        CK(cudaMemcpy(&ph, bases[r], sizeof ph, cudaMemcpyDefault));
+        if (ph.magic != 0x534d5832 || ph.rank != r || ph.nRanks != nRanks)
+            throw std::runtime_error("peer-memory exchange: the block of rank " + std::to_string(r) + " does not carry its header");
+        x.peerStat[r] = reinterpret_cast<smk::P2PStat *>(bases[r] + ph.offStat);
+        const auto it = std::find(pl.nbrRank.begin(), pl.nbrRank.end(), r);
+        if (it == pl.nbrRank.end())
+            continue;
+        const int j = (int)(it - pl.nbrRank.begin());
+        int jj = -1;
+        for (int k = 0; k < ph.nNbr; ++k)
+            if (ph.nbrRank[k] == pl.rank)
+                jj = k;
+        if (jj < 0 || ph.nbrOff[jj + 1] - ph.nbrOff[jj] != pl.nbrOff[j + 1] - pl.nbrOff[j] || ph.tuple != cm->c.tuple)
+            throw std::runtime_error("peer-memory exchange: exchange plans of two ranks disagree");
+        x.peerRecv[j] = reinterpret_cast<double *>(bases[r] + ph.offRecv) + (size_t)ph.nbrOff[jj] * ph.tuple;
+        x.peerRecvFz[j] = bases[r] + ph.offFz + ph.nbrOff[jj];
+        x.peerFlagT[j] = reinterpret_cast<unsigned long long *>(bases[r] + ph.offFlagT) + jj;
+        x.peerFlagF[j] = reinterpret_cast<unsigned long long *>(bases[r] + ph.offFlagF) + jj;
+    }
+    x.slotNbr = h->upload(slotNbr);
+    unsigned long long one = 1;
+    unsigned long long *ep = h->dalloc<unsigned long long>(1);
+    CK(cudaMemcpy(ep, &one, 8, cudaMemcpyHostToDevice));
+    x.epoch = ep;
+    unsigned int *cnt = h->dalloc<unsigned int>(2);
+    CK(cudaMemset(cnt, 0, 8));
+    x.packDone = cnt;
+    x.fzDone = cnt + 1;
+    smk::P2PDev *dx = h->dalloc<smk::P2PDev>(1);
+    CK(cudaMemcpy(dx, &x, sizeof x, cudaMemcpyHostToDevice));
+    cm->c.p2p = dx;
+    cm->p2p = true;
 }
 
 // ---- one iteration with the interface exchanges (src/smoothMesh.C:2257-2399 under -parallel), in the
@@ -832,7 +936,7 @@ static void commPhasePack(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
     h->launchCellCentres();
-    h->profBegin(smgpu_handle::K_EXCHANGE);
+    h->profBegin(smgpu_handle::K_X_PACK);
     if (c.nSlots > 0)
         k_shared_pack<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
@@ -853,7 +957,7 @@ static void commPhaseLocal(Comm *cm, smgpu_handle *h)
 static void commPhaseConstrain(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
-    h->profBegin(smgpu_handle::K_EXCHANGE);
+    h->profBegin(smgpu_handle::K_X_MERGE);
     if (c.nShared > 0)
         k_shared_merge<<<smgpu_handle::grid(c.nShared, 64), 64, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
@@ -861,7 +965,7 @@ static void commPhaseConstrain(Comm *cm, smgpu_handle *h)
     h->launchEdgeConstraints();
     if (h->prm.face_angle_constraint)
         h->launchFaceResolve();
-    h->profBegin(smgpu_handle::K_EXCHANGE);
+    h->profBegin(smgpu_handle::K_X_FROZEN);
     if (c.nSlots > 0)
         k_frozen_pack<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
@@ -871,7 +975,7 @@ static void commPhaseConstrain(Comm *cm, smgpu_handle *h)
 static void commPhaseCommit(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
-    h->profBegin(smgpu_handle::K_EXCHANGE);
+    h->profBegin(smgpu_handle::K_X_FROZEN);
     if (c.nSlots > 0)
         k_frozen_or<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
@@ -881,8 +985,8 @@ static void commPhaseCommit(Comm *cm, smgpu_handle *h)
 // D: statistics and stop flag from the reduced residual / count (:2396-2405)
 static void commPhaseFinish(Comm *cm, smgpu_handle *h)
 {
-    h->profBegin(smgpu_handle::K_EXCHANGE);
-    k_finish_iter<<<1, 32, 0, h->stream>>>(h->d, cm->c);
+    h->profBegin(smgpu_handle::K_X_FINISH);
+    k_finish_iter<<<1, SMK_MAXRANKS, 0, h->stream>>>(h->d, cm->c);
     h->profEnd(1);
     h->launches += 1;
 }
@@ -890,6 +994,16 @@ static void commPhaseFinish(Comm *cm, smgpu_handle *h)
 static void commIterate(Comm *cm, smgpu_handle *h)
 {
     const smk::CommDev &c = cm->c;
+    if (cm->p2p)
+    { // peer-memory exchange: the producer kernels write into the peers' blocks, the consumer kernels wait for
+      // the flags; nothing but this rank's own kernels on this rank's stream
+        commPhasePack(cm, h);
+        commPhaseLocal(cm, h);
+        commPhaseConstrain(cm, h);
+        commPhaseCommit(cm, h);
+        commPhaseFinish(cm, h);
+        return;
+    }
     commPhasePack(cm, h);
     // the predictor exchange runs on its own stream while the main stream works on what does not need it
     h->profBegin(smgpu_handle::K_EXCHANGE);
@@ -1922,7 +2036,8 @@ extern "C"
     int smgpu_profile_get(smgpu_handle *h, int32_t *n, const char **names, double *ms_total, int64_t *launches)
     {
         static const char *kNames[smgpu_handle::K_NUM] = {"k_face_geom", "k_cell_centres", "k_predict",    "k_edge_constraints", "k_face_current",
-                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange", "k_layer", "k_geom_tiles"};
+                                                          "k_active_compact", "k_face_tests", "k_face_resolve",     "k_commit", "halo_exchange", "k_layer", "k_geom_tiles",
+                                                          "x_pack", "x_merge", "x_frozen", "x_finish"};
         if (!h || !n)
             return setErr(SMGPU_ERR_ARG, "null argument");
         *n = smgpu_handle::K_NUM;
@@ -2012,6 +2127,102 @@ extern "C"
             h->comm->nccl = nullptr;
             return setErr(SMGPU_ERR_COMM, e.what());
         }
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_p2p_export(smgpu_handle *h, uint8_t handle_out[64])
+    {
+        if (!h || !handle_out)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (!h->comm || !h->comm->xblock)
+            return setErr(SMGPU_ERR_ARG, "call smgpu_comm_prepare / smgpu_comm_init first");
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+        cudaIpcMemHandle_t mh;
+        if (cudaSetDevice(h->prm.device) != cudaSuccess || cudaIpcGetMemHandle(&mh, h->comm->xblock) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return setErr(SMGPU_ERR_COMM, "cudaIpcGetMemHandle failed for the exchange block");
+        }
+        memcpy(handle_out, &mh, 64);
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_p2p_connect(smgpu_handle *h, const uint8_t *all_handles, smgpu_handle *const *local_peers)
+    {
+        if (!h || (!all_handles && !local_peers))
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        if (!h->comm || !h->comm->xblock || h->comm->group)
+            return setErr(SMGPU_ERR_ARG, "the peer-memory exchange needs a prepared communicator (not an in-process group)");
+        if (getenv("SMGPU_NO_P2P") && atoi(getenv("SMGPU_NO_P2P")) != 0)
+            return setErr(SMGPU_ERR_COMM, "peer-memory exchange disabled by SMGPU_NO_P2P");
+        sm::Comm *cm = h->comm;
+        const int nRanks = cm->plan.nRanks, rank = cm->plan.rank;
+        try
+        {
+            CK(cudaSetDevice(h->prm.device));
+            std::vector<unsigned char *> bases(nRanks, nullptr);
+            for (int r = 0; r < nRanks; ++r)
+            {
+                if (r == rank)
+                {
+                    bases[r] = cm->xblock;
+                    continue;
+                }
+                smgpu_handle *lp = local_peers ? local_peers[r] : nullptr;
+                if (lp)
+                { // a handle of this process: its block is addressable directly once peer access is on
+                    if (!lp->comm || !lp->comm->xblock)
+                        throw std::runtime_error("local peer without a prepared communicator");
+                    if (lp->prm.device != h->prm.device)
+                    {
+                        int can = 0;
+                        CK(cudaDeviceCanAccessPeer(&can, h->prm.device, lp->prm.device));
+                        if (!can)
+                            throw std::runtime_error("no peer access between the devices of two ranks");
+                        const cudaError_t e = cudaDeviceEnablePeerAccess(lp->prm.device, 0);
+                        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                            throw std::runtime_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+                        cudaGetLastError();
+                    }
+                    bases[r] = lp->comm->xblock;
+                    continue;
+                }
+                if (!all_handles)
+                    throw std::runtime_error("no handle for a peer of another process");
+                cudaIpcMemHandle_t mh;
+                memcpy(&mh, all_handles + 64 * (size_t)r, 64);
+                void *p = nullptr;
+                const cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess)
+                {
+                    cudaGetLastError();
+                    throw std::runtime_error(std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+                }
+                cm->ipcMapped.push_back(p);
+                bases[r] = (unsigned char *)p;
+            }
+            sm::commConnectPeers(cm, h, bases);
+        }
+        catch (const std::exception &e)
+        {
+            return setErr(SMGPU_ERR_COMM, e.what());
+        }
+        return SMGPU_OK;
+    }
+
+    int smgpu_comm_p2p_disable(smgpu_handle *h)
+    {
+        if (!h || !h->comm)
+            return setErr(SMGPU_ERR_ARG, "no communicator");
+        h->comm->c.p2p = nullptr;
+        h->comm->p2p = false;
+        // unmap the peers' blocks now: a host that tears a run down calls this on every rank, synchronises, and
+        // only then destroys the handles, so no block is freed while a peer still maps it
+        cudaSetDevice(h->prm.device);
+        cudaStreamSynchronize(h->stream);
+        for (void *p : h->comm->ipcMapped)
+            cudaIpcCloseMemHandle(p);
+        h->comm->ipcMapped.clear();
         return SMGPU_OK;
     }
 

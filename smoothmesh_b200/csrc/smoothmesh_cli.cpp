@@ -266,7 +266,7 @@ static int runParallel(const RunOptions &ro)
     Barrier bar(nProcs);
     std::mutex failMutex;
     std::string failure;
-    std::atomic<bool> failed{false}; // what the worker threads poll; `failure` itself is only touched under the mutex
+    std::atomic<bool> failed{false}, p2pFailed{false}; // what the worker threads poll; `failure` itself is only touched under the mutex
     std::vector<smgpu_handle *> handles(nProcs, nullptr);
     auto failAll = [&](const std::string &msg) {
         std::lock_guard<std::mutex> lk(failMutex);
@@ -380,6 +380,15 @@ static int runParallel(const RunOptions &ro)
                     return;
                 if (smgpu_comm_init(h, k, nProcs, uid, counts.data(), allGids.data()) != SMGPU_OK)
                     failAll(smgpu_last_error());
+                bar.wait();
+                if (failed)
+                    return;
+                // peer-memory exchange between the GPUs of this process (direct peer access); all ranks or none
+                if (smgpu_comm_p2p_connect(h, nullptr, handles.data()) != SMGPU_OK)
+                    p2pFailed = true;
+                bar.wait();
+                if (p2pFailed)
+                    smgpu_comm_p2p_disable(h);
             }
             bar.wait();
             if (failed)

@@ -7,6 +7,8 @@ The reference decomposes with decomposePar and runs `mpirun -np N smoothMesh -pa
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 
@@ -52,7 +54,7 @@ def gather_shared(my_gids: np.ndarray, dist):
     return counts, allg
 
 
-def init_comm(smoother, rank, world, dist):
+def init_comm(smoother, rank, world, dist, p2p_exchange=True):
     import torch
     import smoothmesh_b200 as sm
     counts, allg = gather_shared(smoother.comm_local_shared(), dist)
@@ -75,3 +77,40 @@ def init_comm(smoother, rank, world, dist):
         uid = torch.tensor(list(sm.Smoother.comm_unique_id()), dtype=torch.uint8, device=dev)
     dist.broadcast(uid, src=0)
     smoother.comm_init(rank, world, bytes(uid.cpu().numpy().tolist()), counts, allg)
+    p2p = False
+    if p2p_exchange and backend == "nccl" and not os.environ.get("SMGPU_NO_P2P"):
+        # peer-memory exchange for the iteration loop (include/smgpu.h: smgpu_comm_p2p_*); every rank must end up in
+        # the same mode, so the outcome is agreed on before anybody iterates
+        ok = 1
+        try:
+            mine = torch.tensor(list(smoother.comm_p2p_export()), dtype=torch.uint8, device=dev)
+        except sm.SmoothMeshError:
+            mine = torch.zeros(64, dtype=torch.uint8, device=dev)
+            ok = 0
+        allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()):
+            try:
+                smoother.comm_p2p_connect(b"".join(bytes(t.cpu().numpy().tolist()) for t in allh))
+            except sm.SmoothMeshError:
+                ok = 0
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()):
+                p2p = True
+            else:
+                smoother.comm_p2p_disable()
+    return p2p
+
+
+def shutdown_comm(smoother, dist):
+    """Collective tear-down: every rank unmaps its peers' exchange blocks, the ranks synchronise, and only then
+    the handle (and with it the rank's own block) goes away."""
+    try:
+        smoother.comm_p2p_disable()
+    except Exception:
+        pass
+    dist.barrier()
+    smoother.close()

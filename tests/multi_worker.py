@@ -103,7 +103,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     kw, iters = options(kind)
     g = sm.Smoother(mine, device=local_rank, **kw)
-    multi.init_comm(g, rank, world, dist)
+    p2p = multi.init_comm(g, rank, world, dist)  # SMGPU_NO_P2P=1 keeps the NCCL exchanges
     if mode == "debug":
         # step-by-step comparison against the oracle's rank emulation (every rank runs the oracle)
         from oracle import Oracle
@@ -124,6 +124,7 @@ def main():
         os._exit(0)
     log = g.iterate(iters)
     res = dict(n=log.iterations, nf=log.n_frozen, res=log.residual, pts=g.points(), fz=g.frozen())
+    multi.shutdown_comm(g, dist)
     allres = [None] * world
     dist.all_gather_object(allres, res)
     if rank == 0:
@@ -137,7 +138,7 @@ def main():
             assert np.array_equal(a["res"], rs), (r, a["res"], rs)
             assert np.array_equal(a["fz"], o.get("frozen", r)), f"rank {r}: freeze mask differs"
             assert np.array_equal(a["pts"], o.get("points", r)), f"rank {r}: points differ"
-        print(f"multi-GPU parity ok: world={world} kind={kind} iterations={n} nFrozen[-1]={nf[-1]} "
+        print(f"multi-GPU parity ok: world={world} kind={kind} exchange={'peer-memory' if p2p else 'nccl'} iterations={n} nFrozen[-1]={nf[-1]} "
               f"frozen internal={sum(int(o.get('frozen', r).sum()) for r in range(world))}", flush=True)
     dist.barrier()
     dist.destroy_process_group()

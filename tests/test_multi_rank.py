@@ -12,10 +12,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 WORKER = os.path.join(ROOT, "tests", "multi_worker.py")
 
 
-def _run(world, mode, kind, port):
+def _run(world, mode, kind, port, env=None):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER, mode, kind]
-    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     return r.stdout
 
@@ -27,15 +27,18 @@ def test_exchange_plan_gloo(world, kind):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
 @pytest.mark.parametrize("kind", ["hex", "kelvin", "hexlayers", "prismlayers"])
-def test_multi_gpu_parity(kind):
+def test_multi_gpu_parity(kind, exchange):
+    """One process per GPU: the peer-memory exchange (kernels store into the neighbours' mapped buffers over
+    NVLink, flags with release / acquire) and the NCCL exchange, both bit-exact against the oracle's rank emulation."""
     import torch
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
     world = 4 if n >= 4 else 2
-    out = _run(world, "gpu", kind, 29631)
-    assert "multi-GPU parity ok" in out
+    out = _run(world, "gpu", kind, 29631, env={"SMGPU_NO_P2P": "1"} if exchange == "nccl" else None)
+    assert "multi-GPU parity ok" in out and f"exchange={exchange}" in out
 
 
 @pytest.mark.gpu
