@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <array>
+#include <parallel/algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -201,16 +202,21 @@ PolyMesh buildFromCells(const std::vector<double> &points, const std::vector<int
         out.assign(cfVerts.begin() + cfVertOffsets[cf], cfVerts.begin() + cfVertOffsets[cf + 1]);
         std::sort(out.begin(), out.end());
     };
+#pragma omp parallel for schedule(static)
     for (int32_t c = 0; c < C; ++c)
+    {
+        std::vector<int32_t> sv;
         for (int32_t cf = cellFaceOffsets[c]; cf < cellFaceOffsets[c + 1]; ++cf)
         {
-            sortedVerts(cf, tmp);
-            uint64_t h = 0x1234567ull + tmp.size();
-            for (int32_t v : tmp)
+            sv.assign(cfVerts.begin() + cfVertOffsets[cf], cfVerts.begin() + cfVertOffsets[cf + 1]);
+            std::sort(sv.begin(), sv.end());
+            uint64_t h = 0x1234567ull + sv.size();
+            for (int32_t v : sv)
                 h = mix64(h ^ (uint64_t)(uint32_t)v);
             recs[cf] = {h, c, cf};
         }
-    std::sort(recs.begin(), recs.end(), [](const FaceRec &a, const FaceRec &b) {
+    }
+    __gnu_parallel::sort(recs.begin(), recs.end(), [](const FaceRec &a, const FaceRec &b) {
         return a.key != b.key ? a.key < b.key : a.cell < b.cell;
     });
     struct Out
@@ -240,8 +246,8 @@ PolyMesh buildFromCells(const std::vector<double> &points, const std::vector<int
             fail("buildFromCells: face shared by more than two cells (or hash collision)");
         i = j;
     }
-    std::sort(internal.begin(), internal.end(),
-              [](const Out &a, const Out &b) { return a.own != b.own ? a.own < b.own : a.nei < b.nei; });
+    __gnu_parallel::sort(internal.begin(), internal.end(),
+                         [](const Out &a, const Out &b) { return a.own != b.own ? a.own < b.own : (a.nei != b.nei ? a.nei < b.nei : a.cf < b.cf); });
     std::stable_sort(boundary.begin(), boundary.end(), [](const Out &a, const Out &b) {
         return a.patch != b.patch ? a.patch < b.patch : (a.own != b.own ? a.own < b.own : a.cf < b.cf);
     });

@@ -932,12 +932,20 @@ static void commConnectPeers(Comm *cm, smgpu_handle *h, const std::vector<unsign
 // records carry the normals of the previous iteration, so they are packed before k_layer_normals replaces
 // those; interface points get their normal, blend and second clamp in k_shared_merge, which overwrites
 // whatever the point-wise kernels wrote for them.
-static void commPhasePack(Comm *cm, smgpu_handle *h)
+static void commPhasePack(Comm *cm, smgpu_handle *h, bool ownStream = false)
 {
     const smk::CommDev &c = cm->c;
     h->launchCellCentres();
     h->profBegin(smgpu_handle::K_X_PACK);
-    if (c.nSlots > 0)
+    if (ownStream)
+    { // the records only need the geometry: packed (and, in peer-memory mode, delivered) beside the predictor
+        CK(cudaEventRecord(cm->evPacked, h->stream));
+        CK(cudaStreamWaitEvent(cm->xStream, cm->evPacked, 0));
+        if (c.nSlots > 0)
+            k_shared_pack<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, cm->xStream>>>(h->d, c);
+        CK(cudaEventRecord(cm->evExchanged, cm->xStream));
+    }
+    else if (c.nSlots > 0)
         k_shared_pack<<<smgpu_handle::grid(c.nSlots, 128), 128, 0, h->stream>>>(h->d, c);
     h->profEnd(1);
     h->launches += 1;
@@ -997,8 +1005,12 @@ static void commIterate(Comm *cm, smgpu_handle *h)
     if (cm->p2p)
     { // peer-memory exchange: the producer kernels write into the peers' blocks, the consumer kernels wait for
       // the flags; nothing but this rank's own kernels on this rank's stream
-        commPhasePack(cm, h);
+        // with layer treatment the pack reads the normals k_layer_normals is about to replace: same stream then
+        const bool beside = !h->doLayers && cm->xStream;
+        commPhasePack(cm, h, beside);
         commPhaseLocal(cm, h);
+        if (beside)
+            CK(cudaStreamWaitEvent(h->stream, cm->evExchanged, 0)); // this rank's own records (read by the merge)
         commPhaseConstrain(cm, h);
         commPhaseCommit(cm, h);
         commPhaseFinish(cm, h);
@@ -1516,6 +1528,18 @@ extern "C"
             d.surfPts = h->upload(toP4(surf.points));
             d.surfTris = h->upload(surf.tris);
             d.nSurfTris = (int)surf.nTris();
+            d.nBvhNodes = 0;
+            if (surf.nTris() > 8 && !(getenv("SMGPU_NO_BVH") && atoi(getenv("SMGPU_NO_BVH")) != 0))
+            { // acceleration structure of the surface ray casts (the search tree of the reference's findLine)
+                const sm::TriangleBvh bvh = sm::buildTriangleBvh(surf);
+                d.bvhBox = h->upload(bvh.box);
+                d.bvhLeft = h->upload(bvh.left);
+                d.bvhRight = h->upload(bvh.right);
+                d.bvhFirst = h->upload(bvh.first);
+                d.bvhCount = h->upload(bvh.count);
+                d.bvhOrder = h->upload(bvh.order);
+                d.nBvhNodes = (int)bvh.right.size();
+            }
             d.distanceTolerance = B.distanceTolerance;
             d.internalFraction = internal_smoothing_blending_fraction;
             h->boundaryCounts[0] = B.nCorners;

@@ -112,3 +112,46 @@ def test_shipped_boundary_cases(case):
     log = g.iterate(int(d["cli"][list(d["cli"]).index("-centroidalIters") + 1]))
     assert log.iterations == int(d["iterations"]) and np.array_equal(log.n_frozen, d["n_frozen"])
     assert np.array_equal(g.points(), d["final_points"])
+
+
+def fine_box_surface(lo, hi, n):
+    """The six faces of a box as 12 n^2 triangles (shared vertices along the box edges are duplicated per face)."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    pts, tris = [], []
+    for axis in range(3):
+        a1, a2 = (axis + 1) % 3, (axis + 2) % 3
+        for side in (0, 1):
+            base = len(pts)
+            for j in range(n + 1):
+                for i in range(n + 1):
+                    p = np.zeros(3)
+                    p[axis] = hi[axis] if side else lo[axis]
+                    p[a1] = lo[a1] + (hi[a1] - lo[a1]) * i / n
+                    p[a2] = lo[a2] + (hi[a2] - lo[a2]) * j / n
+                    pts.append(p)
+            for j in range(n):
+                for i in range(n):
+                    v = base + j * (n + 1) + i
+                    tris += [[v, v + 1, v + n + 2], [v, v + n + 2, v + n + 1]]
+    return np.array(pts), np.array(tris, dtype=np.int32)
+
+
+def test_surface_ray_casts_through_the_bvh(monkeypatch):
+    """The surface ray casts (findLine, src/boundaryPointSmoothing.C:702-736) walk a bounding volume hierarchy on
+    the device; it only decides which triangles are tested, so the result must equal the visit-every-triangle
+    search (SMGPU_NO_BVH=1) and the oracle bit for bit -- here on a target surface of 6 912 triangles, where rays
+    through shared triangle edges and vertices (equal parameters on several triangles) are the common case."""
+    hi = (1.2, 1.0, 0.9)
+    mesh = sm.Mesh.hex_block(7, 6, 5, hi=hi).jitter(0.03, 5)
+    ip, ie, _, _ = box_geometry((0, 0, 0), hi, 3)
+    c = np.array(hi) / 2
+    tp, te, _, _ = box_geometry(c - 1.08 * c, c + 1.08 * c, 3)
+    tc, tt = fine_box_surface(c - 1.08 * c, c + 1.08 * c, 24)
+    assert len(tt) == 6912
+    geo = dict(init_edges=(ip, ie), target_edges=(tp, te), surface=(tc, tt))
+    g, o = run_pair(mesh, geo, [1] * 6, None, dict(rel_tol=0.0), 0.0, 6)
+    monkeypatch.setenv("SMGPU_NO_BVH", "1")
+    b = sm.Smoother(mesh, rel_tol=0.0)
+    b.enable_boundary_smoothing(geo, [1] * 6)
+    b.iterate(6)
+    assert np.array_equal(b.points(), g.points()) and np.array_equal(b.frozen(), g.frozen())
