@@ -334,8 +334,6 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
         np = x + (d.relStepFrac * scale) * stepDir;
     }
     st4(d.newPts + p, np, 0.0);
-    if (d.pointMirrors)
-        d.newPtsF[p] = make_float4((float)(np.x - d.ox), (float)(np.y - d.oy), (float)(np.z - d.oz), 0.f);
 }
 
 __global__ void __launch_bounds__(128) k_frozen_pack(Dev d, CommDev c)

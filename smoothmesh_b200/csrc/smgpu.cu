@@ -200,40 +200,30 @@ struct smgpu_handle
         }
         d.cosSmallF = (float)std::cos(d.smallAngle);
         d.cosLargeF = (float)std::cos(d.largeAngle);
-        // the single-precision level is used when its error budget at the mesh's shortest edge is small
-        // (64 epsAbs / (edge/4) + 5e-5 < 0.05); otherwise the FP64 filter (and its face-mean table) is
-        // (and only while the points stay inside the initial hull, which its error bound assumes: boundary
-        // point smoothing moves them out of it, so it runs on the FP64 filter)
-        d.faceFilter32 = d.faceFilter && !getenv("SMGPU_NO_F32") && !doBoundary &&
-                         (64.0 * d.epsAbs / (0.25 * meshMinEdge) + 5e-5 < 0.05);
-        d.edgeFilter32 = d.edgeFilter && !getenv("SMGPU_NO_F32") && !doBoundary &&
-                         (16.0 * d.epsAbs / (0.5 * meshMinEdge) + 2e-5 < 0.02);
+        // Single-precision filter levels: every one of them converts DIFFERENCES taken in FP64
+        // (relative to the edge's end point / the point's proposal / a tile-local origin), with the error budget
+        // computed at run time from the actual vectors, so none has a precondition on the size or position of the
+        // mesh, nor on the points staying inside the initial hull.
+        const bool f32 = !getenv("SMGPU_NO_F32");
+        d.faceFilter32 = d.faceFilter && f32;
+        d.edgeFilter32 = d.edgeFilter && f32;
         if (noFilters)
             d.edgeFilter = d.faceFilter = d.faceFilter32 = d.edgeFilter32 = 0;
-        // Fused face-angle filter of k_geom_tiles_f: single precision relative to a tile-local origin, its error
-        // budget evaluated per cell at run time, so it has no precondition on the size of the mesh.  Off with
-        // boundary point smoothing (kept on the FP64 filter like the other single-precision level, to keep that
-        // feature's validated configuration unchanged) and under SMGPU_NO_F32 / SMGPU_NO_FUSED_FILTER.
-        d.fusedFaceFilter = (tilesF && tilesHavePairs && d.faceFilter && !getenv("SMGPU_NO_F32") && !doBoundary &&
+        // face-angle filter fused into k_geom_tiles_f (per-cell certificates); SMGPU_NO_FUSED_FILTER keeps the
+        // per-edge kernel
+        d.fusedFaceFilter = (tilesF && tilesHavePairs && d.faceFilter && f32 &&
                              !(getenv("SMGPU_NO_FUSED_FILTER") && atoi(getenv("SMGPU_NO_FUSED_FILTER")) != 0))
                                 ? 1
                                 : 0;
         if (d.fusedFaceFilter)
-            d.faceFilter32 = 0; // the per-edge single-precision level is not used (smgpu_op_edge_face_angles is literal)
-        // per-point kernels on tiles: their single-precision level works relative to a tile-local origin with a
-        // run-time error budget, the global mirrors are not needed
-        d.edgeTile32 = (usePointTiles && d.edgeFilter && !getenv("SMGPU_NO_F32") && !doBoundary) ? 1 : 0;
-        if (usePointTiles)
-            d.edgeFilter32 = 0;
-        d.faceMirrors = d.faceFilter32;
-        d.faceMean64 = (!d.fusedFaceFilter && d.faceFilter && !d.faceFilter32) ? 1 : 0;
-        d.pointMirrors = (d.edgeFilter32 || d.faceFilter32) ? 1 : 0;
+            d.faceFilter32 = 0; // the per-edge kernel is not used (smgpu_op_edge_face_angles is literal)
+        d.edgeTile32 = (usePointTiles && d.edgeFilter && f32) ? 1 : 0;
+        d.faceMean64 = (!d.fusedFaceFilter && d.faceFilter) ? 1 : 0;
         ensureBuffers();
     }
     // Buffers only some configurations touch, allocated when a configuration that needs them is selected:
-    // the 64-byte face records (two-kernel geometry; boundary face areas for the point normals), the FP64 /
-    // fp32 face-mean and cell-centre tables and the 48-byte edge records of the per-edge face-angle filter,
-    // the fp32 point mirrors of the single-precision filter levels.  At 368^3 they would add 27 GB.
+    // the 64-byte face records (two-kernel geometry; boundary face areas for the point normals), the FP64
+    // face-mean table and the 48-byte edge records of the per-edge face-angle filter.  At 368^3 they would add 21 GB.
     void ensureBuffers()
     {
         if (!d.pts)
@@ -243,18 +233,6 @@ struct smgpu_handle
             d.faceGeo = dalloc<P4>(2 * topo.F);
         if (!d.faceMean && d.faceMean64)
             d.faceMean = dalloc<P4>(topo.F);
-        if (!d.faceMeanF && d.faceMirrors)
-        {
-            d.faceMeanF = dalloc<float4>(topo.F);
-            d.cellCtrF = dalloc<float4>(topo.C);
-        }
-        if (!d.ptsF && d.pointMirrors)
-        {
-            d.ptsF = dalloc<float4>(topo.P);
-            d.newPtsF = dalloc<float4>(topo.P);
-            CK(cudaMemsetAsync(d.newPtsF, 0, topo.P * sizeof(float4), stream));
-            k_mirror_points<<<grid(d.P, 256), 256, 0, stream>>>(d);
-        }
         if (!d.edgeRec && perEdgeFilter)
         {
             sm::buildEdgeRecords(topo);
@@ -296,28 +274,6 @@ struct smgpu_handle
             h[i] = {pts[3 * o], pts[3 * o + 1], pts[3 * o + 2], topo.isInternal[i] ? 1.0 : 0.0};
         }
         CK(cudaMemcpyAsync(d.pts, h, topo.P * sizeof(P4), cudaMemcpyHostToDevice, stream));
-        // single-precision mirror for the first-level face-angle filter: origin = bounding-box centre,
-        // epsAbs from the half diagonal (points stay inside the hull of the initial mesh: every
-        // predictor step is a convex combination of mesh positions)
-        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-#pragma omp parallel for reduction(min : lo[:3]) reduction(max : hi[:3]) schedule(static)
-        for (int64_t i = 0; i < topo.P; ++i)
-        {
-            const double c[3] = {h[i].x, h[i].y, h[i].z};
-            for (int k = 0; k < 3; ++k)
-            {
-                lo[k] = std::min(lo[k], c[k]);
-                hi[k] = std::max(hi[k], c[k]);
-            }
-        }
-        d.ox = 0.5 * (lo[0] + hi[0]);
-        d.oy = 0.5 * (lo[1] + hi[1]);
-        d.oz = 0.5 * (lo[2] + hi[2]);
-        const double R = 0.5 * std::sqrt((hi[0] - lo[0]) * (hi[0] - lo[0]) + (hi[1] - lo[1]) * (hi[1] - lo[1]) +
-                                         (hi[2] - lo[2]) * (hi[2] - lo[2]));
-        d.epsAbs = (float)(8.0 * 5.9604644775390625e-08 * (1.01 * R + 4.0 * topo.maxEdgeLength)); // 8 x 2^-24 x R
-        if (d.ptsF)
-            k_mirror_points<<<grid(d.P, 256), 256, 0, stream>>>(d);
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -1271,10 +1227,9 @@ extern "C"
             d.pairBits = h->dalloc<uint8_t>(t.pp.size() + 8);
             d.activeList = h->dalloc<int>(t.P);
             d.stack = h->dalloc<int>(t.P);
-            d.compOf = h->dalloc<int>(t.P);
             d.reach = h->dalloc<int>(t.P);
             d.rootHi = h->dalloc<int>(t.P);
-            d.changed = h->dalloc<int>(1);
+            d.changed = h->dalloc<int>(8);
             {
                 // cooperative launch of k_face_resolve: as many blocks as can be co-resident
                 int perSm = 0, sms = 0;

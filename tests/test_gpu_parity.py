@@ -235,3 +235,20 @@ def test_point_tile_kernels_loop_parity(case, monkeypatch):
     log = g.iterate(25)
     assert log.iterations == n and np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
     assert np.array_equal(g.frozen(), o.get("frozen")) and np.array_equal(g.points(), o.get("points"))
+
+
+@pytest.mark.parametrize("n,jit,iters", [(24, 0.35, 10), (40, 0.3, 6)])
+def test_dense_face_angle_worklist_matches_the_sequential_walk(n, jit, iters):
+    """-minAngle 80 -maxAngle 100 on a jittered block: almost every point is active and the freeze decisions
+    cascade through the whole mesh, the regime where the reference's stack walk (src/smoothMesh.C:1347-1434) is
+    most order-dependent.  The parallel schedule of k_face_resolve (fixed point over freeze times) must reproduce
+    the oracle's sequential walk bit for bit."""
+    from meshes import hex_jittered
+    mesh = hex_jittered(n, n, n, jit, seed=99)
+    kw = dict(OPTION_SETS["tight_angles"], rel_tol=0.0)
+    g, o = _pair(mesh, **kw)
+    on, nf, res = o.iterate(iters)
+    log = g.iterate(iters)
+    assert g.filter_stats()["active_points"] > 0.5 * mesh.n_points
+    assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
+    assert np.array_equal(g.frozen(), o.get("frozen")) and np.array_equal(g.points(), o.get("points"))
