@@ -21,6 +21,7 @@ namespace smk
 
 #define SMK_TUPLE 16       /* doubles per interface-point record */
 #define SMK_TUPLE_LAYERS 24 /* with boundary layer treatment: + accumulated normal, face count, outer neighbour */
+#define SMK_TUPLE_BOUNDARY 32 /* with boundary point smoothing: + feature edge projections (sum, count), inner neighbour */
 #define SMK_MAXCOPIES 16
 
 #define SMK_MAXNBR 32   /* neighbour ranks of one rank the peer-memory exchange supports */
@@ -42,8 +43,9 @@ struct P2PDev
     int nNbr, nRanks, rank, pad;
     const unsigned char *slotNbr; // per send slot: index of its neighbour
     int nbrOff[SMK_MAXNBR + 1];
-    double *peerRecv[SMK_MAXNBR];     // where this rank's records for neighbour j go (in j's block)
-    uint8_t *peerRecvFz[SMK_MAXNBR];
+    double *peerRecv[SMK_MAXNBR];     // neighbour j's receive buffer (in j's block) ...
+    int peerSlot0[SMK_MAXNBR];        // ... and the slot of it where this rank's first record goes
+    uint8_t *peerRecvFz[SMK_MAXNBR];  // (already offset to that slot)
     unsigned long long *peerFlagT[SMK_MAXNBR], *peerFlagF[SMK_MAXNBR]; // j's flag words for this rank
     unsigned long long *flagT, *flagF; // this rank's flag words, one per neighbour, written by the neighbours
     P2PStat *peerStat[SMK_MAXRANKS];   // every rank's slot array [2][nRanks]
@@ -89,6 +91,20 @@ struct CommDev
     long long *redFrozen;
 };
 
+// position of boundary point p in the ascending list of boundary points (the per-boundary-point tables are indexed by it)
+__device__ __forceinline__ int boundaryIndex(const Dev &d, int p)
+{
+    int lo = 0, hi = d.nBPoints - 1;
+    while (lo < hi)
+    {
+        const int mid = (lo + hi) >> 1;
+        if (d.bPoints[mid] < p)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
 // local predictor tuple of every send slot's point
 __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
 {
@@ -115,7 +131,7 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
         r[10] = L.r3.x, r[11] = L.r3.y, r[12] = L.r3.z;
         r[13] = hc ? 1.0 : 0.0;
         r[14] = r[15] = 0.0;
-        if (d.layers)
+        if (d.normalsOn)
         {
             // calculateBoundaryPointNormals up to its synchronisation (orthogonalBoundaryBlending.C:151-182):
             // this copy's previous normal minus the unit normals of its boundary faces, and the face count
@@ -129,12 +145,34 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
             r[16] = n.x, r[17] = n.y, r[18] = n.z;
             r[19] = (double)(e - b);
             // updateNeighCoords before its synchronisation (:472-487)
-            const int o = d.pointToOuter[p];
             D3 oc = {SM_GREAT, SM_GREAT, SM_GREAT};
-            if (o >= 0)
-                oc = ld3(d.pts, o);
+            if (d.layers)
+            {
+                const int o = d.pointToOuter[p];
+                if (o >= 0)
+                    oc = ld3(d.pts, o);
+            }
             r[20] = oc.x, r[21] = oc.y, r[22] = oc.z;
             r[23] = 0.0;
+        }
+        if (d.bsmooth)
+        {
+            // boundary point smoothing: this copy's share of calculateFeatureEdgeProjections
+            // (src/boundaryPointSmoothing.C:623-656) and its inner neighbour's coordinates
+            // (updateNeighCoords for the inner map, orthogonalBoundaryBlending.C:472-487)
+            D3 sum = {0, 0, 0};
+            int nProj = 0;
+            const int cls = d.bClass[p];
+            if (!internal && (cls & 2))
+                featureEdgeProjectionLocal(d, p, boundaryIndex(d, p), sum, nProj);
+            r[24] = sum.x, r[25] = sum.y, r[26] = sum.z;
+            r[27] = (double)nProj;
+            D3 ic = {SM_GREAT, SM_GREAT, SM_GREAT};
+            const int inner = d.bInner[p];
+            if (inner >= 0)
+                ic = ld3(d.pts, inner);
+            r[28] = ic.x, r[29] = ic.y, r[30] = ic.z;
+            r[31] = 0.0;
         }
     }
     if (c.p2p)
@@ -151,7 +189,7 @@ __global__ void __launch_bounds__(128) k_shared_pack(Dev d, CommDev c)
             const int slot = s0 + q / perSlot, k = 2 * (q % perSlot);
             const int j = x2->slotNbr[slot];
             const double2 v = *reinterpret_cast<const double2 *>(c.sendBuf + (size_t)slot * c.tuple + k);
-            *reinterpret_cast<double2 *>(x2->peerRecv[j] + (size_t)(slot - x2->nbrOff[j]) * c.tuple + k) = v;
+            *reinterpret_cast<double2 *>(x2->peerRecv[j] + (size_t)(x2->peerSlot0[j] + slot - x2->nbrOff[j]) * c.tuple + k) = v;
         }
         // the last block to finish tells every neighbour that this iteration's records are complete
         __threadfence_system();
@@ -215,8 +253,8 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
     const int n = nOther + 1;
     D3 cp1[SMK_MAXCOPIES], cp2[SMK_MAXCOPIES], cp3[SMK_MAXCOPIES];
     bool hc[SMK_MAXCOPIES];
-    D3 sum = {0, 0, 0}, nrm = {0, 0, 0}, outer = {0, 0, 0};
-    double cnt = 0.0, nBoundaryFaces = 0.0;
+    D3 sum = {0, 0, 0}, nrm = {0, 0, 0}, outer = {0, 0, 0}, fep = {0, 0, 0}, innerCoord = {0, 0, 0};
+    double cnt = 0.0, nBoundaryFaces = 0.0, nFep = 0.0;
     int me = -1;
     // copies in ascending rank order, the local one inserted at its rank
     for (int k = 0, o = 0; k < n; ++k)
@@ -232,7 +270,7 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
             r = c.recvBuf + (size_t)c.copySlot[cb + o] * c.tuple;
             ++o;
         }
-        if (d.layers)
+        if (d.normalsOn)
         {
             const D3 nk = {r[16], r[17], r[18]}, ok = {r[20], r[21], r[22]};
             if (k == 0)
@@ -246,6 +284,22 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
                 nrm = nrm + nk;                           // plusEqOp<vector>, orthogonalBoundaryBlending.C:185
                 nBoundaryFaces = nBoundaryFaces + r[19];  // plusEqOp<label>, :193
                 outer = minMagSqr(outer, ok);             // minMagSqrEqOp<vector>, :491
+            }
+        }
+        if (d.bsmooth)
+        {
+            const D3 fk = {r[24], r[25], r[26]}, ik = {r[28], r[29], r[30]};
+            if (k == 0)
+            {
+                fep = fk;
+                nFep = r[27];
+                innerCoord = ik;
+            }
+            else
+            {
+                fep = fep + fk;                          // plusEqOp<vector>, src/boundaryPointSmoothing.C:660
+                nFep = nFep + r[27];                     // plusEqOp<label>, :668
+                innerCoord = minMagSqr(innerCoord, ik);  // minMagSqrEqOp<vector>, orthogonalBoundaryBlending.C:491
             }
         }
         const D3 part = {r[0], r[1], r[2]};
@@ -306,16 +360,26 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
     if (!anyCommon)
         blend = blendFraction(cp1[me], cp2[me], mag(cp1[me]), mag(cp2[me]), mag(cp3[me]), internal);
     D3 np = blendAndClamp(d, x, cen, cp1[me], cp2[me], blend);
-    if (d.layers)
+    bool sharpNow = false;
+    if (d.normalsOn)
     {
-        // rest of calculateBoundaryPointNormals for this point (:200-230), then
-        // blendWithOrthogonalPoints + the second constrainMaxStepLength (src/smoothMesh.C:2288-2304)
+        // rest of calculateBoundaryPointNormals for this point (:200-230)
         const D3 zero = {0, 0, 0};
         if (nBoundaryFaces >= 1.0 && mag(nrm) < 0.1)
+        {
             nrm = zero;
+            sharpNow = true;
+        }
         if (!veq(nrm, zero))
             nrm = nrm / mag(nrm);
         st4(d.normals + p, nrm, 0.0);
+        if (d.sharp && nBoundaryFaces >= 1.0)
+            d.sharp[p] = sharpNow ? 1 : 0;
+    }
+    if (d.layers)
+    {
+        // blendWithOrthogonalPoints + the second constrainMaxStepLength (src/smoothMesh.C:2288-2304)
+        const D3 zero = {0, 0, 0};
         const int nHops = d.hops[p];
         if (!veq(nrm, zero) && internal && nHops >= 1)
         {
@@ -325,6 +389,31 @@ __global__ void __launch_bounds__(64) k_shared_merge(Dev d, CommDev c)
             const double length = d.layerLength[nHops], blendFrac = d.layerBlend[nHops];
             const D3 ortho = outer + length * nrm;
             np = blendFrac * ortho + (1.0 - blendFrac) * np;
+        }
+        const D3 stepDir = np - x;
+        const double len = mag(stepDir);
+        double scale = 1.0;
+        if (len > d.maxStepLength)
+            scale = d.maxStepLength / (len * d.relStepFrac);
+        np = x + (d.relStepFrac * scale) * stepDir;
+    }
+    if (d.bsmooth)
+    {
+        // :2307-2355 for this point with the synchronised sums: projection onto corner / feature edge / target
+        // surface, prismatic projection (only where THIS copy has an inner neighbour, like the reference, but
+        // with the synchronised coordinates), third constrainMaxStepLength
+        const int cls = d.bClass[p];
+        if (!internal)
+        {
+            const bool frz = boundaryProjectPoint(d, boundaryIndex(d, p), cls, sharpNow, fep, (int)nFep, nrm, np);
+            d.frozen[p] = frz ? 1 : 0; // k_boundary_project decided this from the previous iteration's sharp flag
+            if ((cls & 4) && (cls & 8) && !(cls & 3) && !sharpNow && d.bInner[p] >= 0)
+            {
+                const D3 undef = {SM_GREAT, SM_GREAT, SM_GREAT};
+                if (veq(innerCoord, undef))
+                    *d.errFlag = 5;
+                np = prismaticProjectPoint(d, np, nrm, innerCoord);
+            }
         }
         const D3 stepDir = np - x;
         const double len = mag(stepDir);
