@@ -122,9 +122,13 @@ extern "C"
     /* Turns boundary point smoothing on for the patches with patch_smoothing[i] != 0 (-smoothingPatches): runs
      * the reference's one-time set-up (sanity checks :20-82, edge strings :557-590, classification :269-440,
      * hop counts and inner-neighbour map, point strings src/smoothMesh.C:2234-2250) on the mesh as it is now and
-     * makes smgpu_iterate do :2307-2356 and the restore rule of :2387.  Single-GPU handles only; the target
-     * surface is searched triangle by triangle (test-sized surfaces).  Call after smgpu_create (and again after
-     * smgpu_set_points).  Where the reference aborts the call returns SMGPU_ERR_MESH with its message. */
+     * makes smgpu_iterate do :2307-2356 and the restore rule of :2387.  The target surface is searched through a
+     * bounding volume hierarchy.  Call after smgpu_create (and again after smgpu_set_points).  On a processor mesh
+     * the set-up is COLLECTIVE (global mesh figures, the two synchronised hop-count sweeps, the point normals): call
+     * it on every rank after smgpu_comm_init and before smgpu_comm_p2p_connect (in-process groups:
+     * smgpu_group_enable_boundary_smoothing); the per-iteration synchronisations of the feature (src/
+     * boundaryPointSmoothing.C:660,668, orthogonalBoundaryBlending.C:491 for the inner map) ride in the interface
+     * records of the iteration's one exchange.  Where the reference aborts the call returns SMGPU_ERR_MESH with its message. */
     int smgpu_enable_boundary_smoothing(smgpu_handle *h, const smgpu_boundary_geometry *geometry,
                                         const int32_t *patch_smoothing, double internal_smoothing_blending_fraction);
     /* counts of the boundary point classification after smgpu_enable_boundary_smoothing:
@@ -275,6 +279,9 @@ extern "C"
     int smgpu_group_create(smgpu_handle **handles, int32_t n, smgpu_group **out);
     int smgpu_group_iterate(smgpu_group *g, int32_t max_iters, int64_t *n_frozen, double *residual, int32_t *iters_done);
     int smgpu_group_destroy(smgpu_group *g);
+    /* boundary point smoothing for all members (patch_smoothing[r] = member r's flags); see below */
+    int smgpu_group_enable_boundary_smoothing(smgpu_group *g, const struct smgpu_boundary_geometry *geometry,
+                                              const int32_t *const *patch_smoothing, double internal_smoothing_blending_fraction);
 
     /* Host-only helper (no GPU needed): the exchange plan smgpu_comm_init would build, as
      * flat arrays, so that host-side logic can be tested without devices.  local[i] / gids[i]

@@ -150,6 +150,38 @@ def lib():
     return _lib
 
 
+class _BoundaryGeometry(C.Structure):
+    _fields_ = [(n, t) for k in ("init", "target") for n, t in
+                ((f"n_{k}_points", C.c_int64), (f"{k}_points", C.c_void_p), (f"n_{k}_edges", C.c_int64),
+                 (f"{k}_edges", C.c_void_p))] + [("n_surface_points", C.c_int64), ("surface_points", C.c_void_p),
+                                                 ("n_surface_tris", C.c_int64), ("surface_tris", C.c_void_p),
+                                                 ("is_corner_point", C.c_void_p), ("is_feature_edge_point", C.c_void_p)]
+
+
+def _boundary_geometry(geometry):
+    """smgpu_boundary_geometry from dict(init_edges=(points, pairs), target_edges=..., surface=(points, triangles)[,
+    is_corner_point=..., is_feature_edge_point=...]); returns (struct, arrays to keep alive)."""
+    keep = []
+
+    def arr(a, dt, w):
+        a = np.ascontiguousarray(a, dtype=dt).reshape(-1, w)
+        keep.append(a)
+        return a
+    g = _BoundaryGeometry()
+    ip, ie = arr(geometry["init_edges"][0], np.float64, 3), arr(geometry["init_edges"][1], np.int32, 2)
+    tp, te = arr(geometry["target_edges"][0], np.float64, 3), arr(geometry["target_edges"][1], np.int32, 2)
+    sp, st = arr(geometry["surface"][0], np.float64, 3), arr(geometry["surface"][1], np.int32, 3)
+    g.n_init_points, g.init_points, g.n_init_edges, g.init_edges = len(ip), _ptr(ip), len(ie), _ptr(ie)
+    g.n_target_points, g.target_points, g.n_target_edges, g.target_edges = len(tp), _ptr(tp), len(te), _ptr(te)
+    g.n_surface_points, g.surface_points, g.n_surface_tris, g.surface_tris = len(sp), _ptr(sp), len(st), _ptr(st)
+    for key in ("is_corner_point", "is_feature_edge_point"):   # label lists of an earlier run (restart)
+        if geometry.get(key) is not None:
+            a = np.ascontiguousarray(geometry[key], dtype=np.int32)
+            keep.append(a)
+            setattr(g, key, _ptr(a))
+    return g, keep
+
+
 def default_params(**kw) -> Params:
     p = Params()
     lib().smgpu_default_params(C.byref(p))
@@ -557,31 +589,8 @@ class Smoother:
     def enable_boundary_smoothing(self, geometry, smoothing_patches, internal_smoothing_blending_fraction=0.0):
         """Boundary point smoothing (include/smgpu.h: smgpu_enable_boundary_smoothing).  geometry:
         dict(init_edges=(points, pairs), target_edges=(points, pairs), surface=(points, triangles));
-        smoothing_patches: 0/1 per patch (shorter lists are padded with 0)."""
-        class _Geo(C.Structure):
-            _fields_ = [(n, t) for k in ("init", "target") for n, t in
-                        ((f"n_{k}_points", C.c_int64), (f"{k}_points", C.c_void_p), (f"n_{k}_edges", C.c_int64),
-                         (f"{k}_edges", C.c_void_p))] + [("n_surface_points", C.c_int64), ("surface_points", C.c_void_p),
-                                                         ("n_surface_tris", C.c_int64), ("surface_tris", C.c_void_p),
-                                                         ("is_corner_point", C.c_void_p), ("is_feature_edge_point", C.c_void_p)]
-        keep = []
-
-        def arr(a, dt, w):
-            a = np.ascontiguousarray(a, dtype=dt).reshape(-1, w)
-            keep.append(a)
-            return a
-        g = _Geo()
-        ip, ie = arr(geometry["init_edges"][0], np.float64, 3), arr(geometry["init_edges"][1], np.int32, 2)
-        tp, te = arr(geometry["target_edges"][0], np.float64, 3), arr(geometry["target_edges"][1], np.int32, 2)
-        sp, st = arr(geometry["surface"][0], np.float64, 3), arr(geometry["surface"][1], np.int32, 3)
-        g.n_init_points, g.init_points, g.n_init_edges, g.init_edges = len(ip), _ptr(ip), len(ie), _ptr(ie)
-        g.n_target_points, g.target_points, g.n_target_edges, g.target_edges = len(tp), _ptr(tp), len(te), _ptr(te)
-        g.n_surface_points, g.surface_points, g.n_surface_tris, g.surface_tris = len(sp), _ptr(sp), len(st), _ptr(st)
-        for key in ("is_corner_point", "is_feature_edge_point"):   # label lists of an earlier run (restart)
-            if geometry.get(key) is not None:
-                a = np.ascontiguousarray(geometry[key], dtype=np.int32)
-                keep.append(a)
-                setattr(g, key, _ptr(a))
+        smoothing_patches: 0/1 per patch (shorter lists are padded with 0).  Collective on a processor mesh."""
+        g, keep = _boundary_geometry(geometry)
         flags = np.zeros(self.n_patches, dtype=np.int32)
         k = min(len(smoothing_patches), flags.size)
         flags[:k] = np.asarray(smoothing_patches, dtype=np.int32)[:k]
@@ -695,6 +704,21 @@ class Group:
         lib().smgpu_last_timing(self.members[0]._h, C.byref(ms), C.byref(ln))
         n = done.value
         return IterationLog(n, nf[:n].copy(), res[:n].copy(), ms.value, ln.value)
+
+    def enable_boundary_smoothing(self, geometry, smoothing_patches, internal_smoothing_blending_fraction=0.0):
+        """Boundary point smoothing on every member (collective set-up); smoothing_patches: 0/1 per physical patch."""
+        g, keep = _boundary_geometry(geometry)
+        flags = []
+        for m in self.members:
+            f = np.zeros(m.n_patches, dtype=np.int32)
+            k = min(len(smoothing_patches), f.size)
+            f[:k] = np.asarray(smoothing_patches, dtype=np.int32)[:k]
+            flags.append(f)
+        ptrs = (C.c_void_p * len(flags))(*[f.ctypes.data for f in flags])
+        lib().smgpu_group_enable_boundary_smoothing.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double]
+        rc = lib().smgpu_group_enable_boundary_smoothing(self._h, C.byref(g), ptrs, float(internal_smoothing_blending_fraction))
+        if rc != 0:
+            raise SmoothMeshError(f"libsmgpu error {rc}: {lib().smgpu_last_error().decode()}")
 
     def close(self):
         if getattr(self, "_h", None):

@@ -204,9 +204,26 @@ void readObj(const std::string &file, std::vector<double> &points, std::vector<i
     }
 }
 
+void meshBoundingBox(const Topology &t, const std::vector<double> &points, double lo[3], double hi[3])
+{
+    for (int d = 0; d < 3; ++d)
+        lo[d] = SM_VGREAT, hi[d] = -SM_VGREAT;
+    for (int64_t e = 0; e < t.E; ++e)
+        for (int s = 0; s < 2; ++s)
+            for (int d = 0; d < 3; ++d)
+            {
+                const double c = points[3 * (int64_t)t.edge[2 * e + s] + d];
+                if (c < lo[d])
+                    lo[d] = c;
+                if (c > hi[d])
+                    hi[d] = c;
+            }
+}
+
 BoundarySetup buildBoundarySetup(const PolyMesh &m, const Topology &t, const std::vector<double> &points, const EdgeMesh &initEdges,
                                  const EdgeMesh &targetEdgesIn, const TriSurface &surface, const std::vector<int32_t> &patchSmoothing,
-                                 double layerEdgeLength, const std::vector<int32_t> &cornerIO, const std::vector<int32_t> &featureIO)
+                                 double layerEdgeLength, const std::vector<int32_t> &cornerIO, const std::vector<int32_t> &featureIO,
+                                 const BoundaryParallel *par)
 {
     BoundarySetup B;
     // src/smoothMesh.C:2067-2078: do the label lists of an earlier run hold classification data
@@ -218,22 +235,20 @@ BoundarySetup buildBoundarySetup(const PolyMesh &m, const Topology &t, const std
     const int64_t P = t.P;
     B.targetEdges = targetEdgesIn;
     B.surface = surface;
-    B.distanceTolerance = 1e-4 * ((t.minEdgeLength < layerEdgeLength) ? t.minEdgeLength : layerEdgeLength); // :1921
+    const double meshMinEdgeLength = par ? par->meshMinEdgeLength : t.minEdgeLength;
+    B.distanceTolerance = 1e-4 * ((meshMinEdgeLength < layerEdgeLength) ? meshMinEdgeLength : layerEdgeLength); // :1921
     // getMeshStats' perimeter over the edge end points, src/smoothMesh.C:1495-1538
-    double lo[3] = {SM_VGREAT, SM_VGREAT, SM_VGREAT}, hi[3] = {-SM_VGREAT, -SM_VGREAT, -SM_VGREAT};
-    for (int64_t e = 0; e < t.E; ++e)
-        for (int s = 0; s < 2; ++s)
-            for (int d = 0; d < 3; ++d)
-            {
-                const double c = points[3 * (int64_t)t.edge[2 * e + s] + d];
-                if (c < lo[d])
-                    lo[d] = c;
-                if (c > hi[d])
-                    hi[d] = c;
-            }
-    const double meshPerimeter = hi[0] - lo[0] + hi[1] - lo[1] + hi[2] + lo[2];
-    checkEdgeMeshSanity(initEdges, t.minEdgeLength, meshPerimeter);
-    checkEdgeMeshSanity(B.targetEdges, t.minEdgeLength, meshPerimeter);
+    double meshPerimeter;
+    if (par)
+        meshPerimeter = par->meshPerimeter;
+    else
+    {
+        double lo[3], hi[3];
+        meshBoundingBox(t, points, lo, hi);
+        meshPerimeter = hi[0] - lo[0] + hi[1] - lo[1] + hi[2] + lo[2];
+    }
+    checkEdgeMeshSanity(initEdges, meshMinEdgeLength, meshPerimeter);
+    checkEdgeMeshSanity(B.targetEdges, meshMinEdgeLength, meshPerimeter);
     // findEdgeMeshStrings, :557-590
     B.targetEdgeStrings.assign(B.targetEdges.nEdges(), -1);
     B.nStrings = -1;
@@ -342,6 +357,8 @@ BoundarySetup buildBoundarySetup(const PolyMesh &m, const Topology &t, const std
             for (int64_t p = 0; p < P; ++p)
                 if (newHops[p] > B.hopsToSmoothing[p])
                     B.hopsToSmoothing[p] = newHops[p];
+            if (par && par->maxInt)
+                par->maxInt(B.hopsToSmoothing);
         }
     }
     // propagateInnerNeighInfo, src/orthogonalBoundaryBlending.C:397-458

@@ -8,6 +8,7 @@
 
 #include <array>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -69,9 +70,21 @@ struct BoundarySetup
 // the resolved options (distanceTolerance = REL_TOL min(meshMinEdgeLength, layerEdgeLength), :1921).
 // cornerIO / featureIO: the isCornerPoint / isFeatureEdgePoint label lists of an earlier run (empty = none).
 // When either holds a 1 the classes are taken from them instead of from the initial edges (:336-340).
+// Processor mesh of a decomposed run (`par` non-null): the mesh-wide figures come from all ranks (getMeshStats'
+// reductions, src/smoothMesh.C:1527-1534) and the hop counts to the smoothing patches are synchronised (max) after
+// each of their two sweeps (src/orthogonalBoundaryBlending.C:124-130); everything else is rank-local in the
+// reference too.
+struct BoundaryParallel
+{
+    double meshMinEdgeLength = 0, meshPerimeter = 0;      // global
+    std::function<void(std::vector<int32_t> &)> maxInt;   // syncPointList(maxEqOp<label>)
+};
 BoundarySetup buildBoundarySetup(const PolyMesh &patchesAndFaces, const Topology &t, const std::vector<double> &points,
                                  const EdgeMesh &initEdges, const EdgeMesh &targetEdges, const TriSurface &surface,
                                  const std::vector<int32_t> &patchSmoothing, double layerEdgeLength,
-                                 const std::vector<int32_t> &cornerIO = {}, const std::vector<int32_t> &featureIO = {});
+                                 const std::vector<int32_t> &cornerIO = {}, const std::vector<int32_t> &featureIO = {},
+                                 const BoundaryParallel *par = nullptr);
+// getMeshStats' bounding box over the points (src/smoothMesh.C:1495-1512): lo[3], hi[3]
+void meshBoundingBox(const Topology &t, const std::vector<double> &points, double lo[3], double hi[3]);
 
 } // namespace sm

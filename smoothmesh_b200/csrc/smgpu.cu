@@ -25,6 +25,8 @@ namespace sm
 struct Comm;
 static void commSetupLayers(Comm *cm, struct ::smgpu_handle *h);
 static bool commIsGroupMember(const Comm *cm);
+// global getMeshStats figures and the hop-count synchronisation for the boundary point smoothing set-up of a rank
+static void commBoundaryParallel(Comm *cm, struct ::smgpu_handle *h, const std::vector<double> &points, struct BoundaryParallel &par);
 }
 
 static thread_local std::string g_err;
@@ -601,7 +603,7 @@ static Comm *commPrepare(smgpu_handle *h, int rank, int nRanks, const int64_t *c
         c.copyRank = h->upload(pl.copyRank);
         c.copySlot = h->upload(pl.copySlot);
         c.tuple = h->anyLayerPatch ? SMK_TUPLE_LAYERS : SMK_TUPLE;
-        c.sendBuf = h->dalloc<double>((size_t)c.nSlots * c.tuple);
+        c.sendBuf = h->dalloc<double>((size_t)c.nSlots * SMK_TUPLE_BOUNDARY); // capacity for the largest record
         c.sendFz = h->dalloc<uint8_t>(c.nSlots);
         // the receive side lives in one exchange block that peers can map (smgpu_comm_p2p_*): header (who this
         // rank's neighbours are and where their records go), flag words, statistics slots, receive buffers
@@ -624,7 +626,7 @@ static Comm *commPrepare(smgpu_handle *h, int rank, int nRanks, const int64_t *c
         hdr.offFlagF = hdr.offFlagT + SMK_MAXNBR * 8;
         hdr.offStat = hdr.offFlagF + SMK_MAXNBR * 8;
         hdr.offRecv = hdr.offStat + 2 * SMK_MAXRANKS * (long long)sizeof(smk::P2PStat);
-        hdr.offFz = hdr.offRecv + (((long long)c.nSlots * c.tuple * 8 + 255) / 256) * 256;
+        hdr.offFz = hdr.offRecv + (((long long)c.nSlots * SMK_TUPLE_BOUNDARY * 8 + 255) / 256) * 256;
         cm->xblockBytes = (size_t)hdr.offFz + (size_t)c.nSlots + 256;
         static_assert(sizeof(XHeader) <= 512, "exchange block header");
         cm->xblock = h->dalloc<unsigned char>(cm->xblockBytes);
@@ -754,7 +756,7 @@ static void commSetupLayers(Comm *cm, smgpu_handle *h)
 {
     // whenever a layer patch exists (not only while the blending fraction is positive), so that raising
     // layer_max_blending_fraction later through smgpu_set_params finds the set-up done
-    if (!h->anyLayerPatch || !h->layersParallel)
+    if (!(h->anyLayerPatch || h->doBoundary) || !h->layersParallel)
         return;
     Dev &d = h->d;
     const int64_t P = h->topo.P;
@@ -797,6 +799,44 @@ static void commSetupLayers(Comm *cm, smgpu_handle *h)
     CK(cudaMemcpy(h->dPointToOuter, h->layer.pointToOuter.data(), P * sizeof(int32_t), cudaMemcpyHostToDevice));
     h->layersReady = true;
     h->applyParams(); // per-hop tables for the synchronised hop counts
+}
+
+// getMeshStats' reductions for the boundary point smoothing set-up of this rank (src/smoothMesh.C:1527-1538: the
+// perimeter is hi.x - lo.x + hi.y - lo.y + hi.z PLUS lo.z of the global bounding box) and the max-synchronisation
+// of the hop counts.  Collective.
+static void commBoundaryParallel(Comm *cm, smgpu_handle *h, const std::vector<double> &points, BoundaryParallel &par)
+{
+    double lo[3], hi[3];
+    meshBoundingBox(h->topo, points, lo, hi);
+    double box[6] = {-lo[0], -lo[1], -lo[2], hi[0], hi[1], hi[2]}; // one max-reduction
+    if (cm->group)
+    {
+        LocalGroup *g = cm->group;
+        g->posted[cm->plan.rank] = box;
+        g->bar.wait();
+        double all[6];
+        for (int k = 0; k < 6; ++k)
+            all[k] = ((const double *)g->posted[0])[k];
+        for (size_t r = 1; r < g->members.size(); ++r)
+            for (int k = 0; k < 6; ++k)
+                all[k] = std::max(all[k], ((const double *)g->posted[r])[k]);
+        g->bar.wait();
+        for (int k = 0; k < 6; ++k)
+            box[k] = all[k];
+    }
+    else
+    {
+        double *dbox = h->dalloc<double>(6);
+        CK(cudaMemcpy(dbox, box, sizeof box, cudaMemcpyHostToDevice));
+        NCK(nccl().AllReduce(dbox, dbox, 6, ncclDouble, ncclMax, cm->nccl, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        CK(cudaMemcpy(box, dbox, sizeof box, cudaMemcpyDeviceToHost));
+    }
+    par.meshMinEdgeLength = h->meshMinEdge;
+    par.meshPerimeter = box[3] - (-box[0]) + box[4] - (-box[1]) + box[5] + (-box[2]);
+    par.maxInt = [cm, h](std::vector<int32_t> &f) {
+        hostSync<int32_t, 1>(cm, h, f, [](int32_t *x, const int32_t *y) { x[0] = (x[0] > y[0]) ? x[0] : y[0]; });
+    };
 }
 
 static void commDestroy(Comm *cm)
@@ -860,9 +900,10 @@ static void commConnectPeers(Comm *cm, smgpu_handle *h, const std::vector<unsign
         for (int k = 0; k < ph.nNbr; ++k)
             if (ph.nbrRank[k] == pl.rank)
                 jj = k;
-        if (jj < 0 || ph.nbrOff[jj + 1] - ph.nbrOff[jj] != pl.nbrOff[j + 1] - pl.nbrOff[j] || ph.tuple != cm->c.tuple)
+        if (jj < 0 || ph.nbrOff[jj + 1] - ph.nbrOff[jj] != pl.nbrOff[j + 1] - pl.nbrOff[j])
             throw std::runtime_error("peer-memory exchange: exchange plans of two ranks disagree");
-        x.peerRecv[j] = reinterpret_cast<double *>(bases[r] + ph.offRecv) + (size_t)ph.nbrOff[jj] * ph.tuple;
+        x.peerRecv[j] = reinterpret_cast<double *>(bases[r] + ph.offRecv);
+        x.peerSlot0[j] = ph.nbrOff[jj];
         x.peerRecvFz[j] = bases[r] + ph.offFz + ph.nbrOff[jj];
         x.peerFlagT[j] = reinterpret_cast<unsigned long long *>(bases[r] + ph.offFlagT) + jj;
         x.peerFlagF[j] = reinterpret_cast<unsigned long long *>(bases[r] + ph.offFlagF) + jj;
@@ -909,11 +950,13 @@ static void commPhasePack(Comm *cm, smgpu_handle *h, bool ownStream = false)
 // B1: everything that needs nothing from the exchange (it runs while the tuples are in flight)
 static void commPhaseLocal(Comm *cm, smgpu_handle *h)
 {
-    if (h->doLayers)
-        h->launchLayerNormals();
+    if (h->doLayers || h->doBoundary)
+        h->launchLayerNormals(); // :2266 (the interface points get theirs, with all copies, in k_shared_merge)
     h->launchPredict();
     if (h->doLayers)
         h->launchLayerBlend();
+    if (h->doBoundary)
+        h->launchBoundary(); // :2307-2356; the points shared between ranks are redone by k_shared_merge
     if (h->prm.face_angle_constraint)
         h->launchFaceCurrent(); // current-mesh half of the face-angle constraint
 }
@@ -962,7 +1005,7 @@ static void commIterate(Comm *cm, smgpu_handle *h)
     { // peer-memory exchange: the producer kernels write into the peers' blocks, the consumer kernels wait for
       // the flags; nothing but this rank's own kernels on this rank's stream
         // with layer treatment the pack reads the normals k_layer_normals is about to replace: same stream then
-        const bool beside = !h->doLayers && cm->xStream;
+        const bool beside = !h->doLayers && !h->doBoundary && cm->xStream;
         commPhasePack(cm, h, beside);
         commPhaseLocal(cm, h);
         if (beside)
@@ -1391,9 +1434,11 @@ extern "C"
     {
         if (!h || !g || !patch_smoothing)
             return setErr(SMGPU_ERR_ARG, "null argument");
-        if (h->comm || !h->topo.procPoints.empty())
-            return setErr(SMGPU_ERR_ARG, "boundary point smoothing is single-GPU in this build (its four extra "
-                                         "synchronisations are not in the exchange layer yet)");
+        if (!h->comm && !h->topo.procPoints.empty())
+            return setErr(SMGPU_ERR_ARG, "boundary point smoothing on a processor mesh: its set-up is collective, call "
+                                         "smgpu_comm_init (or create the in-process group) first");
+        if (h->comm && h->comm->p2p)
+            return setErr(SMGPU_ERR_ARG, "enable boundary point smoothing before smgpu_comm_p2p_connect");
         if (!h->pointOldOfNew.empty())
             return setErr(SMGPU_ERR_ARG, "boundary point smoothing cannot be combined with params.renumber");
         bool any = false;
@@ -1434,7 +1479,10 @@ extern "C"
                     cornerIO.assign(g->is_corner_point, g->is_corner_point + t.P);
                 if (g->is_feature_edge_point)
                     featureIO.assign(g->is_feature_edge_point, g->is_feature_edge_point + t.P);
-                B = sm::buildBoundarySetup(pm, t, points, ie, te, surf, ps, layerEdgeLength, cornerIO, featureIO);
+                sm::BoundaryParallel par;
+                if (h->comm)
+                    sm::commBoundaryParallel(h->comm, h, points, par);
+                B = sm::buildBoundarySetup(pm, t, points, ie, te, surf, ps, layerEdgeLength, cornerIO, featureIO, h->comm ? &par : nullptr);
             }
             catch (const std::exception &e)
             {
@@ -1447,6 +1495,12 @@ extern "C"
                 faces.faceOffsets = t.faceOff;
                 faces.faceVerts = t.faceVerts;
                 h->layer = sm::buildLayerSetup(faces, t, std::vector<int32_t>(h->patches.size(), 0), h->prm.max_layers);
+                if (!t.procPoints.empty())
+                { // decomposed case: the normals' set-up is synchronised between the ranks (sm::commSetupLayers)
+                    h->layersParallel = true;
+                    h->layerMesh = faces;
+                    h->patchLayerFlags.assign(h->patches.size(), 0);
+                }
                 h->allocLayerTables();
             }
             auto toP4 = [](const std::vector<double> &xyz) {
@@ -1502,8 +1556,14 @@ extern "C"
             h->boundaryCounts[2] = B.nSmoothingSurfacePoints;
             h->boundaryCounts[3] = B.nStrings + 1;
             h->doBoundary = true;
+            if (h->comm)
+                h->comm->c.tuple = SMK_TUPLE_BOUNDARY; // the interface records carry the feature edge sums and the inner neighbour
             h->applyParams();
-            h->initLayerNormals(); // the set-up call of calculateBoundaryPointNormals (:2219) with the sharp flags
+            // the set-up call of calculateBoundaryPointNormals (:2219) with the sharp flags; collective on a processor mesh
+            if (h->comm && h->layersParallel)
+                sm::commSetupLayers(h->comm, h);
+            else
+                h->initLayerNormals();
             CK(cudaDeviceSynchronize());
         }
         catch (const std::exception &e)
@@ -2069,7 +2129,7 @@ extern "C"
         if (h->comm)
             return setErr(SMGPU_ERR_ARG, "communicator already initialised");
         if (h->doBoundary)
-            return setErr(SMGPU_ERR_ARG, "boundary point smoothing is single-GPU in this build");
+            return setErr(SMGPU_ERR_ARG, "enable boundary point smoothing after the communicator exists (its set-up is collective)");
         try
         {
             h->comm = sm::commPrepare(h, rank, n_ranks, counts, all_gids);
@@ -2320,6 +2380,31 @@ extern "C"
             return setErr(SMGPU_ERR_COMM, e.what());
         }
         *out = grp;
+        return SMGPU_OK;
+    }
+
+    int smgpu_group_enable_boundary_smoothing(smgpu_group *grp, const smgpu_boundary_geometry *geometry,
+                                              const int32_t *const *patch_smoothing, double internal_smoothing_blending_fraction)
+    {
+        if (!grp || !geometry || !patch_smoothing)
+            return setErr(SMGPU_ERR_ARG, "null argument");
+        sm::LocalGroup &g = grp->g;
+        const int n = (int)g.members.size();
+        // the set-up is collective (global mesh figures, hop counts, point normals): one short-lived host thread per member
+        std::vector<int> rc(n, SMGPU_OK);
+        std::vector<std::string> msg(n);
+        std::vector<std::thread> th;
+        for (int r = 0; r < n; ++r)
+            th.emplace_back([&, r] {
+                rc[r] = smgpu_enable_boundary_smoothing(g.members[r], geometry, patch_smoothing[r], internal_smoothing_blending_fraction);
+                if (rc[r] != SMGPU_OK)
+                    msg[r] = smgpu_last_error();
+            });
+        for (auto &t : th)
+            t.join();
+        for (int r = 0; r < n; ++r)
+            if (rc[r] != SMGPU_OK)
+                return setErr(rc[r], msg[r]);
         return SMGPU_OK;
     }
 

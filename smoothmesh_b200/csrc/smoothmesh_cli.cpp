@@ -211,7 +211,55 @@ struct RunOptions
     std::string caseDir, startName;
     std::string layerPatches; // -layerPatches expression, empty = none
     int logPrecision = 6;
+    // boundary point smoothing (src/smoothMesh.C:2080-2171): requested when constant/geometry holds the inputs
+    bool boundaryRequested = false;
+    std::string smoothingPatches; // -smoothingPatches expression, empty = all patches (:1837-1840)
+    double internalFraction = 0.0;
 };
+
+namespace
+{
+// the arrays of constant/geometry/*.obj behind an smgpu_boundary_geometry
+struct BoundaryInputs
+{
+    struct Obj
+    {
+        std::vector<double> p;
+        std::vector<int32_t> e, t;
+    };
+    Obj surf, init, target;
+    bool haveTarget = false;
+    smgpu_boundary_geometry geo;
+    static Obj load(const std::string &f)
+    {
+        Obj o;
+        int64_t np = 0, ne = 0, nt = 0;
+        if (smmesh_read_obj(f.c_str(), &np, nullptr, &ne, nullptr, &nt, nullptr) != SMGPU_OK)
+            fatal(smmesh_last_error());
+        o.p.resize(3 * np);
+        o.e.resize(2 * ne);
+        o.t.resize(3 * nt);
+        smmesh_read_obj(f.c_str(), nullptr, o.p.data(), nullptr, o.e.data(), nullptr, o.t.data());
+        return o;
+    }
+    void read(const std::string &caseDir)
+    {
+        surf = load(caseDir + "/constant/geometry/targetSurfaces.obj");
+        init = load(caseDir + "/constant/geometry/initEdges.obj");
+        target = init;
+        haveTarget = fileExists(caseDir + "/constant/geometry/targetEdges.obj");
+        if (haveTarget)
+            target = load(caseDir + "/constant/geometry/targetEdges.obj");
+        memset(&geo, 0, sizeof geo);
+        geo.n_init_points = (int64_t)init.p.size() / 3, geo.init_points = init.p.data();
+        geo.n_init_edges = (int64_t)init.e.size() / 2, geo.init_edges = init.e.data();
+        geo.n_target_points = (int64_t)target.p.size() / 3, geo.target_points = target.p.data();
+        geo.n_target_edges = (int64_t)target.e.size() / 2, geo.target_edges = target.e.data();
+        geo.n_surface_points = (int64_t)surf.p.size() / 3, geo.surface_points = surf.p.data();
+        geo.n_surface_tris = (int64_t)surf.t.size() / 3, geo.surface_tris = surf.t.data();
+    }
+};
+} // namespace
 
 namespace
 {
@@ -277,6 +325,13 @@ static int runParallel(const RunOptions &ro)
                 if (q)
                     smgpu_comm_abort(q);
     };
+    BoundaryInputs boundary;
+    if (ro.boundaryRequested)
+    {
+        boundary.read(ro.caseDir);
+        printf("Enabled boundary point smoothing\n\n");
+    }
+    std::vector<std::vector<int32_t>> smoothSel(nProcs);
     smgpu_group *group = nullptr;
     int sharedDone = 0;
     bool sharedOk = true;
@@ -313,6 +368,13 @@ static int runParallel(const RunOptions &ro)
                     for (int i = 0; i < nPatches; ++i)
                         names.push_back(smmesh_patch_name(mesh, i));
                     layerSel = selectPatches(ro.layerPatches, names);
+                }
+                if (ro.boundaryRequested)
+                {
+                    std::vector<std::string> names;
+                    for (int i = 0; i < nPatches; ++i)
+                        names.push_back(smmesh_patch_name(mesh, i));
+                    smoothSel[k] = ro.smoothingPatches.empty() ? std::vector<int32_t>(nPatches, 1) : selectPatches(ro.smoothingPatches, names);
                 }
                 smmesh_patches(mesh, pStart.data(), pSize.data(), pKind.data());
                 smgpu_mesh_desc md;
@@ -354,6 +416,14 @@ static int runParallel(const RunOptions &ro)
             {
                 if (smgpu_group_create(handles.data(), nProcs, &group) != SMGPU_OK)
                     failAll(smgpu_last_error());
+                else if (ro.boundaryRequested)
+                {
+                    std::vector<const int32_t *> sel;
+                    for (auto &v : smoothSel)
+                        sel.push_back(v.data());
+                    if (smgpu_group_enable_boundary_smoothing(group, &boundary.geo, sel.data(), ro.internalFraction) != SMGPU_OK)
+                        failAll(smgpu_last_error());
+                }
             }
             else if (k == 0 && !failed)
             {
@@ -379,6 +449,13 @@ static int runParallel(const RunOptions &ro)
                 if (failed)
                     return;
                 if (smgpu_comm_init(h, k, nProcs, uid, counts.data(), allGids.data()) != SMGPU_OK)
+                    failAll(smgpu_last_error());
+                bar.wait();
+                if (failed)
+                    return;
+                // boundary point smoothing: collective set-up on every rank (:2080-2250 under -parallel)
+                if (ro.boundaryRequested &&
+                    smgpu_enable_boundary_smoothing(h, &boundary.geo, smoothSel[k].data(), ro.internalFraction) != SMGPU_OK)
                     failAll(smgpu_last_error());
                 bar.wait();
                 if (failed)
@@ -663,9 +740,6 @@ int main(int argc, char **argv)
     const bool labelIOListsHaveData = std::find(cornerIO.begin(), cornerIO.end(), 1) != cornerIO.end() ||
                                       std::find(featureIO.begin(), featureIO.end(), 1) != featureIO.end();
     const bool boundaryRequested = !has("decompose") && surfaces && (initEdges || labelIOListsHaveData) && !smoothingPatchesEmpty;
-    if (boundaryRequested && parallel)
-        fatal("boundary point smoothing with -parallel: the feature is single-GPU in this build (its four extra "
-              "synchronisations are not in the exchange layer yet); pass -smoothingPatches '()' or run serially");
 
     if (parallel)
     {
@@ -685,6 +759,10 @@ int main(int argc, char **argv)
         ro.timePrecision = timePrecision;
         ro.caseDir = caseDir;
         ro.startName = startName;
+        ro.boundaryRequested = boundaryRequested;
+        if (has("smoothingPatches"))
+            ro.smoothingPatches = opt["smoothingPatches"];
+        ro.internalFraction = num("internalSmoothingBlendingFraction", 0.0);
         printf("Create time\n\n");
         return runParallel(ro);
     }

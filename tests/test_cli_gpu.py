@@ -199,3 +199,57 @@ def test_cli_restart_with_classification_lists(tmp_path):
         assert (res["gpu"][1] / t / "polyMesh" / "points").read_bytes() == (res["ref"][1] / t / "polyMesh" / "points").read_bytes()
         for f in ("isCornerPoint", "isFeatureEdgePoint"):
             assert (res["gpu"][1] / t / f).read_bytes() == (res["ref"][1] / t / f).read_bytes()
+
+
+def _write_obj(path, points, edges=None, tris=None):
+    with open(path, "w") as f:
+        for p in np.asarray(points, float):
+            f.write("v %.17g %.17g %.17g\n" % tuple(p))
+        for e in (edges if edges is not None else []):
+            f.write("l %d %d\n" % (e[0] + 1, e[1] + 1))
+        for t in (tris if tris is not None else []):
+            f.write("f %d %d %d\n" % (t[0] + 1, t[1] + 1, t[2] + 1))
+
+
+def test_cli_parallel_with_boundary_point_smoothing(tmp_path):
+    """`smoothMesh -parallel` with constant/geometry/*.obj present: boundary point smoothing on the processor
+    meshes (collective set-up, per-iteration synchronisations inside the interface exchange), points per processor
+    bit-identical to the oracle's rank emulation."""
+    from test_boundary_smoothing_oracle import box_geometry
+    hi = (1.2, 1.0, 0.8)
+    mesh = sm.Mesh.hex_block(6, 5, 4, hi=hi).jitter(0.03, 3)
+    case = make_case(tmp_path, mesh)
+    ip, ie, _, _ = box_geometry((0, 0, 0), hi, 3)
+    c = np.array(hi) / 2
+    tp, te, tc, tt = box_geometry(c - 1.1 * c, c + 1.1 * c, 3)
+    (case / "constant" / "geometry").mkdir()
+    _write_obj(case / "constant" / "geometry" / "initEdges.obj", ip, edges=ie)
+    _write_obj(case / "constant" / "geometry" / "targetEdges.obj", tp, edges=te)
+    _write_obj(case / "constant" / "geometry" / "targetSurfaces.obj", tc, tris=tt)
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-decompose", "(2 1 1)"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel", "-centroidalIters", "8", "-relTol", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Enabled boundary point smoothing" in r.stdout
+    parts = [sm.Mesh.read_processor(case, k) for k in range(2)]
+    # what the files hold (OBJ text round trip of the geometry)
+    geo = {}
+    for key, name in (("init_edges", "initEdges"), ("target_edges", "targetEdges"), ("surface", "targetSurfaces")):
+        pts, edges, tris = [], [], []
+        for line in (case / "constant" / "geometry" / f"{name}.obj").read_text().splitlines():
+            w = line.split()
+            if w[0] == "v":
+                pts.append([float(x) for x in w[1:4]])
+            elif w[0] == "l":
+                edges.append([int(w[1]) - 1, int(w[2]) - 1])
+            elif w[0] == "f":
+                tris.append([int(x) - 1 for x in w[1:4]])
+        geo[key] = (np.array(pts), np.array(tris if key == "surface" else edges, dtype=np.int32))
+    o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0, smoothing_patches=[1] * 16, geometry=geo)
+    n, nf, res = o.iterate(8)
+    lines = re.findall(r"Smoothing iteration=(\d+) nFrozenPoints=(\d+) residual=(\S+)", r.stdout)
+    assert [int(b) for _, b, _ in lines] == nf.tolist()
+    for k in range(2):
+        parts[k].read_points(case / f"processor{k}" / "8" / "polyMesh" / "points")
+        assert np.array_equal(parts[k].points, o.get("points", rank=k))

@@ -88,7 +88,7 @@ def test_boundary_smoothing_refusals():
         g.enable_boundary_smoothing(dict(init_edges=(ip, ie), target_edges=(tp, te), surface=(tc, tt)), [1] * 6)
     parts = mesh.decompose(2, 1, 1)
     gp = sm.Smoother(parts[0])
-    with pytest.raises(sm.SmoothMeshError, match="single-GPU"):
+    with pytest.raises(sm.SmoothMeshError, match="collective"):   # a processor mesh needs its communicator / group first
         gp.enable_boundary_smoothing(dict(init_edges=(ip, ie), target_edges=(ip, ie), surface=(tc, tt)), [1] * 6)
 
 
@@ -155,3 +155,28 @@ def test_surface_ray_casts_through_the_bvh(monkeypatch):
     b.enable_boundary_smoothing(geo, [1] * 6)
     b.iterate(6)
     assert np.array_equal(b.points(), g.points()) and np.array_equal(b.frozen(), g.frozen())
+
+
+@pytest.mark.parametrize("seed,dims", [(0, (2, 1, 1)), (1, (2, 2, 1)), (2, (1, 2, 2)), (3, (3, 1, 1)), (5, (2, 2, 2)), (6, (2, 1, 2))])
+def test_boundary_smoothing_on_processor_meshes(seed, dims):
+    """Boundary point smoothing under the reference's -parallel semantics: the decomposed synthetic boxes as an
+    in-process group on one GPU against the oracle's rank emulation (itself pinned to the reference's rank
+    processes): the collective set-up (global mesh figures, synchronised hop counts and point normals) and the
+    per-iteration synchronisations of src/boundaryPointSmoothing.C:660,668 and orthogonalBoundaryBlending.C:491
+    carried by the interface records -- bit-exact logs, masks and points on every rank."""
+    mesh, geo, flags, layer, kw, frac, iters = synthetic(seed)
+    parts = mesh.decompose(*dims)
+    members = [sm.Smoother(p, layer_patches=layer, device=0, **kw) for p in parts]
+    grp = sm.Group(members)
+    grp.enable_boundary_smoothing(geo, flags, frac)
+    o = Oracle([p.desc_arrays() for p in parts], layer_patches=layer, smoothing_patches=flags, geometry=geo,
+               internal_smoothing_blending_fraction=frac, **kw)
+    n, nf, res = o.iterate(iters)
+    log = grp.iterate(iters)
+    assert log.iterations == n
+    assert np.array_equal(log.n_frozen, nf), (log.n_frozen, nf)
+    assert np.array_equal(log.residual, res)
+    for r, g in enumerate(members):
+        assert np.array_equal(g.frozen(), o.get("frozen", r)), f"rank {r}: freeze mask differs"
+        assert np.array_equal(g.points(), o.get("points", r)), f"rank {r}: points differ"
+    grp.close()
