@@ -307,7 +307,7 @@ SHIPPED = {
     "testcase5": (["-centroidalIters", "500", "-minAngle", "15", "-layerExpansionRatio", "1.2", "-layerEdgeLength", "0.05",
                    "-maxLayers", "3", "-layerPatches", '("top")', "-smoothingPatches", '(".*")'],
                   dict(min_angle_deg=15.0, layer_expansion_ratio=1.2, layer_edge_length=0.05, max_layers=3), 500, True),
-    "testcase7": (["-centroidalIters", "100", "-layerPatches", "(walls)"], dict(), 100, False),
+    "testcase7": (["-centroidalIters", "100", "-layerPatches", "(walls)"], dict(), 100, True),
     "testcase8": (["-centroidalIters", "50"], dict(), 50, True),
 }
 

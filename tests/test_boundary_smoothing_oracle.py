@@ -234,12 +234,11 @@ def test_restart_uses_the_classification_lists_of_the_first_run(tmp_path):
     assert int(o3.get("isCorner").sum()) == 0 and int(o2.get("isCorner").sum()) == 8
 
 
-@pytest.mark.parametrize("case", ["testcase5", "testcase8"])
+@pytest.mark.parametrize("case", ["testcase5", "testcase7", "testcase8"])
 def test_oracle_reproduces_shipped_boundary_cases(case):
     """testcase5/run_serial (layer treatment on `top`, boundary point smoothing of every patch, 500 iterations, eight
     corner points) and testcase8/run_serial exactly as shipped: fixtures produced by the reference's own translation
-    unit (tests/golden/make_golden.py: shipped_boundary_cases, which also checks testcase7 -- 31 361 points -- where
-    /root/reference is available)."""
+    unit (tests/golden/make_golden.py: shipped_boundary_cases); testcase7/run_serial likewise (31 361 points, 21 edge strings)."""
     d = np.load(os.path.join(ROOT, "tests", "golden", f"{case}_boundary.npz"))
     m = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
                             d["patch_start"], d["patch_size"], d["patch_kind"])

@@ -92,10 +92,11 @@ def test_boundary_smoothing_refusals():
         gp.enable_boundary_smoothing(dict(init_edges=(ip, ie), target_edges=(ip, ie), surface=(tc, tt)), [1] * 6)
 
 
-@pytest.mark.parametrize("case", ["testcase5", "testcase8"])
+@pytest.mark.parametrize("case", ["testcase5", "testcase7", "testcase8"])
 def test_shipped_boundary_cases(case):
     """testcase5/run_serial (500 iterations: layer treatment on `top`, boundary point smoothing with eight corner
-    points) and testcase8/run_serial exactly as shipped; fixtures produced by the reference's own translation unit."""
+    points), testcase7/run_serial (31 361 points, 21 edge strings, layer treatment on `walls`) and
+    testcase8/run_serial exactly as shipped; fixtures produced by the reference's own translation unit."""
     d = np.load(os.path.join(ROOT, "tests", "golden", f"{case}_boundary.npz"))
     mesh = sm.Mesh.from_arrays(d["points"], d["face_offsets"], d["face_verts"], d["owner"], d["neighbour"], int(d["n_cells"]),
                                d["patch_start"], d["patch_size"], d["patch_kind"])
