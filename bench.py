@@ -382,7 +382,7 @@ def main():
                     help="cells per side of the (per-GPU) hex block / of the Kelvin lattice (use --size under torchrun)")
     ap.add_argument("--ref-n", type=int, default=0, help="cells per side of the reference arm's mesh (0 = --size)")
     ap.add_argument("--ref-budget", type=float, default=600.0, help="wall budget [s] of the parallel reference run")
-    ap.add_argument("--ref-serial-budget", type=float, default=150.0, help="wall budget [s] of the serial reference run")
+    ap.add_argument("--ref-serial-budget", type=float, default=90.0, help="wall budget [s] of the serial reference run")
     ap.add_argument("--ref-no-port", action="store_true", help="skip the oracle-port arm of --impl reference")
     ap.add_argument("--cpu-n", type=int, default=96, help="cells per side of the cpu_baseline sample mesh")
     ap.add_argument("--cpu-iters", type=int, default=4)

@@ -474,6 +474,31 @@ __global__ void __launch_bounds__(128) k_frozen_or(Dev d, CommDev c)
     if (i < c.nSlots && c.recvFz[i])
         d.frozen[c.sendPoint[i]] = 1;
 }
+// Peer-memory mode, the points shared between ranks: wait for the neighbours' freeze flags, OR them in (orEqOp<bool>
+// on isFrozenPoint, :2374), then restore / move / residual like k_commit, which has already handled every other
+// point while the flags were on their way; the last block publishes this rank's statistics.
+__global__ void __launch_bounds__(256) k_commit_shared(Dev d, CommDev c)
+{
+    if (*d.done)
+        return;
+    if (threadIdx.x < c.p2p->nNbr)
+        spinUntil(c.p2p->flagF + threadIdx.x, *c.p2p->epoch, d.errFlag);
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    double dist = 0.0;
+    unsigned int nf = 0;
+    if (s < c.nShared)
+    {
+        const int p = c.sharedPoint[s];
+        bool frz = false;
+        for (int k = c.copyOff[s]; k < c.copyOff[s + 1]; ++k)
+            frz = frz || c.recvFz[c.copySlot[k]] != 0;
+        if (frz)
+            d.frozen[p] = 1;
+        commitPoint(d, p, dist, nf);
+    }
+    commitReduce(d, dist, nf, true);
+}
 // publishes the all-reduced statistics of the iteration and the stop flag (:2396-2405).  Peer-memory mode: this
 // rank's (residual, nFrozen) goes into every rank's slot array first (one lane per rank), then the kernel waits
 // for all slots of this iteration and reduces them in rank order (max / exact integer sum), which replaces the
@@ -557,6 +582,9 @@ struct Comm
     size_t xblockBytes = 0;
     std::vector<void *> ipcMapped;
     bool p2p = false;
+    const uint8_t *sharedFlag = nullptr;   // per point: shared between ranks (committed by k_commit_shared)
+    cudaEvent_t evCommitted = nullptr, evFinished = nullptr;
+    bool finishPending = false;            // k_finish_iter of the last iteration is in flight on xStream
     // the predictor exchange runs on its own stream, fenced by these events, so that kernels that do not
     // need its result keep the GPU busy meanwhile
     cudaStream_t xStream = nullptr;

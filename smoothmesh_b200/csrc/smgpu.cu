@@ -470,7 +470,7 @@ struct smgpu_handle
     void launchCommit()
     {
         profBegin(K_COMMIT);
-        k_commit<<<grid(d.P, 256), 256, 0, stream>>>(d);
+        k_commit<<<grid(d.P, 256), 256, 0, stream>>>(d, nullptr);
         profEnd(1);
         ++launches;
     }
@@ -852,6 +852,10 @@ static void commDestroy(Comm *cm)
         cudaEventDestroy(cm->evPacked);
     if (cm->evExchanged)
         cudaEventDestroy(cm->evExchanged);
+    if (cm->evCommitted)
+        cudaEventDestroy(cm->evCommitted);
+    if (cm->evFinished)
+        cudaEventDestroy(cm->evFinished);
     if (cm->nccl)
         nccl().CommDestroy(cm->nccl);
     for (void *p : cm->ipcMapped)
@@ -921,6 +925,15 @@ static void commConnectPeers(Comm *cm, smgpu_handle *h, const std::vector<unsign
     CK(cudaMemcpy(dx, &x, sizeof x, cudaMemcpyHostToDevice));
     cm->c.p2p = dx;
     cm->p2p = true;
+    std::vector<uint8_t> shared((size_t)h->topo.P + 8, 0);
+    for (int32_t p : pl.sharedPoint)
+        shared[p] = 1;
+    cm->sharedFlag = h->upload(shared);
+    if (!cm->evCommitted)
+    {
+        CK(cudaEventCreateWithFlags(&cm->evCommitted, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&cm->evFinished, cudaEventDisableTiming));
+    }
 }
 
 // ---- one iteration with the interface exchanges (src/smoothMesh.C:2257-2399 under -parallel), in the
@@ -933,6 +946,11 @@ static void commPhasePack(Comm *cm, smgpu_handle *h, bool ownStream = false)
 {
     const smk::CommDev &c = cm->c;
     h->launchCellCentres();
+    if (cm->finishPending)
+    { // the previous iteration's statistics / stop flag (k_finish_iter on the exchange stream)
+        CK(cudaStreamWaitEvent(h->stream, cm->evFinished, 0));
+        cm->finishPending = false;
+    }
     h->profBegin(smgpu_handle::K_X_PACK);
     if (ownStream)
     { // the records only need the geometry: packed (and, in peer-memory mode, delivered) beside the predictor
@@ -978,6 +996,19 @@ static void commPhaseConstrain(Comm *cm, smgpu_handle *h)
     h->profEnd(1);
     h->launches += 1;
 }
+// C in peer-memory mode: the points that are not shared between ranks are committed while the other ranks' freeze
+// flags are still on their way; the shared points follow after the OR (:2374) and publish the statistics
+static void commPhaseCommitSplit(Comm *cm, smgpu_handle *h)
+{
+    const smk::CommDev &c = cm->c;
+    h->profBegin(smgpu_handle::K_COMMIT);
+    k_commit<<<smgpu_handle::grid(h->d.P, 256), 256, 0, h->stream>>>(h->d, cm->sharedFlag);
+    h->profEnd(1);
+    h->profBegin(smgpu_handle::K_X_FROZEN);
+    k_commit_shared<<<smgpu_handle::grid(std::max(c.nShared, 1), 256), 256, 0, h->stream>>>(h->d, c);
+    h->profEnd(1);
+    h->launches += 2;
+}
 // C: OR of the freeze flags (:2374), restore + residual + movePoints
 static void commPhaseCommit(Comm *cm, smgpu_handle *h)
 {
@@ -1011,8 +1042,17 @@ static void commIterate(Comm *cm, smgpu_handle *h)
         if (beside)
             CK(cudaStreamWaitEvent(h->stream, cm->evExchanged, 0)); // this rank's own records (read by the merge)
         commPhaseConstrain(cm, h);
-        commPhaseCommit(cm, h);
-        commPhaseFinish(cm, h);
+        commPhaseCommitSplit(cm, h);
+        // the reduction over the ranks runs beside the next iteration's geometry pass (which only writes scratch
+        // data and is harmless after the stop flag): its wait for the slowest rank is off the critical path
+        CK(cudaEventRecord(cm->evCommitted, h->stream));
+        CK(cudaStreamWaitEvent(cm->xStream, cm->evCommitted, 0));
+        h->profBegin(smgpu_handle::K_X_FINISH);
+        k_finish_iter<<<1, SMK_MAXRANKS, 0, cm->xStream>>>(h->d, cm->c);
+        CK(cudaEventRecord(cm->evFinished, cm->xStream));
+        h->profEnd(1);
+        h->launches += 1;
+        cm->finishPending = true;
         return;
     }
     commPhasePack(cm, h);
@@ -1699,6 +1739,11 @@ extern "C"
                         h->launchCommit();
                     }
                     launched += n;
+                    if (h->comm && h->comm->finishPending)
+                    { // the last iteration's reduction runs on the exchange stream: join it
+                        CK(cudaStreamWaitEvent(h->stream, h->comm->evFinished, 0));
+                        h->comm->finishPending = false;
+                    }
                     if (launched < max_iters)
                     {
                         CK(cudaMemcpyAsync(&done, h->d.done, sizeof(int), cudaMemcpyDeviceToHost, h->stream));

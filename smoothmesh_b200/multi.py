@@ -54,7 +54,10 @@ def gather_shared(my_gids: np.ndarray, dist):
     return counts, allg
 
 
-def init_comm(smoother, rank, world, dist, p2p_exchange=True):
+def init_comm(smoother, rank, world, dist, p2p_exchange=True, before_p2p=None):
+    """The start-up steps of include/smgpu.h on every rank; before_p2p: a collective step that must sit between the
+    communicator and the peer mapping (smgpu_enable_boundary_smoothing).  Returns True when the iteration loop uses
+    the peer-memory exchange, False for the NCCL exchanges."""
     import torch
     import smoothmesh_b200 as sm
     counts, allg = gather_shared(smoother.comm_local_shared(), dist)
@@ -77,6 +80,8 @@ def init_comm(smoother, rank, world, dist, p2p_exchange=True):
         uid = torch.tensor(list(sm.Smoother.comm_unique_id()), dtype=torch.uint8, device=dev)
     dist.broadcast(uid, src=0)
     smoother.comm_init(rank, world, bytes(uid.cpu().numpy().tolist()), counts, allg)
+    if before_p2p is not None:
+        before_p2p()
     p2p = False
     if p2p_exchange and backend == "nccl" and not os.environ.get("SMGPU_NO_P2P"):
         # peer-memory exchange for the iteration loop (include/smgpu.h: smgpu_comm_p2p_*); every rank must end up in

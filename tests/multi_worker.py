@@ -35,13 +35,28 @@ def make_parts(world, kind):
     if kind == "kelvin":
         mesh = sm.Mesh.kelvin(3, 1.0).jitter(0.15 * 2 ** 0.5 / 4, 77)
         return mesh.decompose(world, method="rcb")
+    if kind == "boundary":
+        # boundary point smoothing of a box onto a slightly larger box (corners, feature edges, surfaces)
+        mesh = sm.Mesh.hex_block(4 * px, 4 * py, 3 * pz, hi=(1.2, 1.0, 0.9)).jitter(0.03, 5)
+        return mesh.decompose(px, py, pz)
     raise ValueError(kind)
+
+
+def boundary_geometry():
+    from test_boundary_smoothing_oracle import box_geometry
+    hi = (1.2, 1.0, 0.9)
+    ip, ie, _, _ = box_geometry((0, 0, 0), hi, 3)
+    c = np.array(hi) / 2
+    tp, te, tc, tt = box_geometry(c - 1.08 * c, c + 1.08 * c, 3)
+    return dict(init_edges=(ip, ie), target_edges=(tp, te), surface=(tc, tt))
 
 
 def options(kind):
     """(Smoother / Oracle keyword options, iterations) of a multi-rank parity case."""
     if kind == "hexlayers":
         return dict(rel_tol=0.0, layer_patches=[1, 1, 1, 0, 1, 1], max_layers=3, layer_expansion_ratio=1.2), 12
+    if kind == "boundary":
+        return dict(rel_tol=0.0, layer_patches=[1, 0, 1, 0, 0, 0], max_layers=2), 10
     if kind == "prismlayers":  # testcase/run_parallel:22
         return dict(rel_tol=0.0, min_edge_length=0.01, max_step_length=0.002, min_angle_deg=15.0, max_angle_deg=160.0,
                     layer_patches=[1, 0, 0, 0, 0, 0, 0]), 12
@@ -103,7 +118,15 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     kw, iters = options(kind)
     g = sm.Smoother(mine, device=local_rank, **kw)
-    p2p = multi.init_comm(g, rank, world, dist)  # SMGPU_NO_P2P=1 keeps the NCCL exchanges
+    okw = dict(kw)
+    if kind == "boundary":
+        # the collective set-up of boundary point smoothing sits between the communicator and the peer mapping
+        geo = boundary_geometry()
+        p2p = multi.init_comm(g, rank, world, dist,
+                              before_p2p=lambda: g.enable_boundary_smoothing(geo, [1, 1, 1, 1, 0, 1], 0.15))
+        okw.update(smoothing_patches=[1, 1, 1, 1, 0, 1], geometry=geo, internal_smoothing_blending_fraction=0.15)
+    else:
+        p2p = multi.init_comm(g, rank, world, dist)  # SMGPU_NO_P2P=1 keeps the NCCL exchanges
     if mode == "debug":
         # step-by-step comparison against the oracle's rank emulation (every rank runs the oracle)
         from oracle import Oracle
@@ -129,7 +152,7 @@ def main():
     dist.all_gather_object(allres, res)
     if rank == 0:
         from oracle import Oracle
-        o = Oracle([p.desc_arrays() for p in parts], **kw)
+        o = Oracle([p.desc_arrays() for p in parts], **okw)
         n, nf, rs = o.iterate(iters)
         for r in range(world):
             a = allres[r]

@@ -28,7 +28,7 @@ def test_exchange_plan_gloo(world, kind):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("exchange", ["peer-memory", "nccl"])
-@pytest.mark.parametrize("kind", ["hex", "kelvin", "hexlayers", "prismlayers"])
+@pytest.mark.parametrize("kind", ["hex", "kelvin", "hexlayers", "prismlayers", "boundary"])
 def test_multi_gpu_parity(kind, exchange):
     """One process per GPU: the peer-memory exchange (kernels store into the neighbours' mapped buffers over
     NVLink, flags with release / acquire) and the NCCL exchange, both bit-exact against the oracle's rank emulation."""
