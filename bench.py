@@ -474,12 +474,17 @@ def main():
     value = total_points * K / (ms * 1e-3)
 
     # end-to-end through the host-buffer C ABI: H2D points, K iterations, D2H points + log
+    out_pts = np.empty((P, 3), dtype=np.float64)  # the caller's result buffer (a real host keeps its pointField)
+    out_pts.fill(0.0)
     barrier()
     t0 = time.perf_counter()
     g.set_points(init_pts)
+    t_up = time.perf_counter() - t0
     log2 = g.iterate(args.steps)
-    out_pts = g.points()
+    t1 = time.perf_counter()
+    g.points(out=out_pts)
     t_e2e = time.perf_counter() - t0
+    t_down = time.perf_counter() - t1
     barrier()
     t_cold = t_setup + t_e2e
     if dist is not None:
@@ -538,6 +543,7 @@ def main():
         "parity": parity,
         "e2e": {"value": e2e_value, "unit": "point-updates/s", "h2d_bytes_per_step": 24 * P / K,
                 "d2h_bytes_per_step": (24 * P + 16 * K) / K,
+                "upload_s": t_up, "download_s": t_down,
                 "note": "points uploaded once, K iterations, points + log downloaded once; bytes amortised over K steps"},
         "e2e_cold": {"value": total_points * K / t_cold, "unit": "point-updates/s", "seconds": t_cold,
                      "note": "smgpu_create (mesh flattening, connectivity build, tiles, one-time upload) + upload of the points + "

@@ -514,8 +514,12 @@ class Smoother:
         n = done.value
         return IterationLog(n, nf[:n].copy(), res[:n].copy(), ms.value, ln.value)
 
-    def points(self):
-        out = np.zeros((self.n_points, 3), dtype=np.float64)
+    def points(self, out=None):
+        """mesh.points() of the last executed iteration; `out`: a (n_points, 3) float64 array to fill (reused buffers
+        avoid the page faults of a fresh allocation)."""
+        if out is None:
+            out = np.empty((self.n_points, 3), dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == 3 * self.n_points and out.flags.c_contiguous
         self._ck(lib().smgpu_get_points(self._h, _ptr(out)))
         return out
 

@@ -266,16 +266,51 @@ struct smgpu_handle
         }
         return staging;
     }
+    // device-side staging of a pointField (24 bytes per point) and the internal-point flags for k_unpack_points
+    double *dXyz = nullptr;
+    size_t dXyzCap = 0;
+    uint8_t *dIsInternal = nullptr;
+    double *devXyz(size_t n)
+    {
+        if (n > dXyzCap)
+        {
+            dXyz = dalloc<double>(3 * n); // (an earlier, smaller buffer stays in `allocs` until destroy)
+            dXyzCap = n;
+        }
+        return dXyz;
+    }
+    // Upload of the caller's pointField: in chunks, the host copy of chunk k + 1 into page-locked memory runs while
+    // the DMA of chunk k is in flight; the 32-byte records are assembled on the device.
     void setPoints(const double *pts)
     {
-        P4 *h = stage(std::max<size_t>(topo.P, topo.C));
+        const size_t P = (size_t)topo.P;
+        if (!pointOldOfNew.empty())
+        { // renumbered storage: the permutation is applied on the host
+            P4 *h = stage(std::max<size_t>(topo.P, topo.C));
 #pragma omp parallel for schedule(static)
-        for (int64_t i = 0; i < topo.P; ++i)
-        {
-            const int64_t o = pointOldOfNew.empty() ? i : pointOldOfNew[i];
-            h[i] = {pts[3 * o], pts[3 * o + 1], pts[3 * o + 2], topo.isInternal[i] ? 1.0 : 0.0};
+            for (int64_t i = 0; i < topo.P; ++i)
+            {
+                const int64_t o = pointOldOfNew[i];
+                h[i] = {pts[3 * o], pts[3 * o + 1], pts[3 * o + 2], topo.isInternal[i] ? 1.0 : 0.0};
+            }
+            CK(cudaMemcpyAsync(d.pts, h, P * sizeof(P4), cudaMemcpyHostToDevice, stream));
+            CK(cudaStreamSynchronize(stream));
+            return;
         }
-        CK(cudaMemcpyAsync(d.pts, h, topo.P * sizeof(P4), cudaMemcpyHostToDevice, stream));
+        double *hs = reinterpret_cast<double *>(stage(std::max<size_t>(topo.P, topo.C)));
+        double *dx = devXyz(P);
+        if (!dIsInternal)
+            dIsInternal = upload(topo.isInternal);
+        const size_t total = 3 * P, chunk = std::max<size_t>((total + 7) / 8, 1 << 20);
+        for (size_t b = 0; b < total; b += chunk)
+        {
+            const size_t n = std::min(chunk, total - b);
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < (int64_t)n; i += 4096)
+                memcpy(hs + b + i, pts + b + i, std::min<size_t>(4096, n - i) * sizeof(double));
+            CK(cudaMemcpyAsync(dx + b, hs + b, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+        }
+        k_unpack_points<<<grid(d.P, 256), 256, 0, stream>>>(d, dx, dIsInternal);
         CK(cudaStreamSynchronize(stream));
     }
 
@@ -1777,17 +1812,48 @@ extern "C"
         try
         {
             CK(cudaSetDevice(h->prm.device));
-            P4 *tmp = h->stage(std::max<size_t>(h->topo.P, h->topo.C));
-            CK(cudaMemcpyAsync(tmp, src, n * sizeof(P4), cudaMemcpyDeviceToHost, h->stream));
-            CK(cudaStreamSynchronize(h->stream));
-#pragma omp parallel for schedule(static)
-            for (int64_t i = 0; i < n; ++i)
+            if (!oldOfNew.empty())
             {
-                const int64_t o = oldOfNew.empty() ? i : oldOfNew[i];
-                out[3 * o] = tmp[i].x;
-                out[3 * o + 1] = tmp[i].y;
-                out[3 * o + 2] = tmp[i].z;
+                P4 *tmp = h->stage(std::max<size_t>(h->topo.P, h->topo.C));
+                CK(cudaMemcpyAsync(tmp, src, n * sizeof(P4), cudaMemcpyDeviceToHost, h->stream));
+                CK(cudaStreamSynchronize(h->stream));
+#pragma omp parallel for schedule(static)
+                for (int64_t i = 0; i < n; ++i)
+                {
+                    const int64_t o = oldOfNew[i];
+                    out[3 * o] = tmp[i].x;
+                    out[3 * o + 1] = tmp[i].y;
+                    out[3 * o + 2] = tmp[i].z;
+                }
+                return SMGPU_OK;
             }
+            // 24 bytes per point over PCIe, in chunks: the host copy of chunk k out of page-locked memory runs while
+            // the DMA of chunk k + 1 is in flight
+            double *hs = reinterpret_cast<double *>(h->stage(std::max<size_t>(h->topo.P, h->topo.C)));
+            double *dx = h->devXyz(std::max<size_t>(h->topo.P, h->topo.C));
+            k_pack_points<<<smgpu_handle::grid(n, 256), 256, 0, h->stream>>>(src, dx, (int)n);
+            const size_t total = 3 * (size_t)n, chunk = std::max<size_t>((total + 7) / 8, 1 << 20);
+            std::vector<cudaEvent_t> ev;
+            for (size_t b = 0; b < total; b += chunk)
+            {
+                const size_t m = std::min(chunk, total - b);
+                CK(cudaMemcpyAsync(hs + b, dx + b, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                cudaEvent_t e;
+                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                CK(cudaEventRecord(e, h->stream));
+                ev.push_back(e);
+            }
+            size_t k = 0;
+            for (size_t b = 0; b < total; b += chunk, ++k)
+            {
+                const size_t m = std::min(chunk, total - b);
+                CK(cudaEventSynchronize(ev[k]));
+#pragma omp parallel for schedule(static)
+                for (int64_t i = 0; i < (int64_t)m; i += 4096)
+                    memcpy(out + b + i, hs + b + i, std::min<size_t>(4096, m - i) * sizeof(double));
+            }
+            for (cudaEvent_t e : ev)
+                cudaEventDestroy(e);
         }
         catch (const std::exception &e)
         {
