@@ -156,7 +156,7 @@ def kernel_bytes(P, C, F, Fi, E, FV, PC, EC, tiles):
 
 # thread-level FP64-pipe instructions (DADD/DMUL/DFMA/MUFU.64/F2F) per unit, from the ncu source counters of the
 # kernels at 200^3 (profiles/r2_ncu_geom_tiles_f_n200.txt): what the FP64 pipe must issue, at 62.3 per clock and SM
-FP64_SLOTS = {"k_geom_tiles": ("cell", 1004.0)}
+FP64_SLOTS = {"k_geom_tiles": ("cell", 950.0)}
 
 
 def make_mesh(args, world, rank, n=None, small=False):
