@@ -1245,11 +1245,18 @@ extern "C"
         try
         {
             sm::PolyMesh m;
-            m.points.assign(md->points, md->points + 3 * md->n_points);
-            m.faceOffsets.assign(md->face_offsets, md->face_offsets + md->n_faces + 1);
-            m.faceVerts.assign(md->face_verts, md->face_verts + md->face_offsets[md->n_faces]);
-            m.owner.assign(md->owner, md->owner + md->n_faces);
-            m.neighbour.assign(md->neighbour, md->neighbour + md->n_internal_faces);
+            auto parCopy = [](auto &dst, const auto *src, size_t n) {
+                dst.resize(n);
+                auto *out = dst.data();
+#pragma omp parallel for schedule(static)
+                for (int64_t i = 0; i < (int64_t)n; i += 65536)
+                    std::copy(src + i, src + std::min<size_t>(n, i + 65536), out + i);
+            };
+            parCopy(m.points, md->points, 3 * (size_t)md->n_points);
+            parCopy(m.faceOffsets, md->face_offsets, (size_t)md->n_faces + 1);
+            parCopy(m.faceVerts, md->face_verts, (size_t)md->face_offsets[md->n_faces]);
+            parCopy(m.owner, md->owner, (size_t)md->n_faces);
+            parCopy(m.neighbour, md->neighbour, (size_t)md->n_internal_faces);
             m.nCells = md->n_cells;
             for (int i = 0; i < md->n_patches; ++i)
             {
@@ -1439,6 +1446,21 @@ extern "C"
                     CK(cudaFuncSetAttribute(k_geom_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     if (getenv("SMGPU_TILE_MINB"))
                         h->tileMinBlocks = atoi(getenv("SMGPU_TILE_MINB")) == 3 ? 3 : 2;
+                }
+            }
+            // Brick order for the threads of the per-point gather kernels (the storage order is unchanged)
+            if (!noTiles && getenv("SMGPU_POINT_ORDER") && atoi(getenv("SMGPU_POINT_ORDER")) != 0)
+            {
+                const sm::PointTiles T = sm::buildPointTiles(m, t, 256, 1 << 15, 1 << 15);
+                if (T.nTiles > 0)
+                {
+                    std::vector<int32_t> order;
+                    order.reserve(t.P);
+                    for (int32_t k = 0; k < T.nTiles; ++k)
+                        for (int32_t i = 0; i < T.ownOff[k + 1] - T.ownOff[k]; ++i)
+                            order.push_back(T.halo[T.haloOff[k] + i]);
+                    if ((int64_t)order.size() == t.P)
+                        d.pointOrder = h->upload(order);
                 }
             }
             // Per-point kernels on point tiles (k_predict_tiles / k_edge_tiles): built to the same parity bar, but at

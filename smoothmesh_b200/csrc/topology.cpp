@@ -71,26 +71,57 @@ Topology buildTopology(const PolyMesh &m)
     }
 
     // ---- point -> face corners (pointFaces ascending) ----
+    // counted and filled in parallel (atomic cursors), then every row is put in ascending face order
     t.cornerOff.assign(P + 1, 0);
+#pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < FV; ++k)
+    {
+#pragma omp atomic update
         ++t.cornerOff[m.faceVerts[k] + 1];
+    }
     for (int64_t p = 0; p < P; ++p)
         t.cornerOff[p + 1] += t.cornerOff[p];
     t.corner.resize(2 * FV);
     std::vector<int32_t> cornerFace(FV);
     {
         std::vector<int32_t> cur(t.cornerOff.begin(), t.cornerOff.end() - 1);
+        int32_t maxFaceSize = 0;
+#pragma omp parallel for schedule(static) reduction(max : maxFaceSize)
         for (int64_t f = 0; f < F; ++f)
         {
             const int32_t b = m.faceOffsets[f], n = m.faceOffsets[f + 1] - b;
-            t.maxFaceSize = std::max(t.maxFaceSize, n);
+            maxFaceSize = std::max(maxFaceSize, n);
             for (int32_t i = 0; i < n; ++i)
             {
                 const int32_t v = m.faceVerts[b + i];
-                const int32_t slot = cur[v]++;
+                int32_t slot;
+#pragma omp atomic capture
+                slot = cur[v]++;
                 t.corner[2 * (int64_t)slot] = m.faceVerts[b + (i == 0 ? n - 1 : i - 1)];
                 t.corner[2 * (int64_t)slot + 1] = m.faceVerts[b + (i == n - 1 ? 0 : i + 1)];
                 cornerFace[slot] = (int32_t)f;
+            }
+        }
+        t.maxFaceSize = maxFaceSize;
+#pragma omp parallel for schedule(static)
+        for (int64_t p = 0; p < P; ++p)
+        { // insertion sort of the (short) row by (face, previous vertex, next vertex)
+            const int32_t b = t.cornerOff[p], e = t.cornerOff[p + 1];
+            for (int32_t i = b + 1; i < e; ++i)
+            {
+                const int32_t f = cornerFace[i], c0 = t.corner[2 * (int64_t)i], c1 = t.corner[2 * (int64_t)i + 1];
+                int32_t j = i - 1;
+                while (j >= b && (cornerFace[j] > f || (cornerFace[j] == f && (t.corner[2 * (int64_t)j] > c0 ||
+                                                                              (t.corner[2 * (int64_t)j] == c0 && t.corner[2 * (int64_t)j + 1] > c1)))))
+                {
+                    cornerFace[j + 1] = cornerFace[j];
+                    t.corner[2 * (int64_t)(j + 1)] = t.corner[2 * (int64_t)j];
+                    t.corner[2 * (int64_t)(j + 1) + 1] = t.corner[2 * (int64_t)j + 1];
+                    --j;
+                }
+                cornerFace[j + 1] = f;
+                t.corner[2 * (int64_t)(j + 1)] = c0;
+                t.corner[2 * (int64_t)(j + 1) + 1] = c1;
             }
         }
     }
@@ -299,19 +330,44 @@ Topology buildTopology(const PolyMesh &m)
     // ---- cell -> faces in OpenFOAM's accumulation order (owned faces ascending, then
     //      neighbour-side faces ascending; bit 31 marks the neighbour side) ----
     t.cfOff.assign(C + 1, 0);
+#pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < F; ++f)
+    {
+#pragma omp atomic update
         ++t.cfOff[m.owner[f] + 1];
-    for (int64_t f = 0; f < Fi; ++f)
-        ++t.cfOff[m.neighbour[f] + 1];
+        if (f < Fi)
+        {
+#pragma omp atomic update
+            ++t.cfOff[m.neighbour[f] + 1];
+        }
+    }
     for (int64_t c = 0; c < C; ++c)
         t.cfOff[c + 1] += t.cfOff[c];
     t.cf.resize(t.cfOff[C]);
     {
+        // filled in parallel, then every (short) row sorted: owned faces ascending first (bit 31 clear), then the
+        // neighbour-side faces ascending -- as unsigned numbers that is exactly ascending order
         std::vector<int32_t> cur(t.cfOff.begin(), t.cfOff.end() - 1);
+#pragma omp parallel for schedule(static)
         for (int64_t f = 0; f < F; ++f)
-            t.cf[cur[m.owner[f]]++] = (int32_t)f;
-        for (int64_t f = 0; f < Fi; ++f)
-            t.cf[cur[m.neighbour[f]]++] = (int32_t)((uint32_t)f | 0x80000000u);
+        {
+            int32_t slot;
+#pragma omp atomic capture
+            slot = cur[m.owner[f]]++;
+            t.cf[slot] = (int32_t)f;
+            if (f < Fi)
+            {
+#pragma omp atomic capture
+                slot = cur[m.neighbour[f]]++;
+                t.cf[slot] = (int32_t)((uint32_t)f | 0x80000000u);
+            }
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t c = 0; c < C; ++c)
+        {
+            uint32_t *b = reinterpret_cast<uint32_t *>(&t.cf[t.cfOff[c]]), *e = reinterpret_cast<uint32_t *>(&t.cf[t.cfOff[c + 1]]);
+            std::sort(b, e);
+        }
     }
 
     tick("cellFaces");

@@ -119,12 +119,12 @@ def test_cli_rejects_out_of_scope_features_loudly(tmp_path):
     sm.Mesh.hex_block(2, 2, 2).write(case / "constant" / "polyMesh")
     (case / "system").mkdir()
     (case / "system" / "controlDict").write_text("deltaT 1;\nwriteFormat ascii;\n")
-    # boundary point smoothing under -parallel is not built: refused before anything else happens
+    # -parallel without processor directories fails loudly (boundary point smoothing itself is supported there)
     (case / "constant" / "geometry").mkdir()
     for f in ("targetSurfaces.obj", "initEdges.obj"):
         (case / "constant" / "geometry" / f).write_text("# empty\n")
     r = subprocess.run([sm.CLI_PATH, "-case", str(case), "-parallel"], capture_output=True, text=True)
-    assert r.returncode != 0 and "boundary point smoothing with -parallel" in r.stderr
+    assert r.returncode != 0 and "no processor directories" in r.stderr
     # without a GPU the tool fails loudly (there is no CPU path)
     r = subprocess.run([sm.CLI_PATH, "-case", str(case)], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
