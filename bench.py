@@ -445,6 +445,7 @@ def main():
             dist.barrier()
 
     # warm-up, then restart from the initial jittered mesh so the timed region is iterations 1..K
+    barrier()
     g.iterate(args.warmup)
     g.set_points(init_pts)
     g.profile(True)

@@ -64,14 +64,14 @@ __device__ __forceinline__ unsigned long long ldAcquireSys(const unsigned long l
     return v;
 }
 // waits until *p >= want (want == exact for the parity-buffered statistics); a peer that never arrives raises
-// errFlag 6 after about ten seconds instead of hanging the device
+// errFlag 6 after about thirty seconds instead of hanging the device
 __device__ __forceinline__ void spinUntil(const unsigned long long *p, unsigned long long want, int *errFlag)
 {
     const long long t0 = clock64();
     while (ldAcquireSys(p) < want)
     {
         __nanosleep(64);
-        if (clock64() - t0 > 20000000000ll)
+        if (clock64() - t0 > 60000000000ll)
         {
             *errFlag = 6;
             break;
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(SMK_MAXRANKS) k_finish_iter(Dev d, CommDev c)
             while (ldAcquireSys(&x2->stat[par * x2->nRanks + r].epoch) != e)
             {
                 __nanosleep(64);
-                if (clock64() - t0 > 20000000000ll)
+                if (clock64() - t0 > 60000000000ll)
                 {
                     *d.errFlag = 6;
                     break;

@@ -530,7 +530,7 @@ struct smgpu_handle
                                     "A smoothing surface point has zero point normal (src/orthogonalBoundaryBlending.C:611)"};
         CK(cudaMemset(d.errFlag, 0, sizeof(int)));
         if (errFlag == 6)
-            return setErr(SMGPU_ERR_COMM, "peer-memory exchange: a rank did not deliver its records within ten seconds "
+            return setErr(SMGPU_ERR_COMM, "peer-memory exchange: a rank did not deliver its records within thirty seconds "
                                           "(did every rank call smgpu_iterate with the same arguments?)");
         return setErr(SMGPU_ERR_MESH, msg[(errFlag >= 1 && errFlag <= 5) ? errFlag : 1]);
     }

@@ -1134,11 +1134,12 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
             G.maxTileFaces = std::max(G.maxTileFaces, G.tileFaceOff[k + 1] - G.tileFaceOff[k]);
             G.maxTilePoints = std::max(G.maxTilePoints, G.tilePointOff[k + 1] - G.tilePointOff[k]);
         }
-        // one pass: pair counts, closedness, and -- while every cell so far is a topological hexahedron -- the
-        // canonical records; the pair lists themselves are only materialised when some cell is not a hexahedron
-        // (or the caller wants them for checking)
-        bool allHex = true;
-        G.hexRec.assign(16 * (size_t)C, 0);
+        // one pass: pair counts, closedness, and the canonical record of every cell that is a topological
+        // hexahedron; then the uniform tiles (all faces quadrilaterals, all cells such hexahedra) get their
+        // fixed-stride reference copies, and the pair lists are materialised for the cells of the other tiles
+        // (for all cells when the caller wants them for checking)
+        std::vector<uint8_t> cellIsHex(C, 0);
+        std::vector<uint16_t> recAll(16 * (size_t)C, 0); // cell-major, by slot
 #pragma omp parallel
         {
             std::vector<Half> hs;
@@ -1164,43 +1165,73 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
                         closed = false;
                     }
                     nPairs[slot + 1] = std::max(n, 0);
-                    bool hexOk = false;
-                    uint16_t rec[16];
-                    if (n == 12)
-                        hexOk = hexRecord(k, slot, tmp.data(), rec);
-                    if (hexOk)
-                    {
-                        uint16_t *o1 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)i], *o2 = &G.hexRec[16 * (size_t)cb + 8 * (size_t)nc + 8 * (size_t)i];
-                        for (int q = 0; q < 8; ++q)
-                            o1[q] = rec[q], o2[q] = rec[8 + q];
-                    }
-                    else
-                    {
-#pragma omp atomic write
-                        allHex = false;
-                    }
+                    if (n == 12 && hexRecord(k, slot, tmp.data(), &recAll[16 * (size_t)slot]))
+                        cellIsHex[slot] = 1;
                 }
             }
         }
-        if (!closed || !allHex)
-        {
-            G.hexRec.clear();
-            G.hexRec.shrink_to_fit();
-        }
+        G.tileUFaceOff.assign(G.nTiles, -1);
+        G.tileUCellOff.assign(G.nTiles, -1);
         if (closed)
         {
+            int64_t uf = 0, uc = 0;
+            for (int32_t k = 0; k < G.nTiles; ++k)
+            {
+                bool uni = true;
+                for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1] && uni; ++slot)
+                    uni = cellIsHex[slot] != 0;
+                for (int32_t i = G.tileFaceOff[k]; i < G.tileFaceOff[k + 1] && uni; ++i)
+                    uni = G.faceRefOff[i + 1] - G.faceRefOff[i] == 4;
+                if (!uni)
+                    continue;
+                G.tileUFaceOff[k] = (int32_t)uf;
+                G.tileUCellOff[k] = (int32_t)uc;
+                uf += G.tileFaceOff[k + 1] - G.tileFaceOff[k];
+                uc += G.tileCellOff[k + 1] - G.tileCellOff[k];
+            }
+            G.nUniformCells = uc;
+            G.uFaceRef.resize(4 * (size_t)uf);
+            G.uSlotRef.resize(6 * (size_t)uc);
+            G.hexRec.resize(16 * (size_t)uc);
+#pragma omp parallel for schedule(dynamic, 16)
+            for (int32_t k = 0; k < G.nTiles; ++k)
+            {
+                if (G.tileUCellOff[k] < 0)
+                    continue;
+                const int32_t fb = G.tileFaceOff[k], nf = G.tileFaceOff[k + 1] - fb, cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
+                const size_t ufb = (size_t)G.tileUFaceOff[k], ucb = (size_t)G.tileUCellOff[k];
+                for (int32_t i = 0; i < nf; ++i)
+                    for (int q = 0; q < 4; ++q)
+                        G.uFaceRef[4 * (ufb + i) + q] = G.faceRef[G.faceRefOff[fb + i] + q];
+                for (int32_t i = 0; i < nc; ++i)
+                {
+                    for (int q = 0; q < 6; ++q)
+                        G.uSlotRef[6 * (ucb + i) + q] = G.slotRef[G.slotOff[cb + i] + q];
+                    const uint16_t *rec = &recAll[16 * (size_t)(cb + i)];
+                    uint16_t *o1 = &G.hexRec[16 * ucb + 8 * (size_t)i], *o2 = &G.hexRec[16 * ucb + 8 * (size_t)nc + 8 * (size_t)i];
+                    for (int q = 0; q < 8; ++q)
+                        o1[q] = rec[q], o2[q] = rec[8 + q];
+                }
+            }
             G.uniformCellEdges = C ? nPairs[1] : 0;
             for (int64_t c = 0; c < C && G.uniformCellEdges; ++c)
                 if (nPairs[c + 1] != G.uniformCellEdges)
                     G.uniformCellEdges = 0;
+            // pair lists: for the cells of the non-uniform tiles (all cells if asked for)
             int64_t total = 0;
-            for (int64_t c = 0; c < C; ++c)
-                total += nPairs[c + 1];
-            if ((G.hexRec.empty() || keepPairs) && total < (int64_t)INT32_MAX / 2)
+            std::vector<uint8_t> wantPairs(C, 0);
+            for (int32_t k = 0; k < G.nTiles; ++k)
+                if (keepPairs || G.tileUCellOff[k] < 0)
+                    for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
+                    {
+                        wantPairs[slot] = 1;
+                        total += nPairs[slot + 1];
+                    }
+            if (total > 0 && total < (int64_t)INT32_MAX / 2)
             {
                 G.cellEdgeOff.assign(C + 1, 0);
                 for (int64_t c = 0; c < C; ++c)
-                    G.cellEdgeOff[c + 1] = G.cellEdgeOff[c] + nPairs[c + 1];
+                    G.cellEdgeOff[c + 1] = G.cellEdgeOff[c] + (wantPairs[c] ? nPairs[c + 1] : 0);
                 G.cellEdgeRef.resize(4 * (size_t)total);
                 for (int32_t k = 0; k < G.nTiles; ++k)
                     G.maxTileEdgePairs = std::max(G.maxTileEdgePairs, G.cellEdgeOff[G.tileCellOff[k + 1]] - G.cellEdgeOff[G.tileCellOff[k]]);
@@ -1210,7 +1241,8 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
 #pragma omp for schedule(dynamic, 16)
                     for (int32_t k = 0; k < G.nTiles; ++k)
                         for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
-                            cellPairs(k, slot, hs, G.cellEdgeRef.data() + 4 * (size_t)G.cellEdgeOff[slot]);
+                            if (wantPairs[slot])
+                                cellPairs(k, slot, hs, G.cellEdgeRef.data() + 4 * (size_t)G.cellEdgeOff[slot]);
                 }
             }
         }

@@ -108,9 +108,17 @@ struct GeomTiles
     //   v0..v3 (vertex loop of one face A), w0..w3 (w_i = the vertex joined to v_i by an edge, on the opposite
     //   face B), A, B, S0..S3 (S_i = the side face through v_i, v_i+1, w_i+1, w_i), 2 x padding.
     // The twelve (edge, cell) pairs are then a fixed pattern: (v_i, v_i+1 | A, S_i), (w_i, w_i+1 | B, S_i),
-    // (v_i, w_i | S_i-1, S_i).  Per tile: the first 8 entries of all its cells, then the second 8 (two
-    // conflict-free 16-byte reads per thread).  Empty unless every cell matched.
+    // (v_i, w_i | S_i-1, S_i).  Stored for the uniform tiles only (see below), per tile: the first 8 entries of all
+    // its cells, then the second 8 (two conflict-free 16-byte reads per thread), at 16 * tileUCellOff[t].
     std::vector<uint16_t> hexRec;
+    // Per-tile fast path: a tile all of whose listed faces are quadrilaterals and all of whose cells are
+    // topological hexahedra is "uniform" and reads fixed-stride copies of its references -- uFaceRef: 4 x uint16 per
+    // listed face, uSlotRef: 6 x uint16 per cell, hexRec as above -- at tileUFaceOff[t] / tileUCellOff[t] (counted
+    // over the uniform tiles only; -1 for the other tiles, which go through the offset tables).  A mesh of
+    // hexahedra only has tileUFaceOff == tileFaceOff and tileUCellOff == tileCellOff.
+    std::vector<int32_t> tileUFaceOff, tileUCellOff;
+    std::vector<uint16_t> uFaceRef, uSlotRef;
+    int64_t nUniformCells = 0;
     int32_t uniformCellEdges = 0;
     int32_t maxTileCells = 0, maxTileFaces = 0, maxTilePoints = 0, maxTileEdgePairs = 0;
 };
