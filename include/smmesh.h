@@ -78,9 +78,10 @@ extern "C"
      * of faces its cells touch; see smoothmesh_b200/csrc/topology.hpp GeomTiles), built and checked on the
      * host: out = {tiles (0 = a cell does not fit: two-kernel path), listed faces summed over tiles, largest
      * face list, faces of the mesh, largest point list, (edge, cell) pairs listed for the fused face-angle filter
-     * (0 = some cell is not closed: per-edge kernel), edges per cell if uniform else 0}.  Fails if an invariant
-     * the kernel relies on does not hold. */
-    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[7]);
+     * (0 = some cell is not closed: per-edge kernel), edges per cell if uniform else 0, cells in uniform tiles (all
+     * faces quadrilaterals, all cells hexahedra: the kernel's fast path)}.  Fails if an invariant the kernel relies
+     * on does not hold. */
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[8]);
 
     /* One-time host set-up of boundary point smoothing (smoothmesh_b200/csrc/boundary.hpp; the reference's
      * classifyBoundaryPoints, findEdgeMeshStrings, calculatePointHopsToBoundary(smoothingPatches),

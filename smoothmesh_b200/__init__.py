@@ -412,11 +412,11 @@ class Mesh:
     def geom_tiles(self, max_cells=256, max_faces=1024, max_points=1024):
         """Host-side tiling of the fused geometry kernel, checked:
         dict(tiles, listed_faces, max_faces, faces, max_points)."""
-        out = (C.c_int64 * 7)()
+        out = (C.c_int64 * 8)()
         if lib().smmesh_geom_tiles(self._h, int(max_cells), int(max_faces), int(max_points), out) != 0:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
         return dict(tiles=out[0], listed_faces=out[1], max_faces=out[2], faces=out[3], max_points=out[4],
-                    edge_cell_pairs=out[5], uniform_cell_edges=out[6])
+                    edge_cell_pairs=out[5], uniform_cell_edges=out[6], uniform_tile_cells=out[7])
 
     def decompose(self, px, py=1, pz=1, method="bricks"):
         n = px * py * pz if method == "bricks" else px

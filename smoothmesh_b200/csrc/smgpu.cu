@@ -341,10 +341,7 @@ struct smgpu_handle
             profBegin(K_GEOM_TILES);
             if (d.fusedFaceFilter)
                 CK(cudaMemsetAsync(d.suspect, 0, (size_t)d.P, stream));
-            if (tilesUniform)
-                k_geom_tiles_f<true><<<d.nTiles, SMK_TILE_CELLS, tileSmem, stream>>>(d);
-            else
-                k_geom_tiles_f<false><<<d.nTiles, SMK_TILE_CELLS, tileSmem, stream>>>(d);
+            k_geom_tiles_f<<<d.nTiles, SMK_TILE_CELLS, tileSmem, stream>>>(d);
             profEnd(1);
             ++launches;
             return;
@@ -1382,66 +1379,78 @@ extern "C"
             h->noFilters = getenv("SMGPU_NO_FILTERS") && atoi(getenv("SMGPU_NO_FILTERS")) != 0;
             d.nInternalFaces = (int)md->n_internal_faces;
             d.nTiles = 0;
-            // The fused kernel wins on all-quad/all-hex meshes (0.91 vs 1.26 ms at 200^3); on polyhedral meshes
-            // its generic path (dependent reference loads, few cells per tile) measured slower than the
-            // two-kernel path (1.59 vs 1.25 ms on 1.8 M Kelvin cells), so it is not used there unless forced.
+            // The fused tile kernel has a fast path per tile (all faces quadrilaterals, all cells hexahedra) and a
+            // generic one; on polyhedral meshes the generic path measured slower than the per-face / per-cell /
+            // per-edge kernels (Kelvin cells: 3.62 vs 1.93 ms), so tiles are used where hexahedra dominate -- a
+            // hex-dominant mesh with prisms or polyhedra keeps the fast path on every all-hex tile -- or when forced.
             const bool noTiles = getenv("SMGPU_NO_TILES") && atoi(getenv("SMGPU_NO_TILES")) != 0;
             const bool forceTiles = getenv("SMGPU_FORCE_TILES") && atoi(getenv("SMGPU_FORCE_TILES")) != 0;
-            if (!noTiles && (forceTiles || (d.uniformFaceSize == 4 && d.uniformCellFaces == 6)))
+            int64_t hexLike = 0;
+#pragma omp parallel for schedule(static) reduction(+ : hexLike)
+            for (int64_t c = 0; c < t.C; ++c)
+            {
+                bool hex = t.cfOff[c + 1] - t.cfOff[c] == 6;
+                for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1] && hex; ++k)
+                {
+                    const int32_t f = t.cf[k] & 0x7fffffff;
+                    hex = t.faceOff[f + 1] - t.faceOff[f] == 4;
+                }
+                hexLike += hex ? 1 : 0;
+            }
+            if (!noTiles && (forceTiles || 2 * hexLike >= t.C))
             {
                 const sm::GeomTiles G = sm::buildGeomTiles(m, t, SMK_TILE_CELLS, SMK_TILE_FACES, SMK_TILE_POINTS);
                 if (G.nTiles > 0)
                 {
                     h->useTiles = true;
                     d.nTiles = G.nTiles;
+                    const bool oldTiles = getenv("SMGPU_OLD_TILES") && atoi(getenv("SMGPU_OLD_TILES")) != 0;
+                    const bool allUniform = G.nUniformCells == t.C;
                     d.tileCellOff = h->upload(G.tileCellOff);
                     d.tileCells = h->upload(G.tileCells);
                     d.tileFaceOff = h->upload(G.tileFaceOff);
                     d.tileFaces = h->upload(G.tileFaces);
-                    d.slotOff = h->upload(G.slotOff);
-                    d.slotRef = h->upload(G.slotRef);
                     d.tilePointOff = h->upload(G.tilePointOff);
                     d.tilePoints = h->upload(G.tilePoints);
-                    d.faceRefOff = h->upload(G.faceRefOff);
-                    d.faceRef = h->upload(G.faceRef);
-                    const bool oldTiles = getenv("SMGPU_OLD_TILES") && atoi(getenv("SMGPU_OLD_TILES")) != 0;
-                    h->tilesHavePairs = !G.cellEdgeRef.empty() || !G.hexRec.empty();
-                    h->tilesUniform = d.uniformFaceSize == 4 && d.uniformCellFaces == 6 && (!h->tilesHavePairs || !G.hexRec.empty());
+                    if (!allUniform || oldTiles)
+                    { // the offset tables and variable-length references: only tiles off the fast path read them
+                        d.slotOff = h->upload(G.slotOff);
+                        d.slotRef = h->upload(G.slotRef);
+                        d.faceRefOff = h->upload(G.faceRefOff);
+                        d.faceRef = h->upload(G.faceRef);
+                    }
+                    d.tileUFaceOff = h->upload(G.tileUFaceOff);
+                    d.tileUCellOff = h->upload(G.tileUCellOff);
+                    d.uFaceRef = (const uint2 *)h->upload(G.uFaceRef);
+                    d.uSlotRef = (const unsigned int *)h->upload(G.uSlotRef);
+                    d.hexRec = (const uint2 *)h->upload(G.hexRec);
+                    // certificates: every cell has its (edge, cell) pairs either as a canonical record (uniform
+                    // tiles) or in the pair lists (the other tiles); none at all if some cell is not closed
+                    bool pairsComplete = !G.tileUCellOff.empty();
+                    for (int32_t k = 0; k < G.nTiles && pairsComplete; ++k)
+                        pairsComplete = G.tileUCellOff[k] >= 0 || !G.cellEdgeOff.empty();
+                    h->tilesHavePairs = pairsComplete;
+                    h->tilesUniform = allUniform;
                     h->tileListedFaces = (int64_t)G.tileFaces.size();
                     h->tileListedPoints = (int64_t)G.tilePoints.size();
                     d.uniformCellEdges = G.uniformCellEdges;
                     d.tileSF = (G.maxTileFaces + 31) / 32 * 32;
                     d.tileSP = (G.maxTilePoints + 31) / 32 * 32;
-                    d.tileSE = h->tilesUniform && h->tilesHavePairs ? 4 * G.maxTileCells : 0; // 32-byte record per cell
+                    d.tileSE = (G.nUniformCells > 0 && pairsComplete) ? 4 * G.maxTileCells : 0; // 32-byte record per cell
                     h->tileSmem = tileSmemBytes(d.tileSF, d.tileSP, d.tileSE);
-                    if (h->tilesHavePairs)
+                    if (!G.cellEdgeOff.empty())
                     {
-                        if (!h->tilesUniform)
-                            d.cellEdgeOff = h->upload(G.cellEdgeOff);
-                        if (h->tilesUniform)
-                            d.hexRec = (const uint2 *)h->upload(G.hexRec); // the pair lists stay on the host
-                        else
-                            d.cellEdgeRef = (const uint2 *)h->upload(G.cellEdgeRef);
+                        d.cellEdgeOff = h->upload(G.cellEdgeOff);
+                        d.cellEdgeRef = (const uint2 *)h->upload(G.cellEdgeRef);
                     }
                     d.suspect = h->dalloc<uint8_t>(t.P + 8);
                     CK(cudaMemset(d.suspect, 0, t.P + 8));
                     h->tilesF = !oldTiles && h->tileSmem <= 110 * 1024;
-                    {
-                        int perSm = 0, sms = 0;
-                        CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, params->device));
-                        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, k_geom_tiles_f<true>, SMK_TILE_CELLS, h->tileSmem));
-                        // L2 warm-up one generation of resident blocks ahead: measured slower at 200^3 (1.31 vs 1.23 ms,
-                        // the extra loads cost more than the colder prologue), so it stays an experiment switch
-                        d.tilePrefetch = 0;
-                        if (getenv("SMGPU_TILE_PREFETCH"))
-                            d.tilePrefetch = atoi(getenv("SMGPU_TILE_PREFETCH")) * std::max(1, perSm) * sms;
-                    }
                     // the attribute belongs to the function, not to this handle: always the device's opt-in maximum,
                     // so that a later handle with smaller tiles does not lower it under an earlier handle's launches
                     int smemOptin = 0;
                     CK(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, params->device));
-                    CK(cudaFuncSetAttribute(k_geom_tiles_f<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
-                    CK(cudaFuncSetAttribute(k_geom_tiles_f<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
+                    CK(cudaFuncSetAttribute(k_geom_tiles_f, cudaFuncAttributeMaxDynamicSharedMemorySize, smemOptin));
                     CK(cudaFuncSetAttribute(k_geom_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     CK(cudaFuncSetAttribute(k_geom_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMK_TILE_SMEM));
                     if (getenv("SMGPU_TILE_MINB"))

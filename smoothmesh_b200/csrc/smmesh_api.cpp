@@ -247,7 +247,7 @@ extern "C"
         }
         return SMGPU_OK;
     }
-    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[7])
+    int smmesh_geom_tiles(const smmesh *m, int32_t max_cells, int32_t max_faces, int32_t max_points, int64_t out[8])
     {
         try
         {
@@ -342,6 +342,39 @@ extern "C"
                 if (listed != (int64_t)t.ecCell.size())
                     throw std::runtime_error("(edge, cell) pairs do not cover the mesh exactly once");
             }
+            // uniform tiles: the fixed-stride copies equal the offset-table entries, and are laid out back to back
+            if (G.nTiles > 0 && !G.tileUCellOff.empty())
+            {
+                int64_t uf = 0, uc = 0;
+                for (int32_t k = 0; k < G.nTiles; ++k)
+                {
+                    if (G.tileUCellOff[k] < 0)
+                        continue;
+                    if (G.tileUCellOff[k] != uc || G.tileUFaceOff[k] != uf)
+                        throw std::runtime_error("uniform tile offsets are not consecutive");
+                    const int32_t fb = G.tileFaceOff[k], nf = G.tileFaceOff[k + 1] - fb, cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
+                    for (int32_t i = 0; i < nf; ++i)
+                    {
+                        if (G.faceRefOff[fb + i + 1] - G.faceRefOff[fb + i] != 4)
+                            throw std::runtime_error("uniform tile with a face that is not a quadrilateral");
+                        for (int q = 0; q < 4; ++q)
+                            if (G.uFaceRef[4 * (uf + i) + q] != G.faceRef[G.faceRefOff[fb + i] + q])
+                                throw std::runtime_error("uniform tile: face reference copy differs");
+                    }
+                    for (int32_t i = 0; i < nc; ++i)
+                    {
+                        if (G.slotOff[cb + i + 1] - G.slotOff[cb + i] != 6)
+                            throw std::runtime_error("uniform tile with a cell that has not six faces");
+                        for (int q = 0; q < 6; ++q)
+                            if (G.uSlotRef[6 * (uc + i) + q] != G.slotRef[G.slotOff[cb + i] + q])
+                                throw std::runtime_error("uniform tile: cell reference copy differs");
+                    }
+                    uf += nf;
+                    uc += nc;
+                }
+                if (uc != G.nUniformCells || (int64_t)G.hexRec.size() != 16 * uc)
+                    throw std::runtime_error("uniform cell count differs");
+            }
             if (G.nTiles > 0)
             {
                 for (int32_t c = 0; c < t.C; ++c)
@@ -358,6 +391,7 @@ extern "C"
             out[4] = maxPoints;
             out[5] = (int64_t)G.cellEdgeRef.size() / 4;
             out[6] = G.uniformCellEdges;
+            out[7] = G.nUniformCells;
         }
         catch (const std::exception &e)
         {

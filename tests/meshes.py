@@ -63,3 +63,40 @@ def tet_block(n=3, frac=0.15, seed=5):
 
 CASES["tets3_j15"] = lambda: tet_block()
 EXTRA_CASES = {"tets3_j15": CASES["tets3_j15"]}
+
+
+def mixed_hex_prism_block(n=9, frac=0.2, seed=11):
+    """Hex-dominant mesh: an n^3 block whose columns with i < n // 3 are split into two prisms each (the same
+    diagonal in every layer, so the triangles of stacked prisms match), the rest stay hexahedra.  Triangular and
+    quadrilateral faces, five- and six-faced cells: the per-tile fast path of the fused geometry kernel applies
+    to the all-hex tiles only."""
+    idx = lambda i, j, k: i + (n + 1) * (j + (n + 1) * k)
+    pts = np.array([[i / n, j / n, k / n] for k in range(n + 1) for j in range(n + 1) for i in range(n + 1)], dtype=float)
+    cells = []
+
+    def oriented(faces, verts):
+        cc = pts[list(verts)].mean(axis=0)
+        out = []
+        for f in faces:
+            p = pts[f]
+            nrm = np.cross(p[1] - p[0], p[2] - p[0])
+            out.append(f if np.dot(nrm, p.mean(axis=0) - cc) > 0 else f[::-1])
+        return out
+
+    for k in range(n):
+        for j in range(n):
+            for i in range(n):
+                a, b, c, d = idx(i, j, k), idx(i + 1, j, k), idx(i + 1, j + 1, k), idx(i, j + 1, k)
+                e, f, g, h = idx(i, j, k + 1), idx(i + 1, j, k + 1), idx(i + 1, j + 1, k + 1), idx(i, j + 1, k + 1)
+                if i < n // 3:
+                    # two prisms sharing the vertical quad a-c-g-e
+                    cells.append(oriented([[a, b, c], [e, f, g], [a, b, f, e], [b, c, g, f], [a, c, g, e]], (a, b, c, e, f, g)))
+                    cells.append(oriented([[a, c, d], [e, g, h], [c, d, h, g], [d, a, e, h], [a, c, g, e]], (a, c, d, e, g, h)))
+                else:
+                    cells.append(oriented([[a, b, c, d], [e, f, g, h], [a, b, f, e], [b, c, g, f], [c, d, h, g], [d, a, e, h]],
+                                          (a, b, c, d, e, f, g, h)))
+    m = sm.Mesh.from_cells(pts, cells)
+    return m.jitter(frac / n, seed)
+
+
+CASES["mixed9_j20"] = lambda: mixed_hex_prism_block()

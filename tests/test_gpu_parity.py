@@ -252,3 +252,19 @@ def test_dense_face_angle_worklist_matches_the_sequential_walk(n, jit, iters):
     assert g.filter_stats()["active_points"] > 0.5 * mesh.n_points
     assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
     assert np.array_equal(g.frozen(), o.get("frozen")) and np.array_equal(g.points(), o.get("points"))
+
+
+@pytest.mark.parametrize("n,frac", [(24, 0.2), (18, 0.4)])
+def test_hex_dominant_mesh_uses_both_tile_paths_and_matches_oracle(n, frac):
+    """Hexahedra and prisms in one mesh: the fused geometry kernel takes its fixed-stride path on the all-hex
+    tiles and the offset tables elsewhere, inside one launch; points, flags and log bit-exact against the oracle."""
+    from meshes import mixed_hex_prism_block
+    mesh = mixed_hex_prism_block(n, frac=frac)
+    tiles = mesh.geom_tiles()
+    assert 0 < tiles["uniform_tile_cells"] < mesh.n_cells
+    g, o = sm.Smoother(mesh, rel_tol=0.0), Oracle(mesh.desc_arrays(), rel_tol=0.0)
+    assert g.filter_stats()["fused"]
+    n_it, nf, res = o.iterate(4)
+    log = g.iterate(4)
+    assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
+    assert np.array_equal(g.points(), o.get("points")) and np.array_equal(g.frozen(), o.get("frozen"))

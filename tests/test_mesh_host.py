@@ -360,3 +360,14 @@ def test_kelvin_bricks_generated_per_rank_form_the_global_mesh(n, dims):
     # the rank-emulating oracle accepts the bricks (interface points found through point_global_id)
     o = Oracle([p.desc_arrays() for p in parts], rel_tol=0.0)
     assert o.iterate(2)[0] == 2
+
+
+def test_geometry_tiles_of_a_hex_dominant_mesh_keep_the_fast_path_per_tile():
+    """A mesh of hexahedra and prisms: every tile whose faces are all quadrilaterals and whose cells are all
+    hexahedra is on the kernel's fast path (fixed-stride reference copies, canonical hexahedron records), the other
+    tiles go through the offset tables; smmesh_geom_tiles checks both representations against each other."""
+    from meshes import mixed_hex_prism_block
+    g = mixed_hex_prism_block(12).geom_tiles(max_cells=32, max_faces=200, max_points=200)
+    assert 0 < g["uniform_tile_cells"] < 12 ** 3 + 4 * 12 * 12 and g["uniform_cell_edges"] == 0
+    h = hex_jittered(8, 8, 8, 0.2).geom_tiles()
+    assert h["uniform_tile_cells"] == 512 and h["uniform_cell_edges"] == 12
