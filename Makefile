@@ -58,3 +58,7 @@ clean:
 	rm -rf $(OBJDIR) $(LIBDIR) $(BINDIR) oracle/_build
 
 .PHONY: all clean
+
+# host set-up timing / fingerprint tool (not part of `all`)
+build/setup_timing: tools/setup_timing.cpp $(OBJDIR)/topology.o $(OBJDIR)/polymesh.o
+	$(CXX) $(CXXFLAGS) -I$(CSRC) -o $@ $^

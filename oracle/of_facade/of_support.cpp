@@ -54,7 +54,10 @@ std::string facadeLoadMesh(const std::string &topoDir, const std::string &points
     {
         sm::PolyMesh pm = sm::readPolyMesh(topoDir);
         if (!pointsFile.empty())
-            pm.points = sm::readPoints(pointsFile);
+        {
+            const std::vector<double> pts = sm::readPoints(pointsFile);
+            pm.points.assign(pts.begin(), pts.end());
+        }
         for (const sm::Patch &p : pm.patches)
         {
             A.patchStart.push_back(p.start);
@@ -86,7 +89,7 @@ std::string facadeLoadMesh(const std::string &topoDir, const std::string &points
         if (!R->init(in, prm))
             return R->err;
         A.P = R->P, A.C = R->C, A.F = R->F, A.Fi = R->Fi;
-        A.points = pm.points;
+        A.points.assign(pm.points.begin(), pm.points.end());
         A.faceOff = R->fOff;
         A.faceVerts = R->fV;
         A.owner = R->own;

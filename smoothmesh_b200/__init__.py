@@ -426,14 +426,16 @@ class Mesh:
             raise SmoothMeshError(lib().smmesh_last_error().decode())
         return [Mesh(out[i]) for i in range(n)]
 
-    def desc_arrays(self):
-        """The arrays of smgpu_mesh_desc as contiguous numpy copies (also what the oracle takes)."""
+    def desc_arrays(self, copy=True):
+        """The arrays of smgpu_mesh_desc as contiguous numpy arrays (also what the oracle takes): copies, or with
+        copy=False views of this mesh's own storage (valid while the mesh lives; smgpu_create copies what it keeps)."""
         s, z, k = self.patches
         gid = self.point_global_id
-        return dict(points=np.array(self.points, dtype=np.float64), face_offsets=np.array(self.face_offsets),
-                    face_verts=np.array(self.face_verts), owner=np.array(self.owner), neighbour=np.array(self.neighbour),
+        arr = (lambda a: np.array(a)) if copy else (lambda a: a)
+        return dict(points=arr(self.points), face_offsets=arr(self.face_offsets),
+                    face_verts=arr(self.face_verts), owner=arr(self.owner), neighbour=arr(self.neighbour),
                     n_cells=self.n_cells, patch_start=s, patch_size=z, patch_kind=k,
-                    point_global_id=None if gid is None else np.array(gid))
+                    point_global_id=None if gid is None else arr(gid))
 
 
 @dataclass
@@ -454,7 +456,7 @@ class Smoother:
         come last).  On a processor mesh the layer set-up completes in comm_init (it is collective)."""
         L = lib()
         self.params_in = params if params is not None else default_params(**kw)
-        self._arrays = mesh.desc_arrays()  # keep alive during create
+        self._arrays = mesh.desc_arrays(copy=False)  # views of the mesh's storage: alive during create
         a = self._arrays
         d = _MeshDesc()
         d.n_points, d.n_cells = len(a["points"]), a["n_cells"]

@@ -17,6 +17,9 @@
 namespace sm
 {
 
+template <class T, class V> static void assignVec(Vec<T> &dst, const V &src) { dst.assign(src.begin(), src.end()); }
+
+
 static void fail(const std::string &s) { throw std::runtime_error(s); }
 
 // ----------------------------------------------------------------- check ----
@@ -29,22 +32,39 @@ void PolyMesh::check() const
         fail("more neighbours than faces");
     if (faceOffsets[0] != 0 || (int64_t)faceVerts.size() != faceOffsets[F])
         fail("faceVerts size mismatch");
+    // the first violation in label order, found by all threads (meshes of 10^8 faces are checked on every create)
+    const int64_t none = INT64_MAX;
+    int64_t badFace = none, badVert = none, badNbr = none;
+#pragma omp parallel for schedule(static) reduction(min : badFace)
     for (int64_t f = 0; f < F; ++f)
+        if (faceOffsets[f + 1] - faceOffsets[f] < 3 || owner[f] < 0 || owner[f] >= nCells)
+            badFace = std::min(badFace, f);
+    if (badFace != none)
     {
-        if (faceOffsets[f + 1] - faceOffsets[f] < 3)
-            fail("face " + std::to_string(f) + " has fewer than 3 vertices");
-        if (owner[f] < 0 || owner[f] >= nCells)
-            fail("owner out of range at face " + std::to_string(f));
+        if (faceOffsets[badFace + 1] - faceOffsets[badFace] < 3)
+            fail("face " + std::to_string(badFace) + " has fewer than 3 vertices");
+        fail("owner out of range at face " + std::to_string(badFace));
     }
-    for (int32_t v : faceVerts)
-        if (v < 0 || v >= P)
-            fail("face vertex label out of range");
+    const int64_t FV = (int64_t)faceVerts.size();
+#pragma omp parallel for schedule(static) reduction(min : badVert)
+    for (int64_t k = 0; k < FV; ++k)
+        if (faceVerts[k] < 0 || faceVerts[k] >= P)
+            badVert = std::min(badVert, k);
+    if (badVert != none)
+        fail("face vertex label out of range");
+    auto nbrRange = [&](int64_t f) { return neighbour[f] <= owner[f] || neighbour[f] >= nCells; };
+    auto nbrOrder = [&](int64_t f) {
+        return f > 0 && (owner[f] < owner[f - 1] || (owner[f] == owner[f - 1] && neighbour[f] < neighbour[f - 1]));
+    };
+#pragma omp parallel for schedule(static) reduction(min : badNbr)
     for (int64_t f = 0; f < Fi; ++f)
+        if (nbrRange(f) || nbrOrder(f))
+            badNbr = std::min(badNbr, f);
+    if (badNbr != none)
     {
-        if (neighbour[f] <= owner[f] || neighbour[f] >= nCells)
-            fail("neighbour <= owner or out of range at face " + std::to_string(f));
-        if (f > 0 && (owner[f] < owner[f - 1] || (owner[f] == owner[f - 1] && neighbour[f] < neighbour[f - 1])))
-            fail("internal faces not in upper-triangular order at face " + std::to_string(f));
+        if (nbrRange(badNbr))
+            fail("neighbour <= owner or out of range at face " + std::to_string(badNbr));
+        fail("internal faces not in upper-triangular order at face " + std::to_string(badNbr));
     }
     int64_t next = Fi;
     for (const Patch &p : patches)
@@ -252,7 +272,7 @@ PolyMesh buildFromCells(const std::vector<double> &points, const std::vector<int
         return a.patch != b.patch ? a.patch < b.patch : (a.own != b.own ? a.own < b.own : a.cf < b.cf);
     });
     PolyMesh m;
-    m.points = points;
+    m.points.assign(points.begin(), points.end());
     m.nCells = C;
     m.faceOffsets.push_back(0);
     auto emit = [&](const Out &o) {
@@ -1013,15 +1033,18 @@ std::vector<double> readPoints(const std::string &file)
 PolyMesh readPolyMesh(const std::string &dir)
 {
     PolyMesh m;
-    m.points = readPoints(dir + "/points");
+    {
+        const std::vector<double> pts = readPoints(dir + "/points");
+        m.points.assign(pts.begin(), pts.end());
+    }
     {
         Lexer lx;
         lx.s = slurp(dir + "/faces");
         const Header h = readHeader(lx);
         if (h.cls.find("faceCompactList") != std::string::npos)
         {
-            m.faceOffsets = readLabelList(lx, h.binary);
-            m.faceVerts = readLabelList(lx, h.binary);
+            assignVec(m.faceOffsets, readLabelList(lx, h.binary));
+            assignVec(m.faceVerts, readLabelList(lx, h.binary));
         }
         else
         {
@@ -1046,13 +1069,13 @@ PolyMesh readPolyMesh(const std::string &dir)
         Lexer lx;
         lx.s = slurp(dir + "/owner");
         const Header h = readHeader(lx);
-        m.owner = readLabelList(lx, h.binary);
+        assignVec(m.owner, readLabelList(lx, h.binary));
     }
     {
         Lexer lx;
         lx.s = slurp(dir + "/neighbour");
         const Header h = readHeader(lx);
-        m.neighbour = readLabelList(lx, h.binary);
+        assignVec(m.neighbour, readLabelList(lx, h.binary));
     }
     {
         Lexer lx;
@@ -1173,7 +1196,7 @@ void writePolyMesh(const PolyMesh &m, const std::string &dir, bool binary, int p
     const std::string note = "nPoints:" + std::to_string(m.nPoints()) + "  nCells:" + std::to_string(m.nCells) +
                              "  nFaces:" + std::to_string(m.nFaces()) +
                              "  nInternalFaces:" + std::to_string(m.nInternalFaces());
-    auto writeLabels = [&](std::ofstream &o, const std::vector<int32_t> &v) {
+    auto writeLabels = [&](std::ofstream &o, const auto &v) {
         o << v.size() << "\n(";
         if (binary)
             o.write((const char *)v.data(), sizeof(int32_t) * v.size());
@@ -1317,9 +1340,9 @@ PolyMesh genHexBlockPart(int nx, int ny, int nz, int px, int py, int pz, int ran
         p.size = (int32_t)newOwner.size() - p.start;
         newPatches.push_back(p);
     }
-    m.faceOffsets.swap(newOff);
-    m.faceVerts.swap(newVerts);
-    m.owner.swap(newOwner);
+    assignVec(m.faceOffsets, newOff);
+    assignVec(m.faceVerts, newVerts);
+    assignVec(m.owner, newOwner);
     m.patches.swap(newPatches);
     return m;
 }

@@ -6,6 +6,7 @@
 // src/smoothMesh.C:1814-1818, and writing points, :2416-2431); grammar as in
 // SURVEY.md appendix A.1.
 #pragma once
+#include "bigvec.hpp"
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -31,11 +32,11 @@ struct Patch
 
 struct PolyMesh
 {
-    std::vector<double> points;      // 3*nPoints, AoS
-    std::vector<int32_t> faceOffsets; // nFaces+1
-    std::vector<int32_t> faceVerts;
-    std::vector<int32_t> owner;     // nFaces
-    std::vector<int32_t> neighbour; // nInternalFaces
+    Vec<double> points;       // 3*nPoints, AoS
+    Vec<int32_t> faceOffsets; // nFaces+1
+    Vec<int32_t> faceVerts;
+    Vec<int32_t> owner;     // nFaces
+    Vec<int32_t> neighbour; // nInternalFaces
     std::vector<Patch> patches;
     int64_t nCells = 0;
     // decomposed meshes only: local -> global addressing (decomposePar's *ProcAddressing)

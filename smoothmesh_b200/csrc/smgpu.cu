@@ -16,7 +16,9 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
+#include <omp.h>
 
 using namespace smk;
 
@@ -146,12 +148,171 @@ struct smgpu_handle
         allocs.push_back(p);
         return (T *)p;
     }
-    template <class T> T *upload(const std::vector<T> &v)
+    template <class T, class A> T *upload(const std::vector<T, A> &v)
     {
         T *p = dalloc<T>(v.size());
-        if (!v.empty())
+        if (v.empty())
+            return p;
+        if (deferUploads)
+            uploadJobs.push_back({p, v.data(), v.size() * sizeof(T)});
+        else if (pipeReady && !uploadThread.joinable() && v.size() * sizeof(T) >= ((size_t)1 << 20))
+        { // during the set-up, after the helper thread has finished: same pipe, from this thread
+            CK(pipe.copy(p, v.data(), v.size() * sizeof(T), 8));
+            CK(pipe.finish()); // the source may be a temporary
+        }
+        else
             CK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
         return p;
+    }
+    // One-time uploads go through a small page-locked double buffer: the host copy of chunk k + 1 into it (a few
+    // threads) runs while the DMA of chunk k is in flight, several times the rate of cudaMemcpy from pageable memory.
+    struct PinnedPipe
+    {
+        static constexpr size_t CHUNK = (size_t)32 << 20;
+        char *buf[2] = {nullptr, nullptr};
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        bool busy[2] = {false, false};
+        cudaStream_t s = nullptr;
+        int next = 0;
+        cudaError_t init()
+        {
+            const bool timing = getenv("SMGPU_TIMING") && atoi(getenv("SMGPU_TIMING")) != 0;
+            auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+            const double t0 = wall();
+            struct Report
+            {
+                bool on;
+                double t0;
+                decltype(wall) &w;
+                ~Report()
+                {
+                    if (on)
+                        fprintf(stderr, "[smgpu create]   page-locked double buffer  %.3f s\n", w() - t0);
+                }
+            } report{timing, t0, wall};
+            cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+            for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+            {
+                e = cudaMallocHost((void **)&buf[i], CHUNK);
+                if (e == cudaSuccess)
+                    e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+            }
+            return e;
+        }
+        cudaError_t copy(void *dst, const void *src, size_t bytes, int threads)
+        {
+            for (size_t off = 0; off < bytes; off += CHUNK)
+            {
+                const size_t n = std::min(CHUNK, bytes - off);
+                const int b = next;
+                next ^= 1;
+                if (busy[b])
+                {
+                    const cudaError_t e = cudaEventSynchronize(ev[b]);
+                    if (e != cudaSuccess)
+                        return e;
+                }
+                const char *from = static_cast<const char *>(src) + off;
+                char *to = buf[b];
+#pragma omp parallel for schedule(static) num_threads(threads)
+                for (int64_t i = 0; i < (int64_t)n; i += 1 << 20)
+                    memcpy(to + i, from + i, std::min<size_t>((size_t)1 << 20, n - i));
+                cudaError_t e = cudaMemcpyAsync(static_cast<char *>(dst) + off, to, n, cudaMemcpyHostToDevice, s);
+                if (e == cudaSuccess)
+                    e = cudaEventRecord(ev[b], s);
+                if (e != cudaSuccess)
+                    return e;
+                busy[b] = true;
+            }
+            return cudaSuccess;
+        }
+        // device -> host: chunk k + 2 is in flight while chunk k is copied out of the buffer
+        cudaError_t copyOut(void *dstHost, const void *srcDev, size_t bytes, int threads)
+        {
+            cudaError_t e = finish();
+            const size_t nChunks = (bytes + CHUNK - 1) / CHUNK;
+            auto issue = [&](size_t k) {
+                const size_t off = k * CHUNK, n = std::min(CHUNK, bytes - off);
+                cudaError_t x = cudaMemcpyAsync(buf[k & 1], static_cast<const char *>(srcDev) + off, n, cudaMemcpyDeviceToHost, s);
+                return x == cudaSuccess ? cudaEventRecord(ev[k & 1], s) : x;
+            };
+            for (size_t k = 0; k < std::min<size_t>(2, nChunks) && e == cudaSuccess; ++k)
+                e = issue(k);
+            for (size_t k = 0; k < nChunks && e == cudaSuccess; ++k)
+            {
+                e = cudaEventSynchronize(ev[k & 1]);
+                if (e != cudaSuccess)
+                    break;
+                const size_t off = k * CHUNK, n = std::min(CHUNK, bytes - off);
+                const char *from = buf[k & 1];
+                char *to = static_cast<char *>(dstHost) + off;
+#pragma omp parallel for schedule(static) num_threads(threads)
+                for (int64_t i = 0; i < (int64_t)n; i += 1 << 20)
+                    memcpy(to + i, from + i, std::min<size_t>((size_t)1 << 20, n - i));
+                if (k + 2 < nChunks)
+                    e = issue(k + 2);
+            }
+            busy[0] = busy[1] = false;
+            next = 0;
+            return e;
+        }
+        cudaError_t finish() { return s ? cudaStreamSynchronize(s) : cudaSuccess; }
+        void destroy()
+        {
+            for (int i = 0; i < 2; ++i)
+            {
+                if (buf[i])
+                    cudaFreeHost(buf[i]);
+                if (ev[i])
+                    cudaEventDestroy(ev[i]);
+                buf[i] = nullptr, ev[i] = nullptr, busy[i] = false;
+            }
+            if (s)
+                cudaStreamDestroy(s);
+            s = nullptr;
+        }
+    } pipe;
+    bool pipeReady = false;
+    // Uploads of the connectivity tables run on a helper thread while the host builds the geometry tiles
+    // (smgpu_create): upload() only allocates and queues while deferUploads is set, startUploads() hands the queue to
+    // the thread, joinUploads() waits for it and reports its error.  The sources must stay untouched until then.
+    struct UploadJob
+    {
+        void *dst;
+        const void *src;
+        size_t bytes;
+    };
+    std::vector<UploadJob> uploadJobs;
+    bool deferUploads = false;
+    std::thread uploadThread;
+    cudaError_t uploadErr = cudaSuccess;
+    void ensurePipe()
+    {
+        if (pipeReady)
+            return;
+        CK(pipe.init());
+        pipeReady = true;
+    }
+    void startUploads(int device)
+    {
+        deferUploads = false;
+        ensurePipe();
+        std::vector<UploadJob> jobs;
+        jobs.swap(uploadJobs);
+        uploadThread = std::thread([this, device, jobs]() {
+            cudaError_t e = cudaSetDevice(device);
+            for (size_t i = 0; i < jobs.size() && e == cudaSuccess; ++i)
+                e = pipe.copy(jobs[i].dst, jobs[i].src, jobs[i].bytes, 4);
+            if (e == cudaSuccess)
+                e = pipe.finish();
+            uploadErr = e;
+        });
+    }
+    void joinUploads()
+    {
+        if (uploadThread.joinable())
+            uploadThread.join();
+        CK(uploadErr);
     }
     void applyParams()
     {
@@ -239,7 +400,7 @@ struct smgpu_handle
         {
             sm::buildEdgeRecords(topo);
             d.edgeRec = (const int4 *)upload(topo.edgeRec);
-            std::vector<int32_t>().swap(topo.edgeRec);
+            sm::Vec<int32_t>().swap(topo.edgeRec);
         }
     }
     bool noFilters = false; // SMGPU_NO_FILTERS=1: always take the literal path (testing aid)
@@ -279,8 +440,8 @@ struct smgpu_handle
         }
         return dXyz;
     }
-    // Upload of the caller's pointField: in chunks, the host copy of chunk k + 1 into page-locked memory runs while
-    // the DMA of chunk k is in flight; the 32-byte records are assembled on the device.
+    // Upload of the caller's pointField through the page-locked double buffer (the host copy of chunk k + 1 runs while
+    // the DMA of chunk k is in flight); the 32-byte records are assembled on the device.
     void setPoints(const double *pts)
     {
         const size_t P = (size_t)topo.P;
@@ -297,19 +458,12 @@ struct smgpu_handle
             CK(cudaStreamSynchronize(stream));
             return;
         }
-        double *hs = reinterpret_cast<double *>(stage(std::max<size_t>(topo.P, topo.C)));
         double *dx = devXyz(P);
         if (!dIsInternal)
             dIsInternal = upload(topo.isInternal);
-        const size_t total = 3 * P, chunk = std::max<size_t>((total + 7) / 8, 1 << 20);
-        for (size_t b = 0; b < total; b += chunk)
-        {
-            const size_t n = std::min(chunk, total - b);
-#pragma omp parallel for schedule(static)
-            for (int64_t i = 0; i < (int64_t)n; i += 4096)
-                memcpy(hs + b + i, pts + b + i, std::min<size_t>(4096, n - i) * sizeof(double));
-            CK(cudaMemcpyAsync(dx + b, hs + b, n * sizeof(double), cudaMemcpyHostToDevice, stream));
-        }
+        ensurePipe();
+        CK(pipe.copy(dx, pts, 3 * P * sizeof(double), omp_get_max_threads()));
+        CK(pipe.finish());
         k_unpack_points<<<grid(d.P, 256), 256, 0, stream>>>(d, dx, dIsInternal);
         CK(cudaStreamSynchronize(stream));
     }
@@ -1228,6 +1382,21 @@ extern "C"
         if (params->device < 0 || params->device >= nDev)
             return setErr(SMGPU_ERR_ARG, "device ordinal out of range");
         smgpu_handle *h = new smgpu_handle;
+        // the CUDA context of the device is created on a helper thread while the host builds the connectivity
+        const int device = params->device;
+        std::thread contextThread([device]() {
+            if (cudaSetDevice(device) == cudaSuccess)
+                cudaFree(nullptr);
+        });
+        struct Joiner
+        {
+            std::thread &t;
+            ~Joiner()
+            {
+                if (t.joinable())
+                    t.join();
+            }
+        } contextJoiner{contextThread};
         // SMGPU_TIMING=1: wall time of the set-up phases on stderr (topology.cpp prints its own)
         const bool timing = getenv("SMGPU_TIMING") && atoi(getenv("SMGPU_TIMING")) != 0;
         auto wall = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -1242,18 +1411,11 @@ extern "C"
         try
         {
             sm::PolyMesh m;
-            auto parCopy = [](auto &dst, const auto *src, size_t n) {
-                dst.resize(n);
-                auto *out = dst.data();
-#pragma omp parallel for schedule(static)
-                for (int64_t i = 0; i < (int64_t)n; i += 65536)
-                    std::copy(src + i, src + std::min<size_t>(n, i + 65536), out + i);
-            };
-            parCopy(m.points, md->points, 3 * (size_t)md->n_points);
-            parCopy(m.faceOffsets, md->face_offsets, (size_t)md->n_faces + 1);
-            parCopy(m.faceVerts, md->face_verts, (size_t)md->face_offsets[md->n_faces]);
-            parCopy(m.owner, md->owner, (size_t)md->n_faces);
-            parCopy(m.neighbour, md->neighbour, (size_t)md->n_internal_faces);
+            sm::parCopy(m.points, md->points, 3 * (size_t)md->n_points);
+            sm::parCopy(m.faceOffsets, md->face_offsets, (size_t)md->n_faces + 1);
+            sm::parCopy(m.faceVerts, md->face_verts, (size_t)md->face_offsets[md->n_faces]);
+            sm::parCopy(m.owner, md->owner, (size_t)md->n_faces);
+            sm::parCopy(m.neighbour, md->neighbour, (size_t)md->n_internal_faces);
             m.nCells = md->n_cells;
             for (int i = 0; i < md->n_patches; ++i)
             {
@@ -1299,6 +1461,7 @@ extern "C"
             for (uint8_t f : t.isInternal)
                 h->nInternal += f;
 
+            contextThread.join();
             CK(cudaSetDevice(params->device));
             CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
             CK(cudaEventCreate(&h->ev0));
@@ -1315,6 +1478,7 @@ extern "C"
             d.newPts = h->dalloc<P4>(t.P);
             d.cellCtr = h->dalloc<P4>(t.C);
             d.frozen = h->dalloc<uint8_t>(t.P + 8);
+            h->deferUploads = true; // the tables go up while the tiles are built
             d.pcOff = h->upload(t.pcOff);
             d.pc = h->upload(t.pc);
             d.ppOff = h->upload(t.ppOff);
@@ -1332,7 +1496,10 @@ extern "C"
             d.faceVerts = h->upload(t.faceVerts);
             d.cfOff = h->upload(t.cfOff);
             d.cf = h->upload(t.cf);
-            tick("allocation + upload of tables");
+            d.pointRec = (const int4 *)h->upload(t.pointRec);
+            tick("  cudaMalloc of the tables");
+            h->startUploads(params->device);
+            tick("allocation of tables");
             d.uniformFaceSize = t.maxFaceSize;
             for (int64_t f = 0; f < t.F && d.uniformFaceSize; ++f)
                 if (t.faceOff[f + 1] - t.faceOff[f] != d.uniformFaceSize)
@@ -1341,7 +1508,6 @@ extern "C"
             for (int64_t c = 0; c < t.C && d.uniformCellFaces; ++c)
                 if (t.cfOff[c + 1] - t.cfOff[c] != d.uniformCellFaces)
                     d.uniformCellFaces = 0;
-            d.pointRec = (const int4 *)h->upload(t.pointRec);
             d.curMin = h->dalloc<unsigned long long>(t.P);
             d.curMax = h->dalloc<unsigned long long>(t.P);
             d.activeFlag = h->dalloc<uint8_t>(t.P + 8);
@@ -1400,6 +1566,9 @@ extern "C"
             if (!noTiles && (forceTiles || 2 * hexLike >= t.C))
             {
                 const sm::GeomTiles G = sm::buildGeomTiles(m, t, SMK_TILE_CELLS, SMK_TILE_FACES, SMK_TILE_POINTS);
+                tick("  tiles built");
+                h->joinUploads(); // the tables went up meanwhile; the tile arrays follow through the same pipe
+                tick("  wait for the table uploads");
                 if (G.nTiles > 0)
                 {
                     h->useTiles = true;
@@ -1502,7 +1671,9 @@ extern "C"
                     h->usePointTiles = true;
                 }
             }
-            tick("records, work space, tiles");
+            tick("work space, tiles");
+            h->joinUploads();
+            tick("upload of tables (remainder)");
             d.errFlag = h->dalloc<int>(1);
             CK(cudaMemset(d.errFlag, 0, sizeof(int)));
             if (h->anyLayerPatch)
@@ -1708,7 +1879,14 @@ extern "C"
     {
         if (!h)
             return SMGPU_OK;
+        if (h->uploadThread.joinable()) // a create that failed half-way
+            h->uploadThread.join();
         cudaSetDevice(h->prm.device); // the frees below must hit this handle's context in multi-GPU processes
+        if (h->pipeReady)
+        {
+            h->pipe.finish();
+            h->pipe.destroy();
+        }
         if (h->comm && !h->comm->group) // members of an in-process group are detached by smgpu_group_destroy
             sm::commDestroy(h->comm);
         for (void *p : h->allocs)
@@ -1858,33 +2036,13 @@ extern "C"
                 }
                 return SMGPU_OK;
             }
-            // 24 bytes per point over PCIe, in chunks: the host copy of chunk k out of page-locked memory runs while
-            // the DMA of chunk k + 1 is in flight
-            double *hs = reinterpret_cast<double *>(h->stage(std::max<size_t>(h->topo.P, h->topo.C)));
+            // 24 bytes per point over PCIe through the page-locked double buffer: the host copy of chunk k out of it
+            // runs while the DMA of chunk k + 1 is in flight
             double *dx = h->devXyz(std::max<size_t>(h->topo.P, h->topo.C));
             k_pack_points<<<smgpu_handle::grid(n, 256), 256, 0, h->stream>>>(src, dx, (int)n);
-            const size_t total = 3 * (size_t)n, chunk = std::max<size_t>((total + 7) / 8, 1 << 20);
-            std::vector<cudaEvent_t> ev;
-            for (size_t b = 0; b < total; b += chunk)
-            {
-                const size_t m = std::min(chunk, total - b);
-                CK(cudaMemcpyAsync(hs + b, dx + b, m * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                cudaEvent_t e;
-                CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-                CK(cudaEventRecord(e, h->stream));
-                ev.push_back(e);
-            }
-            size_t k = 0;
-            for (size_t b = 0; b < total; b += chunk, ++k)
-            {
-                const size_t m = std::min(chunk, total - b);
-                CK(cudaEventSynchronize(ev[k]));
-#pragma omp parallel for schedule(static)
-                for (int64_t i = 0; i < (int64_t)m; i += 4096)
-                    memcpy(out + b + i, hs + b + i, std::min<size_t>(4096, m - i) * sizeof(double));
-            }
-            for (cudaEvent_t e : ev)
-                cudaEventDestroy(e);
+            CK(cudaStreamSynchronize(h->stream));
+            h->ensurePipe();
+            CK(h->pipe.copyOut(out, dx, 3 * (size_t)n * sizeof(double), omp_get_max_threads()));
         }
         catch (const std::exception &e)
         {
@@ -2179,7 +2337,7 @@ extern "C"
             return setErr(SMGPU_ERR_ARG, "null argument");
         const sm::Topology &t = h->topo;
         const std::string n = name;
-        const std::vector<int32_t> *off = nullptr, *val = nullptr;
+        const sm::Vec<int32_t> *off = nullptr, *val = nullptr;
         if (n == "pointCells")
             off = &t.pcOff, val = &t.pc;
         else if (n == "pointPoints")

@@ -122,7 +122,7 @@ extern "C"
             std::vector<double> pts = sm::readPoints(file);
             if (pts.size() != m->m.points.size())
                 throw std::runtime_error("point count differs from the mesh topology");
-            m->m.points.swap(pts);
+            m->m.points.assign(pts.begin(), pts.end());
         }
         catch (const std::exception &e)
         {
@@ -419,7 +419,7 @@ extern "C"
             te.finish();
             std::vector<int32_t> ps(patch_smoothing, patch_smoothing + m->m.patches.size());
             const double lel = layer_edge_length < 0 ? 0.5 * t.minEdgeLength : layer_edge_length;
-            const sm::BoundarySetup B = sm::buildBoundarySetup(m->m, t, m->m.points, ie, te, sm::TriSurface(), ps, lel);
+            const sm::BoundarySetup B = sm::buildBoundarySetup(m->m, t, std::vector<double>(m->m.points.begin(), m->m.points.end()), ie, te, sm::TriSurface(), ps, lel);
             auto put = [](auto *dst, const auto &src) {
                 if (dst)
                     std::copy(src.begin(), src.end(), dst);

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <omp.h>
 #include <stdexcept>
 #include <string>
 
@@ -16,6 +17,66 @@ namespace sm
 {
 
 static void fail(const std::string &s) { throw std::runtime_error(s); }
+
+namespace
+{
+// Rows of variable length are computed once: every thread takes a contiguous range of rows (rangeOf), appends them
+// to a private buffer (plain stores: vector::insert per row costs several times the row) and leaves the row lengths
+// in the offset array; after the prefix sums (parScan) the buffers are copied to their places.
+struct RowBuf
+{
+    Vec<int32_t> v;
+    int64_t n = 0;
+    explicit RowBuf(int64_t cap = 0) { v.resize(cap); }
+    int32_t *need(int64_t k)
+    {
+        if (n + k > (int64_t)v.size())
+            v.resize(std::max<int64_t>(2 * (int64_t)v.size(), n + k + 4096));
+        return v.data() + n;
+    }
+};
+inline void rangeOf(int64_t n, int tid, int nThreads, int64_t &lo, int64_t &hi)
+{
+    lo = n * tid / nThreads;
+    hi = n * (tid + 1) / nThreads;
+}
+// off[0] = 0 and off[i + 1] = length of row i on entry, the running sums on exit; returns the longest row.  Every
+// thread scans the range of rows it filled (the same rangeOf partition), so the lengths are read where they were written.
+int32_t parScan(Vec<int32_t> &off, int64_t n, int nThreads)
+{
+    std::vector<int64_t> sum(nThreads + 1, 0);
+    std::vector<int32_t> longest(nThreads, 0);
+    off[0] = 0;
+#pragma omp parallel num_threads(nThreads)
+    {
+        const int tid = omp_get_thread_num();
+        int64_t lo, hi;
+        rangeOf(n, tid, nThreads, lo, hi);
+        int64_t s = 0;
+        int32_t mx = 0;
+        for (int64_t i = lo; i < hi; ++i)
+        {
+            s += off[i + 1];
+            mx = std::max(mx, off[i + 1]);
+        }
+        sum[tid + 1] = s;
+        longest[tid] = mx;
+#pragma omp barrier
+#pragma omp single
+        for (int k = 0; k < nThreads; ++k)
+            sum[k + 1] += sum[k];
+        int64_t run = sum[tid];
+        for (int64_t i = lo; i < hi; ++i)
+        {
+            run += off[i + 1];
+            off[i + 1] = (int32_t)run;
+        }
+    }
+    if (sum[nThreads] >= (int64_t)INT32_MAX)
+        fail("mesh too large for 32-bit offsets");
+    return *std::max_element(longest.begin(), longest.end());
+}
+} // namespace
 
 Topology buildTopology(const PolyMesh &m)
 {
@@ -38,14 +99,14 @@ Topology buildTopology(const PolyMesh &m)
     t.C = C;
     t.F = F;
     t.Fi = Fi;
-    t.faceOff = m.faceOffsets;
-    t.faceVerts = m.faceVerts;
+    parCopy(t.faceOff, m.faceOffsets.data(), m.faceOffsets.size());
+    parCopy(t.faceVerts, m.faceVerts.data(), m.faceVerts.size());
     const int64_t FV = (int64_t)m.faceVerts.size();
     if (2 * FV >= (int64_t)INT32_MAX)
         fail("mesh too large for 32-bit offsets");
 
     // src/smoothMesh.C:52-80: internal = not on any non-processor patch; empty patches abort
-    t.isInternal.assign(P, 1);
+    parFill(t.isInternal, (size_t)P, (uint8_t)1);
     for (const Patch &p : m.patches)
     {
         if (p.kind() == PATCH_PROCESSOR)
@@ -59,32 +120,33 @@ Topology buildTopology(const PolyMesh &m)
 
     // points on processor patches: the candidates for inter-rank sharing
     {
-        std::vector<uint8_t> onProc(P, 0);
         for (const Patch &p : m.patches)
             if (p.kind() == PATCH_PROCESSOR)
                 for (int32_t f = p.start; f < p.start + p.size; ++f)
                     for (int32_t k = m.faceOffsets[f]; k < m.faceOffsets[f + 1]; ++k)
-                        onProc[m.faceVerts[k]] = 1;
-        for (int64_t p = 0; p < P; ++p)
-            if (onProc[p])
-                t.procPoints.push_back((int32_t)p);
+                        t.procPoints.push_back(m.faceVerts[k]);
+        std::sort(t.procPoints.begin(), t.procPoints.end());
+        t.procPoints.erase(std::unique(t.procPoints.begin(), t.procPoints.end()), t.procPoints.end());
     }
 
     // ---- point -> face corners (pointFaces ascending) ----
     // counted and filled in parallel (atomic cursors), then every row is put in ascending face order
-    t.cornerOff.assign(P + 1, 0);
+    parFill(t.cornerOff, (size_t)P + 1, (int32_t)0);
 #pragma omp parallel for schedule(static)
     for (int64_t k = 0; k < FV; ++k)
     {
 #pragma omp atomic update
         ++t.cornerOff[m.faceVerts[k] + 1];
     }
-    for (int64_t p = 0; p < P; ++p)
-        t.cornerOff[p + 1] += t.cornerOff[p];
+    const int nThreads = omp_get_max_threads();
+    tick("  corner count");
+    const int32_t maxRow = parScan(t.cornerOff, P, nThreads);
+    tick("  corner scan");
     t.corner.resize(2 * FV);
-    std::vector<int32_t> cornerFace(FV);
+    Vec<int32_t> cornerFace(FV);
     {
-        std::vector<int32_t> cur(t.cornerOff.begin(), t.cornerOff.end() - 1);
+        Vec<int32_t> cur;
+        parCopy(cur, t.cornerOff.data(), (size_t)P);
         int32_t maxFaceSize = 0;
 #pragma omp parallel for schedule(static) reduction(max : maxFaceSize)
         for (int64_t f = 0; f < F; ++f)
@@ -103,6 +165,7 @@ Topology buildTopology(const PolyMesh &m)
             }
         }
         t.maxFaceSize = maxFaceSize;
+        tick("  corner fill");
 #pragma omp parallel for schedule(static)
         for (int64_t p = 0; p < P; ++p)
         { // insertion sort of the (short) row by (face, previous vertex, next vertex)
@@ -127,73 +190,71 @@ Topology buildTopology(const PolyMesh &m)
     }
 
     tick("point corners");
+    // sorted insertion without duplicates into a short row
+    auto insertUnique = [](int32_t *row, int32_t &n, int32_t v) {
+        int32_t i = n;
+        while (i > 0 && row[i - 1] > v)
+            --i;
+        if (i > 0 && row[i - 1] == v)
+            return;
+        for (int32_t j = n; j > i; --j)
+            row[j] = row[j - 1];
+        row[i] = v;
+        ++n;
+    };
     // ---- point -> cells (ascending) and point -> points (ascending) ----
-    std::vector<int32_t> pcCount(P), ppCount(P);
-#pragma omp parallel
+    t.pcOff.resize(P + 1);
+    t.ppOff.resize(P + 1);
+    Vec<int32_t> upStart(P + 1); // first edge label of point p = #edges (a,b) with a<p
     {
-        std::vector<int32_t> tmp;
-#pragma omp for schedule(static)
-        for (int64_t p = 0; p < P; ++p)
+        std::vector<RowBuf> pcPart(nThreads), ppPart(nThreads);
+#pragma omp parallel num_threads(nThreads)
         {
-            tmp.clear();
-            for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
+            const int tid = omp_get_thread_num();
+            int64_t lo, hi;
+            rangeOf(P, tid, nThreads, lo, hi);
+            const int64_t rows = t.cornerOff[hi] - t.cornerOff[lo];
+            RowBuf pcl(rows + rows / 8 + 64), ppl(rows + 64);
+            for (int64_t p = lo; p < hi; ++p)
             {
-                const int32_t f = cornerFace[s];
-                tmp.push_back(m.owner[f]);
-                if (f < Fi)
-                    tmp.push_back(m.neighbour[f]);
+                const int32_t nCorners = t.cornerOff[p + 1] - t.cornerOff[p];
+                int32_t *rowC = pcl.need(2 * (int64_t)nCorners), *rowP = ppl.need(2 * (int64_t)nCorners);
+                int32_t nc = 0, np = 0;
+                for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
+                {
+                    const int32_t f = cornerFace[s];
+                    insertUnique(rowC, nc, m.owner[f]);
+                    if (f < Fi)
+                        insertUnique(rowC, nc, m.neighbour[f]);
+                    insertUnique(rowP, np, t.corner[2 * (int64_t)s]);
+                    insertUnique(rowP, np, t.corner[2 * (int64_t)s + 1]);
+                }
+                pcl.n += nc;
+                ppl.n += np;
+                int32_t up = 0;
+                for (int32_t i = 0; i < np; ++i)
+                    up += (rowP[i] > (int32_t)p);
+                t.pcOff[p + 1] = nc;
+                t.ppOff[p + 1] = np;
+                upStart[p + 1] = up;
             }
-            std::sort(tmp.begin(), tmp.end());
-            pcCount[p] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
-            tmp.clear();
-            for (int32_t s = 2 * t.cornerOff[p]; s < 2 * t.cornerOff[p + 1]; ++s)
-                tmp.push_back(t.corner[s]);
-            std::sort(tmp.begin(), tmp.end());
-            ppCount[p] = (int32_t)(std::unique(tmp.begin(), tmp.end()) - tmp.begin());
+            pcPart[tid] = std::move(pcl);
+            ppPart[tid] = std::move(ppl);
+        }
+        parScan(t.pcOff, P, nThreads);
+        t.maxPointDegree = parScan(t.ppOff, P, nThreads);
+        parScan(upStart, P, nThreads);
+        t.pc.resize(t.pcOff[P]);
+        t.pp.resize(t.ppOff[P]);
+#pragma omp parallel num_threads(nThreads)
+        {
+            const int tid = omp_get_thread_num();
+            int64_t lo, hi;
+            rangeOf(P, tid, nThreads, lo, hi);
+            std::copy(pcPart[tid].v.begin(), pcPart[tid].v.begin() + pcPart[tid].n, t.pc.begin() + t.pcOff[lo]);
+            std::copy(ppPart[tid].v.begin(), ppPart[tid].v.begin() + ppPart[tid].n, t.pp.begin() + t.ppOff[lo]);
         }
     }
-    t.pcOff.assign(P + 1, 0);
-    t.ppOff.assign(P + 1, 0);
-    for (int64_t p = 0; p < P; ++p)
-    {
-        t.pcOff[p + 1] = t.pcOff[p] + pcCount[p];
-        t.ppOff[p + 1] = t.ppOff[p] + ppCount[p];
-        t.maxPointDegree = std::max(t.maxPointDegree, ppCount[p]);
-    }
-    t.pc.resize(t.pcOff[P]);
-    t.pp.resize(t.ppOff[P]);
-    std::vector<int32_t> upStart(P + 1, 0); // first edge label of point p = #edges (a,b) with a<p
-#pragma omp parallel
-    {
-        std::vector<int32_t> tmp;
-#pragma omp for schedule(static)
-        for (int64_t p = 0; p < P; ++p)
-        {
-            tmp.clear();
-            for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
-            {
-                const int32_t f = cornerFace[s];
-                tmp.push_back(m.owner[f]);
-                if (f < Fi)
-                    tmp.push_back(m.neighbour[f]);
-            }
-            std::sort(tmp.begin(), tmp.end());
-            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-            std::copy(tmp.begin(), tmp.end(), t.pc.begin() + t.pcOff[p]);
-            tmp.clear();
-            for (int32_t s = 2 * t.cornerOff[p]; s < 2 * t.cornerOff[p + 1]; ++s)
-                tmp.push_back(t.corner[s]);
-            std::sort(tmp.begin(), tmp.end());
-            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-            std::copy(tmp.begin(), tmp.end(), t.pp.begin() + t.ppOff[p]);
-            int32_t up = 0;
-            for (int32_t q : tmp)
-                up += (q > (int32_t)p);
-            upStart[p + 1] = up;
-        }
-    }
-    for (int64_t p = 0; p < P; ++p)
-        upStart[p + 1] += upStart[p];
     const int64_t E = upStart[P];
     t.E = E;
     if ((int64_t)t.pp.size() != 2 * E)
@@ -234,91 +295,92 @@ Topology buildTopology(const PolyMesh &m)
 
     tick("edges");
     // ---- edge -> faces (ascending), edge -> cells with face pairs ----
-    std::vector<int32_t> efCount(E), ecCount(E);
-    auto edgeFacesOf = [&](int64_t e, int32_t *out) {
-        const int32_t p = t.edge[2 * e], q = t.edge[2 * e + 1];
-        int32_t n = 0;
-        for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
-            if (t.corner[2 * (int64_t)s] == q || t.corner[2 * (int64_t)s + 1] == q)
-                out[n++] = cornerFace[s];
-        return n;
-    };
-    int32_t maxRow = 0;
-    for (int64_t p = 0; p < P; ++p)
-        maxRow = std::max(maxRow, t.cornerOff[p + 1] - t.cornerOff[p]);
-#pragma omp parallel
-    {
-        std::vector<int32_t> fs(maxRow), cs;
-#pragma omp for schedule(static)
-        for (int64_t e = 0; e < E; ++e)
-        {
-            const int32_t n = edgeFacesOf(e, fs.data());
-            efCount[e] = n;
-            cs.clear();
-            for (int32_t i = 0; i < n; ++i)
-            {
-                const int32_t f = fs[i];
-                if (std::find(cs.begin(), cs.end(), m.owner[f]) == cs.end())
-                    cs.push_back(m.owner[f]);
-                if (f < Fi && std::find(cs.begin(), cs.end(), m.neighbour[f]) == cs.end())
-                    cs.push_back(m.neighbour[f]);
-            }
-            ecCount[e] = (int32_t)cs.size();
-        }
-    }
-    t.efOff.assign(E + 1, 0);
-    t.ecOff.assign(E + 1, 0);
-    for (int64_t e = 0; e < E; ++e)
-    {
-        t.efOff[e + 1] = t.efOff[e] + efCount[e];
-        t.ecOff[e + 1] = t.ecOff[e] + ecCount[e];
-        t.maxEdgeFaces = std::max(t.maxEdgeFaces, efCount[e]);
-    }
-    t.ef.resize(t.efOff[E]);
-    t.ecCell.resize(t.ecOff[E]);
-    t.ecPair.resize(t.ecOff[E]);
+    t.efOff.resize(E + 1);
+    t.ecOff.resize(E + 1);
     int bad = 0;
-#pragma omp parallel
     {
-        std::vector<int32_t> fs(maxRow), cs;
-#pragma omp for schedule(static)
-        for (int64_t e = 0; e < E; ++e)
+        std::vector<RowBuf> efPart(nThreads), ccPart(nThreads), cpPart(nThreads);
+#pragma omp parallel num_threads(nThreads)
         {
-            const int32_t n = edgeFacesOf(e, fs.data());
-            std::copy(fs.begin(), fs.begin() + n, t.ef.begin() + t.efOff[e]);
-            cs.clear();
-            for (int32_t i = 0; i < n; ++i)
+            const int tid = omp_get_thread_num();
+            int64_t lo, hi;
+            rangeOf(E, tid, nThreads, lo, hi);
+            // sum over the edges of their faces = sum over the faces of their vertices
+            const int64_t guess = FV / nThreads + FV / (8 * nThreads) + 64;
+            RowBuf efl(guess), ccl(guess), cpl(guess);
+            std::vector<int32_t> cnt(2 * (size_t)maxRow + 2);
+            for (int64_t e = lo; e < hi; ++e)
             {
-                const int32_t f = fs[i];
-                if (std::find(cs.begin(), cs.end(), m.owner[f]) == cs.end())
-                    cs.push_back(m.owner[f]);
-                if (f < Fi && std::find(cs.begin(), cs.end(), m.neighbour[f]) == cs.end())
-                    cs.push_back(m.neighbour[f]);
-            }
-            for (size_t ci = 0; ci < cs.size(); ++ci)
-            {
-                const int32_t c = cs[ci];
-                int32_t f0 = -1, f1 = -1, cnt = 0;
+                const int32_t p = t.edge[2 * e], q = t.edge[2 * e + 1];
+                const int32_t nCorners = t.cornerOff[p + 1] - t.cornerOff[p];
+                int32_t *fs = efl.need(nCorners), *cs = ccl.need(2 * (int64_t)nCorners), *pr = cpl.need(2 * (int64_t)nCorners);
+                int32_t n = 0;
+                for (int32_t s = t.cornerOff[p]; s < t.cornerOff[p + 1]; ++s)
+                    if (t.corner[2 * (int64_t)s] == q || t.corner[2 * (int64_t)s + 1] == q)
+                        fs[n++] = cornerFace[s];
+                // the cells of those faces, in order of first appearance (owner before neighbour), each with the
+                // positions of its first two faces in the row
+                int32_t ncs = 0;
+                bool over = false;
                 for (int32_t i = 0; i < n; ++i)
-                {
-                    const int32_t f = fs[i];
-                    if (m.owner[f] == c || (f < Fi && m.neighbour[f] == c))
+                    for (int side = 0; side < 2; ++side)
                     {
-                        if (cnt == 0)
-                            f0 = i;
-                        else if (cnt == 1)
-                            f1 = i;
-                        ++cnt;
+                        if (side == 1 && fs[i] >= Fi)
+                            break;
+                        const int32_t c = side ? m.neighbour[fs[i]] : m.owner[fs[i]];
+                        int32_t k = 0;
+                        while (k < ncs && cs[k] != c)
+                            ++k;
+                        if (k == ncs)
+                        {
+                            cs[ncs] = c;
+                            pr[ncs] = i & 0xffff;
+                            cnt[ncs++] = 1;
+                        }
+                        else
+                        {
+                            if (cnt[k] == 1)
+                                pr[k] |= i << 16;
+                            else
+                                over = true;
+                            ++cnt[k];
+                        }
                     }
-                }
-                if (cnt != 2 || n >= 65536)
+                bool under = n >= 65536;
+                for (int32_t k = 0; k < ncs; ++k)
+                    if (cnt[k] == 1)
+                    {
+                        under = true;
+                        pr[k] |= (int32_t)0xffff0000u; // no second face: position -1, as a search would leave it
+                    }
+                if (over || under)
                 {
 #pragma omp atomic write
-                    bad = (cnt > 2) ? 1 : 2;
+                    bad = over ? 1 : 2;
                 }
-                t.ecCell[t.ecOff[e] + ci] = c;
-                t.ecPair[t.ecOff[e] + ci] = (f0 & 0xffff) | (f1 << 16);
+                efl.n += n;
+                ccl.n += ncs;
+                cpl.n += ncs;
+                t.efOff[e + 1] = n;
+                t.ecOff[e + 1] = ncs;
             }
+            efPart[tid] = std::move(efl);
+            ccPart[tid] = std::move(ccl);
+            cpPart[tid] = std::move(cpl);
+        }
+        t.maxEdgeFaces = parScan(t.efOff, E, nThreads);
+        parScan(t.ecOff, E, nThreads);
+        t.ef.resize(t.efOff[E]);
+        t.ecCell.resize(t.ecOff[E]);
+        t.ecPair.resize(t.ecOff[E]);
+#pragma omp parallel num_threads(nThreads)
+        {
+            const int tid = omp_get_thread_num();
+            int64_t lo, hi;
+            rangeOf(E, tid, nThreads, lo, hi);
+            std::copy(efPart[tid].v.begin(), efPart[tid].v.begin() + efPart[tid].n, t.ef.begin() + t.efOff[lo]);
+            std::copy(ccPart[tid].v.begin(), ccPart[tid].v.begin() + ccPart[tid].n, t.ecCell.begin() + t.ecOff[lo]);
+            std::copy(cpPart[tid].v.begin(), cpPart[tid].v.begin() + cpPart[tid].n, t.ecPair.begin() + t.ecOff[lo]);
         }
     }
     if (bad == 1)
@@ -329,7 +391,7 @@ Topology buildTopology(const PolyMesh &m)
     tick("edgeFaces / edgeCells");
     // ---- cell -> faces in OpenFOAM's accumulation order (owned faces ascending, then
     //      neighbour-side faces ascending; bit 31 marks the neighbour side) ----
-    t.cfOff.assign(C + 1, 0);
+    parFill(t.cfOff, (size_t)C + 1, (int32_t)0);
 #pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < F; ++f)
     {
@@ -341,13 +403,13 @@ Topology buildTopology(const PolyMesh &m)
             ++t.cfOff[m.neighbour[f] + 1];
         }
     }
-    for (int64_t c = 0; c < C; ++c)
-        t.cfOff[c + 1] += t.cfOff[c];
+    parScan(t.cfOff, C, nThreads);
     t.cf.resize(t.cfOff[C]);
     {
         // filled in parallel, then every (short) row sorted: owned faces ascending first (bit 31 clear), then the
         // neighbour-side faces ascending -- as unsigned numbers that is exactly ascending order
-        std::vector<int32_t> cur(t.cfOff.begin(), t.cfOff.end() - 1);
+        Vec<int32_t> cur;
+        parCopy(cur, t.cfOff.data(), (size_t)C);
 #pragma omp parallel for schedule(static)
         for (int64_t f = 0; f < F; ++f)
         {
@@ -398,11 +460,13 @@ Topology buildTopology(const PolyMesh &m)
 
     tick("mesh stats");
     // ---- fixed-size records for the common low-valence case (see topology.hpp) ----
-    t.pointRec.assign(16 * P, 0);
+    t.pointRec.resize(16 * P);
 #pragma omp parallel for schedule(static)
     for (int64_t p = 0; p < P; ++p)
     {
         int32_t *r = &t.pointRec[16 * p];
+        for (int k = 0; k < 16; ++k)
+            r[k] = 0;
         const int32_t npc = t.pcOff[p + 1] - t.pcOff[p], npp = t.ppOff[p + 1] - t.ppOff[p];
         const bool generic = npc > 8 || npp > 6;
         if (!generic)
@@ -808,6 +872,179 @@ inline uint64_t spreadBits21(uint64_t v)
 }
 } // namespace
 
+namespace
+{
+// label -> position in a tile's (short) list: open addressing, sized per tile, reset per tile
+struct LocalMap
+{
+    std::vector<int32_t> key, val;
+    uint32_t mask = 0;
+    int shift = 0;
+    void reset(size_t expected)
+    {
+        size_t cap = 1024;
+        int bits = 10;
+        while (cap < 2 * expected)
+            cap *= 2, ++bits;
+        if (key.size() < cap)
+            key.resize(cap), val.resize(cap);
+        std::fill(key.begin(), key.begin() + cap, -1);
+        mask = (uint32_t)cap - 1;
+        shift = 32 - bits;
+    }
+    uint32_t home(int32_t k) const { return ((uint32_t)k * 0x9E3779B1u) >> shift; }
+    bool insert(int32_t k)
+    { // true if k was not there
+        uint32_t h = home(k);
+        while (key[h] != -1)
+        {
+            if (key[h] == k)
+                return false;
+            h = (h + 1) & mask;
+        }
+        key[h] = k;
+        return true;
+    }
+    int32_t &at(int32_t k)
+    {
+        uint32_t h = home(k);
+        while (key[h] != k)
+            h = (h + 1) & mask;
+        return val[h];
+    }
+};
+
+// Everything one tile contributes, built by the thread that accepted the tile; the global arrays are filled
+// from these after the prefix sums over the tiles.
+struct TileOut
+{
+    int32_t a = 0, b = 0;                 // cells keys[a .. b)
+    std::vector<int32_t> cells;           // ascending
+    std::vector<int32_t> faces, points;   // ascending
+    std::vector<int32_t> faceRefOff;      // per listed face + 1, tile-local
+    std::vector<uint16_t> faceRef;        // vertices as positions in points
+    std::vector<int32_t> slotOff;         // per cell + 1, tile-local
+    std::vector<uint16_t> slotRef;        // faces as positions in faces, bit 15 = neighbour side
+    std::vector<int32_t> nPairs;          // per cell; -1 = not closed
+    std::vector<uint16_t> pairs;          // 4 per pair, cell-major
+    std::vector<uint16_t> rec;            // canonical hexahedron records, 16 per cell (valid where isHex)
+    bool allHex = false, allQuads = false; // every cell a topological hexahedron / every listed face a quadrilateral
+};
+
+// The (edge, cell) pairs of one cell: half edges of its faces sorted by end points; a closed cell has every edge
+// exactly twice.  keys: scratch; out: 4 x uint16 per pair (p0 < p1, then the two faces, ascending).  -1 if not closed.
+inline int32_t cellPairsOf(const TileOut &T, int32_t i, std::vector<uint64_t> &keys, uint16_t *out)
+{
+    keys.clear();
+    for (int32_t q = T.slotOff[i]; q < T.slotOff[i + 1]; ++q)
+    {
+        const uint16_t li = T.slotRef[q] & 0x7fff;
+        const int32_t rb = T.faceRefOff[li], nv = T.faceRefOff[li + 1] - rb;
+        for (int32_t v = 0; v < nv; ++v)
+        {
+            const uint16_t a = T.faceRef[rb + v], b = T.faceRef[rb + (v + 1 == nv ? 0 : v + 1)];
+            keys.push_back((uint64_t)std::min(a, b) << 32 | (uint64_t)std::max(a, b) << 16 | li);
+        }
+    }
+    std::sort(keys.begin(), keys.end());
+    if (keys.size() % 2)
+        return -1;
+    int32_t n = 0;
+    for (size_t i2 = 0; i2 < keys.size(); i2 += 2)
+    {
+        const uint64_t e0 = keys[i2] >> 16, e1 = keys[i2 + 1] >> 16;
+        if (e0 != e1 || (e0 >> 16) == (e0 & 0xffff) || (i2 + 2 < keys.size() && (keys[i2 + 2] >> 16) == e0))
+            return -1;
+        out[4 * n] = (uint16_t)(e0 >> 16), out[4 * n + 1] = (uint16_t)(e0 & 0xffff);
+        out[4 * n + 2] = (uint16_t)(keys[i2] & 0xffff), out[4 * n + 3] = (uint16_t)(keys[i2 + 1] & 0xffff);
+        ++n;
+    }
+    return n;
+}
+
+// Canonical hexahedron record of cell i (see topology.hpp).  True only if the record's fixed pattern of twelve
+// (edge, cell) pairs is exactly the cell's pair list: the six faces are distinct quadrilaterals, every pattern edge
+// is a side of both of its faces, and the twelve edges are distinct -- then each face meets four distinct pattern
+// edges, which are its four sides, so all 24 half edges are matched in pairs (the cell is closed) and nothing else is.
+inline bool hexRecordOf(const TileOut &T, int32_t i, uint16_t rec[16])
+{
+    if (T.slotOff[i + 1] - T.slotOff[i] != 6)
+        return false;
+    uint16_t fl[6], fv[6][4];
+    for (int q = 0; q < 6; ++q)
+    {
+        fl[q] = T.slotRef[T.slotOff[i] + q] & 0x7fff;
+        const int32_t rb = T.faceRefOff[fl[q]];
+        if (T.faceRefOff[fl[q] + 1] - rb != 4)
+            return false;
+        for (int v = 0; v < 4; ++v)
+            fv[q][v] = T.faceRef[rb + v];
+    }
+    auto has = [&](int q, uint16_t p) { return fv[q][0] == p || fv[q][1] == p || fv[q][2] == p || fv[q][3] == p; };
+    for (int q = 0; q < 16; ++q)
+        rec[q] = 0;
+    int B = -1;
+    for (int q = 1; q < 6; ++q)
+        if (!has(q, fv[0][0]) && !has(q, fv[0][1]) && !has(q, fv[0][2]) && !has(q, fv[0][3]))
+            B = (B < 0) ? q : 99;
+    if (B < 1 || B > 5)
+        return false;
+    int side[4];
+    for (int e = 0; e < 4; ++e)
+    {
+        const uint16_t a = fv[0][e], b = fv[0][(e + 1) & 3];
+        int S = -1;
+        for (int q = 1; q < 6; ++q)
+            if (q != B && has(q, a) && has(q, b))
+                S = (S < 0) ? q : 99;
+        if (S < 1 || S > 5)
+            return false;
+        int at = 0;
+        while (fv[S][at] != a)
+            ++at;
+        // w_e: the neighbour of a in S's loop that is not b
+        const uint16_t n1 = fv[S][(at + 1) & 3], n2 = fv[S][(at + 3) & 3];
+        const uint16_t w = (n1 == b) ? n2 : n1;
+        if (!((n1 == b || n2 == b) && has(B, w)))
+            return false;
+        rec[e] = a;
+        rec[4 + e] = w;
+        rec[10 + e] = fl[S];
+        side[e] = S;
+    }
+    rec[8] = fl[0];
+    rec[9] = fl[B];
+    // six distinct faces (as slots of the cell and as faces of the tile)
+    const int slots[6] = {0, B, side[0], side[1], side[2], side[3]};
+    for (int x = 0; x < 6; ++x)
+        for (int y = x + 1; y < 6; ++y)
+            if (slots[x] == slots[y] || fl[slots[x]] == fl[slots[y]])
+                return false;
+    // every pattern edge is a side of both of its faces; the twelve edges are distinct
+    auto isSide = [&](int q, uint16_t p0, uint16_t p1) {
+        for (int v = 0; v < 4; ++v)
+            if (fv[q][v] == p0)
+                return fv[q][(v + 1) & 3] == p1 || fv[q][(v + 3) & 3] == p1;
+        return false;
+    };
+    uint32_t edges[12];
+    int ne = 0;
+    auto add = [&](uint16_t p0, uint16_t p1, int q0, int q1) {
+        edges[ne++] = (uint32_t)std::min(p0, p1) << 16 | std::max(p0, p1);
+        return p0 != p1 && isSide(q0, p0, p1) && isSide(q1, p0, p1);
+    };
+    for (int e = 0; e < 4; ++e)
+        if (!add(rec[e], rec[(e + 1) & 3], 0, side[e]) || !add(rec[4 + e], rec[4 + ((e + 1) & 3)], B, side[e]) ||
+            !add(rec[e], rec[4 + e], side[(e + 3) & 3], side[e]))
+            return false;
+    for (int x = 0; x < 12; ++x)
+        for (int y = x + 1; y < 12; ++y)
+            if (edges[x] == edges[y])
+                return false;
+    return true;
+}
+} // namespace
+
 GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int maxFaces, int maxPoints, bool keepPairs)
 {
     GeomTiles G;
@@ -827,12 +1064,17 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
     // cell order: Morton curve over the cells' vertex averages, quantised by the mean cell size so that
     // on block-structured meshes 2^k consecutive cells form a brick
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int64_t p = 0; p < P; ++p)
-        for (int d = 0; d < 3; ++d)
+    {
+        double l0 = 1e300, l1 = 1e300, l2 = 1e300, h0 = -1e300, h1 = -1e300, h2 = -1e300;
+#pragma omp parallel for schedule(static) reduction(min : l0, l1, l2) reduction(max : h0, h1, h2)
+        for (int64_t p = 0; p < P; ++p)
         {
-            lo[d] = std::min(lo[d], m.points[3 * p + d]);
-            hi[d] = std::max(hi[d], m.points[3 * p + d]);
+            l0 = std::min(l0, m.points[3 * p]), h0 = std::max(h0, m.points[3 * p]);
+            l1 = std::min(l1, m.points[3 * p + 1]), h1 = std::max(h1, m.points[3 * p + 1]);
+            l2 = std::min(l2, m.points[3 * p + 2]), h2 = std::max(h2, m.points[3 * p + 2]);
         }
+        lo[0] = l0, lo[1] = l1, lo[2] = l2, hi[0] = h0, hi[1] = h1, hi[2] = h2;
+    }
     double vol = 1.0;
     int dims = 0;
     for (int d = 0; d < 3; ++d)
@@ -843,7 +1085,7 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         }
     const double h = dims ? std::pow(vol / double(C), 1.0 / dims) : 1.0;
     const double invH = h > 0 ? 1.0 / h : 0.0;
-    std::vector<std::pair<uint64_t, int32_t>> keys(C);
+    Vec<std::pair<uint64_t, int32_t>> keys(C);
 #pragma omp parallel for schedule(static)
     for (int64_t c = 0; c < C; ++c)
     {
@@ -877,28 +1119,6 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
     // Tiles = runs of consecutive cells of that order.  Start from runs of maxCells cells and halve a run
     // until its face and point lists fit the budgets (deterministic, and independent per initial run, so
     // the construction is parallel; halving only happens on polyhedral or very irregular meshes).
-    struct Tile
-    {
-        int32_t a, b; // cells keys[a .. b)
-        std::vector<int32_t> faces, points;
-    };
-    auto collect = [&](Tile &T) {
-        T.faces.clear();
-        T.points.clear();
-        for (int32_t i = T.a; i < T.b; ++i)
-        {
-            const int32_t c = keys[i].second;
-            for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
-                T.faces.push_back(t.cf[k] & 0x7fffffff);
-        }
-        std::sort(T.faces.begin(), T.faces.end());
-        T.faces.erase(std::unique(T.faces.begin(), T.faces.end()), T.faces.end());
-        for (int32_t f : T.faces)
-            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
-                T.points.push_back(m.faceVerts[q]);
-        std::sort(T.points.begin(), T.points.end());
-        T.points.erase(std::unique(T.points.begin(), T.points.end()), T.points.end());
-    };
     // runs are closed at maxCells cells and at every aligned block of 2^8 keys (an 8 x 8 x 4 brick of a
     // block-structured mesh), so that a brick cut short by the mesh boundary does not shift all later tiles
     // off the brick grid (271^3: 33 full bricks and one of 7 cells per row)
@@ -913,341 +1133,289 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
         i = j;
     }
     const int64_t nRuns = (int64_t)runs.size();
-    std::vector<std::vector<Tile>> perRun(nRuns);
-    bool cellTooLarge = false;
-#pragma omp parallel for schedule(dynamic, 16)
-    for (int64_t r = 0; r < nRuns; ++r)
+    std::vector<std::vector<TileOut>> perRun(nRuns);
+    bool cellTooLarge = false, closed = true;
+    double tCollect = 0, tFinish = 0, tPairs = 0;
+#pragma omp parallel reduction(+ : tCollect, tFinish, tPairs)
     {
-        std::vector<Tile> todo, done;
-        todo.push_back({runs[r].first, runs[r].second, {}, {}});
-        while (!todo.empty())
-        {
-            Tile T = std::move(todo.back());
-            todo.pop_back();
-            collect(T);
-            if ((int)T.faces.size() <= maxFaces && (int)T.points.size() <= maxPoints)
-                done.push_back(std::move(T));
-            else if (T.b - T.a == 1)
+        LocalMap faceMap, pointMap;
+        std::vector<uint64_t> scratch;
+        // lists of a run of cells; false if they do not fit the budgets
+        auto collect = [&](TileOut &T) -> bool {
+            size_t nSlots = 0;
+            for (int32_t i = T.a; i < T.b; ++i)
+                nSlots += t.cfOff[keys[i].second + 1] - t.cfOff[keys[i].second];
+            faceMap.reset(nSlots);
+            T.faces.clear();
+            for (int32_t i = T.a; i < T.b; ++i)
             {
-#pragma omp atomic write
-                cellTooLarge = true;
+                const int32_t c = keys[i].second;
+                for (int32_t k = t.cfOff[c]; k < t.cfOff[c + 1]; ++k)
+                    if (faceMap.insert(t.cf[k] & 0x7fffffff))
+                        T.faces.push_back(t.cf[k] & 0x7fffffff);
             }
-            else
-            { // second half first on the stack, so the first half is finished first (keeps the order)
-                const int32_t mid = T.a + (T.b - T.a) / 2;
-                todo.push_back({mid, T.b, {}, {}});
-                todo.push_back({T.a, mid, {}, {}});
+            if ((int)T.faces.size() > maxFaces)
+                return false;
+            std::sort(T.faces.begin(), T.faces.end());
+            size_t nVerts = 0;
+            for (int32_t f : T.faces)
+                nVerts += m.faceOffsets[f + 1] - m.faceOffsets[f];
+            pointMap.reset(nVerts);
+            T.points.clear();
+            for (int32_t f : T.faces)
+                for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+                    if (pointMap.insert(m.faceVerts[q]))
+                        T.points.push_back(m.faceVerts[q]);
+            if ((int)T.points.size() > maxPoints)
+                return false;
+            std::sort(T.points.begin(), T.points.end());
+            return true;
+        };
+        // references, pairs and records of an accepted tile (the maps still hold its labels)
+        auto finish = [&](TileOut &T) {
+            for (size_t i = 0; i < T.faces.size(); ++i)
+                faceMap.at(T.faces[i]) = (int32_t)i;
+            for (size_t i = 0; i < T.points.size(); ++i)
+                pointMap.at(T.points[i]) = (int32_t)i;
+            T.cells.clear();
+            for (int32_t i = T.a; i < T.b; ++i)
+                T.cells.push_back(keys[i].second);
+            std::sort(T.cells.begin(), T.cells.end());
+            T.faceRefOff.assign(1, 0);
+            T.allQuads = true;
+            for (int32_t f : T.faces)
+            {
+                for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
+                    T.faceRef.push_back((uint16_t)pointMap.at(m.faceVerts[q]));
+                T.faceRefOff.push_back((int32_t)T.faceRef.size());
+                T.allQuads = T.allQuads && m.faceOffsets[f + 1] - m.faceOffsets[f] == 4;
+            }
+            T.slotOff.assign(1, 0);
+            for (int32_t c : T.cells)
+            {
+                for (int32_t q = t.cfOff[c]; q < t.cfOff[c + 1]; ++q)
+                {
+                    const int32_t w = t.cf[q];
+                    T.slotRef.push_back((uint16_t)(faceMap.at(w & 0x7fffffff) | (w < 0 ? 0x8000 : 0)));
+                }
+                T.slotOff.push_back((int32_t)T.slotRef.size());
+            }
+            // (edge, cell) pairs of the fused face-angle filter: the edges of a cell are the vertex pairs that two
+            // of its faces share; both faces and both end points are already tile-local references
+            const double p0 = timing ? clock() : 0;
+            const int32_t nc = (int32_t)T.cells.size();
+            T.nPairs.assign(nc, 0);
+            T.rec.assign(16 * (size_t)nc, 0);
+            T.allHex = true;
+            // cells that are hexahedra by the record's own check have twelve pairs and are closed; the pair list is
+            // only materialised where it is read (tiles off the fast path, or on request)
+            std::vector<uint8_t> isHex(nc, 0);
+            for (int32_t i = 0; i < nc; ++i)
+            {
+                isHex[i] = hexRecordOf(T, i, &T.rec[16 * (size_t)i]) ? 1 : 0;
+                T.allHex = T.allHex && isHex[i];
+            }
+            const bool listAll = keepPairs || !(T.allHex && T.allQuads);
+            for (int32_t i = 0; i < nc; ++i)
+            {
+                if (isHex[i] && !listAll)
+                {
+                    T.nPairs[i] = 12;
+                    continue;
+                }
+                int32_t nHalf = 0;
+                for (int32_t q = T.slotOff[i]; q < T.slotOff[i + 1]; ++q)
+                {
+                    const int32_t li = T.slotRef[q] & 0x7fff;
+                    nHalf += T.faceRefOff[li + 1] - T.faceRefOff[li];
+                }
+                const size_t at = T.pairs.size();
+                T.pairs.resize(at + 2 * (size_t)nHalf + 4);
+                const int32_t n = cellPairsOf(T, i, scratch, T.pairs.data() + at);
+                T.nPairs[i] = n;
+                T.pairs.resize(at + 4 * (size_t)std::max(n, 0));
+            }
+            tPairs += (timing ? clock() : 0) - p0;
+        };
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t r = 0; r < nRuns; ++r)
+        {
+            std::vector<std::pair<int32_t, int32_t>> todo;
+            todo.push_back(runs[r]);
+            while (!todo.empty())
+            {
+                TileOut T;
+                T.a = todo.back().first, T.b = todo.back().second;
+                todo.pop_back();
+                const double c0 = timing ? clock() : 0;
+                const bool fits = collect(T);
+                const double c1 = timing ? clock() : 0;
+                tCollect += c1 - c0;
+                if (fits)
+                {
+                    finish(T);
+                    tFinish += (timing ? clock() : 0) - c1;
+                    for (int32_t n : T.nPairs)
+                        if (n < 0)
+                        {
+#pragma omp atomic write
+                            closed = false;
+                        }
+                    perRun[r].push_back(std::move(T));
+                }
+                else if (T.b - T.a == 1)
+                {
+#pragma omp atomic write
+                    cellTooLarge = true;
+                }
+                else
+                { // second half first on the stack, so the first half is finished first (keeps the order)
+                    const int32_t mid = T.a + (T.b - T.a) / 2;
+                    todo.push_back({mid, T.b});
+                    todo.push_back({T.a, mid});
+                }
             }
         }
-        perRun[r] = std::move(done);
     }
-    tick("tiles: face / point lists");
+    if (timing)
+        fprintf(stderr, "[smgpu set-up]   thread-seconds: lists %.3f, references + pairs %.3f (pairs %.3f)\n", tCollect, tFinish, tPairs);
+    tick("tiles: lists, references, pairs");
     if (cellTooLarge)
         return GeomTiles(); // a cell that does not fit a tile: the caller keeps the two-kernel path
-    std::vector<Tile *> tiles;
+    std::vector<TileOut *> tiles;
     for (auto &v : perRun)
-        for (Tile &T : v)
+        for (TileOut &T : v)
             tiles.push_back(&T);
     G.nTiles = (int32_t)tiles.size();
-    // offsets
-    G.tileCellOff.assign(G.nTiles + 1, 0);
-    G.tileFaceOff.assign(G.nTiles + 1, 0);
-    G.tilePointOff.assign(G.nTiles + 1, 0);
-    std::vector<int64_t> slotRefOff(G.nTiles + 1, 0), faceRefBase(G.nTiles + 1, 0);
-    for (int32_t k = 0; k < G.nTiles; ++k)
+    const int32_t nT = G.nTiles;
+    // offsets; uniform tiles (all faces quadrilaterals, all cells topological hexahedra) are counted separately
+    G.tileCellOff.assign(nT + 1, 0);
+    G.tileFaceOff.assign(nT + 1, 0);
+    G.tilePointOff.assign(nT + 1, 0);
+    G.tileUFaceOff.assign(nT, -1);
+    G.tileUCellOff.assign(nT, -1);
+    std::vector<int64_t> slotRefOff(nT + 1, 0), faceRefBase(nT + 1, 0), pairBase(nT + 1, 0);
+    int64_t uf = 0, uc = 0;
+    for (int32_t k = 0; k < nT; ++k)
     {
-        const Tile &T = *tiles[k];
-        int64_t nSlotRefs = 0, nFaceRefs = 0;
-        for (int32_t i = T.a; i < T.b; ++i)
-            nSlotRefs += t.cfOff[keys[i].second + 1] - t.cfOff[keys[i].second];
-        for (int32_t f : T.faces)
-            nFaceRefs += m.faceOffsets[f + 1] - m.faceOffsets[f];
-        G.tileCellOff[k + 1] = G.tileCellOff[k] + (T.b - T.a);
+        const TileOut &T = *tiles[k];
+        G.tileCellOff[k + 1] = G.tileCellOff[k] + (int32_t)T.cells.size();
         G.tileFaceOff[k + 1] = G.tileFaceOff[k] + (int32_t)T.faces.size();
         G.tilePointOff[k + 1] = G.tilePointOff[k] + (int32_t)T.points.size();
-        slotRefOff[k + 1] = slotRefOff[k] + nSlotRefs;
-        faceRefBase[k + 1] = faceRefBase[k] + nFaceRefs;
+        slotRefOff[k + 1] = slotRefOff[k] + (int64_t)T.slotRef.size();
+        faceRefBase[k + 1] = faceRefBase[k] + (int64_t)T.faceRef.size();
+        G.maxTileCells = std::max(G.maxTileCells, (int32_t)T.cells.size());
+        G.maxTileFaces = std::max(G.maxTileFaces, (int32_t)T.faces.size());
+        G.maxTilePoints = std::max(G.maxTilePoints, (int32_t)T.points.size());
+        const bool uniform = closed && T.allHex && T.allQuads;
+        if (uniform)
+        {
+            G.tileUFaceOff[k] = (int32_t)uf;
+            G.tileUCellOff[k] = (int32_t)uc;
+            uf += (int64_t)T.faces.size();
+            uc += (int64_t)T.cells.size();
+        }
+        int64_t np = 0;
+        if (closed && (keepPairs || !uniform))
+            for (int32_t n : T.nPairs)
+                np += n;
+        pairBase[k + 1] = pairBase[k] + np;
+        G.maxTileEdgePairs = std::max<int64_t>(G.maxTileEdgePairs, np);
     }
-    if (faceRefBase[G.nTiles] >= (int64_t)INT32_MAX)
+    if (faceRefBase[nT] >= (int64_t)INT32_MAX)
         return GeomTiles();
     // the first tile (in tile order) that lists a face stores the face's global outputs
-    std::vector<int32_t> firstTile(F, -1);
-    for (int32_t k = 0; k < G.nTiles; ++k)
+    Vec<int32_t> firstTile;
+    parFill(firstTile, (size_t)F, INT32_MAX);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int32_t k = 0; k < nT; ++k)
         for (int32_t f : tiles[k]->faces)
-            if (firstTile[f] < 0)
-                firstTile[f] = k;
+        {
+            int32_t seen;
+#pragma omp atomic read
+            seen = firstTile[f];
+            while (k < seen)
+            { // atomic minimum
+                if (__atomic_compare_exchange_n(&firstTile[f], &seen, k, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+                    break;
+            }
+        }
     tick("tiles: offsets, first tile");
     G.tileCells.resize(C);
-    G.tileFaces.resize(G.tileFaceOff[G.nTiles]);
-    G.tilePoints.resize(G.tilePointOff[G.nTiles]);
+    G.tileFaces.resize(G.tileFaceOff[nT]);
+    G.tilePoints.resize(G.tilePointOff[nT]);
     G.slotOff.resize(C + 1);
-    G.slotRef.resize(slotRefOff[G.nTiles]);
-    G.faceRefOff.resize(G.tileFaceOff[G.nTiles] + 1);
-    G.faceRef.resize(faceRefBase[G.nTiles]);
-    G.slotOff[C] = (int32_t)slotRefOff[G.nTiles];
-    G.faceRefOff[G.tileFaceOff[G.nTiles]] = (int32_t)faceRefBase[G.nTiles];
-#pragma omp parallel for schedule(dynamic, 16)
-    for (int32_t k = 0; k < G.nTiles; ++k)
+    G.slotRef.resize(slotRefOff[nT]);
+    G.faceRefOff.resize(G.tileFaceOff[nT] + 1);
+    G.faceRef.resize(faceRefBase[nT]);
+    G.slotOff[C] = (int32_t)slotRefOff[nT];
+    G.faceRefOff[G.tileFaceOff[nT]] = (int32_t)faceRefBase[nT];
+    G.nUniformCells = uc;
+    G.uFaceRef.resize(4 * (size_t)uf);
+    G.uSlotRef.resize(6 * (size_t)uc);
+    G.hexRec.resize(16 * (size_t)uc);
+    const int64_t totalPairs = closed ? pairBase[nT] : 0;
+    const bool storePairs = totalPairs > 0 && totalPairs < (int64_t)INT32_MAX / 2;
+    if (storePairs)
     {
-        const Tile &T = *tiles[k];
-        std::vector<int32_t> cells;
-        for (int32_t i = T.a; i < T.b; ++i)
-            cells.push_back(keys[i].second);
-        std::sort(cells.begin(), cells.end());
-        auto localPoint = [&](int32_t p) { return (int32_t)(std::lower_bound(T.points.begin(), T.points.end(), p) - T.points.begin()); };
-        auto localFace = [&](int32_t f) { return (int32_t)(std::lower_bound(T.faces.begin(), T.faces.end(), f) - T.faces.begin()); };
+        G.cellEdgeOff.resize(C + 1);
+        G.cellEdgeOff[C] = (int32_t)totalPairs;
+        G.cellEdgeRef.resize(4 * (size_t)totalPairs);
+    }
+    else
+        G.maxTileEdgePairs = 0;
+    const int32_t firstCellEdges = closed ? tiles[0]->nPairs[0] : 0;
+    bool sameEdges = closed;
+#pragma omp parallel for schedule(dynamic, 16) reduction(&& : sameEdges)
+    for (int32_t k = 0; k < nT; ++k)
+    {
+        const TileOut &T = *tiles[k];
+        const int32_t fb = G.tileFaceOff[k], cb = G.tileCellOff[k], nf = (int32_t)T.faces.size(), nc = (int32_t)T.cells.size();
         std::copy(T.points.begin(), T.points.end(), G.tilePoints.begin() + G.tilePointOff[k]);
-        int64_t fr = faceRefBase[k];
-        for (size_t i = 0; i < T.faces.size(); ++i)
+        for (int32_t i = 0; i < nf; ++i)
         {
             const int32_t f = T.faces[i];
-            G.tileFaces[G.tileFaceOff[k] + i] = (firstTile[f] == k) ? (int32_t)(f | 0x80000000u) : f;
-            G.faceRefOff[G.tileFaceOff[k] + i] = (int32_t)fr;
-            for (int32_t q = m.faceOffsets[f]; q < m.faceOffsets[f + 1]; ++q)
-                G.faceRef[fr++] = (uint16_t)localPoint(m.faceVerts[q]);
+            G.tileFaces[fb + i] = (firstTile[f] == k) ? (int32_t)(f | 0x80000000u) : f;
+            G.faceRefOff[fb + i] = (int32_t)(faceRefBase[k] + T.faceRefOff[i]);
         }
-        int64_t sr = slotRefOff[k];
-        for (size_t i = 0; i < cells.size(); ++i)
+        std::copy(T.faceRef.begin(), T.faceRef.end(), G.faceRef.begin() + faceRefBase[k]);
+        for (int32_t i = 0; i < nc; ++i)
         {
-            const int32_t c = cells[i], slot = G.tileCellOff[k] + (int32_t)i;
-            G.tileCells[slot] = c;
-            G.slotOff[slot] = (int32_t)sr;
-            for (int32_t q = t.cfOff[c]; q < t.cfOff[c + 1]; ++q)
+            G.tileCells[cb + i] = T.cells[i];
+            G.slotOff[cb + i] = (int32_t)(slotRefOff[k] + T.slotOff[i]);
+        }
+        std::copy(T.slotRef.begin(), T.slotRef.end(), G.slotRef.begin() + slotRefOff[k]);
+        if (G.tileUCellOff[k] >= 0)
+        { // fixed-stride copies of the references, and the records: first halves of all cells, then second halves
+            const size_t ufb = (size_t)G.tileUFaceOff[k], ucb = (size_t)G.tileUCellOff[k];
+            std::copy(T.faceRef.begin(), T.faceRef.end(), G.uFaceRef.begin() + 4 * ufb);
+            std::copy(T.slotRef.begin(), T.slotRef.end(), G.uSlotRef.begin() + 6 * ucb);
+            for (int32_t i = 0; i < nc; ++i)
             {
-                const int32_t w = t.cf[q];
-                G.slotRef[sr++] = (uint16_t)(localFace(w & 0x7fffffff) | (w < 0 ? 0x8000 : 0));
+                const uint16_t *rec = &T.rec[16 * (size_t)i];
+                uint16_t *o1 = &G.hexRec[16 * ucb + 8 * (size_t)i], *o2 = &G.hexRec[16 * ucb + 8 * (size_t)nc + 8 * (size_t)i];
+                for (int q = 0; q < 8; ++q)
+                    o1[q] = rec[q], o2[q] = rec[8 + q];
             }
+        }
+        for (int32_t n : T.nPairs)
+            sameEdges = sameEdges && n == firstCellEdges;
+        if (storePairs)
+        {
+            const bool mine = pairBase[k + 1] > pairBase[k];
+            int64_t at = pairBase[k];
+            for (int32_t i = 0; i < nc; ++i)
+            {
+                G.cellEdgeOff[cb + i] = (int32_t)at;
+                if (mine)
+                    at += T.nPairs[i];
+            }
+            if (mine)
+                std::copy(T.pairs.begin(), T.pairs.end(), G.cellEdgeRef.begin() + 4 * pairBase[k]);
         }
     }
-    tick("tiles: references");
-    // ---- (edge, cell) pairs of the fused face-angle filter: the edges of a cell are the vertex pairs that two
-    //      of its faces share; both faces and both end points are already tile-local references ----
-    {
-        std::vector<int32_t> nPairs(C + 1, 0);
-        bool closed = true;
-        struct Half
-        {
-            uint16_t a, b, f;
-        };
-        auto cellPairs = [&](int32_t k, int32_t slot, std::vector<Half> &hs, uint16_t *out) -> int32_t {
-            // half edges of the cell's faces, sorted by end points; a closed cell has every edge exactly twice
-            hs.clear();
-            const int32_t fb = G.tileFaceOff[k];
-            for (int32_t q = G.slotOff[slot]; q < G.slotOff[slot + 1]; ++q)
-            {
-                const uint16_t li = G.slotRef[q] & 0x7fff;
-                const int32_t rb = G.faceRefOff[fb + li], nv = G.faceRefOff[fb + li + 1] - rb;
-                for (int32_t v = 0; v < nv; ++v)
-                {
-                    const uint16_t a = G.faceRef[rb + v], b = G.faceRef[rb + (v + 1 == nv ? 0 : v + 1)];
-                    hs.push_back({std::min(a, b), std::max(a, b), li});
-                }
-            }
-            std::sort(hs.begin(), hs.end(), [](const Half &x, const Half &y) {
-                return x.a != y.a ? x.a < y.a : (x.b != y.b ? x.b < y.b : x.f < y.f);
-            });
-            if (hs.size() % 2)
-                return -1;
-            int32_t n = 0;
-            for (size_t i = 0; i < hs.size(); i += 2)
-            {
-                if (hs[i].a != hs[i + 1].a || hs[i].b != hs[i + 1].b || hs[i].a == hs[i].b ||
-                    (i + 2 < hs.size() && hs[i + 2].a == hs[i].a && hs[i + 2].b == hs[i].b))
-                    return -1;
-                if (out)
-                {
-                    out[4 * n] = hs[i].a, out[4 * n + 1] = hs[i].b;
-                    out[4 * n + 2] = hs[i].f, out[4 * n + 3] = hs[i + 1].f;
-                }
-                ++n;
-            }
-            return n;
-        };
-        // canonical hexahedron record of a cell (see topology.hpp), checked against its pair list
-        auto hexRecord = [&](int32_t k, int32_t slot, const uint16_t *pairs, uint16_t rec[16]) -> bool {
-            const int32_t fb = G.tileFaceOff[k];
-            if (G.slotOff[slot + 1] - G.slotOff[slot] != 6)
-                return false;
-            uint16_t fl[6], fv[6][4];
-            for (int q = 0; q < 6; ++q)
-            {
-                fl[q] = G.slotRef[G.slotOff[slot] + q] & 0x7fff;
-                const int32_t rb = G.faceRefOff[fb + fl[q]];
-                if (G.faceRefOff[fb + fl[q] + 1] - rb != 4)
-                    return false;
-                for (int v = 0; v < 4; ++v)
-                    fv[q][v] = G.faceRef[rb + v];
-            }
-            auto has = [&](int q, uint16_t p) { return fv[q][0] == p || fv[q][1] == p || fv[q][2] == p || fv[q][3] == p; };
-            for (int q = 0; q < 16; ++q)
-                rec[q] = 0;
-            int B = -1;
-            for (int q = 1; q < 6; ++q)
-                if (!has(q, fv[0][0]) && !has(q, fv[0][1]) && !has(q, fv[0][2]) && !has(q, fv[0][3]))
-                    B = (B < 0) ? q : 99;
-            if (B < 1 || B > 5)
-                return false;
-            for (int e = 0; e < 4; ++e)
-            {
-                const uint16_t a = fv[0][e], b = fv[0][(e + 1) & 3];
-                int S = -1;
-                for (int q = 1; q < 6; ++q)
-                    if (q != B && has(q, a) && has(q, b))
-                        S = (S < 0) ? q : 99;
-                if (S < 1 || S > 5)
-                    return false;
-                int at = 0;
-                while (fv[S][at] != a)
-                    ++at;
-                // w_e: the neighbour of a in S's loop that is not b
-                const uint16_t n1 = fv[S][(at + 1) & 3], n2 = fv[S][(at + 3) & 3];
-                const uint16_t w = (n1 == b) ? n2 : n1;
-                if (!((n1 == b || n2 == b) && has(B, w)))
-                    return false;
-                rec[e] = a;
-                rec[4 + e] = w;
-                rec[10 + e] = fl[S];
-            }
-            rec[8] = fl[0];
-            rec[9] = fl[B];
-            // the fixed pattern must reproduce the cell's pair list
-            std::array<std::array<uint16_t, 4>, 12> want, got;
-            for (int j = 0; j < 12; ++j)
-                want[j] = {pairs[4 * j], pairs[4 * j + 1], std::min(pairs[4 * j + 2], pairs[4 * j + 3]), std::max(pairs[4 * j + 2], pairs[4 * j + 3])};
-            int ng = 0;
-            auto add = [&](uint16_t p0, uint16_t p1, uint16_t f0, uint16_t f1) {
-                got[ng++] = {std::min(p0, p1), std::max(p0, p1), std::min(f0, f1), std::max(f0, f1)};
-            };
-            for (int e = 0; e < 4; ++e)
-            {
-                add(rec[e], rec[(e + 1) & 3], rec[8], rec[10 + e]);
-                add(rec[4 + e], rec[4 + ((e + 1) & 3)], rec[9], rec[10 + e]);
-                add(rec[e], rec[4 + e], rec[10 + ((e + 3) & 3)], rec[10 + e]);
-            }
-            std::sort(want.begin(), want.end());
-            std::sort(got.begin(), got.end());
-            return want == got;
-        };
-        for (int32_t k = 0; k < G.nTiles; ++k)
-        {
-            G.maxTileCells = std::max(G.maxTileCells, G.tileCellOff[k + 1] - G.tileCellOff[k]);
-            G.maxTileFaces = std::max(G.maxTileFaces, G.tileFaceOff[k + 1] - G.tileFaceOff[k]);
-            G.maxTilePoints = std::max(G.maxTilePoints, G.tilePointOff[k + 1] - G.tilePointOff[k]);
-        }
-        // one pass: pair counts, closedness, and the canonical record of every cell that is a topological
-        // hexahedron; then the uniform tiles (all faces quadrilaterals, all cells such hexahedra) get their
-        // fixed-stride reference copies, and the pair lists are materialised for the cells of the other tiles
-        // (for all cells when the caller wants them for checking)
-        std::vector<uint8_t> cellIsHex(C, 0);
-        std::vector<uint16_t> recAll(16 * (size_t)C, 0); // cell-major, by slot
-#pragma omp parallel
-        {
-            std::vector<Half> hs;
-            std::vector<uint16_t> tmp;
-#pragma omp for schedule(dynamic, 16)
-            for (int32_t k = 0; k < G.nTiles; ++k)
-            {
-                const int32_t cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
-                for (int32_t i = 0; i < nc; ++i)
-                {
-                    const int32_t slot = cb + i;
-                    int32_t nHalf = 0;
-                    for (int32_t q = G.slotOff[slot]; q < G.slotOff[slot + 1]; ++q)
-                    {
-                        const int32_t at = G.tileFaceOff[k] + (G.slotRef[q] & 0x7fff);
-                        nHalf += G.faceRefOff[at + 1] - G.faceRefOff[at];
-                    }
-                    tmp.resize(2 * (size_t)nHalf + 4);
-                    const int32_t n = cellPairs(k, slot, hs, tmp.data());
-                    if (n < 0)
-                    {
-#pragma omp atomic write
-                        closed = false;
-                    }
-                    nPairs[slot + 1] = std::max(n, 0);
-                    if (n == 12 && hexRecord(k, slot, tmp.data(), &recAll[16 * (size_t)slot]))
-                        cellIsHex[slot] = 1;
-                }
-            }
-        }
-        G.tileUFaceOff.assign(G.nTiles, -1);
-        G.tileUCellOff.assign(G.nTiles, -1);
-        if (closed)
-        {
-            int64_t uf = 0, uc = 0;
-            for (int32_t k = 0; k < G.nTiles; ++k)
-            {
-                bool uni = true;
-                for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1] && uni; ++slot)
-                    uni = cellIsHex[slot] != 0;
-                for (int32_t i = G.tileFaceOff[k]; i < G.tileFaceOff[k + 1] && uni; ++i)
-                    uni = G.faceRefOff[i + 1] - G.faceRefOff[i] == 4;
-                if (!uni)
-                    continue;
-                G.tileUFaceOff[k] = (int32_t)uf;
-                G.tileUCellOff[k] = (int32_t)uc;
-                uf += G.tileFaceOff[k + 1] - G.tileFaceOff[k];
-                uc += G.tileCellOff[k + 1] - G.tileCellOff[k];
-            }
-            G.nUniformCells = uc;
-            G.uFaceRef.resize(4 * (size_t)uf);
-            G.uSlotRef.resize(6 * (size_t)uc);
-            G.hexRec.resize(16 * (size_t)uc);
-#pragma omp parallel for schedule(dynamic, 16)
-            for (int32_t k = 0; k < G.nTiles; ++k)
-            {
-                if (G.tileUCellOff[k] < 0)
-                    continue;
-                const int32_t fb = G.tileFaceOff[k], nf = G.tileFaceOff[k + 1] - fb, cb = G.tileCellOff[k], nc = G.tileCellOff[k + 1] - cb;
-                const size_t ufb = (size_t)G.tileUFaceOff[k], ucb = (size_t)G.tileUCellOff[k];
-                for (int32_t i = 0; i < nf; ++i)
-                    for (int q = 0; q < 4; ++q)
-                        G.uFaceRef[4 * (ufb + i) + q] = G.faceRef[G.faceRefOff[fb + i] + q];
-                for (int32_t i = 0; i < nc; ++i)
-                {
-                    for (int q = 0; q < 6; ++q)
-                        G.uSlotRef[6 * (ucb + i) + q] = G.slotRef[G.slotOff[cb + i] + q];
-                    const uint16_t *rec = &recAll[16 * (size_t)(cb + i)];
-                    uint16_t *o1 = &G.hexRec[16 * ucb + 8 * (size_t)i], *o2 = &G.hexRec[16 * ucb + 8 * (size_t)nc + 8 * (size_t)i];
-                    for (int q = 0; q < 8; ++q)
-                        o1[q] = rec[q], o2[q] = rec[8 + q];
-                }
-            }
-            G.uniformCellEdges = C ? nPairs[1] : 0;
-            for (int64_t c = 0; c < C && G.uniformCellEdges; ++c)
-                if (nPairs[c + 1] != G.uniformCellEdges)
-                    G.uniformCellEdges = 0;
-            // pair lists: for the cells of the non-uniform tiles (all cells if asked for)
-            int64_t total = 0;
-            std::vector<uint8_t> wantPairs(C, 0);
-            for (int32_t k = 0; k < G.nTiles; ++k)
-                if (keepPairs || G.tileUCellOff[k] < 0)
-                    for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
-                    {
-                        wantPairs[slot] = 1;
-                        total += nPairs[slot + 1];
-                    }
-            if (total > 0 && total < (int64_t)INT32_MAX / 2)
-            {
-                G.cellEdgeOff.assign(C + 1, 0);
-                for (int64_t c = 0; c < C; ++c)
-                    G.cellEdgeOff[c + 1] = G.cellEdgeOff[c] + (wantPairs[c] ? nPairs[c + 1] : 0);
-                G.cellEdgeRef.resize(4 * (size_t)total);
-                for (int32_t k = 0; k < G.nTiles; ++k)
-                    G.maxTileEdgePairs = std::max(G.maxTileEdgePairs, G.cellEdgeOff[G.tileCellOff[k + 1]] - G.cellEdgeOff[G.tileCellOff[k]]);
-#pragma omp parallel
-                {
-                    std::vector<Half> hs;
-#pragma omp for schedule(dynamic, 16)
-                    for (int32_t k = 0; k < G.nTiles; ++k)
-                        for (int32_t slot = G.tileCellOff[k]; slot < G.tileCellOff[k + 1]; ++slot)
-                            if (wantPairs[slot])
-                                cellPairs(k, slot, hs, G.cellEdgeRef.data() + 4 * (size_t)G.cellEdgeOff[slot]);
-                }
-            }
-        }
-        tick("tiles: (edge, cell) pairs");
-    }
+    G.uniformCellEdges = sameEdges ? firstCellEdges : 0;
+    tick("tiles: global arrays");
     return G;
 }
 

@@ -22,32 +22,32 @@ struct Topology
     int64_t P = 0, C = 0, F = 0, Fi = 0, E = 0;
 
     // point -> cells (ascending)
-    std::vector<int32_t> pcOff, pc;
+    Vec<int32_t> pcOff, pc;
     // point -> edge-connected points (ascending) and the matching edge labels
-    std::vector<int32_t> ppOff, pp, pe;
+    Vec<int32_t> ppOff, pp, pe;
     // point -> face corners: for each face of pointFaces(p) (ascending) the previous and
     // next vertex of p in that face: corner[2*k], corner[2*k+1]
-    std::vector<int32_t> cornerOff, corner;
+    Vec<int32_t> cornerOff, corner;
     // edges (lo,hi), numbered upper-triangular
-    std::vector<int32_t> edge;
+    Vec<int32_t> edge;
     // edge -> faces (ascending)
-    std::vector<int32_t> efOff, ef;
+    Vec<int32_t> efOff, ef;
     // edge -> cells, each with the positions (within the edge's face row) of the two
     // faces of that cell that meet at the edge: ecPair = f0 | f1<<16
-    std::vector<int32_t> ecOff, ecCell, ecPair;
+    Vec<int32_t> ecOff, ecCell, ecPair;
     // faces (copied from the mesh; vertex loops)
-    std::vector<int32_t> faceOff, faceVerts;
+    Vec<int32_t> faceOff, faceVerts;
     // cell -> faces in OpenFOAM's cell-centre accumulation order: faces the cell owns
     // (ascending), then faces it neighbours (ascending, bit 31 set)
-    std::vector<int32_t> cfOff, cf;
+    Vec<int32_t> cfOff, cf;
     // Fixed-size, vector-loadable records for the common low-valence case; the CSR tables above
     // stay authoritative and serve the generic path (flag bit 31 of the meta word).
     //   pointRec  16 words/point: pc[0..7], pp[8..13], [14] = nCells | nNbrs<<8 | generic<<31,
     //             [15] = mask over the 15 unordered pairs of pp positions that are face corners of the point
     //   edgeRec   12 words/edge : e0,e1, f[4], c[4], [10] = nf | nc<<4 | generic<<31; faces in fan order around
     //             the edge, cell k lies between face k and face (k+1) mod nf
-    std::vector<int32_t> pointRec, edgeRec;
-    std::vector<uint8_t> isInternal; // src/smoothMesh.C:40-91
+    Vec<int32_t> pointRec, edgeRec;
+    Vec<uint8_t> isInternal; // src/smoothMesh.C:40-91
     std::vector<int32_t> procPoints; // points on processor patches (ascending)
     double minEdgeLength = 0, maxEdgeLength = 0; // src/smoothMesh.C:1478-1541
     int32_t maxPointDegree = 0, maxFaceSize = 0, maxEdgeFaces = 0;
@@ -86,15 +86,15 @@ LayerSetup buildLayerSetupParallel(const PolyMesh &m, const Topology &t, const s
 struct GeomTiles
 {
     int32_t nTiles = 0;
-    std::vector<int32_t> tileCellOff, tileCells; // cells of tile t: tileCells[tileCellOff[t] .. tileCellOff[t+1])
-    std::vector<int32_t> tileFaceOff, tileFaces; // its faces, ascending; bit 31: this tile stores the face's global outputs
-    std::vector<int32_t> slotOff;                // per cell slot (position in tileCells): offsets into slotRef
-    std::vector<uint16_t> slotRef;               // index of the face in the tile's list, in the order of Topology::cf; bit 15 = neighbour side
+    Vec<int32_t> tileCellOff, tileCells; // cells of tile t: tileCells[tileCellOff[t] .. tileCellOff[t+1])
+    Vec<int32_t> tileFaceOff, tileFaces; // its faces, ascending; bit 31: this tile stores the face's global outputs
+    Vec<int32_t> slotOff;                // per cell slot (position in tileCells): offsets into slotRef
+    Vec<uint16_t> slotRef;               // index of the face in the tile's list, in the order of Topology::cf; bit 15 = neighbour side
     // the points the tile's faces use (staged in shared memory before the face pass) and, per listed face,
     // its vertices as indices into that list
-    std::vector<int32_t> tilePointOff, tilePoints; // ascending point labels
-    std::vector<int32_t> faceRefOff;               // per listed face (position in tileFaces) + 1: offsets into faceRef
-    std::vector<uint16_t> faceRef;
+    Vec<int32_t> tilePointOff, tilePoints; // ascending point labels
+    Vec<int32_t> faceRefOff;               // per listed face (position in tileFaces) + 1: offsets into faceRef
+    Vec<uint16_t> faceRef;
     // The (edge, cell) pairs of the fused face-angle filter: for every cell slot, each edge of the cell with its
     // end points (indices into the tile's point list) and the two faces of the cell that meet at it (indices
     // into the tile's face list) -- what calcMinMaxFaceAngleForEdge (src/smoothMesh.C:1135-1231) visits for this
@@ -102,22 +102,22 @@ struct GeomTiles
     // uniformCellEdges > 0 when every cell has that many.  Empty when some cell is not closed (an edge not shared
     // by exactly two of its faces: the caller then keeps the per-edge kernel) and, unless asked for, on
     // all-hexahedra meshes, where hexRec replaces them.
-    std::vector<int32_t> cellEdgeOff;
-    std::vector<uint16_t> cellEdgeRef;
+    Vec<int32_t> cellEdgeOff;
+    Vec<uint16_t> cellEdgeRef;
     // All-hexahedra meshes: the same pairs as a canonical record per cell slot, 16 x uint16:
     //   v0..v3 (vertex loop of one face A), w0..w3 (w_i = the vertex joined to v_i by an edge, on the opposite
     //   face B), A, B, S0..S3 (S_i = the side face through v_i, v_i+1, w_i+1, w_i), 2 x padding.
     // The twelve (edge, cell) pairs are then a fixed pattern: (v_i, v_i+1 | A, S_i), (w_i, w_i+1 | B, S_i),
     // (v_i, w_i | S_i-1, S_i).  Stored for the uniform tiles only (see below), per tile: the first 8 entries of all
     // its cells, then the second 8 (two conflict-free 16-byte reads per thread), at 16 * tileUCellOff[t].
-    std::vector<uint16_t> hexRec;
+    Vec<uint16_t> hexRec;
     // Per-tile fast path: a tile all of whose listed faces are quadrilaterals and all of whose cells are
     // topological hexahedra is "uniform" and reads fixed-stride copies of its references -- uFaceRef: 4 x uint16 per
     // listed face, uSlotRef: 6 x uint16 per cell, hexRec as above -- at tileUFaceOff[t] / tileUCellOff[t] (counted
     // over the uniform tiles only; -1 for the other tiles, which go through the offset tables).  A mesh of
     // hexahedra only has tileUFaceOff == tileFaceOff and tileUCellOff == tileCellOff.
-    std::vector<int32_t> tileUFaceOff, tileUCellOff;
-    std::vector<uint16_t> uFaceRef, uSlotRef;
+    Vec<int32_t> tileUFaceOff, tileUCellOff;
+    Vec<uint16_t> uFaceRef, uSlotRef;
     int64_t nUniformCells = 0;
     int32_t uniformCellEdges = 0;
     int32_t maxTileCells = 0, maxTileFaces = 0, maxTilePoints = 0, maxTileEdgePairs = 0;
