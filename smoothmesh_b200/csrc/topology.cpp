@@ -1122,12 +1122,13 @@ GeomTiles buildGeomTiles(const PolyMesh &m, const Topology &t, int maxCells, int
     // runs are closed at maxCells cells and at every aligned block of 2^8 keys (an 8 x 8 x 4 brick of a
     // block-structured mesh), so that a brick cut short by the mesh boundary does not shift all later tiles
     // off the brick grid (271^3: 33 full bricks and one of 7 cells per row)
+    const int alignBits = maxCells >= 256 ? 8 : (maxCells == 128 ? 7 : 0);
     std::vector<std::pair<int32_t, int32_t>> runs;
     for (int64_t i = 0; i < C;)
     {
         int64_t j = i;
-        const uint64_t block = keys[i].first >> 8;
-        while (j < C && j - i < maxCells && (maxCells < 256 || (keys[j].first >> 8) == block))
+        const uint64_t block = keys[i].first >> alignBits;
+        while (j < C && j - i < maxCells && (alignBits == 0 || (keys[j].first >> alignBits) == block))
             ++j;
         runs.push_back({(int32_t)i, (int32_t)j});
         i = j;
