@@ -13,20 +13,27 @@ def launches(path):
     hdr = next(i for i, r in enumerate(rows) if r[0] == "ID")
     H = rows[hdr]
     d = collections.defaultdict(list)
+    dram = collections.defaultdict(float)  # bytes read + written, if the pass collected them
     for r in rows[hdr + 1:]:
         rec = dict(zip(H, r))
+        name = rec["Kernel Name"].split("(")[0]
+        val = float(rec["Metric Value"].replace(",", "") or 0)
         if rec.get("Metric Name") == "gpu__time_duration.sum":
-            d[rec["Kernel Name"].split("(")[0]].append(float(rec["Metric Value"].replace(",", "")) / 1e3)
+            d[name].append(val / 1e3)
+        elif rec.get("Metric Name") in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(rec.get("Metric Unit", "byte"), 1.0)
+            dram[name] += val * scale
     tot = sum(sum(v) for v in d.values())
-    print(f"{'kernel':24s} {'launches':>8s} {'avg us':>10s} {'share':>7s}   (ncu-serialised, cold cache: compare shares)")
+    print(f"{'kernel':24s} {'launches':>8s} {'avg us':>10s} {'share':>7s} {'DRAM MB/launch':>15s}   (ncu-serialised, cold cache: compare shares)")
     for k, v in sorted(d.items(), key=lambda kv: -sum(kv[1])):
-        print(f"{k:24s} {len(v):8d} {sum(v) / len(v):10.1f} {sum(v) / tot:7.3f}")
+        mb = f"{dram[k] / len(v) / 1e6:15.1f}" if k in dram else f"{'-':>15s}"
+        print(f"{k:24s} {len(v):8d} {sum(v) / len(v):10.1f} {sum(v) / tot:7.3f} {mb}")
 
 
 def full(path):
     rows = list(csv.reader(open(path)))
     H = rows[0]
-    cols = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "rd"), ("dram__bytes_write.sum", "wr"),
+    cols = [("gpu__time_duration.sum", "t"), ("dram__bytes_read.sum", "rd"), ("dram__bytes_write.sum", "wr"),
             ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
             ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"),
             ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
@@ -41,7 +48,7 @@ def full(path):
         for c, label in cols:
             if c in H:
                 i = H.index(c)
-                out.append(f"{label}={r[i]}{units[i] if label in ('rd', 'wr') else ''}")
+                out.append(f"{label}={r[i]}{units[i] if label in ('rd', 'wr', 't') else ''}")
         top = sorted(((float(r[i].replace(',', '') or 0), h.split('stalled_')[1].replace('_per_issue_active.ratio', '')) for i, h in stall), reverse=True)[:3]
         print(f"{name:22s} " + " ".join(out))
         print(f"{'':22s} top stalls (warps per issue): " + ", ".join(f"{n} {v:.1f}" for v, n in top))
