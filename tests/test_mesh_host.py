@@ -371,3 +371,22 @@ def test_geometry_tiles_of_a_hex_dominant_mesh_keep_the_fast_path_per_tile():
     assert 0 < g["uniform_tile_cells"] < 12 ** 3 + 4 * 12 * 12 and g["uniform_cell_edges"] == 0
     h = hex_jittered(8, 8, 8, 0.2).geom_tiles()
     assert h["uniform_tile_cells"] == 512 and h["uniform_cell_edges"] == 12
+
+
+def test_setup_tables_do_not_depend_on_the_thread_count(tmp_path):
+    """The set-up builds every connectivity table and the geometry tiles with per-thread row buffers, atomic
+    cursors and parallel prefix sums (topology.cpp); the result must be the same for any number of threads.
+    tools/setup_timing.cpp prints a fingerprint of every table."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["make", "-s", "build/setup_timing"], cwd=root, check=True, capture_output=True)
+    from meshes import mixed_hex_prism_block
+    mixed_hex_prism_block(7).write(str(tmp_path / "mixed" / "constant" / "polyMesh"))
+    for args in (["hex", "19"], ["kelvin", "5"], ["dir", str(tmp_path / "mixed" / "constant" / "polyMesh")]):
+        outs = []
+        for threads in ("1", "3", "8"):
+            env = dict(os.environ, OMP_NUM_THREADS=threads)
+            r = subprocess.run([os.path.join(root, "build", "setup_timing")] + args, env=env, check=True, capture_output=True, text=True)
+            assert "t.ecPair" in r.stdout and "T.hexRec" in r.stdout
+            outs.append(r.stdout)
+        assert outs[0] == outs[1] == outs[2], args
