@@ -627,7 +627,7 @@ struct smgpu_handle
         const int nChunks = grid(d.P, SMK_CHUNK);
         profBegin(K_FACE_CUR);
         if (d.fusedFaceFilter && !dbgMin)
-            k_face_suspects<<<grid(d.P, 128), 128, 0, stream>>>(d); // the pairs k_geom_tiles_f did not certify
+            k_face_suspects<<<grid(d.P, 4 * SMK_SUSPECT_WINDOW), 128, 0, stream>>>(d); // the pairs k_geom_tiles_f did not certify
         else
             k_face_current<<<grid(d.E, 128), 128, 0, stream>>>(d, dbgMin, dbgMax);
         profEnd(1);
@@ -1518,6 +1518,7 @@ extern "C"
             d.reach = h->dalloc<int>(t.P);
             d.rootHi = h->dalloc<int>(t.P);
             d.changed = h->dalloc<int>(8);
+            CK(cudaMemset(d.changed, 0, 8 * sizeof(int))); // [6]: running count of active points (k_active_count -> k_active_scan)
             {
                 // cooperative launch of k_face_resolve: as many blocks as can be co-resident
                 int perSm = 0, sms = 0;
@@ -1612,8 +1613,8 @@ extern "C"
                         d.cellEdgeOff = h->upload(G.cellEdgeOff);
                         d.cellEdgeRef = (const uint2 *)h->upload(G.cellEdgeRef);
                     }
-                    d.suspect = h->dalloc<uint8_t>(t.P + 8);
-                    CK(cudaMemset(d.suspect, 0, t.P + 8));
+                    d.suspect = h->dalloc<uint8_t>(t.P + 16); // k_face_suspects reads whole 16-byte words
+                    CK(cudaMemset(d.suspect, 0, t.P + 16));
                     h->tilesF = !oldTiles && h->tileSmem <= 110 * 1024;
                     // the attribute belongs to the function, not to this handle: always the device's opt-in maximum,
                     // so that a later handle with smaller tiles does not lower it under an earlier handle's launches
@@ -1674,6 +1675,9 @@ extern "C"
             tick("work space, tiles");
             h->joinUploads();
             tick("upload of tables (remainder)");
+            // share-a-cell bits of the point records (kernels.cuh shareCellRec), from the tables now on the device
+            if (!(getenv("SMGPU_NO_SHARE_MASK") && atoi(getenv("SMGPU_NO_SHARE_MASK")) != 0))
+                k_share_mask<<<smgpu_handle::grid(d.P, 128), 128, 0, h->stream>>>(d);
             d.errFlag = h->dalloc<int>(1);
             CK(cudaMemset(d.errFlag, 0, sizeof(int)));
             if (h->anyLayerPatch)

@@ -134,7 +134,7 @@ def test_no_gpu_fallback_message():
 
 @pytest.mark.parametrize("case", ["hex_8x6x5_j45", "kelvin3_j20"])
 @pytest.mark.parametrize("env", ["SMGPU_NO_FILTERS", "SMGPU_NO_F32", "SMGPU_NO_TILES", "SMGPU_FORCE_TILES",
-                                 "SMGPU_NO_FUSED_FILTER", "SMGPU_OLD_TILES", "SMGPU_POINT_TILES"])
+                                 "SMGPU_NO_FUSED_FILTER", "SMGPU_OLD_TILES", "SMGPU_POINT_TILES", "SMGPU_NO_SHARE_MASK"])
 def test_literal_path_without_filters(case, env, monkeypatch):
     # SMGPU_NO_FILTERS=1 disables the guard-banded cosine-space filters so that every point /
     # edge takes the literal evaluation; SMGPU_NO_F32=1 disables only the single-precision first
@@ -268,3 +268,21 @@ def test_hex_dominant_mesh_uses_both_tile_paths_and_matches_oracle(n, frac):
     log = g.iterate(4)
     assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
     assert np.array_equal(g.points(), o.get("points")) and np.array_equal(g.frozen(), o.get("frozen"))
+
+
+def test_share_a_cell_bits_of_the_point_records_match_the_literal_test(monkeypatch):
+    """High-aspect-ratio layers: the midpoint-of-two-closest-points blend is active at most points, so the
+    hasCommonCell short cut (src/smoothMesh.C:383) decides positions.  The predictor reads it from the bits
+    k_share_mask put into the point records; SMGPU_NO_SHARE_MASK=1 keeps the literal row intersection."""
+    from meshes import prism_layers
+    mesh = prism_layers(n=10, layers=8, thickness=0.01, frac=0.3, seed=17)
+    g = sm.Smoother(mesh, rel_tol=0.0)
+    log = g.iterate(5)
+    o = Oracle(mesh.desc_arrays(), rel_tol=0.0)
+    n, nf, res = o.iterate(5)
+    assert np.array_equal(log.n_frozen, nf) and np.array_equal(log.residual, res)
+    assert np.array_equal(g.points(), o.get("points"))
+    monkeypatch.setenv("SMGPU_NO_SHARE_MASK", "1")
+    lit = sm.Smoother(mesh, rel_tol=0.0)
+    lit.iterate(5)
+    assert np.array_equal(g.points(), lit.points()) and np.array_equal(g.frozen(), lit.frozen())
