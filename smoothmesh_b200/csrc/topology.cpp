@@ -40,18 +40,20 @@ inline void rangeOf(int64_t n, int tid, int nThreads, int64_t &lo, int64_t &hi)
     lo = n * tid / nThreads;
     hi = n * (tid + 1) / nThreads;
 }
-// off[0] = 0 and off[i + 1] = length of row i on entry, the running sums on exit; returns the longest row.  Every
-// thread scans the range of rows it filled (the same rangeOf partition), so the lengths are read where they were written.
-int32_t parScan(Vec<int32_t> &off, int64_t n, int nThreads)
+// off[0] = 0 and off[i + 1] = length of row i on entry, the running sums on exit; returns the longest row.  The
+// rows are cut into the same nParts ranges as where they were filled (rangeOf), so the lengths are mostly read by
+// the thread that wrote them.  The ranges are work items of an `omp for`, not thread numbers: the result does not
+// depend on how many threads the runtime actually grants.
+int32_t parScan(Vec<int32_t> &off, int64_t n, int nParts)
 {
-    std::vector<int64_t> sum(nThreads + 1, 0);
-    std::vector<int32_t> longest(nThreads, 0);
+    std::vector<int64_t> sum(nParts + 1, 0);
+    std::vector<int32_t> longest(nParts, 0);
     off[0] = 0;
-#pragma omp parallel num_threads(nThreads)
+#pragma omp parallel for schedule(static, 1)
+    for (int part = 0; part < nParts; ++part)
     {
-        const int tid = omp_get_thread_num();
         int64_t lo, hi;
-        rangeOf(n, tid, nThreads, lo, hi);
+        rangeOf(n, part, nParts, lo, hi);
         int64_t s = 0;
         int32_t mx = 0;
         for (int64_t i = lo; i < hi; ++i)
@@ -59,21 +61,25 @@ int32_t parScan(Vec<int32_t> &off, int64_t n, int nThreads)
             s += off[i + 1];
             mx = std::max(mx, off[i + 1]);
         }
-        sum[tid + 1] = s;
-        longest[tid] = mx;
-#pragma omp barrier
-#pragma omp single
-        for (int k = 0; k < nThreads; ++k)
-            sum[k + 1] += sum[k];
-        int64_t run = sum[tid];
+        sum[part + 1] = s;
+        longest[part] = mx;
+    }
+    for (int k = 0; k < nParts; ++k)
+        sum[k + 1] += sum[k];
+    if (sum[nParts] >= (int64_t)INT32_MAX)
+        fail("mesh too large for 32-bit offsets");
+#pragma omp parallel for schedule(static, 1)
+    for (int part = 0; part < nParts; ++part)
+    {
+        int64_t lo, hi;
+        rangeOf(n, part, nParts, lo, hi);
+        int64_t run = sum[part];
         for (int64_t i = lo; i < hi; ++i)
         {
             run += off[i + 1];
             off[i + 1] = (int32_t)run;
         }
     }
-    if (sum[nThreads] >= (int64_t)INT32_MAX)
-        fail("mesh too large for 32-bit offsets");
     return *std::max_element(longest.begin(), longest.end());
 }
 } // namespace
@@ -208,9 +214,9 @@ Topology buildTopology(const PolyMesh &m)
     Vec<int32_t> upStart(P + 1); // first edge label of point p = #edges (a,b) with a<p
     {
         std::vector<RowBuf> pcPart(nThreads), ppPart(nThreads);
-#pragma omp parallel num_threads(nThreads)
-        {
-            const int tid = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1)
+        for (int tid = 0; tid < nThreads; ++tid)
+        { // tid numbers a range of rows (a work item), not a thread
             int64_t lo, hi;
             rangeOf(P, tid, nThreads, lo, hi);
             const int64_t rows = t.cornerOff[hi] - t.cornerOff[lo];
@@ -246,9 +252,9 @@ Topology buildTopology(const PolyMesh &m)
         parScan(upStart, P, nThreads);
         t.pc.resize(t.pcOff[P]);
         t.pp.resize(t.ppOff[P]);
-#pragma omp parallel num_threads(nThreads)
-        {
-            const int tid = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1)
+        for (int tid = 0; tid < nThreads; ++tid)
+        { // tid numbers a range of rows (a work item), not a thread
             int64_t lo, hi;
             rangeOf(P, tid, nThreads, lo, hi);
             std::copy(pcPart[tid].v.begin(), pcPart[tid].v.begin() + pcPart[tid].n, t.pc.begin() + t.pcOff[lo]);
@@ -300,9 +306,9 @@ Topology buildTopology(const PolyMesh &m)
     int bad = 0;
     {
         std::vector<RowBuf> efPart(nThreads), ccPart(nThreads), cpPart(nThreads);
-#pragma omp parallel num_threads(nThreads)
-        {
-            const int tid = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1)
+        for (int tid = 0; tid < nThreads; ++tid)
+        { // tid numbers a range of rows (a work item), not a thread
             int64_t lo, hi;
             rangeOf(E, tid, nThreads, lo, hi);
             // sum over the edges of their faces = sum over the faces of their vertices
@@ -373,9 +379,9 @@ Topology buildTopology(const PolyMesh &m)
         t.ef.resize(t.efOff[E]);
         t.ecCell.resize(t.ecOff[E]);
         t.ecPair.resize(t.ecOff[E]);
-#pragma omp parallel num_threads(nThreads)
-        {
-            const int tid = omp_get_thread_num();
+#pragma omp parallel for schedule(static, 1)
+        for (int tid = 0; tid < nThreads; ++tid)
+        { // tid numbers a range of rows (a work item), not a thread
             int64_t lo, hi;
             rangeOf(E, tid, nThreads, lo, hi);
             std::copy(efPart[tid].v.begin(), efPart[tid].v.begin() + efPart[tid].n, t.ef.begin() + t.efOff[lo]);

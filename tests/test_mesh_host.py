@@ -384,9 +384,10 @@ def test_setup_tables_do_not_depend_on_the_thread_count(tmp_path):
     mixed_hex_prism_block(7).write(str(tmp_path / "mixed" / "constant" / "polyMesh"))
     for args in (["hex", "19"], ["kelvin", "5"], ["dir", str(tmp_path / "mixed" / "constant" / "polyMesh")]):
         outs = []
-        for threads in ("1", "3", "8"):
-            env = dict(os.environ, OMP_NUM_THREADS=threads)
+        # the last entry: the runtime grants fewer threads than asked for (the row ranges are work items, not threads)
+        for threads, extra in (("1", {}), ("3", {}), ("8", {}), ("8", {"OMP_THREAD_LIMIT": "3", "OMP_DYNAMIC": "true"})):
+            env = dict(os.environ, OMP_NUM_THREADS=threads, **extra)
             r = subprocess.run([os.path.join(root, "build", "setup_timing")] + args, env=env, check=True, capture_output=True, text=True)
             assert "t.ecPair" in r.stdout and "T.hexRec" in r.stdout
             outs.append(r.stdout)
-        assert outs[0] == outs[1] == outs[2], args
+        assert outs[0] == outs[1] == outs[2] == outs[3], args
